@@ -1,0 +1,141 @@
+/*
+ * srnn_b200.h -- C-ABI of the B200-native SampleRNN hot path.
+ *
+ * The reference (mahdeslami11/jalil-saboorizadeh-Multi-speaker-Neural-Vocoder) has no FFI layer: its
+ * boundary is the Python class API of model.py (SampleRNN / Predictor / Generator) plus the
+ * checkpoint layout.  This header is the seam a maintainer binds underneath those classes
+ * (ctypes stub in INTEGRATION.md); every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - every call returns 0 on success, <0 on error (text via srnn_last_error()); nothing throws;
+ *   - no call synchronises the device; work is enqueued on `stream`;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns SRNN_ERR_CUDA.
+ */
+#ifndef SRNN_B200_H
+#define SRNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SRNN_API __attribute__((visibility("default")))
+#else
+#define SRNN_API
+#endif
+
+#define SRNN_MAX_TIERS 4
+#define SRNN_MAX_RNN   4
+#define SRNN_Q         256   /* q_levels supported by the kernels (train.py:36 default) */
+
+#define SRNN_OK            0
+#define SRNN_ERR_ARG      -1
+#define SRNN_ERR_CUDA     -2
+#define SRNN_ERR_STATE    -3
+#define SRNN_ERR_UNSUPPORTED -4
+
+/* arithmetic mode of the GEMM-shaped work */
+#define SRNN_MODE_FP32   0   /* fp32 FFMA everywhere: the 1e-3 "fp32 parity" gate                        */
+#define SRNN_MODE_BF16   1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: the speed mode */
+
+typedef struct srnn_ctx srnn_ctx;
+
+/* Constructor arguments of SampleRNN (model.py:20). */
+typedef struct {
+    int32_t n_tiers;                        /* len(frame_sizes) = number of FrameLevelRNN tiers            */
+    int32_t frame_sizes[SRNN_MAX_TIERS];    /* frame_sizes[0] = lowest tier (model.py:46-55)               */
+    int32_t n_rnn;                          /* GRU layers per tier                                         */
+    int32_t dim;                            /* H                                                           */
+    int32_t q_levels;                       /* must equal SRNN_Q                                           */
+    int32_t cond_dim;                       /* conditioner width (43, or 86 with look-ahead)               */
+    int32_t spk_dim;                        /* speaker count = embedding width (model.py:103-106)          */
+    int32_t ulaw;                           /* 1: utils.udequantize, 0: utils.linear_dequantize            */
+} srnn_config;
+
+/* One Conv1d / ConvTranspose1d as stored in Predictor.state_dict():
+ * either `weight`, or the weight_norm pair `weight_g` + `weight_v`; `bias` may be NULL. fp32. */
+typedef struct {
+    const float* weight;
+    const float* weight_g;
+    const float* weight_v;
+    const float* bias;
+} srnn_conv_params;
+
+/* FrameLevelRNN parameters (model.py:67-178), reference layouts, fp32. */
+typedef struct {
+    const float* h0;                        /* (n_rnn, H)                                                  */
+    srnn_conv_params input_expand;          /* (H, n_frame_samples, 1)                                     */
+    srnn_conv_params cond_expand;           /* (H, cond_dim, 1)   top tier only                            */
+    const float* spk_embedding;             /* (spk_dim, spk_dim) top tier only                            */
+    srnn_conv_params spk_expand;            /* (H, spk_dim, 1)    top tier only                            */
+    const float* weight_ih[SRNN_MAX_RNN];   /* (3H, H) gate row blocks r, z, n                             */
+    const float* weight_hh[SRNN_MAX_RNN];
+    const float* bias_ih[SRNN_MAX_RNN];     /* (3H)                                                        */
+    const float* bias_hh[SRNN_MAX_RNN];
+    srnn_conv_params upsampling;            /* conv_t weight (H_in, H_out, k); .bias = upsampling.bias (H, k) */
+} srnn_tier_params;
+
+typedef struct {
+    srnn_tier_params tiers[SRNN_MAX_TIERS];
+    const float* embedding;                 /* (Q, Q)        model.py:274-277                              */
+    srnn_conv_params mlp_input;             /* (H, Q, FS0), no bias  model.py:279-284                      */
+    srnn_conv_params mlp_hidden;            /* (H, H, 1)     model.py:287-293                              */
+    srnn_conv_params mlp_output;            /* (Q, H, 1)     model.py:295-301                              */
+} srnn_params;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+SRNN_API const char* srnn_last_error(void);
+SRNN_API int srnn_version(void);
+/* Replaces SampleRNN.__init__ (model.py:20-62) as far as device state goes. */
+SRNN_API int srnn_create(const srnn_config* cfg, srnn_ctx** out);
+SRNN_API int srnn_destroy(srnn_ctx* ctx);
+SRNN_API int srnn_lookback(const srnn_ctx* ctx);                 /* SampleRNN.lookback  model.py:60-62            */
+
+/* Snapshot the parameters into the kernels' layouts: weight-norm fold (model.py:119-121,130-131,
+ * 177-178,303-306 recompute it every forward), K-concatenated top-tier input matrix
+ * [input_expand | cond_expand | spk_expand . spk_embedding^T], phase-major upsampling matrix
+ * (nn.py:33-43), the exact embedding-o-conv fold Tbl[j][q][:] = W_in[:,:,j] . E[q,:]
+ * (model.py:311-317), the dequantiser LUT (utils.py:18-19,39-63) and bf16 copies. */
+SRNN_API int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* params, void* stream);
+
+/* ---- Predictor.forward (model.py:357-436) ----------------------------------------------------- */
+/* input_seq (B, lookback+T-1) int64 in [0,Q); cond (B, T/lookback, cond_dim) fp32 or fp64 (cond_is_f64);
+ * spk (B) int64; hidden_io[t] (n_rnn, B, H) fp32 per tier, always overwritten with the carry
+ * (Runner.run_rnn model.py:348); reset_mask bit t set = tier t starts from its h0 (hidden_states[rnn] is
+ * None, model.py:222-228), clear = starts from hidden_io[t]; logp_out (B, T, Q) fp32 log-probabilities. */
+SRNN_API int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_seq, const void* cond,
+                     int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
+                     float* logp_out, int32_t mode, void* stream);
+
+/* ---- Generator.__call__ (model.py:445-520) ---------------------------------------------------- */
+/* cond (cond_rows, n_cond, cond_dim) fp32 with cond_rows == 1 (reference form: one conditioner for all
+ * sequences, model.py:484-487) or == B (per-utterance extension); spk (cond_rows) int64;
+ * uniforms (n_cond*lookback, B) fp32 in [0,1), indexed [t][b] (defined sampler, see srnn_sample_rows);
+ * samples_out (B, n_cond*lookback) uint8 quantised samples; audio_out (same shape) fp32 dequantised
+ * audio = what the reference returns (model.py:520), may be NULL; logp_out (B, T, Q) fp32 per-step
+ * log-probs for parity tests, may be NULL.  The whole autoregressive loop runs on the device. */
+SRNN_API int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, int32_t cond_rows,
+                  const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
+                  float* logp_out, int32_t mode, void* stream);
+
+/* ---- per-kernel test hooks -------------------------------------------------------------------- */
+/* The defined sampler replacing Tensor.multinomial (model.py:517): p (rows, 256) fp32 unnormalised,
+ * u (rows) fp32 -> idx (rows) int32.  Bit-exact with oracle/srnn_oracle.py:sample_rows. */
+SRNN_API int srnn_sample_rows(const float* p, const float* u, int32_t rows, int32_t* idx, void* stream);
+/* out (256) fp32 = 2*dequantize(q) (model.py:385,471). */
+SRNN_API int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream);
+/* C (M,N) = A (M,K) . B (N,K)^T + bias (N) [+ addend (M,N)] [relu]; row-major fp32; mode as above. */
+SRNN_API int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
+              const float* addend, int32_t relu, float* C, int32_t mode, void* stream);
+/* number of kernels this library has launched since load (bench.py's gpu_launches). */
+SRNN_API int64_t srnn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRNN_B200_H */

@@ -1,0 +1,12 @@
+"""B200-native SampleRNN hot path (generation + teacher-forced step) behind the reference ``model.py`` API.
+
+The directory name carries hyphens (it mirrors the reference repository's name), so import it with
+``importlib.import_module("jalil-saboorizadeh-multi-speaker-neural-vocoder_b200")`` or through the root-level
+alias module ``srnn_b200``.
+"""
+from . import _lib
+from ._lib import MODE_BF16, MODE_FP32, SrnnError
+from .model import FrameLevelRNN, Generator, LearnedUpsampling1d, Predictor, Runner, SampleLevelMLP, SampleRNN
+
+__all__ = ["SampleRNN", "Predictor", "Generator", "Runner", "FrameLevelRNN", "SampleLevelMLP",
+           "LearnedUpsampling1d", "MODE_FP32", "MODE_BF16", "SrnnError", "_lib"]

@@ -1,0 +1,421 @@
+// C-ABI entry points (include/srnn_b200.h): context, weight packing, Predictor.forward, Generator.__call__.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace srnn {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int Arena::alloc(void** p, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    SRNN_CUDA(cudaMalloc(p, bytes));
+    ptrs.push_back(*p);
+    return SRNN_OK;
+}
+void Arena::release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+}
+
+int ensure_ws(srnn_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return SRNN_OK;
+    if (ctx->ws) {
+        SRNN_CUDA(cudaDeviceSynchronize());
+        SRNN_CUDA(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+    }
+    bytes += bytes / 8;
+    SRNN_CUDA(cudaMalloc(&ctx->ws, bytes));
+    ctx->ws_bytes = bytes;
+    return SRNN_OK;
+}
+
+// two-pass bump allocator over the scratch buffer: pass 1 (base == nullptr) sizes it, pass 2 hands out pointers
+struct Bump {
+    char* base;
+    size_t off = 0;
+    explicit Bump(void* b) : base((char*)b) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static int check_ready(const srnn_ctx* ctx) {
+    if (!ctx) return fail(SRNN_ERR_ARG, "null context");
+    if (!ctx->packed) return fail(SRNN_ERR_STATE, "srnn_pack_weights has not been called");
+    return SRNN_OK;
+}
+
+}  // namespace srnn
+
+using namespace srnn;
+
+extern "C" {
+
+const char* srnn_last_error(void) { return g_err; }
+int srnn_version(void) { return 100; }
+int64_t srnn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int srnn_create(const srnn_config* cfg, srnn_ctx** out) {
+    if (!cfg || !out) return fail(SRNN_ERR_ARG, "null argument");
+    if (cfg->n_tiers < 1 || cfg->n_tiers > SRNN_MAX_TIERS) return fail(SRNN_ERR_ARG, "n_tiers must be in [1,%d]", SRNN_MAX_TIERS);
+    if (cfg->n_rnn < 1 || cfg->n_rnn > SRNN_MAX_RNN) return fail(SRNN_ERR_ARG, "n_rnn must be in [1,%d]", SRNN_MAX_RNN);
+    if (cfg->q_levels != SRNN_Q) return fail(SRNN_ERR_UNSUPPORTED, "q_levels must be %d", SRNN_Q);
+    if (cfg->dim < 1 || cfg->cond_dim < 1 || cfg->spk_dim < 1) return fail(SRNN_ERR_ARG, "dim/cond_dim/spk_dim must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SRNN_ERR_CUDA, "no CUDA device: this library has no CPU fallback (%s)", cudaGetErrorString(e));
+    }
+    srnn_ctx* c = new srnn_ctx();
+    c->cfg = *cfg;
+    c->H = cfg->dim;
+    c->FS0 = cfg->frame_sizes[0];
+    int n = 1;
+    for (int i = 0; i < cfg->n_tiers; ++i) {
+        if (cfg->frame_sizes[i] < 1) { delete c; return fail(SRNN_ERR_ARG, "frame_sizes[%d] must be positive", i); }
+        n *= cfg->frame_sizes[i];                       // np.cumprod(frame_sizes)  model.py:34
+        c->tiers[i].fs = cfg->frame_sizes[i];
+        c->tiers[i].n = n;
+        c->tiers[i].top = (i == cfg->n_tiers - 1);      // only the top tier is conditioned  model.py:46-47
+        c->tiers[i].kin = n + (c->tiers[i].top ? cfg->cond_dim + cfg->spk_dim : 0);
+    }
+    c->lookback = n;
+    cudaGetDevice(&c->device);
+    *out = c;
+    return SRNN_OK;
+}
+
+int srnn_destroy(srnn_ctx* ctx) {
+    if (!ctx) return SRNN_OK;
+    cudaDeviceSynchronize();
+    ctx->weights.release();
+    if (ctx->ws) cudaFree(ctx->ws);
+    delete ctx;
+    return SRNN_OK;
+}
+
+int srnn_lookback(const srnn_ctx* ctx) { return ctx ? ctx->lookback : fail(SRNN_ERR_ARG, "null context"); }
+
+int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
+    if (!ctx || !P) return fail(SRNN_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, Q = ctx->Q, FS0 = ctx->FS0, L = c.n_rnn;
+    if (!ctx->tbl) {   // first call: allocate the packed buffers
+        for (int i = 0; i < c.n_tiers; ++i) {
+            TierPacked& t = ctx->tiers[i];
+            SRNN_TRY(ctx->weights.alloc((void**)&t.w_in, sizeof(float) * H * t.kin));
+            SRNN_TRY(ctx->weights.alloc((void**)&t.b_in, sizeof(float) * H));
+            for (int l = 0; l < L; ++l) {
+                SRNN_TRY(ctx->weights.alloc((void**)&t.w_ih[l], sizeof(float) * 3 * H * H));
+                SRNN_TRY(ctx->weights.alloc((void**)&t.w_hh[l], sizeof(float) * 3 * H * H));
+                SRNN_TRY(ctx->weights.alloc((void**)&t.b_ih[l], sizeof(float) * 3 * H));
+                SRNN_TRY(ctx->weights.alloc((void**)&t.b_hh[l], sizeof(float) * 3 * H));
+            }
+            SRNN_TRY(ctx->weights.alloc((void**)&t.w_up, sizeof(float) * (size_t)t.fs * H * H));
+            SRNN_TRY(ctx->weights.alloc((void**)&t.b_up, sizeof(float) * t.fs * H));
+            SRNN_TRY(ctx->weights.alloc((void**)&t.h0, sizeof(float) * L * H));
+        }
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_hid, sizeof(float) * H * H));
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->b_hid, sizeof(float) * H));
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_out, sizeof(float) * Q * H));
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->b_out, sizeof(float) * Q));
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->lut, sizeof(float) * Q));
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->tbl, sizeof(float) * (size_t)FS0 * Q * H));
+    }
+    // scratch: folded conv weights before re-layout
+    int max_fs = 1, max_kin = 1;
+    for (int i = 0; i < c.n_tiers; ++i) {
+        if (ctx->tiers[i].fs > max_fs) max_fs = ctx->tiers[i].fs;
+        if (ctx->tiers[i].kin > max_kin) max_kin = ctx->tiers[i].kin;
+    }
+    size_t need = 0;
+    float *t_in = nullptr, *t_c = nullptr, *t_s = nullptr, *t_up = nullptr, *t_mi = nullptr, *t_mit = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump b(pass ? ctx->ws : nullptr);
+        t_in = b.take<float>((size_t)H * max_kin);
+        t_c = b.take<float>((size_t)H * c.cond_dim);
+        t_s = b.take<float>((size_t)H * c.spk_dim);
+        t_up = b.take<float>((size_t)H * H * max_fs);
+        t_mi = b.take<float>((size_t)H * Q * FS0);
+        t_mit = b.take<float>((size_t)H * Q * FS0);
+        need = b.off;
+        if (!pass) SRNN_TRY(ensure_ws(ctx, need));
+    }
+    for (int i = 0; i < c.n_tiers; ++i) {
+        TierPacked& t = ctx->tiers[i];
+        const srnn_tier_params& tp = P->tiers[i];
+        if (!tp.h0 || !tp.input_expand.bias || !tp.upsampling.bias) return fail(SRNN_ERR_ARG, "tier %d: missing h0/bias", i);
+        if (t.top) {
+            if (!tp.cond_expand.bias || !tp.spk_expand.bias || !tp.spk_embedding) return fail(SRNN_ERR_ARG, "top tier: missing cond/spk parameters");
+            SRNN_TRY(wn_fold(tp.input_expand, t_in, H, t.n, st));
+            SRNN_TRY(wn_fold(tp.cond_expand, t_c, H, c.cond_dim, st));
+            SRNN_TRY(wn_fold(tp.spk_expand, t_s, H, c.spk_dim, st));
+            SRNN_TRY(pack_top_in(t_in, t_c, t_s, tp.spk_embedding, tp.input_expand.bias, tp.cond_expand.bias,
+                                 tp.spk_expand.bias, t.w_in, t.b_in, H, t.n, c.cond_dim, c.spk_dim, st));
+        } else {
+            SRNN_TRY(wn_fold(tp.input_expand, t.w_in, H, t.n, st));
+            SRNN_TRY(copy_f32(tp.input_expand.bias, t.b_in, H, st));
+        }
+        for (int l = 0; l < L; ++l) {
+            if (!tp.weight_ih[l] || !tp.weight_hh[l] || !tp.bias_ih[l] || !tp.bias_hh[l]) return fail(SRNN_ERR_ARG, "tier %d: missing GRU layer %d", i, l);
+            SRNN_TRY(copy_f32(tp.weight_ih[l], t.w_ih[l], (size_t)3 * H * H, st));
+            SRNN_TRY(copy_f32(tp.weight_hh[l], t.w_hh[l], (size_t)3 * H * H, st));
+            SRNN_TRY(copy_f32(tp.bias_ih[l], t.b_ih[l], (size_t)3 * H, st));
+            SRNN_TRY(copy_f32(tp.bias_hh[l], t.b_hh[l], (size_t)3 * H, st));
+        }
+        SRNN_TRY(wn_fold(tp.upsampling, t_up, H, H * t.fs, st));       // norm over (out,k) per INPUT channel
+        SRNN_TRY(pack_up(t_up, tp.upsampling.bias, t.w_up, t.b_up, H, t.fs, st));
+        SRNN_TRY(copy_f32(tp.h0, t.h0, (size_t)L * H, st));
+    }
+    if (!P->embedding || !P->mlp_hidden.bias || !P->mlp_output.bias) return fail(SRNN_ERR_ARG, "missing MLP parameters");
+    SRNN_TRY(wn_fold(P->mlp_input, t_mi, H, Q * FS0, st));
+    SRNN_TRY(transpose_mlp_in(t_mi, t_mit, H, Q, FS0, st));
+    for (int j = 0; j < FS0; ++j)   // Tbl[j] (Q,H) = E (Q,Q) . W_in[:,:,j]^T
+        SRNN_TRY(gemm_f32(Q, H, Q, P->embedding, Q, t_mit + (size_t)j * H * Q, Q, nullptr, nullptr, 0, 0,
+                          ctx->tbl + (size_t)j * Q * H, H, st));
+    SRNN_TRY(wn_fold(P->mlp_hidden, ctx->w_hid, H, H, st));
+    SRNN_TRY(copy_f32(P->mlp_hidden.bias, ctx->b_hid, H, st));
+    SRNN_TRY(wn_fold(P->mlp_output, ctx->w_out, Q, H, st));
+    SRNN_TRY(copy_f32(P->mlp_output.bias, ctx->b_out, Q, st));
+    SRNN_TRY(build_lut(ctx->lut, Q, c.ulaw, st));
+    ctx->packed = true;
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Predictor.forward  (model.py:357-436)
+// ------------------------------------------------------------------------------------------------
+int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_seq, const void* cond,
+                     int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
+                     float* logp_out, int32_t mode, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    if (!input_seq || !cond || !spk || !hidden_io || !logp_out) return fail(SRNN_ERR_ARG, "null argument");
+    if (B < 1 || T < 1 || T % ctx->lookback) return fail(SRNN_ERR_ARG, "T=%d must be a positive multiple of lookback=%d", T, ctx->lookback);
+    if (mode != SRNN_MODE_FP32) return fail(SRNN_ERR_UNSUPPORTED, "predict_fwd: mode %d not available", mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback;
+    const int Lseq = lookback + T - 1;
+
+    uint8_t* seq = nullptr;
+    float *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS], *Y0[SRNN_MAX_TIERS],
+        *Y1[SRNN_MAX_TIERS], *UP[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump b(pass ? ctx->ws : nullptr);
+        seq = b.take<uint8_t>((size_t)B * Lseq);
+        for (int i = 0; i < NT; ++i) {
+            const TierPacked& t = ctx->tiers[i];
+            const size_t M = (size_t)B * (T / t.n);
+            A[i] = b.take<float>(M * t.kin);
+            X[i] = b.take<float>(M * H);
+            GI[i] = b.take<float>(M * 3 * H);
+            GH[i] = b.take<float>((size_t)B * 3 * H);
+            Y0[i] = b.take<float>(M * H);
+            Y1[i] = b.take<float>(M * H);
+            UP[i] = b.take<float>(M * t.fs * H);
+        }
+        X1 = b.take<float>((size_t)B * T * H);
+        X2 = b.take<float>((size_t)B * T * H);
+        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
+    }
+    SRNN_TRY(i64_to_u8(input_seq, seq, (size_t)B * Lseq, st));
+    const float* upper = nullptr;
+    for (int i = NT - 1; i >= 0; --i) {                                     // model.py:378 top tier first
+        const TierPacked& t = ctx->tiers[i];
+        const int F = T / t.n, M = B * F;
+        if (!hidden_io[i]) return fail(SRNN_ERR_ARG, "hidden_io[%d] is null", i);
+        SRNN_TRY(frame_input(seq, Lseq, lookback - t.n, nullptr, t.n, B, F, cond, cond_is_f64, B, T / lookback, spk,
+                             c.cond_dim, c.spk_dim, ctx->lut, A[i], t.kin, t.top, st));
+        SRNN_TRY(gemm_f32(M, H, t.kin, A[i], t.kin, t.w_in, t.kin, t.b_in, upper, H, 0, X[i], H, st));
+        const float* in = X[i];
+        float* Y = nullptr;
+        for (int l = 0; l < NL; ++l) {
+            Y = (l & 1) ? Y1[i] : Y0[i];
+            float* hid = hidden_io[i] + (size_t)l * B * H;
+            if ((reset_mask >> i) & 1) SRNN_TRY(bcast_rows(t.h0 + (size_t)l * H, hid, B, H, st));   // model.py:222-228
+            SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
+            for (int f = 0; f < F; ++f) {
+                const float* hp = f ? Y + (size_t)(f - 1) * H : hid;
+                const int hp_ld = f ? F * H : H;
+                SRNN_TRY(gemm_f32(B, 3 * H, H, hp, hp_ld, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
+                SRNN_TRY(gru_gates(GI[i] + (size_t)f * 3 * H, F * 3 * H, GH[i], 3 * H, hp, hp_ld, Y + (size_t)f * H,
+                                   F * H, f == F - 1 ? hid : nullptr, B, H, st));   // carry: model.py:348
+            }
+            in = Y;
+        }
+        SRNN_TRY(gemm_f32(M, t.fs * H, H, Y, H, t.w_up, H, t.b_up, nullptr, 0, 0, UP[i], t.fs * H, st));
+        upper = UP[i];
+    }
+    // sample-level MLP  (model.py:422-436, 308-325)
+    const int FS0 = ctx->FS0;
+    SRNN_TRY(mlp_gather(seq, Lseq, lookback - FS0, nullptr, ctx->tbl, upper, (long long)T * H, H, X1, B, T, H, FS0, st));
+    SRNN_TRY(gemm_f32(B * T, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
+    SRNN_TRY(gemm_f32(B * T, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st));
+    SRNN_TRY(logsoftmax_rows(logp_out, B * T, st));
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generator.__call__  (model.py:445-520) -- fp32 mode: one CUDA graph per top-tier period, replayed n_cond times
+// ------------------------------------------------------------------------------------------------
+static int generate_f32(srnn_ctx* ctx, int B, int n_cond, const float* cond, int cond_rows, const int64_t* spk,
+                        const float* uniforms, uint8_t* samples_out, float* audio_out, float* logp_out,
+                        cudaStream_t user) {
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
+    const int T = n_cond * lookback, Lseq = lookback + T;
+    uint8_t* seq = nullptr;
+    int* step_base = nullptr;
+    float *hid[SRNN_MAX_TIERS], *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS],
+        *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump b(pass ? ctx->ws : nullptr);
+        seq = b.take<uint8_t>((size_t)B * Lseq);
+        step_base = b.take<int>(1);
+        for (int i = 0; i < NT; ++i) {
+            const TierPacked& t = ctx->tiers[i];
+            hid[i] = b.take<float>((size_t)NL * B * H);
+            A[i] = b.take<float>((size_t)B * t.kin);
+            X[i] = b.take<float>((size_t)B * H);
+            GI[i] = b.take<float>((size_t)B * 3 * H);
+            GH[i] = b.take<float>((size_t)B * 3 * H);
+            OUT[i] = b.take<float>((size_t)B * t.fs * H);
+        }
+        X1 = b.take<float>((size_t)B * H);
+        X2 = b.take<float>((size_t)B * H);
+        LG = b.take<float>((size_t)B * Q);
+        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
+    }
+    // private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
+    cudaStream_t st;
+    cudaEvent_t ev_in, ev_out;
+    SRNN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    SRNN_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    SRNN_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    SRNN_CUDA(cudaEventRecord(ev_in, user));
+    SRNN_CUDA(cudaStreamWaitEvent(st, ev_in, 0));
+
+    SRNN_TRY(fill_u8(seq, (uint8_t)(Q / 2), (size_t)B * Lseq, st));                  // q_zero  model.py:459
+    SRNN_CUDA(cudaMemsetAsync(step_base, 0, sizeof(int), st));
+    SRNN_TRY(add_int(step_base, lookback, st));                                      // i starts at lookback  model.py:462
+    for (int i = 0; i < NT; ++i)
+        for (int l = 0; l < NL; ++l)                                                 // reset_hidden_states  model.py:451
+            SRNN_TRY(bcast_rows(ctx->tiers[i].h0 + (size_t)l * H, hid[i] + (size_t)l * B * H, B, H, st));
+
+    const long long before = g_launches.load();
+    SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = SRNN_OK;
+    auto body = [&]() -> int {
+        for (int pos = 0; pos < lookback; ++pos) {                                   // i = *step_base + pos
+            for (int i = NT - 1; i >= 0; --i) {
+                const TierPacked& t = ctx->tiers[i];
+                if (pos % t.n) continue;                                             // model.py:465
+                SRNN_TRY(frame_input(seq, Lseq, pos - t.n, step_base, t.n, B, 1, cond, 0, cond_rows, n_cond, spk,
+                                     c.cond_dim, c.spk_dim, ctx->lut, A[i], t.kin, t.top, st));
+                const float* upper = nullptr;
+                int up_ld = 0;
+                if (!t.top) {                                                        // model.py:491-495
+                    const TierPacked& u = ctx->tiers[i + 1];
+                    upper = OUT[i + 1] + (size_t)((pos / t.n) % u.fs) * H;
+                    up_ld = u.fs * H;
+                }
+                SRNN_TRY(gemm_f32(B, H, t.kin, A[i], t.kin, t.w_in, t.kin, t.b_in, upper, up_ld, 0, X[i], H, st));
+                const float* in = X[i];
+                for (int l = 0; l < NL; ++l) {
+                    float* h = hid[i] + (size_t)l * B * H;
+                    SRNN_TRY(gemm_f32(B, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
+                    SRNN_TRY(gemm_f32(B, 3 * H, H, h, H, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
+                    SRNN_TRY(gru_gates(GI[i], 3 * H, GH[i], 3 * H, h, H, h, H, nullptr, B, H, st));
+                    in = h;
+                }
+                SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
+            }
+            SRNN_TRY(mlp_gather(seq, Lseq, pos - FS0, step_base, ctx->tbl, OUT[0] + (size_t)(pos % FS0) * H,
+                                (long long)FS0 * H, 0, X1, B, 1, H, FS0, st));      // model.py:504-513
+            SRNN_TRY(gemm_f32(B, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
+            SRNN_TRY(gemm_f32(B, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, LG, Q, st));
+            SRNN_TRY(softmax_sample(LG, uniforms, B, seq, Lseq, pos, lookback, step_base, logp_out,
+                                    (long long)T * Q, B, st));                       // model.py:514-517
+        }
+        SRNN_TRY(add_int(step_base, lookback, st));
+        return SRNN_OK;
+    };
+    rc = body();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const long long nodes = g_launches.load() - before;
+    if (rc != SRNN_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(st);
+        return rc;
+    }
+    if (ce != cudaSuccess) return fail(SRNN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    SRNN_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(exec, st));
+    g_launches.fetch_add(nodes * (long long)(n_cond - 1));
+    SRNN_TRY(dequant_audio(seq, Lseq, lookback, ctx->lut, samples_out, audio_out, B, T, st));   // model.py:520
+    SRNN_CUDA(cudaEventRecord(ev_out, st));
+    SRNN_CUDA(cudaStreamWaitEvent(user, ev_out, 0));
+    // the graph/stream objects can be released once the work is enqueued; CUDA defers destruction until completion
+    SRNN_CUDA(cudaGraphExecDestroy(exec));
+    SRNN_CUDA(cudaGraphDestroy(graph));
+    SRNN_CUDA(cudaEventDestroy(ev_in));
+    SRNN_CUDA(cudaEventDestroy(ev_out));
+    SRNN_CUDA(cudaStreamDestroy(st));
+    return SRNN_OK;
+}
+
+int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, int32_t cond_rows,
+                  const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
+                  float* logp_out, int32_t mode, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    if (!cond || !spk || !uniforms) return fail(SRNN_ERR_ARG, "null argument");
+    if (!samples_out && !audio_out) return fail(SRNN_ERR_ARG, "need samples_out or audio_out");
+    if (B < 1 || n_cond < 1) return fail(SRNN_ERR_ARG, "B and n_cond must be positive");
+    if (cond_rows != 1 && cond_rows != B) return fail(SRNN_ERR_ARG, "cond_rows must be 1 or B");
+    if (mode == SRNN_MODE_FP32)
+        return generate_f32(ctx, B, n_cond, cond, cond_rows, spk, uniforms, samples_out, audio_out, logp_out,
+                            (cudaStream_t)stream);
+    return fail(SRNN_ERR_UNSUPPORTED, "generate: mode %d not available", mode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------------
+int srnn_sample_rows(const float* p, const float* u, int32_t rows, int32_t* idx, void* stream) {
+    if (!p || !u || !idx) return fail(SRNN_ERR_ARG, "null argument");
+    return sample_rows(p, u, rows, idx, (cudaStream_t)stream);
+}
+
+int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    if (!out) return fail(SRNN_ERR_ARG, "null argument");
+    return copy_f32(ctx->lut, out, ctx->Q, (cudaStream_t)stream);
+}
+
+int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
+              const float* addend, int32_t relu, float* C, int32_t mode, void* stream) {
+    if (!A || !B || !C) return fail(SRNN_ERR_ARG, "null argument");
+    if (mode == SRNN_MODE_FP32) return gemm_f32(M, N, K, A, K, B, K, bias, addend, N, relu, C, N, (cudaStream_t)stream);
+    return fail(SRNN_ERR_UNSUPPORTED, "gemm: mode %d not available", mode);
+}
+
+}  // extern "C"

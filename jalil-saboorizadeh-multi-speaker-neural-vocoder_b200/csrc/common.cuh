@@ -1,0 +1,130 @@
+// Shared declarations of the SampleRNN B200 library (internal; the public C-ABI is include/srnn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <vector>
+#include "srnn_b200.h"
+
+namespace srnn {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+int fail(int code, const char* fmt, ...);
+
+#define SRNN_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return ::srnn::fail(SRNN_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,      \
+                                cudaGetErrorString(_e));                                         \
+    } while (0)
+
+#define SRNN_TRY(expr)                                                                           \
+    do {                                                                                         \
+        int _r = (expr);                                                                         \
+        if (_r != SRNN_OK) return _r;                                                            \
+    } while (0)
+
+// every kernel launch goes through here so srnn_launch_count() is the library's own claim
+#define SRNN_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
+    do {                                                                                         \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                              \
+        ::srnn::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+        cudaError_t _e = cudaPeekAtLastError();                                                  \
+        if (_e != cudaSuccess)                                                                   \
+            return ::srnn::fail(SRNN_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__,      \
+                                #kernel, cudaGetErrorString(_e));                                \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- packed weights of one FrameLevelRNN tier (model.py:67-178) --------------------------------
+struct TierPacked {
+    int fs = 0;        // frame_size (upsampling ratio)
+    int n = 0;         // n_frame_samples
+    int kin = 0;       // K of the input GEMM: n (+ cond_dim + spk_dim on the top tier)
+    bool top = false;
+    float* w_in = nullptr;    // (H, kin)   [input_expand | cond_expand | spk_expand . E^T]
+    float* b_in = nullptr;    // (H)        summed biases
+    float* w_ih[SRNN_MAX_RNN] = {};   // (3H, H)
+    float* w_hh[SRNN_MAX_RNN] = {};
+    float* b_ih[SRNN_MAX_RNN] = {};
+    float* b_hh[SRNN_MAX_RNN] = {};
+    float* w_up = nullptr;    // (fs*H, H)  row j*H+o = conv_t.weight[:, o, j]   (nn.py:33-43)
+    float* b_up = nullptr;    // (fs*H)     j*H+o -> upsampling.bias[o, j]
+    float* h0 = nullptr;      // (n_rnn, H)
+};
+
+struct Arena {
+    std::vector<void*> ptrs;
+    int alloc(void** p, size_t bytes);
+    void release();
+};
+
+}  // namespace srnn
+
+struct srnn_ctx {
+    srnn_config cfg{};
+    int lookback = 0;
+    int H = 0, Q = SRNN_Q, FS0 = 0;
+    bool packed = false;
+    srnn::TierPacked tiers[SRNN_MAX_TIERS];
+    float* tbl = nullptr;     // (FS0, Q, H) folded embedding o conv table
+    float* w_hid = nullptr;   // (H, H)
+    float* b_hid = nullptr;
+    float* w_out = nullptr;   // (Q, H)
+    float* b_out = nullptr;
+    float* lut = nullptr;     // (Q) 2*dequantize(q)
+    srnn::Arena weights;      // freed on destroy
+    // grow-only scratch for predict / generate
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    int device = 0;
+};
+
+namespace srnn {
+
+int ensure_ws(srnn_ctx* ctx, size_t bytes);
+
+// ---- fp32 kernels (kernels_f32.cu) --------------------------------------------------------------
+int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
+             const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st);
+int wn_fold(const srnn_conv_params& p, float* out, int rows, int cols, cudaStream_t st);
+int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
+int fill_u8(uint8_t* dst, uint8_t v, size_t n, cudaStream_t st);
+int build_lut(float* lut, int q_levels, int ulaw, cudaStream_t st);
+int i64_to_u8(const int64_t* src, uint8_t* dst, size_t n, cudaStream_t st);
+int pack_top_in(const float* w_in, const float* w_c, const float* w_s, const float* emb, const float* b_in,
+                const float* b_c, const float* b_s, float* w_out, float* b_out, int H, int n, int cond_dim,
+                int spk_dim, cudaStream_t st);
+int pack_up(const float* wf, const float* bias, float* w_up, float* b_up, int H, int k, cudaStream_t st);
+int transpose_mlp_in(const float* w, float* wt, int H, int Q, int FS, cudaStream_t st);
+// A[b*F+f, :] = [lut[seq[b, off + f*n + i]] (i<n) | cond[crow(b), f0+f, :] | onehot(spk[crow(b)])]
+int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, int F,
+                const void* cond, int cond_is_f64, int cond_rows, int cond_frames,
+                const int64_t* spk, int cond_dim, int spk_dim, const float* lut, float* A, int kin, bool top,
+                cudaStream_t st);
+// GRU cell tail (model.py:244): h' from gi (+bias already in), gh (+bias already in), h
+int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
+              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st);
+int bcast_rows(const float* src, float* dst, int B, int H, cudaStream_t st);
+// x1[r,:] = relu(sum_j Tbl[j][seq[b, off + t + j]] + upper[r,:])
+int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, const float* tbl,
+               const float* upper, long long up_bstride, long long up_tstride, float* x1, int B, int T, int H,
+               int FS, cudaStream_t st);
+int logsoftmax_rows(float* x, int rows, cudaStream_t st);
+// generation tail: logits (B, 256) -> [logp] -> defined sampler -> seq[b, pos]
+int softmax_sample(const float* logits, const float* uniforms, int u_ld, uint8_t* seq, int seq_ld, int pos_off,
+                   int lookback, const int* step_base, float* logp_out, long long logp_bstride, int B,
+                   cudaStream_t st);
+int sample_rows(const float* p, const float* u, int rows, int* idx, cudaStream_t st);
+int dequant_audio(const uint8_t* seq, int seq_ld, int off, const float* lut, uint8_t* samples, float* audio,
+                  int B, int T, cudaStream_t st);
+int add_int(int* p, int v, cudaStream_t st);
+
+}  // namespace srnn

@@ -1,0 +1,416 @@
+// fp32 kernels of the SampleRNN hot path: the SRNN_MODE_FP32 ("fp32 parity") arithmetic, the weight packers and
+// all the non-GEMM pieces shared with the tensor-core mode (dequantiser LUT, frame assembly, GRU gates,
+// folded-table gather, log-softmax, the defined inverse-CDF sampler).
+#include "common.cuh"
+#include "sampler.cuh"
+
+namespace srnn {
+
+// ------------------------------------------------------------------------------------------------
+// C (M,N) = A (M,K) . B (N,K)^T + bias + addend, optional ReLU.  64x64x16 tiles, 4x4 per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+__global__ void __launch_bounds__(256)
+k_gemm_f32_tn(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+              const float* __restrict__ bias, const float* __restrict__ add, int ldadd, int relu,
+              float* __restrict__ C, int ldc) {
+    __shared__ float As[GBK][GBM + 4];
+    __shared__ float Bs[GBK][GBN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += GBK) {
+#pragma unroll
+        for (int i = tid; i < GBM * GBK; i += 256) {
+            const int r = i / GBK, c = i % GBK;
+            const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
+            As[c][r] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.f;
+            Bs[c][r] = (gn < N && gk < K) ? B[(size_t)gn * ldb + gk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[gn];
+            if (add) v += add[(size_t)gm * ldadd + gn];
+            if (relu) v = fmaxf(v, 0.f);
+            C[(size_t)gm * ldc + gn] = v;
+        }
+    }
+}
+
+int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
+             const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return SRNN_OK;
+    dim3 grid(cdiv(N, GBN), cdiv(M, GBM));
+    SRNN_LAUNCH(k_gemm_f32_tn, grid, 256, 0, st, M, N, K, A, lda, B, ldb, bias, add, ldadd, relu, C, ldc);
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packers
+// ------------------------------------------------------------------------------------------------
+// out[r,:] = v[r,:] * g[r] / ||v[r,:]||   (torch weight_norm, dim=0)   or a plain copy of `weight`
+__global__ void k_wn_fold(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ v,
+                          float* __restrict__ out, int cols) {
+    const int r = blockIdx.x;
+    __shared__ float red[32];
+    __shared__ float scale_s;
+    if (w) {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) out[(size_t)r * cols + c] = w[(size_t)r * cols + c];
+        return;
+    }
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        const float x = v[(size_t)r * cols + c];
+        s = fmaf(x, x, s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) scale_s = g[r] / sqrtf(t);
+    }
+    __syncthreads();
+    const float sc = scale_s;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) out[(size_t)r * cols + c] = v[(size_t)r * cols + c] * sc;
+}
+
+int wn_fold(const srnn_conv_params& p, float* out, int rows, int cols, cudaStream_t st) {
+    if (!p.weight && !(p.weight_g && p.weight_v)) return fail(SRNN_ERR_ARG, "conv params: neither weight nor weight_g/weight_v");
+    SRNN_LAUNCH(k_wn_fold, rows, 256, 0, st, p.weight, p.weight_g, p.weight_v, out, cols);
+    return SRNN_OK;
+}
+
+__global__ void k_copy_f32(const float* __restrict__ s, float* __restrict__ d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st) {
+    if (!n) return SRNN_OK;
+    SRNN_LAUNCH(k_copy_f32, (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, src, dst, n);
+    return SRNN_OK;
+}
+
+__global__ void k_fill_u8(uint8_t* d, uint8_t v, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = v;
+}
+int fill_u8(uint8_t* dst, uint8_t v, size_t n, cudaStream_t st) {
+    if (!n) return SRNN_OK;
+    SRNN_LAUNCH(k_fill_u8, (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, dst, v, n);
+    return SRNN_OK;
+}
+
+__global__ void k_i64_to_u8(const int64_t* __restrict__ s, uint8_t* __restrict__ d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = (uint8_t)(s[i] & 0xff);
+}
+int i64_to_u8(const int64_t* src, uint8_t* dst, size_t n, cudaStream_t st) {
+    if (!n) return SRNN_OK;
+    SRNN_LAUNCH(k_i64_to_u8, (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st, src, dst, n);
+    return SRNN_OK;
+}
+
+// lut[q] = 2 * dequantize(q)   (utils.py:18-19 linear; utils.py:39-42,54-55,62-63 mu-law; model.py:385,471 the 2x)
+__global__ void k_build_lut(float* lut, int q_levels, int ulaw) {
+    const int q = threadIdx.x;
+    if (q >= q_levels) return;
+    float y;
+    if (ulaw) {
+        const float c = (float)q * 2.0f / (float)q_levels - 1.0f;
+        const float x = expf(fabsf(c) * 5.5451774444795623f) - 1.0f;
+        const float sg = (c > 0.f) ? 1.f : ((c < 0.f) ? -1.f : 0.f);
+        y = sg * x / 255.0f;
+    } else {
+        y = (float)q / (float)(q_levels / 2) - 1.0f;
+    }
+    lut[q] = 2.0f * y;
+}
+int build_lut(float* lut, int q_levels, int ulaw, cudaStream_t st) {
+    SRNN_LAUNCH(k_build_lut, 1, 256, 0, st, lut, q_levels, ulaw);
+    return SRNN_OK;
+}
+
+// top tier: W (H, n + cond_dim + spk_dim) = [W_in | W_c | W_s . E^T], bias = b_in + b_c + b_s  (model.py:196-218)
+__global__ void k_pack_top_in(const float* __restrict__ w_in, const float* __restrict__ w_c,
+                              const float* __restrict__ w_s, const float* __restrict__ emb,
+                              const float* __restrict__ b_in, const float* __restrict__ b_c,
+                              const float* __restrict__ b_s, float* __restrict__ w_out, float* __restrict__ b_out,
+                              int n, int cond_dim, int spk_dim) {
+    const int h = blockIdx.x;
+    const int kin = n + cond_dim + spk_dim;
+    for (int k = threadIdx.x; k < kin; k += blockDim.x) {
+        float v;
+        if (k < n) v = w_in[(size_t)h * n + k];
+        else if (k < n + cond_dim) v = w_c[(size_t)h * cond_dim + (k - n)];
+        else {
+            const int s = k - n - cond_dim;
+            v = 0.f;
+            for (int e = 0; e < spk_dim; ++e) v = fmaf(w_s[(size_t)h * spk_dim + e], emb[s * spk_dim + e], v);
+        }
+        w_out[(size_t)h * kin + k] = v;
+    }
+    if (threadIdx.x == 0) b_out[h] = b_in[h] + b_c[h] + b_s[h];
+}
+int pack_top_in(const float* w_in, const float* w_c, const float* w_s, const float* emb, const float* b_in,
+                const float* b_c, const float* b_s, float* w_out, float* b_out, int H, int n, int cond_dim,
+                int spk_dim, cudaStream_t st) {
+    SRNN_LAUNCH(k_pack_top_in, H, 128, 0, st, w_in, w_c, w_s, emb, b_in, b_c, b_s, w_out, b_out, n, cond_dim, spk_dim);
+    return SRNN_OK;
+}
+
+// conv_t weight (H_in, H_out, k) [already weight-norm folded] -> (k*H_out, H_in); bias (H_out, k) -> (k*H_out)
+__global__ void k_pack_up(const float* __restrict__ wf, const float* __restrict__ bias, float* __restrict__ w_up,
+                          float* __restrict__ b_up, int H, int k) {
+    const int row = blockIdx.x;           // j*H + o
+    const int j = row / H, o = row % H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) w_up[(size_t)row * H + c] = wf[((size_t)c * H + o) * k + j];
+    if (threadIdx.x == 0) b_up[row] = bias[o * k + j];
+}
+int pack_up(const float* wf, const float* bias, float* w_up, float* b_up, int H, int k, cudaStream_t st) {
+    SRNN_LAUNCH(k_pack_up, k * H, 128, 0, st, wf, bias, w_up, b_up, H, k);
+    return SRNN_OK;
+}
+
+// (H, Q, FS) -> (FS, H, Q)
+__global__ void k_transpose_mlp_in(const float* __restrict__ w, float* __restrict__ wt, int H, int Q, int FS) {
+    const int h = blockIdx.x, j = blockIdx.y;
+    for (int e = threadIdx.x; e < Q; e += blockDim.x) wt[((size_t)j * H + h) * Q + e] = w[((size_t)h * Q + e) * FS + j];
+}
+int transpose_mlp_in(const float* w, float* wt, int H, int Q, int FS, cudaStream_t st) {
+    SRNN_LAUNCH(k_transpose_mlp_in, dim3(H, FS), 256, 0, st, w, wt, H, Q, FS);
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame assembly (model.py:379-408 teacher forcing; 470-487 generation)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_frame_input(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
+                              const int* __restrict__ step_base, int n, int F, const void* __restrict__ cond,
+                              int cond_is_f64, int cond_rows, int cond_frames, const int64_t* __restrict__ spk,
+                              int cond_dim, int spk_dim, const float* __restrict__ lut, float* __restrict__ A,
+                              int kin, int top) {
+    const int r = blockIdx.x;             // b*F + f
+    const int b = r / F, f = r % F;
+    const int start = start_static + (step_base ? *step_base : 0);
+    const uint8_t* s = seq + (size_t)b * seq_ld + start + (size_t)f * n;
+    float* a = A + (size_t)r * kin;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = lut[s[i]];
+    if (top) {
+        const int crow = cond_rows == 1 ? 0 : b;
+        const int cf = start / n + f;     // conditioner row aligned with the target window
+        const size_t cbase = ((size_t)crow * cond_frames + cf) * cond_dim;
+        for (int i = threadIdx.x; i < cond_dim; i += blockDim.x)
+            a[n + i] = cond_is_f64 ? (float)((const double*)cond)[cbase + i] : ((const float*)cond)[cbase + i];
+        const int sp = (int)spk[crow];
+        for (int i = threadIdx.x; i < spk_dim; i += blockDim.x) a[n + cond_dim + i] = (i == sp) ? 1.f : 0.f;
+    }
+}
+int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, int F,
+                const void* cond, int cond_is_f64, int cond_rows, int cond_frames,
+                const int64_t* spk, int cond_dim, int spk_dim, const float* lut, float* A, int kin, bool top,
+                cudaStream_t st) {
+    SRNN_LAUNCH(k_frame_input, B * F, 128, 0, st, seq, seq_ld, off, step_base, n, F, cond, cond_is_f64, cond_rows,
+                cond_frames, spk, cond_dim, spk_dim, lut, A, kin, top ? 1 : 0);
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU cell tail: gi, gh include their biases.  r,z,n row blocks (torch nn.GRU, model.py:154-159,244)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gru_gates(const float* __restrict__ gi, int gi_ld, const float* __restrict__ gh, int gh_ld,
+                            const float* __restrict__ h_prev, int hp_ld, float* __restrict__ h_out, int ho_ld,
+                            float* __restrict__ h_out2, int H) {
+    const int b = blockIdx.y;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= H) return;
+    const float* gir = gi + (size_t)b * gi_ld;
+    const float* ghr = gh + (size_t)b * gh_ld;
+    const float r = 1.f / (1.f + expf(-(gir[u] + ghr[u])));
+    const float z = 1.f / (1.f + expf(-(gir[H + u] + ghr[H + u])));
+    const float nn = tanhf(gir[2 * H + u] + r * ghr[2 * H + u]);
+    const float hp = h_prev[(size_t)b * hp_ld + u];
+    const float hn = (1.f - z) * nn + z * hp;
+    h_out[(size_t)b * ho_ld + u] = hn;
+    if (h_out2) h_out2[(size_t)b * H + u] = hn;
+}
+int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
+              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st) {
+    SRNN_LAUNCH(k_gru_gates, dim3(cdiv(H, 128), B), 128, 0, st, gi, gi_ld, gh, gh_ld, h_prev, hp_ld, h_out, ho_ld,
+                h_out2, H);
+    return SRNN_OK;
+}
+
+// dst[b,:] = src[:]  (h0 expanded over the batch, model.py:222-228)
+__global__ void k_bcast_rows(const float* __restrict__ src, float* __restrict__ dst, int H) {
+    const int b = blockIdx.y;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < H) dst[(size_t)b * H + u] = src[u];
+}
+int bcast_rows(const float* src, float* dst, int B, int H, cudaStream_t st) {
+    SRNN_LAUNCH(k_bcast_rows, dim3(cdiv(H, 128), B), 128, 0, st, src, dst, H);
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample-level MLP front: embedding o conv(k=FS) folded into table gathers  (model.py:311-320)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mlp_gather(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
+                             const int* __restrict__ step_base, const float* __restrict__ tbl,
+                             const float* __restrict__ upper, long long up_bstride, long long up_tstride,
+                             float* __restrict__ x1, int T, int H, int FS) {
+    const int r = blockIdx.x;             // b*T + t
+    const int b = r / T, t = r % T;
+    const int start = start_static + (step_base ? *step_base : 0);
+    const uint8_t* s = seq + (size_t)b * seq_ld + start + t;
+    extern __shared__ int qs[];
+    for (int j = threadIdx.x; j < FS; j += blockDim.x) qs[j] = s[j];
+    __syncthreads();
+    const float* up = upper + (size_t)b * up_bstride + (size_t)t * up_tstride;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float acc = up[h];
+        for (int j = 0; j < FS; ++j) acc += tbl[((size_t)j * SRNN_Q + qs[j]) * H + h];
+        x1[(size_t)r * H + h] = fmaxf(acc, 0.f);
+    }
+}
+int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, const float* tbl,
+               const float* upper, long long up_bstride, long long up_tstride, float* x1,
+               int B, int T, int H, int FS, cudaStream_t st) {
+    SRNN_LAUNCH(k_mlp_gather, B * T, H >= 256 ? 256 : 64, FS * sizeof(int), st, seq, seq_ld, off, step_base, tbl,
+                upper, up_bstride, up_tstride, x1, T, H, FS);
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 256-way log-softmax, one warp per row (model.py:324-325)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_logsoftmax8(float (&x)[8]) {
+    float m = x[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, x[i]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += expf(x[i] - m);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = m + logf(s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] -= lse;
+}
+
+__global__ void k_logsoftmax_rows(float* __restrict__ x, int rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4* p = reinterpret_cast<float4*>(x + (size_t)row * SRNN_Q + lane * 8);
+    float4 a = p[0], b = p[1];
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    warp_logsoftmax8(v);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+int logsoftmax_rows(float* x, int rows, cudaStream_t st) {
+    SRNN_LAUNCH(k_logsoftmax_rows, cdiv(rows, 8), 256, 0, st, x, rows);
+    return SRNN_OK;
+}
+
+// generation tail: logits -> log-probs -> p = exp(logp) -> defined sampler (model.py:514-517)
+__global__ void k_softmax_sample(const float* __restrict__ logits, const float* __restrict__ uniforms, int u_ld,
+                                 uint8_t* __restrict__ seq, int seq_ld, int pos_static, int lookback,
+                                 const int* __restrict__ step_base, float* __restrict__ logp_out,
+                                 long long logp_bstride, int B) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int i = pos_static + (step_base ? *step_base : 0);
+    const int t = i - lookback;
+    const float4* p = reinterpret_cast<const float4*>(logits + (size_t)b * SRNN_Q + lane * 8);
+    float4 a = p[0], c = p[1];
+    float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    warp_logsoftmax8(v);
+    if (logp_out) {
+        float4* o = reinterpret_cast<float4*>(logp_out + (size_t)b * logp_bstride + (size_t)t * SRNN_Q + lane * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = expf(v[k]);
+    const float u = uniforms[(size_t)t * u_ld + b];
+    const int idx = sampler_warp(v, u, lane);
+    if (lane == 0) seq[(size_t)b * seq_ld + i] = (uint8_t)idx;
+}
+int softmax_sample(const float* logits, const float* uniforms, int u_ld, uint8_t* seq, int seq_ld, int pos_off,
+                   int lookback, const int* step_base, float* logp_out, long long logp_bstride, int B,
+                   cudaStream_t st) {
+    SRNN_LAUNCH(k_softmax_sample, cdiv(B, 8), 256, 0, st, logits, uniforms, u_ld, seq, seq_ld, pos_off, lookback,
+                step_base, logp_out, logp_bstride, B);
+    return SRNN_OK;
+}
+
+__global__ void k_sample_rows(const float* __restrict__ p, const float* __restrict__ u, int rows, int* __restrict__ idx) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* q = reinterpret_cast<const float4*>(p + (size_t)row * SRNN_Q + lane * 8);
+    float4 a = q[0], c = q[1];
+    float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    const int r = sampler_warp(v, u[row], lane);
+    if (lane == 0) idx[row] = r;
+}
+int sample_rows(const float* p, const float* u, int rows, int* idx, cudaStream_t st) {
+    if (rows <= 0) return SRNN_OK;
+    SRNN_LAUNCH(k_sample_rows, cdiv(rows, 8), 256, 0, st, p, u, rows, idx);
+    return SRNN_OK;
+}
+
+__global__ void k_dequant_audio(const uint8_t* __restrict__ seq, int seq_ld, int off, const float* __restrict__ lut,
+                                uint8_t* __restrict__ samples, float* __restrict__ audio, int T) {
+    const int b = blockIdx.y;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        const uint8_t q = seq[(size_t)b * seq_ld + off + t];
+        if (samples) samples[(size_t)b * T + t] = q;
+        if (audio) audio[(size_t)b * T + t] = 0.5f * lut[q];     // model.py:520 dequantize (lut holds 2x)
+    }
+}
+int dequant_audio(const uint8_t* seq, int seq_ld, int off, const float* lut, uint8_t* samples, float* audio,
+                  int B, int T, cudaStream_t st) {
+    int gx = cdiv(T, 256);
+    if (gx > 1024) gx = 1024;
+    SRNN_LAUNCH(k_dequant_audio, dim3(gx, B), 256, 0, st, seq, seq_ld, off, lut, samples, audio, T);
+    return SRNN_OK;
+}
+
+__global__ void k_add_int(int* p, int v) { *p += v; }
+int add_int(int* p, int v, cudaStream_t st) {
+    SRNN_LAUNCH(k_add_int, 1, 1, 0, st, p, v);
+    return SRNN_OK;
+}
+
+}  // namespace srnn
+

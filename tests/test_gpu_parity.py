@@ -1,0 +1,147 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the committed golden vectors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import srnn_b200 as S
+from oracle import srnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+L = S._lib
+
+
+def build(golden_or_cfg, sd=None, mode=S.MODE_FP32):
+    c = golden_or_cfg.c if hasattr(golden_or_cfg, "c") else golden_or_cfg
+    m = S.SampleRNN(c["frame_sizes"], c["n_rnn"], c["dim"], c["learn_h0"], c["q_levels"], c["ulaw"],
+                    c["weight_norm"], c["cond_dim"], c["spk_dim"])
+    p = S.Predictor(m, mode=mode)
+    p.load_state_dict(sd if sd is not None else golden_or_cfg.state_dict())
+    p.cuda()
+    return m, p
+
+
+def logp_gate(got, ref, rel=1e-3):
+    """north_star fp32 gate: |dlogp| <= 1e-3 * max(1, |ref|) element-wise."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    viol = np.abs(got - ref) > rel * np.maximum(1.0, np.abs(ref))
+    assert not viol.any(), "max |d| %.3e (%d violations)" % (np.abs(got - ref).max(), int(viol.sum()))
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---- sampler in isolation: bit-exact on identical probabilities + uniforms --------------------------------------
+def test_sampler_bit_exact():
+    rng = np.random.default_rng(7)
+    rows = 4096
+    p = rng.random((rows, 256), dtype=np.float32)
+    p[:512] = np.exp(8 * rng.standard_normal((512, 256))).astype(np.float32)       # peaky rows
+    p[512:600] *= (rng.random((88, 256)) < 0.1)                                      # sparse rows with zeros
+    p[600:700] = 0
+    p[np.arange(600, 700), rng.integers(0, 256, 100)] = 1                            # one-hot rows
+    p[700:800] = np.float32(1e-30) * rng.random((100, 256), dtype=np.float32)       # denormal-range mass
+    u = rng.random(rows, dtype=np.float32)
+    u[:16] = 0.0
+    u[16:32] = np.float32(1) - np.float32(2 ** -24)
+    dp, du = torch.from_numpy(p).cuda(), torch.from_numpy(u).cuda()
+    idx = torch.empty(rows, dtype=torch.int32, device="cuda")
+    L.check(L.load().srnn_sample_rows(dp.data_ptr(), du.data_ptr(), rows, idx.data_ptr(), stream()))
+    np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), O.sample_rows(p, u))
+
+
+def test_gemm_hook_fp32():
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K) in [(1, 7, 5), (3, 96, 32), (130, 70, 166), (256, 256, 1024)]:
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+        bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+        ref = torch.relu(A.double() @ B.double().t() + bias.double() + add.double()).float()
+        dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
+        out = torch.empty(M, N, device="cuda")
+        L.check(L.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), db.data_ptr(), da.data_ptr(), 1,
+                                   out.data_ptr(), S.MODE_FP32, stream()))
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-4 * K ** 0.5, rtol=1e-5)
+
+
+def test_dequant_lut(golden):
+    m, p = build(golden)
+    h = m._ensure_packed()
+    out = torch.empty(256, device="cuda")
+    L.check(L.load().srnn_dequant_lut(h, out.data_ptr(), stream()))
+    np.testing.assert_allclose(out.cpu().numpy(), golden["lut"], atol=1e-6)
+
+
+# ---- Predictor.forward against the reference's own outputs -------------------------------------------------------
+def test_predict_golden_chunks_with_carry(golden):
+    m, p = build(golden)
+    spk = torch.from_numpy(golden["spk"])
+    with torch.no_grad():
+        for i in range(3):
+            x, y, c = golden.chunk(i)
+            logp = p(x, i == 0, c, spk, None, None)
+            assert logp.is_cuda and tuple(logp.shape) == (x.shape[0], y.shape[1], 256)
+            logp_gate(logp.cpu().numpy(), golden[f"tf/logp{i}"])
+            assert abs(float(O.nll_bits(logp.cpu(), y)) - float(golden[f"tf/loss{i}"])) < 1e-4
+            for t, rnn in enumerate(m.frame_level_rnns):
+                np.testing.assert_allclose(p.hidden_states[rnn].cpu().numpy(), golden[f"tf/hidden{i}_{t}"], atol=2e-5)
+
+
+def test_predict_matches_oracle_seeded_wider():
+    torch.manual_seed(5)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=96, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c)
+    p = S.Predictor(m)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    B, T = 5, 240
+    x = torch.randint(0, 256, (B, 80 + T - 1))
+    cond = torch.rand(B, T // 80, 86, dtype=torch.float64)
+    spk = torch.randint(0, 6, (B, 1))
+    w = O.unpack_state_dict(sd, O.Config(**c))
+    with torch.no_grad():
+        ref = O.Predictor(w).forward(x, True, cond, spk)
+        got = p(x, True, cond, spk, None, None)
+    logp_gate(got.cpu().numpy(), ref.numpy())
+
+
+# ---- Generator ------------------------------------------------------------------------------------------------------
+def test_generate_golden_shared_conditioner(golden):
+    m, p = build(golden)
+    gen = S.Generator(m, cuda=True)
+    audio, samples, logp = gen(3, 0, golden["gen/cond"], int(golden["gen/spk"]), uniforms=golden["gen/uniforms"],
+                               return_samples=True, return_logp=True)
+    assert audio.device.type == "cpu" and audio.dtype == torch.float32
+    logp_gate(logp.numpy(), golden["gen/logp"])
+    np.testing.assert_array_equal(audio.numpy(), golden["gen/audio"])            # identical indices -> identical audio
+    w = O.unpack_state_dict(golden.state_dict(), golden.cfg())
+    np.testing.assert_array_equal(O.Generator(w).audio(samples.long()).numpy(), audio.numpy())
+
+
+def test_generate_golden_batched_conditioner(golden):
+    m, p = build(golden)
+    B = golden["genb/cond"].shape[0]
+    audio = S.Generator(m, cuda=True)(B, 0, golden["genb/cond"], golden["genb/spk"],
+                                      uniforms=golden["gen/uniforms"][:, :B])
+    np.testing.assert_array_equal(audio.numpy(), golden["genb/audio"])
+
+
+def test_teacher_forced_equals_autoregressive(golden):
+    """Self-consistency: the log-probs the generator sampled from == Predictor on the generated sequence."""
+    m, p = build(golden)
+    cfg = golden.cfg()
+    B, n_cond = 4, 3
+    g = torch.Generator().manual_seed(11)
+    cond = torch.rand(B, n_cond, cfg.cond_dim, generator=g)
+    spk = torch.randint(0, cfg.spk_dim, (B,), generator=g)
+    audio, samples, logp = S.Generator(m, cuda=True)(B, 0, cond, spk, seed=3, return_samples=True, return_logp=True)
+    seq = torch.cat([torch.full((B, cfg.lookback), 128, dtype=torch.long), samples.long()], 1)
+    with torch.no_grad():
+        tf = p(seq[:, :-1], True, cond, spk.reshape(B, 1), None, None)
+    np.testing.assert_allclose(tf.cpu().numpy(), logp.numpy(), atol=2e-4)
