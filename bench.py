@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Headline benchmark: autoregressive generation throughput of the 3-tier speaker-conditioned SampleRNN
+(BASELINE.json configs[1] = "C2": frame_sizes [20,4], 2 GRU layers, dim 1024, q 256, look-ahead cond 86,
+weight-norm, 6 speakers), batch 256 utterances PER GPU, random-init weights, synthetic conditioners.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fp32|bf16]
+
+One "step" = one pass of the hot path over one batch: generate `--n-cond` conditioner frames (x80 samples) for 256
+utterances.  `value` = generated samples/s over all GPUs with inputs resident in HBM (CUDA events around
+srnn_generate); `e2e` = the same through the public `Generator.__call__` with HOST (pinned) inputs and the audio
+read back to the host inside the timed region.  Utterances shard across ranks with no collective ("weak").
+`--impl reference` times the reference algorithm's CPU port (oracle/) on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+          cond_dim=86, spk_dim=6)
+F_ALG = 6.423e6      # FLOP per generated sample per utterance, embedding-o-conv folded; what the kernels execute
+F_DENSE = 16.889e6   # the reference graph's dense work, for context
+SAMPLE_RATE = 16000
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def synth_inputs(B, n_cond, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    cond = torch.rand(B, n_cond, C2["cond_dim"], generator=g)                     # features are min-max scaled to [0,1]
+    spk = torch.randint(0, C2["spk_dim"], (B,), generator=g)
+    uni = torch.rand(n_cond * 80, B, generator=g)
+    return cond, spk, uni
+
+
+def cpu_port_rate(n_cond, B, threads=None):
+    """The oracle (CPU port of the reference algorithm) on a bounded sample of the same workload."""
+    import torch
+    from oracle import srnn_oracle as O
+    import srnn_b200 as S
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(77977)
+    m = S.SampleRNN(**C2)
+    sd = {"model." + k: v.detach() for k, v in m.state_dict().items()}
+    w = O.unpack_state_dict(sd, O.Config(**C2))
+    cond, spk, uni = synth_inputs(B, n_cond, 0)
+    gen = O.Generator(w)
+    t0 = time.perf_counter()
+    gen(B, cond.numpy(), spk.numpy(), uni.numpy())
+    dt = time.perf_counter() - t0
+    return B * n_cond * 80 / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path = the oracle port (the reference itself is a
+    Python program under /root/reference, which does not exist on the GPU box), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    n_cond = args.ref_n_cond
+    rates, times = [], []
+    for i in range(args.warmup + args.steps):
+        r, dt, th = cpu_port_rate(n_cond, args.batch)
+        if i >= args.warmup:
+            rates.append(r)
+            times.append(dt)
+    v = sum(rates) / len(rates)
+    sample = "C2 model, B=%d utterances x %d cond frames (%d samples each) per step" % (args.batch, n_cond, n_cond * 80)
+    print(json.dumps({
+        "impl": "reference", "metric": "generated samples/sec", "value": v, "unit": "samples/s",
+        "x_realtime_16k": v / SAMPLE_RATE, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN dim 1024, batch %d" % args.batch, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": th, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("SRNN_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
+    ap.add_argument("--n-cond", type=int, default=100, help="conditioner frames (x80 samples) per step")
+    ap.add_argument("--ref-n-cond", type=int, default=2)
+    ap.add_argument("--cpu-n-cond", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import srnn_b200 as S
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mode = {"fp32": S.MODE_FP32, "bf16": S.MODE_BF16}.get(args.mode)
+    if mode is None:
+        mode = S.MODE_BF16 if getattr(S.package, "HAS_BF16", False) else S.MODE_FP32
+    lib = S._lib.load()
+
+    torch.manual_seed(77977)                                   # train.py:62; same weights on every rank
+    model = S.SampleRNN(**C2).to(dev)
+    gen = S.Generator(model, cuda=True, mode=mode)
+    B, n_cond = args.batch, args.n_cond
+    T = n_cond * 80
+    cond_h, spk_h, uni_h = [t.pin_memory() for t in synth_inputs(B, n_cond, 1000 + rank)]   # each rank: its own utterances
+    cond_d, spk_d, uni_d = cond_h.to(dev), spk_h.to(dev), uni_h.to(dev)
+    audio_h = torch.empty(B, T, dtype=torch.float32).pin_memory()
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return gen(B, 0, cond_d, spk_d, uniforms=uni_d, device_output=True)
+
+    def step_e2e():
+        a = gen(B, 0, cond_h.to(dev, non_blocking=True), spk_h.to(dev, non_blocking=True),
+                uniforms=uni_h.to(dev, non_blocking=True), device_output=True)
+        audio_h.copy_(a, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return audio_h
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = lib.srnn_launch_count()
+        t0 = time.perf_counter()
+        for a, b in evs:
+            flush.fill_(1)                                     # L2 flush between timed iterations (untimed)
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
+        return float(t.item()) / 1e3, lib.srnn_launch_count() - l0, wall
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    secs, launches, _ = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    secs_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 3))
+
+    total = world * B * T * args.steps
+    value = total / secs
+    e2e = total / secs_e2e
+    peak_tf, peak_gbs, peak_src = measured_peaks()
+    ach = value * F_ALG / 1e12 / world                                          # per-GPU TFLOP/s, algorithmic
+    h2d = cond_h.numel() * 4 + spk_h.numel() * 8 + uni_h.numel() * 4
+    d2h = audio_h.numel() * 4
+    line = {
+        "metric": "generated samples/sec", "value": value, "unit": "samples/s", "x_realtime_16k": value / SAMPLE_RATE,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
+        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond 86, weight-norm",
+                   "batch_per_gpu": B, "total_batch": B * world, "samples_per_utterance": T,
+                   "l2": "192 MiB flush write between timed iterations", "us_per_sample_step": 1e6 * secs / args.steps / T},
+        "e2e": {"value": e2e, "unit": "samples/s", "x_realtime_16k": e2e / SAMPLE_RATE, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                     "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                     "flops_per_sample": F_ALG, "achieved_dense_equiv": value * F_DENSE / 1e12 / world,
+                     "kernel": "whole generation step (all launches of srnn_generate)"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r, dt, th = cpu_port_rate(args.cpu_n_cond, B)
+        line["cpu_baseline"] = {"value": r, "unit": "samples/s", "cores": th, "kind": "port",
+                                "sample": "C2 model, B=%d x %d cond frames (%.1f s of CPU work)" % (B, args.cpu_n_cond, dt)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,7 @@ class TierWeights:
     spk_emb: Optional[torch.Tensor] = None  # (spk_dim, spk_dim)
     w_spk: Optional[torch.Tensor] = None    # (H, spk_dim)
     b_spk: Optional[torch.Tensor] = None
+    w_up_mat: Optional[torch.Tensor] = None  # cache, see learned_upsampling
 
 
 @dataclass
@@ -99,6 +100,7 @@ class Weights:
     b_mlp_hid: torch.Tensor
     w_mlp_out: torch.Tensor              # (Q, H)
     b_mlp_out: torch.Tensor
+    w_mlp_in_taps: Optional[torch.Tensor] = None   # cache (FS0, Q, H): tap j = W_in[:, :, j]^T, contiguous
 
 
 def unpack_state_dict(sd: Dict[str, torch.Tensor], cfg: Config, dtype=torch.float32) -> Weights:
@@ -193,7 +195,9 @@ def learned_upsampling(x: torch.Tensor, tw: TierWeights) -> torch.Tensor:
     x (B, F, H) -> (B, F*k, H):  out[b, t*k+j, o] = sum_c x[b,t,c] W[c,o,j] + bias[o,j]."""
     B, F, H = x.shape
     k = tw.frame_size
-    y = torch.einsum("btc,coj->btjo", x, tw.w_up) + tw.b_up.t().reshape(1, 1, k, -1)
+    if tw.w_up_mat is None:      # (H_in, k*H_out), column j*H+o = W[c,o,j]; cached contiguous copy (speed only)
+        tw.w_up_mat = tw.w_up.permute(0, 2, 1).reshape(H, -1).contiguous()
+    y = x.reshape(B * F, H) @ tw.w_up_mat + tw.b_up.t().reshape(1, -1)
     return y.reshape(B, F * k, -1)
 
 
@@ -225,9 +229,11 @@ def mlp_logits(w: Weights, prev_q: torch.Tensor, upper: torch.Tensor) -> torch.T
     FS = w.w_mlp_in.shape[-1]
     T = upper.shape[1]
     e = w.emb[prev_q.long()]                                             # (B, T+FS-1, Q)  model.py:311-315
+    if w.w_mlp_in_taps is None:
+        w.w_mlp_in_taps = w.w_mlp_in.permute(2, 1, 0).contiguous()
     x = upper
     for j in range(FS):                                                  # Conv1d(Q->H, k=FS, no bias) model.py:317
-        x = x + e[:, j:j + T] @ w.w_mlp_in[:, :, j].t()
+        x = x + e[:, j:j + T] @ w.w_mlp_in_taps[j]
     x = torch.relu(x)
     x = torch.relu(x @ w.w_mlp_hid.t() + w.b_mlp_hid)                    # model.py:321
     return x @ w.w_mlp_out.t() + w.b_mlp_out                             # model.py:322
