@@ -414,7 +414,23 @@ int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream) {
 int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
               const float* addend, int32_t relu, float* C, int32_t mode, void* stream) {
     if (!A || !B || !C) return fail(SRNN_ERR_ARG, "null argument");
-    if (mode == SRNN_MODE_FP32) return gemm_f32(M, N, K, A, K, B, K, bias, addend, N, relu, C, N, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SRNN_MODE_FP32) return gemm_f32(M, N, K, A, K, B, K, bias, addend, N, relu, C, N, st);
+    if ((mode & 0xff) == SRNN_MODE_BF16) {
+        // tile selector for tests: bits 8..15 = UMMA M (0 -> 128), bits 16..27 = batch-row tile (0 -> 64)
+        const int bm = ((mode >> 8) & 0xff) ? ((mode >> 8) & 0xff) : 128;
+        const int bn = ((mode >> 16) & 0xfff) ? ((mode >> 16) & 0xfff) : 64;
+        const int Kp = (K + 63) / 64 * 64, Np = (N + bm - 1) / bm * bm;
+        __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;
+        SRNN_CUDA(cudaMallocAsync((void**)&a16, sizeof(__nv_bfloat16) * (size_t)M * Kp, st));
+        SRNN_CUDA(cudaMallocAsync((void**)&w16, sizeof(__nv_bfloat16) * (size_t)Np * Kp, st));
+        SRNN_TRY(f32_to_bf16_pad(A, M, K, K, a16, M, Kp, st));
+        SRNN_TRY(f32_to_bf16_pad(B, N, K, K, w16, Np, Kp, st));
+        int rc = gemm_umma(w16, N, a16, M, Kp, Kp, Kp, bias, addend, N, C, nullptr, N, relu, bm, bn, st);
+        cudaFreeAsync(a16, st);
+        cudaFreeAsync(w16, st);
+        return rc;
+    }
     return fail(SRNN_ERR_UNSUPPORTED, "gemm: mode %d not available", mode);
 }
 

@@ -1,0 +1,218 @@
+// tcgen05 / TMA GEMM for the weight-streaming contractions of the frame tiers (GRU input + recurrent projections,
+// learned upsampling) in SRNN_MODE_BF16.
+//
+// "Swap-AB" orientation: the WEIGHT matrix (features x K, bf16, K-major) is the UMMA A operand (M = 128 or 64
+// features per CTA) and the ACTIVATIONS (rows x K, bf16, K-major) are the B operand (N = BN batch rows), so the
+// accumulator in TMEM is D[feature lane][batch-row column] and the big streamed operand (the weights) is read once
+// per row tile.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> coalesced stores of out[row][feature]).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace srnn {
+
+using namespace ptx;
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// bf16 row-major (rows x cols, leading dimension ld elements) -> 2-D tensor map with a {64, box_rows} box, 128B swizzle
+int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (((uintptr_t)base & 15) || (ld * 2) % 16) return fail(SRNN_ERR_ARG, "tensor map: base/stride must be 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SRNN_OK;
+}
+
+constexpr int UMMA_STAGES = 4;
+
+template <int BM, int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = UMMA_STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(192, 1)
+k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int n_feat, int n_rows,
+            int K, const float* __restrict__ bias, const float* __restrict__ addend, int ld_add,
+            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ld_out, int relu) {
+    using S = GemmSmem<BM, BN>;
+    constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + UMMA_STAGES * S::STAGE);
+    uint64_t* empty = full + UMMA_STAGES;
+    uint64_t* tmem_full = empty + UMMA_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int KB = K / 64;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < UMMA_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % UMMA_STAGES;
+                const uint32_t ph = (kb / UMMA_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], S::STAGE);
+                tma_load_2d(smem + s * S::STAGE, &tmA, &full[s], kb * 64, m0);
+                tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &tmB, &full[s], kb * 64, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % UMMA_STAGES;
+                const uint32_t ph = (kb / UMMA_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t da = umma_desc_sw128(smem_u32(smem + s * S::STAGE));
+                const uint64_t db = umma_desc_sw128(smem_u32(smem + s * S::STAGE + S::A_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)       // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // epilogue: a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        int m;
+        bool lane_ok;
+        if (BM == 128) {
+            m = m0 + 32 * q + lane;
+            lane_ok = true;
+        } else {                                   // M = 64: rows 16q..16q+15 live in lanes 0..15 of quadrant q
+            m = m0 + 16 * q + lane;
+            lane_ok = lane < 16;
+        }
+        const bool m_ok = lane_ok && m < n_feat;
+        const float bv = (bias && m_ok) ? bias[m] : 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
+            if (m_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = n0 + c + i;
+                    if (n < n_rows) {
+                        float x = v[i] + bv;
+                        if (addend) x += addend[(size_t)n * ld_add + m];
+                        if (relu) x = fmaxf(x, 0.f);
+                        if (out_f32) out_f32[(size_t)n * ld_out + m] = x;
+                        if (out_bf16) out_bf16[(size_t)n * ld_out + m] = __float2bfloat16(x);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TCOLS>(tmem_d);
+}
+
+template <int BM, int BN>
+static int launch_gemm_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, int n_feat, int n_rows, int K,
+                            const float* bias, const float* addend, int ld_add, float* out_f32,
+                            __nv_bfloat16* out_bf16, int ld_out, int relu, cudaStream_t st) {
+    using S = GemmSmem<BM, BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma<BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(n_feat, BM), cdiv(n_rows, BN));
+    SRNN_LAUNCH((k_gemm_umma<BM, BN>), grid, 192, S::TOTAL, st, tmA, tmB, n_feat, n_rows, K, bias, addend, ld_add,
+                out_f32, out_bf16, ld_out, relu);
+    return SRNN_OK;
+}
+
+// out (rows, feat) = act (rows, K) . W (feat, K)^T + bias [+ addend] [relu]; W / act are bf16, K % 64 == 0.
+// bn selects the batch-row tile (16..256); bm = 128 (default) or 64.
+int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
+              const float* bias, const float* addend, int ld_add, float* out_f32, __nv_bfloat16* out_bf16,
+              int ld_out, int relu, int bm, int bn, cudaStream_t st) {
+    if (K % 64 || K <= 0) return fail(SRNN_ERR_ARG, "gemm_umma: K=%d must be a positive multiple of 64", K);
+    CUtensorMap tmA, tmB;
+    SRNN_TRY(make_tmap_bf16(&tmA, W, n_feat, K, ld_w, bm));
+    SRNN_TRY(make_tmap_bf16(&tmB, act, n_rows, K, ld_act, bn));
+#define SRNN_GEMM_CASE(BM_, BN_)                                                                              \
+    if (bm == BM_ && bn == BN_)                                                                               \
+        return launch_gemm_umma<BM_, BN_>(tmA, tmB, n_feat, n_rows, K, bias, addend, ld_add, out_f32, out_bf16, \
+                                          ld_out, relu, st);
+    SRNN_GEMM_CASE(128, 256)
+    SRNN_GEMM_CASE(128, 128)
+    SRNN_GEMM_CASE(128, 64)
+    SRNN_GEMM_CASE(128, 32)
+    SRNN_GEMM_CASE(64, 32)
+    SRNN_GEMM_CASE(64, 64)
+#undef SRNN_GEMM_CASE
+    return fail(SRNN_ERR_UNSUPPORTED, "gemm_umma: tile %dx%d not instantiated", bm, bn);
+}
+
+// ---- fp32 -> bf16 with zero padding (test hook + weight packing) ------------------------------------------------
+__global__ void k_f32_to_bf16_pad(const float* __restrict__ src, int rows, int cols, int ld_src,
+                                  __nv_bfloat16* __restrict__ dst, int rows_p, int cols_p) {
+    const size_t total = (size_t)rows_p * cols_p;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols_p), c = (int)(i % cols_p);
+        const float v = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.f;
+        dst[i] = __float2bfloat16(v);
+    }
+}
+int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
+                    cudaStream_t st) {
+    const size_t total = (size_t)rows_p * cols_p;
+    int grid = (int)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+    if (grid < 1) grid = 1;
+    SRNN_LAUNCH(k_f32_to_bf16_pad, grid, 256, 0, st, src, rows, cols, ld_src, dst, rows_p, cols_p);
+    return SRNN_OK;
+}
+
+}  // namespace srnn
