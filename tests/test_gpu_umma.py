@@ -1,0 +1,36 @@
+"""tcgen05/TMA GEMM building block (SRNN_MODE_BF16) against an fp32 torch reference on bf16-rounded operands."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import srnn_b200 as S
+
+pytestmark = pytest.mark.gpu
+L = S._lib
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("bm,bn", [(128, 64), (128, 256), (128, 128), (128, 32), (64, 32), (64, 64)])
+@pytest.mark.parametrize("shape", [(256, 1024, 1024), (100, 300, 200), (32, 128, 64)])
+def test_umma_gemm(bm, bn, shape):
+    M, N, K = shape                       # rows, features, K
+    g = torch.Generator().manual_seed(M + N + K + bm + bn)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    Ab, Bb = A.bfloat16().double(), B.bfloat16().double()
+    ref = torch.relu(Ab @ Bb.t() + bias.double() + add.double()).float()
+    dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    mode = S.MODE_BF16 | (bm << 8) | (bn << 16)
+    L.check(L.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), db.data_ptr(), da.data_ptr(), 1,
+                               out.data_ptr(), mode, stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    err = np.abs(got - ref.numpy()).max()
+    assert np.isfinite(got).all(), "non-finite output"
+    assert err < 2e-3 * K ** 0.5, "max err %g" % err
