@@ -138,6 +138,21 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
         SRNN_TRY(ctx->weights.alloc((void**)&ctx->b_out, sizeof(float) * Q));
         SRNN_TRY(ctx->weights.alloc((void**)&ctx->lut, sizeof(float) * Q));
         SRNN_TRY(ctx->weights.alloc((void**)&ctx->tbl, sizeof(float) * (size_t)FS0 * Q * H));
+        ctx->has_bf16 = (H % 64 == 0);
+        if (ctx->has_bf16) {
+            typedef __nv_bfloat16 bf;
+            for (int i = 0; i < c.n_tiers; ++i) {
+                TierPacked& t = ctx->tiers[i];
+                for (int l = 0; l < L; ++l) {
+                    SRNN_TRY(ctx->weights.alloc((void**)&t.w_ih16[l], sizeof(bf) * 3 * H * H));
+                    SRNN_TRY(ctx->weights.alloc((void**)&t.w_hh16[l], sizeof(bf) * 3 * H * H));
+                }
+                SRNN_TRY(ctx->weights.alloc((void**)&t.w_up16, sizeof(bf) * (size_t)t.fs * H * H));
+            }
+            SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_hid16, sizeof(bf) * H * H));
+            SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_out16, sizeof(bf) * Q * H));
+            SRNN_TRY(ctx->weights.alloc((void**)&ctx->tbl16, sizeof(bf) * (size_t)FS0 * Q * H));
+        }
     }
     // scratch: folded conv weights before re-layout
     int max_fs = 1, max_kin = 1;
@@ -195,6 +210,19 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
     SRNN_TRY(wn_fold(P->mlp_output, ctx->w_out, Q, H, st));
     SRNN_TRY(copy_f32(P->mlp_output.bias, ctx->b_out, Q, st));
     SRNN_TRY(build_lut(ctx->lut, Q, c.ulaw, st));
+    if (ctx->has_bf16) {   // bf16 operand copies for the tcgen05 path
+        for (int i = 0; i < c.n_tiers; ++i) {
+            TierPacked& t = ctx->tiers[i];
+            for (int l = 0; l < L; ++l) {
+                SRNN_TRY(f32_to_bf16_pad(t.w_ih[l], 3 * H, H, H, t.w_ih16[l], 3 * H, H, st));
+                SRNN_TRY(f32_to_bf16_pad(t.w_hh[l], 3 * H, H, H, t.w_hh16[l], 3 * H, H, st));
+            }
+            SRNN_TRY(f32_to_bf16_pad(t.w_up, t.fs * H, H, H, t.w_up16, t.fs * H, H, st));
+        }
+        SRNN_TRY(f32_to_bf16_pad(ctx->w_hid, H, H, H, ctx->w_hid16, H, H, st));
+        SRNN_TRY(f32_to_bf16_pad(ctx->w_out, Q, H, H, ctx->w_out16, Q, H, st));
+        SRNN_TRY(f32_to_bf16_pad(ctx->tbl, FS0 * Q, H, H, ctx->tbl16, FS0 * Q, H, st));
+    }
     ctx->packed = true;
     return SRNN_OK;
 }
@@ -273,18 +301,21 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generator.__call__  (model.py:445-520) -- fp32 mode: one CUDA graph per top-tier period, replayed n_cond times
+// Generator.__call__  (model.py:445-520): one CUDA graph per top-tier period (lookback samples), replayed n_cond
+// times.  fp32 mode: FFMA GEMMs.  bf16 mode: the same schedule with every H-wide contraction on tcgen05 (gemm_umma).
 // ------------------------------------------------------------------------------------------------
-static int generate_f32(srnn_ctx* ctx, int B, int n_cond, const float* cond, int cond_rows, const int64_t* spk,
-                        const float* uniforms, uint8_t* samples_out, float* audio_out, float* logp_out,
-                        cudaStream_t user) {
+static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const float* cond, int cond_rows,
+                          const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
+                          float* logp_out, cudaStream_t user) {
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
     const int T = n_cond * lookback, Lseq = lookback + T;
+    typedef __nv_bfloat16 bf;
     uint8_t* seq = nullptr;
     int* step_base = nullptr;
     float *hid[SRNN_MAX_TIERS], *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS],
         *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
+    bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         Bump b(pass ? ctx->ws : nullptr);
         seq = b.take<uint8_t>((size_t)B * Lseq);
@@ -297,10 +328,14 @@ static int generate_f32(srnn_ctx* ctx, int B, int n_cond, const float* cond, int
             GI[i] = b.take<float>((size_t)B * 3 * H);
             GH[i] = b.take<float>((size_t)B * 3 * H);
             OUT[i] = b.take<float>((size_t)B * t.fs * H);
+            hid16[i] = b.take<bf>((size_t)NL * B * H);
+            X16[i] = b.take<bf>((size_t)B * H);
         }
         X1 = b.take<float>((size_t)B * H);
         X2 = b.take<float>((size_t)B * H);
         LG = b.take<float>((size_t)B * Q);
+        X1h = b.take<bf>((size_t)B * H);
+        X2h = b.take<bf>((size_t)B * H);
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
     }
     // private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
@@ -315,13 +350,15 @@ static int generate_f32(srnn_ctx* ctx, int B, int n_cond, const float* cond, int
     SRNN_TRY(fill_u8(seq, (uint8_t)(Q / 2), (size_t)B * Lseq, st));                  // q_zero  model.py:459
     SRNN_CUDA(cudaMemsetAsync(step_base, 0, sizeof(int), st));
     SRNN_TRY(add_int(step_base, lookback, st));                                      // i starts at lookback  model.py:462
-    for (int i = 0; i < NT; ++i)
+    for (int i = 0; i < NT; ++i) {
         for (int l = 0; l < NL; ++l)                                                 // reset_hidden_states  model.py:451
             SRNN_TRY(bcast_rows(ctx->tiers[i].h0 + (size_t)l * H, hid[i] + (size_t)l * B * H, B, H, st));
+        if (bf16) SRNN_TRY(f32_to_bf16_pad(hid[i], NL * B, H, H, hid16[i], NL * B, H, st));
+    }
+    const int bn_tier = B <= 32 ? 32 : 64;     // batch-row tile of the tier GEMMs (UMMA M = 128 features)
 
     const long long before = g_launches.load();
     SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = SRNN_OK;
     auto body = [&]() -> int {
         for (int pos = 0; pos < lookback; ++pos) {                                   // i = *step_base + pos
             for (int i = NT - 1; i >= 0; --i) {
@@ -336,28 +373,51 @@ static int generate_f32(srnn_ctx* ctx, int B, int n_cond, const float* cond, int
                     upper = OUT[i + 1] + (size_t)((pos / t.n) % u.fs) * H;
                     up_ld = u.fs * H;
                 }
-                SRNN_TRY(gemm_f32(B, H, t.kin, A[i], t.kin, t.w_in, t.kin, t.b_in, upper, up_ld, 0, X[i], H, st));
+                SRNN_TRY(gemm_f32(B, H, t.kin, A[i], t.kin, t.w_in, t.kin, t.b_in, upper, up_ld, 0, X[i], H, st,
+                                  bf16 ? X16[i] : nullptr));
                 const float* in = X[i];
+                const bf* in16 = X16[i];
                 for (int l = 0; l < NL; ++l) {
                     float* h = hid[i] + (size_t)l * B * H;
-                    SRNN_TRY(gemm_f32(B, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
-                    SRNN_TRY(gemm_f32(B, 3 * H, H, h, H, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
-                    SRNN_TRY(gru_gates(GI[i], 3 * H, GH[i], 3 * H, h, H, h, H, nullptr, B, H, st));
+                    bf* h16 = hid16[i] + (size_t)l * B * H;
+                    if (bf16) {
+                        SRNN_TRY(gemm_umma(t.w_ih16[l], 3 * H, in16, B, H, H, H, t.b_ih[l], nullptr, 0, GI[i], nullptr,
+                                           3 * H, 0, 128, bn_tier, st));
+                        SRNN_TRY(gemm_umma(t.w_hh16[l], 3 * H, h16, B, H, H, H, t.b_hh[l], nullptr, 0, GH[i], nullptr,
+                                           3 * H, 0, 128, bn_tier, st));
+                    } else {
+                        SRNN_TRY(gemm_f32(B, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
+                        SRNN_TRY(gemm_f32(B, 3 * H, H, h, H, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
+                    }
+                    SRNN_TRY(gru_gates(GI[i], 3 * H, GH[i], 3 * H, h, H, h, H, nullptr, B, H, st, bf16 ? h16 : nullptr));
                     in = h;
+                    in16 = h16;
                 }
-                SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
+                if (bf16)
+                    SRNN_TRY(gemm_umma(t.w_up16, t.fs * H, in16, B, H, H, H, t.b_up, nullptr, 0, OUT[i], nullptr,
+                                       t.fs * H, 0, 128, bn_tier, st));
+                else
+                    SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
             }
-            SRNN_TRY(mlp_gather(seq, Lseq, pos - FS0, step_base, ctx->tbl, OUT[0] + (size_t)(pos % FS0) * H,
-                                (long long)FS0 * H, 0, X1, B, 1, H, FS0, st));      // model.py:504-513
-            SRNN_TRY(gemm_f32(B, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
-            SRNN_TRY(gemm_f32(B, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, LG, Q, st));
+            const float* up0 = OUT[0] + (size_t)(pos % FS0) * H;                     // model.py:504-513
+            if (bf16) {
+                SRNN_TRY(mlp_gather_bf16(seq, Lseq, pos - FS0, step_base, ctx->tbl16, up0, (long long)FS0 * H, 0, X1h, B,
+                                         1, H, FS0, st));
+                SRNN_TRY(gemm_umma(ctx->w_hid16, H, X1h, B, H, H, H, ctx->b_hid, nullptr, 0, nullptr, X2h, H, 1, 64, 32, st));
+                SRNN_TRY(gemm_umma(ctx->w_out16, Q, X2h, B, H, H, H, ctx->b_out, nullptr, 0, LG, nullptr, Q, 0, 64, 32, st));
+            } else {
+                SRNN_TRY(mlp_gather(seq, Lseq, pos - FS0, step_base, ctx->tbl, up0, (long long)FS0 * H, 0, X1, B, 1, H,
+                                    FS0, st));
+                SRNN_TRY(gemm_f32(B, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
+                SRNN_TRY(gemm_f32(B, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, LG, Q, st));
+            }
             SRNN_TRY(softmax_sample(LG, uniforms, B, seq, Lseq, pos, lookback, step_base, logp_out,
                                     (long long)T * Q, B, st));                       // model.py:514-517
         }
         SRNN_TRY(add_int(step_base, lookback, st));
         return SRNN_OK;
     };
-    rc = body();
+    const int rc = body();
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     const long long nodes = g_launches.load() - before;
@@ -391,9 +451,11 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
     if (!samples_out && !audio_out) return fail(SRNN_ERR_ARG, "need samples_out or audio_out");
     if (B < 1 || n_cond < 1) return fail(SRNN_ERR_ARG, "B and n_cond must be positive");
     if (cond_rows != 1 && cond_rows != B) return fail(SRNN_ERR_ARG, "cond_rows must be 1 or B");
-    if (mode == SRNN_MODE_FP32)
-        return generate_f32(ctx, B, n_cond, cond, cond_rows, spk, uniforms, samples_out, audio_out, logp_out,
-                            (cudaStream_t)stream);
+    if (mode == SRNN_MODE_BF16 && !ctx->has_bf16)
+        return fail(SRNN_ERR_UNSUPPORTED, "bf16 tensor-core mode needs dim %% 64 == 0 (dim=%d)", ctx->H);
+    if (mode == SRNN_MODE_FP32 || mode == SRNN_MODE_BF16)
+        return generate_graph(ctx, mode == SRNN_MODE_BF16, B, n_cond, cond, cond_rows, spk, uniforms, samples_out,
+                              audio_out, logp_out, (cudaStream_t)stream);
     return fail(SRNN_ERR_UNSUPPORTED, "generate: mode %d not available", mode);
 }
 

@@ -58,6 +58,10 @@ struct TierPacked {
     float* w_up = nullptr;    // (fs*H, H)  row j*H+o = conv_t.weight[:, o, j]   (nn.py:33-43)
     float* b_up = nullptr;    // (fs*H)     j*H+o -> upsampling.bias[o, j]
     float* h0 = nullptr;      // (n_rnn, H)
+    // bf16 copies for the tcgen05 path (present when H % 64 == 0)
+    __nv_bfloat16* w_ih16[SRNN_MAX_RNN] = {};
+    __nv_bfloat16* w_hh16[SRNN_MAX_RNN] = {};
+    __nv_bfloat16* w_up16 = nullptr;
 };
 
 struct Arena {
@@ -80,6 +84,10 @@ struct srnn_ctx {
     float* w_out = nullptr;   // (Q, H)
     float* b_out = nullptr;
     float* lut = nullptr;     // (Q) 2*dequantize(q)
+    bool has_bf16 = false;    // tcgen05 path available (H % 64 == 0)
+    __nv_bfloat16* tbl16 = nullptr;
+    __nv_bfloat16* w_hid16 = nullptr;
+    __nv_bfloat16* w_out16 = nullptr;
     srnn::Arena weights;      // freed on destroy
     // grow-only scratch for predict / generate
     void* ws = nullptr;
@@ -93,7 +101,8 @@ int ensure_ws(srnn_ctx* ctx, size_t bytes);
 
 // ---- fp32 kernels (kernels_f32.cu) --------------------------------------------------------------
 int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
-             const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st);
+             const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st,
+             __nv_bfloat16* C16 = nullptr);
 int wn_fold(const srnn_conv_params& p, float* out, int rows, int cols, cudaStream_t st);
 int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
 int fill_u8(uint8_t* dst, uint8_t v, size_t n, cudaStream_t st);
@@ -111,12 +120,16 @@ int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, i
                 cudaStream_t st);
 // GRU cell tail (model.py:244): h' from gi (+bias already in), gh (+bias already in), h
 int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
-              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st);
+              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st,
+              __nv_bfloat16* h16 = nullptr);
 int bcast_rows(const float* src, float* dst, int B, int H, cudaStream_t st);
 // x1[r,:] = relu(sum_j Tbl[j][seq[b, off + t + j]] + upper[r,:])
 int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, const float* tbl,
                const float* upper, long long up_bstride, long long up_tstride, float* x1, int B, int T, int H,
                int FS, cudaStream_t st);
+int mlp_gather_bf16(const uint8_t* seq, int seq_ld, int off, const int* step_base, const __nv_bfloat16* tbl,
+                    const float* upper, long long up_bstride, long long up_tstride, __nv_bfloat16* x1, int B, int T,
+                    int H, int FS, cudaStream_t st);
 int logsoftmax_rows(float* x, int rows, cudaStream_t st);
 // generation tail: logits (B, 256) -> [logp] -> defined sampler -> seq[b, pos]
 int softmax_sample(const float* logits, const float* uniforms, int u_ld, uint8_t* seq, int seq_ld, int pos_off,

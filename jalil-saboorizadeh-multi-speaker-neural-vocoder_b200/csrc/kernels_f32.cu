@@ -14,7 +14,7 @@ constexpr int GBM = 64, GBN = 64, GBK = 16;
 __global__ void __launch_bounds__(256)
 k_gemm_f32_tn(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
               const float* __restrict__ bias, const float* __restrict__ add, int ldadd, int relu,
-              float* __restrict__ C, int ldc) {
+              float* __restrict__ C, int ldc, __nv_bfloat16* __restrict__ C16) {
     __shared__ float As[GBK][GBM + 4];
     __shared__ float Bs[GBK][GBN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -59,16 +59,17 @@ k_gemm_f32_tn(int M, int N, int K, const float* __restrict__ A, int lda, const f
             if (bias) v += bias[gn];
             if (add) v += add[(size_t)gm * ldadd + gn];
             if (relu) v = fmaxf(v, 0.f);
-            C[(size_t)gm * ldc + gn] = v;
+            if (C) C[(size_t)gm * ldc + gn] = v;
+            if (C16) C16[(size_t)gm * ldc + gn] = __float2bfloat16(v);
         }
     }
 }
 
 int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
-             const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st) {
+             const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st, __nv_bfloat16* C16) {
     if (M <= 0 || N <= 0) return SRNN_OK;
     dim3 grid(cdiv(N, GBN), cdiv(M, GBM));
-    SRNN_LAUNCH(k_gemm_f32_tn, grid, 256, 0, st, M, N, K, A, lda, B, ldb, bias, add, ldadd, relu, C, ldc);
+    SRNN_LAUNCH(k_gemm_f32_tn, grid, 256, 0, st, M, N, K, A, lda, B, ldb, bias, add, ldadd, relu, C, ldc, C16);
     return SRNN_OK;
 }
 
@@ -246,7 +247,7 @@ int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, i
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gru_gates(const float* __restrict__ gi, int gi_ld, const float* __restrict__ gh, int gh_ld,
                             const float* __restrict__ h_prev, int hp_ld, float* __restrict__ h_out, int ho_ld,
-                            float* __restrict__ h_out2, int H) {
+                            float* __restrict__ h_out2, int H, __nv_bfloat16* __restrict__ h16) {
     const int b = blockIdx.y;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= H) return;
@@ -259,11 +260,12 @@ __global__ void k_gru_gates(const float* __restrict__ gi, int gi_ld, const float
     const float hn = (1.f - z) * nn + z * hp;
     h_out[(size_t)b * ho_ld + u] = hn;
     if (h_out2) h_out2[(size_t)b * H + u] = hn;
+    if (h16) h16[(size_t)b * H + u] = __float2bfloat16(hn);
 }
 int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
-              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st) {
+              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st, __nv_bfloat16* h16) {
     SRNN_LAUNCH(k_gru_gates, dim3(cdiv(H, 128), B), 128, 0, st, gi, gi_ld, gh, gh_ld, h_prev, hp_ld, h_out, ho_ld,
-                h_out2, H);
+                h_out2, H, h16);
     return SRNN_OK;
 }
 
@@ -281,10 +283,16 @@ int bcast_rows(const float* src, float* dst, int B, int H, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // sample-level MLP front: embedding o conv(k=FS) folded into table gathers  (model.py:311-320)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_f(const float* p) { return *p; }
+__device__ __forceinline__ float ld_f(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_f(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_f(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename TT, typename OT>
 __global__ void k_mlp_gather(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
-                             const int* __restrict__ step_base, const float* __restrict__ tbl,
+                             const int* __restrict__ step_base, const TT* __restrict__ tbl,
                              const float* __restrict__ upper, long long up_bstride, long long up_tstride,
-                             float* __restrict__ x1, int T, int H, int FS) {
+                             OT* __restrict__ x1, int T, int H, int FS) {
     const int r = blockIdx.x;             // b*T + t
     const int b = r / T, t = r % T;
     const int start = start_static + (step_base ? *step_base : 0);
@@ -295,15 +303,22 @@ __global__ void k_mlp_gather(const uint8_t* __restrict__ seq, int seq_ld, int st
     const float* up = upper + (size_t)b * up_bstride + (size_t)t * up_tstride;
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
         float acc = up[h];
-        for (int j = 0; j < FS; ++j) acc += tbl[((size_t)j * SRNN_Q + qs[j]) * H + h];
-        x1[(size_t)r * H + h] = fmaxf(acc, 0.f);
+        for (int j = 0; j < FS; ++j) acc += ld_f(&tbl[((size_t)j * SRNN_Q + qs[j]) * H + h]);
+        st_f(&x1[(size_t)r * H + h], fmaxf(acc, 0.f));
     }
 }
 int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, const float* tbl,
                const float* upper, long long up_bstride, long long up_tstride, float* x1,
                int B, int T, int H, int FS, cudaStream_t st) {
-    SRNN_LAUNCH(k_mlp_gather, B * T, H >= 256 ? 256 : 64, FS * sizeof(int), st, seq, seq_ld, off, step_base, tbl,
-                upper, up_bstride, up_tstride, x1, T, H, FS);
+    SRNN_LAUNCH((k_mlp_gather<float, float>), B * T, H >= 256 ? 256 : 64, FS * sizeof(int), st, seq, seq_ld, off,
+                step_base, tbl, upper, up_bstride, up_tstride, x1, T, H, FS);
+    return SRNN_OK;
+}
+int mlp_gather_bf16(const uint8_t* seq, int seq_ld, int off, const int* step_base, const __nv_bfloat16* tbl,
+                    const float* upper, long long up_bstride, long long up_tstride, __nv_bfloat16* x1, int B, int T,
+                    int H, int FS, cudaStream_t st) {
+    SRNN_LAUNCH((k_mlp_gather<__nv_bfloat16, __nv_bfloat16>), B * T, H >= 256 ? 256 : 64, FS * sizeof(int), st, seq,
+                seq_ld, off, step_base, tbl, upper, up_bstride, up_tstride, x1, T, H, FS);
     return SRNN_OK;
 }
 

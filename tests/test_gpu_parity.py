@@ -152,3 +152,38 @@ def test_teacher_forced_equals_autoregressive(golden):
     with torch.no_grad():
         tf = p(seq[:, :-1], True, cond, spk.reshape(B, 1), None, None)
     np.testing.assert_allclose(tf.cpu().numpy(), logp.numpy(), atol=2e-4)
+
+
+# ---- bf16 tensor-core mode (tcgen05): stated tolerance = 1.5x the reference's own bf16-autocast drift ----
+BF16_MAX_ABS, BF16_MEAN_ABS = 0.08, 0.015
+
+
+@pytest.mark.parametrize("dim,B", [(64, 5), (128, 37)])
+def test_generate_bf16_mode_against_oracle(dim, B):
+    torch.manual_seed(dim)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=dim, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c)
+    p = S.Predictor(m)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    n_cond = 2
+    cond = torch.rand(B, n_cond, 86)
+    spk = torch.randint(0, 6, (B,))
+    audio, samples, logp = S.Generator(m, cuda=True, mode=S.MODE_BF16)(B, 0, cond, spk, seed=5, return_samples=True,
+                                                                        return_logp=True)
+    assert int(samples.min()) >= 0 and int(samples.max()) <= 255
+    seq = torch.cat([torch.full((B, 80), 128, dtype=torch.long), samples.long()], 1)
+    w = O.unpack_state_dict(sd, O.Config(**c))
+    with torch.no_grad():
+        ref = O.Predictor(w).forward(seq[:, :-1], True, cond, spk.reshape(B, 1))
+    d = (ref - logp).abs()
+    assert float(d.max()) <= BF16_MAX_ABS and float(d.mean()) <= BF16_MEAN_ABS, (float(d.max()), float(d.mean()))
+    # and the fp32-mode run of the same generator on the same sequence stays inside the fp32 gate
+    with torch.no_grad():
+        tf32 = p(seq[:, :-1], True, cond, spk.reshape(B, 1), None, None)
+    logp_gate(tf32.cpu().numpy(), ref.numpy())
