@@ -42,6 +42,8 @@ extern "C" {
 /* arithmetic mode of the GEMM-shaped work */
 #define SRNN_MODE_FP32   0   /* fp32 FFMA everywhere: the 1e-3 "fp32 parity" gate                        */
 #define SRNN_MODE_BF16   1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: the speed mode */
+#define SRNN_MODE_BF16_GRAPH 2 /* generation only: bf16 arithmetic, one tcgen05 GEMM launch per contraction
+                                  (no persistent sample kernel); kept as an A/B reference for the fused kernel */
 
 typedef struct srnn_ctx srnn_ctx;
 

@@ -6,7 +6,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsrnn_b200.so")
 
 MAX_TIERS, MAX_RNN, Q = 4, 4, 256
-MODE_FP32, MODE_BF16 = 0, 1
+MODE_FP32, MODE_BF16, MODE_BF16_GRAPH = 0, 1, 2
 
 f32p = C.POINTER(C.c_float)
 

@@ -304,7 +304,26 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
 // Generator.__call__  (model.py:445-520): one CUDA graph per top-tier period (lookback samples), replayed n_cond
 // times.  fp32 mode: FFMA GEMMs.  bf16 mode: the same schedule with every H-wide contraction on tcgen05 (gemm_umma).
 // ------------------------------------------------------------------------------------------------
-static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const float* cond, int cond_rows,
+namespace srnn {
+struct MlpPersistParams {   // must match mlp_persist.cu
+    int B, H, FS, nsteps, pos0, lookback, Lseq, T;
+    const int* step_base;
+    uint8_t* seq;
+    const float* c0;
+    const __nv_bfloat16* tbl;
+    const float* b_hid;
+    const float* b_out;
+    __nv_bfloat16* x1;
+    float* part;
+    unsigned* ctr;
+    const float* uniforms;
+    float* logp_out;
+};
+int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
+                       cudaStream_t st);
+}  // namespace srnn
+
+static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_cond, const float* cond, int cond_rows,
                           const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
                           float* logp_out, cudaStream_t user) {
     const srnn_config& c = ctx->cfg;
@@ -316,6 +335,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const flo
     float *hid[SRNN_MAX_TIERS], *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS],
         *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
     bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr;
+    float* part = nullptr;
+    unsigned* gctr = nullptr;
+    const int RG = (B + 31) / 32, NS = H / 64;
     for (int pass = 0; pass < 2; ++pass) {
         Bump b(pass ? ctx->ws : nullptr);
         seq = b.take<uint8_t>((size_t)B * Lseq);
@@ -334,8 +356,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const flo
         X1 = b.take<float>((size_t)B * H);
         X2 = b.take<float>((size_t)B * H);
         LG = b.take<float>((size_t)B * Q);
-        X1h = b.take<bf>((size_t)B * H);
+        X1h = b.take<bf>((size_t)RG * 32 * H);
         X2h = b.take<bf>((size_t)B * H);
+        part = b.take<float>(persist ? (size_t)RG * NS * 32 * Q : 1);
+        gctr = b.take<unsigned>(RG);
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
     }
     // private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
@@ -357,8 +381,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const flo
     }
     const int bn_tier = B <= 32 ? 32 : 64;     // batch-row tile of the tier GEMMs (UMMA M = 128 features)
 
+    if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
+    const bool use_graph = !persist;   // the persistent kernel is a cooperative launch; it is issued directly
     const long long before = g_launches.load();
-    SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
         for (int pos = 0; pos < lookback; ++pos) {                                   // i = *step_base + pos
             for (int i = NT - 1; i >= 0; --i) {
@@ -400,6 +426,16 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const flo
                     SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
             }
             const float* up0 = OUT[0] + (size_t)(pos % FS0) * H;                     // model.py:504-513
+            if (persist) {
+                if (pos % FS0) continue;             // one persistent launch covers the FS0 samples of a tier-0 frame
+                srnn::MlpPersistParams mp;
+                mp.B = B; mp.H = H; mp.FS = FS0; mp.nsteps = FS0; mp.pos0 = pos; mp.lookback = lookback;
+                mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
+                mp.tbl = ctx->tbl16; mp.b_hid = ctx->b_hid; mp.b_out = ctx->b_out; mp.x1 = X1h; mp.part = part;
+                mp.ctr = gctr; mp.uniforms = uniforms; mp.logp_out = logp_out;
+                SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
+                continue;
+            }
             if (bf16) {
                 SRNN_TRY(mlp_gather_bf16(seq, Lseq, pos - FS0, step_base, ctx->tbl16, up0, (long long)FS0 * H, 0, X1h, B,
                                          1, H, FS0, st));
@@ -417,26 +453,30 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, int B, int n_cond, const flo
         SRNN_TRY(add_int(step_base, lookback, st));
         return SRNN_OK;
     };
-    const int rc = body();
     cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    const long long nodes = g_launches.load() - before;
-    if (rc != SRNN_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaStreamDestroy(st);
-        return rc;
-    }
-    if (ce != cudaSuccess) return fail(SRNN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
     cudaGraphExec_t exec = nullptr;
-    SRNN_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-    for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(exec, st));
-    g_launches.fetch_add(nodes * (long long)(n_cond - 1));
+    if (use_graph) {
+        const int rc = body();
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        const long long nodes = g_launches.load() - before;
+        if (rc != SRNN_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(st);
+            return rc;
+        }
+        if (ce != cudaSuccess) return fail(SRNN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        SRNN_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(exec, st));
+        g_launches.fetch_add(nodes * (long long)(n_cond - 1));
+    } else {
+        for (int p = 0; p < n_cond; ++p) SRNN_TRY(body());
+    }
     SRNN_TRY(dequant_audio(seq, Lseq, lookback, ctx->lut, samples_out, audio_out, B, T, st));   // model.py:520
     SRNN_CUDA(cudaEventRecord(ev_out, st));
     SRNN_CUDA(cudaStreamWaitEvent(user, ev_out, 0));
     // the graph/stream objects can be released once the work is enqueued; CUDA defers destruction until completion
-    SRNN_CUDA(cudaGraphExecDestroy(exec));
-    SRNN_CUDA(cudaGraphDestroy(graph));
+    if (exec) SRNN_CUDA(cudaGraphExecDestroy(exec));
+    if (graph) SRNN_CUDA(cudaGraphDestroy(graph));
     SRNN_CUDA(cudaEventDestroy(ev_in));
     SRNN_CUDA(cudaEventDestroy(ev_out));
     SRNN_CUDA(cudaStreamDestroy(st));
@@ -451,11 +491,16 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
     if (!samples_out && !audio_out) return fail(SRNN_ERR_ARG, "need samples_out or audio_out");
     if (B < 1 || n_cond < 1) return fail(SRNN_ERR_ARG, "B and n_cond must be positive");
     if (cond_rows != 1 && cond_rows != B) return fail(SRNN_ERR_ARG, "cond_rows must be 1 or B");
-    if (mode == SRNN_MODE_BF16 && !ctx->has_bf16)
+    if (mode != SRNN_MODE_FP32 && !ctx->has_bf16)
         return fail(SRNN_ERR_UNSUPPORTED, "bf16 tensor-core mode needs dim %% 64 == 0 (dim=%d)", ctx->H);
-    if (mode == SRNN_MODE_FP32 || mode == SRNN_MODE_BF16)
-        return generate_graph(ctx, mode == SRNN_MODE_BF16, B, n_cond, cond, cond_rows, spk, uniforms, samples_out,
-                              audio_out, logp_out, (cudaStream_t)stream);
+    if (mode == SRNN_MODE_FP32 || mode == SRNN_MODE_BF16 || mode == SRNN_MODE_BF16_GRAPH) {
+        const bool bf16 = mode != SRNN_MODE_FP32;
+        int n_sms = 0;
+        SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        const bool persist = mode == SRNN_MODE_BF16 && mlp_persist_supported(ctx->H, ctx->FS0, B, n_sms);
+        return generate_graph(ctx, bf16, persist, B, n_cond, cond, cond_rows, spk, uniforms, samples_out, audio_out,
+                              logp_out, (cudaStream_t)stream);
+    }
     return fail(SRNN_ERR_UNSUPPORTED, "generate: mode %d not available", mode);
 }
 

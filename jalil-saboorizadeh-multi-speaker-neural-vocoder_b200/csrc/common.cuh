@@ -144,6 +144,9 @@ int add_int(int* p, int v, cudaStream_t st);
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
               const float* bias, const float* addend, int ld_add, float* out_f32, __nv_bfloat16* out_bf16,
               int ld_out, int relu, int bm, int bn, cudaStream_t st);
+struct MlpPersistParams;
+size_t mlp_persist_smem(int H);
+bool mlp_persist_supported(int H, int FS, int B, int n_sms);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);
 

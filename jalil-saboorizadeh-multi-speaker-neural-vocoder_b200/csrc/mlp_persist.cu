@@ -1,0 +1,428 @@
+// Persistent fused sample-level kernel for generation (SRNN_MODE_BF16): for `nsteps` consecutive audio samples it
+// runs  table-gather -> ReLU -> hidden GEMM -> ReLU -> output GEMM -> log-softmax -> inverse-CDF sample  with NO
+// host round trip and NO per-step launch (replaces model.py:504-517 executed once per sample by the reference).
+//
+// Decomposition (H = dim, NS = H/64 feature slices, 32 utterance rows per group, RPC = 32/NS rows owned per CTA):
+//   CTA (rg, sl) keeps the bf16 weight slices resident in shared memory for the whole launch:
+//       W_hid[sl*64 .. +64, :]   (64 x H,  the UMMA A operand of the hidden GEMM, M = 64)
+//       W_out[:, sl*64 .. +64]   (256 x 64, the A operand of a split-K output GEMM, 2 x M = 128)
+//   and OWNS rows  rg*32 + sl*RPC .. +RPC  for everything that is per-row (table gathers, softmax, sampling).
+//   per step:  owner rows: x1 = relu(P + Tbl[FS-1][newest sample])           -> global X1 (bf16)      [CUDA cores]
+//              -- group barrier A (the NS CTAs of a row group) --
+//              D1[64 feat x 32 rows]  = W_hid slice . X1(32 rows)^T           (TMA ring -> tcgen05, TMEM)
+//              x2 = relu(D1 + b_hid) -> smem (bf16, swizzled B operand)        [epilogue warps]
+//              D2[256 x 32 rows]      = W_out[:, slice] . x2^T  (split-K partial logits) -> global Part
+//              -- group barrier B --
+//              owner rows: logits = b_out + sum_slices Part; log-softmax; defined sampler -> seq      [CUDA cores]
+//   The (FS-1)-tap part of the gather for the NEXT step (P) is prefetched by 4 dedicated warps during the GEMMs, so
+//   only one table row per utterance is on the serial path.
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue/"E" warps,
+// 6..9 = gather/"G" warps.
+#include "common.cuh"
+#include "sampler.cuh"
+#include "umma.cuh"
+
+namespace srnn {
+
+using namespace ptx;
+int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+struct MlpPersistParams {
+    int B, H, FS, nsteps, pos0, lookback, Lseq, T;
+    const int* step_base;
+    uint8_t* seq;                 // (B, Lseq) quantised samples (read + written)
+    const float* c0;              // tier-0 output (B, FS*H): conditioning of sample phase p at [b][p*H + f]
+    const __nv_bfloat16* tbl;     // (FS, 256, H) folded embedding-o-conv table
+    const float* b_hid;
+    const float* b_out;
+    __nv_bfloat16* x1;            // (RG*32, H) exchange buffer
+    float* part;                  // (RG, NS, 32, 256) split-K partial logits
+    unsigned* ctr;                // (RG) group-barrier counters, zero at launch
+    const float* uniforms;        // (T, B)
+    float* logp_out;              // (B, T, 256) or null
+};
+
+constexpr int MP_THREADS = 320;
+constexpr int MP_MAX_STAGES = 8;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// barrier among the NS CTAs of one row group; executed by the 128 E threads (named barrier 1)
+__device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target, int tidE) {
+    named_bar_sync(1, 128);
+    if (tidE == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_gpu(ctr) < target) {
+        }
+        __threadfence();
+    }
+    named_bar_sync(1, 128);
+}
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+__global__ void __launch_bounds__(MP_THREADS, 1)
+k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWo,
+              const __grid_constant__ CUtensorMap tmX1, const MlpPersistParams p) {
+    const int H = p.H, KB = H >> 6, NS = H >> 6, RPC = 32 / NS, FS = p.FS;
+    const int NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
+    const int rg = blockIdx.x / NS, sl = blockIdx.x % NS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sWh = smem;                                  // KB x (64 rows x 128 B)
+    uint8_t* sWo = sWh + (size_t)KB * 8192;               // 2 x (128 rows x 128 B)
+    uint8_t* sRing = sWo + 32768;                         // NSTG x (32 rows x 128 B)
+    uint8_t* sX2 = sRing + (size_t)NSTG * 4096;           // 32 rows x 128 B
+    float* sP = (float*)(sX2 + 4096);                     // 2 x 2048 fp32
+    uint8_t* sQ = (uint8_t*)(sP + 4096);                  // 32 owned rows x 32-entry sample ring
+    uint64_t* bars = (uint64_t*)(sQ + 1024);
+    uint64_t* w_ready = bars + 0;
+    uint64_t* full = bars + 1;                            // [MP_MAX_STAGES]
+    uint64_t* empty = full + MP_MAX_STAGES;               // [MP_MAX_STAGES]
+    uint64_t* x1_ready = empty + MP_MAX_STAGES;
+    uint64_t* bar_d1 = x1_ready + 1;
+    uint64_t* x2_ready = bar_d1 + 1;
+    uint64_t* bar_d2 = x2_ready + 1;
+    uint64_t* p_ready = bar_d2 + 1;                       // [2]
+    uint64_t* p_free = p_ready + 2;                       // [2]
+    volatile int* q_count = (volatile int*)(p_free + 2);   // number of samples drawn so far in this launch
+    uint32_t* tmem_slot = (uint32_t*)(p_free + 3);
+
+    const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
+    const int row0 = rg * 32 + sl * RPC;                  // first owned row (global utterance index)
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmWh);
+        prefetch_tmap(&tmWo);
+        prefetch_tmap(&tmX1);
+        mbar_init(w_ready, 1);
+        for (int s = 0; s < MP_MAX_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(x1_ready, 1);
+        mbar_init(bar_d1, 1);
+        mbar_init(x2_ready, 1);
+        mbar_init(bar_d2, 1);
+        mbar_init(&p_ready[0], 128);
+        mbar_init(&p_ready[1], 128);
+        mbar_init(&p_free[0], 1);
+        mbar_init(&p_free[1], 1);
+        *q_count = 0;
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<128>(tmem_slot);
+    // owned rows' sample ring: the FS most recent samples before i0 (written by earlier launches / the q_zero prefix)
+    for (int e = threadIdx.x; e < RPC * 32; e += MP_THREADS) {
+        const int rl = e >> 5, w = e & 31;
+        const int b = row0 + rl;
+        const int a = i0 - 32 + w;                        // absolute sample index, slot a & 31
+        uint8_t q = 128;
+        if (b < p.B && a >= 0 && a >= i0 - FS) q = __ldcg(p.seq + (size_t)b * p.Lseq + a);
+        sQ[rl * 32 + (a & 31)] = q;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 32;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(w_ready, (uint32_t)(KB * 8192 + 32768));
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sWh + (size_t)kb * 8192, &tmWh, w_ready, kb * 64, sl * 64);
+            tma_load_2d(sWo, &tmWo, w_ready, sl * 64, 0);
+            tma_load_2d(sWo + 16384, &tmWo, w_ready, sl * 64, 128);
+            int it = 0;
+            for (int k = 0; k < p.nsteps; ++k) {
+                mbar_wait(x1_ready, k & 1);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % NSTG;
+                    const uint32_t ph = (it / NSTG) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], 4096);
+                    tma_load_2d(sRing + (size_t)s * 4096, &tmX1, &full[s], kb * 64, rg * 32);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = umma_idesc_bf16(64, 32);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(128, 32);
+            mbar_wait(w_ready, 0);
+            int it = 0;
+            for (int k = 0; k < p.nsteps; ++k) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % NSTG;
+                    const uint32_t ph = (it / NSTG) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(sWh + (size_t)kb * 8192));
+                    const uint64_t db = umma_desc_sw128(smem_u32(sRing + (size_t)s * 4096));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_bf16(tm_d1, da + 2 * kk, db + 2 * kk, idesc1, (kb | kk) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(bar_d1);
+                mbar_wait(x2_ready, k & 1);
+                tc_fence_after();
+                const uint64_t db2 = umma_desc_sw128(smem_u32(sX2));
+#pragma unroll
+                for (int t2 = 0; t2 < 2; ++t2) {
+                    const uint64_t da2 = umma_desc_sw128(smem_u32(sWo + t2 * 16384));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_bf16(tm_d2 + 32 * t2, da2 + 2 * kk, db2 + 2 * kk, idesc2, kk != 0);
+                }
+                umma_commit(bar_d2);
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== E warps: per-row work, epilogues, group barriers =====================
+        const int tidE = threadIdx.x - 64;
+        const int q4 = warp & 3;                          // TMEM lane quadrant this warp may access
+        const int flat = tidE * 16;                       // 16 consecutive features of one owned row
+        const int rl = flat / H, f0 = flat % H;
+        const int b = row0 + rl;
+        unsigned bar_no = 0;
+        unsigned* ctr = p.ctr + rg;
+        for (int k = 0; k < p.nsteps; ++k) {
+            const int i = i0 + k;
+            // ---- E1: x1 = relu(P + Tbl[FS-1][newest sample]) for the owned rows -> global X1 ----
+            mbar_wait(&p_ready[k & 1], (k >> 1) & 1);
+            {
+                const int qn = sQ[rl * 32 + ((i - 1) & 31)];
+                const uint4* tp = reinterpret_cast<const uint4*>(p.tbl + ((size_t)(FS - 1) * SRNN_Q + qn) * H + f0);
+                const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                float tv[16];
+                bf16x8_to_f32(t0, tv);
+                bf16x8_to_f32(t1, tv + 8);
+                const float4* pp = reinterpret_cast<const float4*>(sP + (k & 1) * 2048 + flat);
+                uint32_t o[8];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 pv = pp[v];
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(pv.x + tv[4 * v], 0.f), fmaxf(pv.y + tv[4 * v + 1], 0.f));
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaxf(pv.z + tv[4 * v + 2], 0.f), fmaxf(pv.w + tv[4 * v + 3], 0.f));
+                    o[2 * v] = *reinterpret_cast<const uint32_t*>(&lo);
+                    o[2 * v + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+                }
+                uint4* xp = reinterpret_cast<uint4*>(p.x1 + (size_t)b * H + f0);   // x1 has RG*32 rows: always in range
+                xp[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                xp[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+            // ---- group barrier A: the whole X1 of this row group is in global memory ----
+            group_barrier(ctr, (++bar_no) * NS, tidE);
+            if (tidE == 0) {
+                mbar_arrive(&p_free[k & 1]);              // P[k&1] consumed (all E threads passed the barrier above)
+                fence_proxy_async_all();                  // generic-proxy global writes -> visible to TMA reads
+                mbar_arrive(x1_ready);
+            }
+            // ---- epilogue 1: D1 (+bias, ReLU) -> bf16 swizzled B operand in smem ----
+            mbar_wait(bar_d1, k & 1);
+            tc_fence_after();
+            {
+                float v0[16], v1[16];
+                tmem_ld16(tm_d1 + ((uint32_t)(32 * q4) << 16), v0);
+                tmem_ld16(tm_d1 + ((uint32_t)(32 * q4) << 16) + 16, v1);
+                if (lane < 16) {
+                    const int f = 16 * q4 + lane;         // feature inside the slice = K index of the output GEMM
+                    const float bv = p.b_hid[sl * 64 + f];
+                    uint8_t* base = sX2 + (f & 7) * 2;
+                    const int chunk = f >> 3;
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        *reinterpret_cast<__nv_bfloat16*>(base + n * 128 + ((chunk ^ (n & 7)) << 4)) =
+                            __float2bfloat16(fmaxf(v0[n] + bv, 0.f));
+                        *reinterpret_cast<__nv_bfloat16*>(base + (n + 16) * 128 + ((chunk ^ ((n + 16) & 7)) << 4)) =
+                            __float2bfloat16(fmaxf(v1[n] + bv, 0.f));
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();                     // generic smem writes -> visible to the UMMA operand reads
+            named_bar_sync(1, 128);
+            if (tidE == 0) mbar_arrive(x2_ready);
+            // ---- epilogue 2: split-K partial logits -> global Part[rg][sl][row][256] ----
+            mbar_wait(bar_d2, k & 1);
+            tc_fence_after();
+            {
+                float* dst = p.part + ((size_t)(rg * NS + sl) * 32) * SRNN_Q + 32 * q4 + lane;
+#pragma unroll
+                for (int t2 = 0; t2 < 2; ++t2) {
+                    float v0[16], v1[16];
+                    tmem_ld16(tm_d2 + 32 * t2 + ((uint32_t)(32 * q4) << 16), v0);
+                    tmem_ld16(tm_d2 + 32 * t2 + ((uint32_t)(32 * q4) << 16) + 16, v1);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        dst[(size_t)n * SRNN_Q + t2 * 128] = v0[n];
+                        dst[(size_t)(n + 16) * SRNN_Q + t2 * 128] = v1[n];
+                    }
+                }
+            }
+            tc_fence_before();
+            // ---- group barrier B: all slices' partial logits are in global memory ----
+            group_barrier(ctr, (++bar_no) * NS, tidE);
+            // ---- reduce + log-softmax + defined sampler for the owned rows ----
+            for (int r2 = warp - 2; r2 < RPC; r2 += 4) {
+                const int n = sl * RPC + r2, bb = row0 + r2;
+                float v[8];
+                {
+                    const float4* bo = reinterpret_cast<const float4*>(p.b_out + lane * 8);
+                    const float4 a0 = __ldg(bo), a1 = __ldg(bo + 1);
+                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                }
+                for (int s2 = 0; s2 < NS; ++s2) {
+                    const float4* pp = reinterpret_cast<const float4*>(p.part + ((size_t)(rg * NS + s2) * 32 + n) * SRNN_Q + lane * 8);
+                    const float4 a0 = __ldcg(pp), a1 = __ldcg(pp + 1);
+                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                }
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) m = fmaxf(m, v[j]);
+                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += expf(v[j] - m);
+                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float lse = m + logf(s);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] -= lse;
+                const int t = i - p.lookback;
+                if (bb < p.B) {
+                    if (p.logp_out) {
+                        float4* o4 = reinterpret_cast<float4*>(p.logp_out + ((size_t)bb * p.T + t) * SRNN_Q + lane * 8);
+                        o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = expf(v[j]);
+                    const float u = __ldg(p.uniforms + (size_t)t * p.B + bb);
+                    const int idx = sampler_warp(v, u, lane);
+                    if (lane == 0) {
+                        p.seq[(size_t)bb * p.Lseq + i] = (uint8_t)idx;
+                        sQ[r2 * 32 + (i & 31)] = (uint8_t)idx;
+                    }
+                } else if (lane == 0) {
+                    sQ[r2 * 32 + (i & 31)] = 128;
+                }
+            }
+            named_bar_sync(1, 128);                       // sample i of every owned row is in sQ
+            if (tidE == 0) {
+                __threadfence_block();
+                *q_count = k + 1;
+            }
+        }
+    } else {
+        // ===================== G warps: prefetch P_g = c0 + taps 0..FS-2 for step g =====================
+        const int tidG = threadIdx.x - 192;
+        const int flat = tidG * 16;
+        const int rl = flat / H, f0 = flat % H;
+        const int b = row0 + rl;
+        const int bc = b < p.B ? b : p.B - 1;             // clamp: padded rows compute garbage that is never used
+        for (int g = 0; g < p.nsteps; ++g) {
+            const int i = i0 + g;
+            if (g >= 2) {
+                while (*q_count < g - 1) {                // sample i-2 (tap FS-2) has been drawn (a counter, not an
+                }                                         // mbarrier: E may be two samples ahead of this wait)
+                __threadfence_block();
+                mbar_wait(&p_free[g & 1], ((g >> 1) - 1) & 1);
+            }
+            float acc[16];
+            {
+                const float4* cp = reinterpret_cast<const float4*>(p.c0 + (size_t)bc * FS * H + (size_t)(i % FS) * H + f0);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 c = __ldg(cp + v);
+                    acc[4 * v] = c.x; acc[4 * v + 1] = c.y; acc[4 * v + 2] = c.z; acc[4 * v + 3] = c.w;
+                }
+            }
+            const uint8_t* qrow = sQ + rl * 32;
+#pragma unroll 4
+            for (int j = 0; j < FS - 1; ++j) {
+                const int qj = qrow[(i - FS + j) & 31];
+                const uint4* tp = reinterpret_cast<const uint4*>(p.tbl + ((size_t)j * SRNN_Q + qj) * H + f0);
+                const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                float tv[16];
+                bf16x8_to_f32(t0, tv);
+                bf16x8_to_f32(t1, tv + 8);
+#pragma unroll
+                for (int v = 0; v < 16; ++v) acc[v] += tv[v];
+            }
+            float4* pp = reinterpret_cast<float4*>(sP + (g & 1) * 2048 + flat);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) pp[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+            mbar_arrive(&p_ready[g & 1]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<128>(tmem);
+}
+
+size_t mlp_persist_smem(int H) {
+    const int KB = H / 64, NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
+    return (size_t)KB * 8192 + 32768 + (size_t)NSTG * 4096 + 4096 + 16384 + 1024 + 512 + 1024;
+}
+
+bool mlp_persist_supported(int H, int FS, int B, int n_sms) {
+    if (H % 64 || H > 1024) return false;
+    const int NS = H / 64;
+    if (32 % NS) return false;
+    if (FS < 2 || FS > 31) return false;
+    const int RG = (B + 31) / 32;
+    return RG * NS <= n_sms;
+}
+
+// x1 must hold RG*32 rows; part RG*NS*32*256 floats; ctr RG counters (zeroed here).
+int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
+                       cudaStream_t st) {
+    const int H = p.H, NS = H / 64, RG = (p.B + 31) / 32;
+    CUtensorMap tmWh, tmWo, tmX1;
+    SRNN_TRY(make_tmap_bf16(&tmWh, w_hid16, H, H, H, 64));
+    SRNN_TRY(make_tmap_bf16(&tmWo, w_out16, SRNN_Q, H, H, 128));
+    SRNN_TRY(make_tmap_bf16(&tmX1, p.x1, (uint64_t)RG * 32, H, H, 32));
+    const size_t smem = mlp_persist_smem(H);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        SRNN_CUDA(cudaFuncSetAttribute(k_mlp_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    SRNN_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(unsigned) * RG, st));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(RG * NS);
+    cfg.blockDim = dim3(MP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;          // co-residency of all CTAs (they barrier on each other)
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_mlp_persist, tmWh, tmWo, tmX1, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(SRNN_ERR_CUDA, "k_mlp_persist launch: %s", cudaGetErrorString(e));
+    return SRNN_OK;
+}
+
+}  // namespace srnn

@@ -158,8 +158,9 @@ def test_teacher_forced_equals_autoregressive(golden):
 BF16_MAX_ABS, BF16_MEAN_ABS = 0.08, 0.015
 
 
-@pytest.mark.parametrize("dim,B", [(64, 5), (128, 37)])
-def test_generate_bf16_mode_against_oracle(dim, B):
+@pytest.mark.parametrize("mode", [S.MODE_BF16, S.MODE_BF16_GRAPH])
+@pytest.mark.parametrize("dim,B", [(64, 5), (128, 37), (128, 256), (1024, 40)])
+def test_generate_bf16_mode_against_oracle(dim, B, mode):
     torch.manual_seed(dim)
     c = dict(frame_sizes=[20, 4], n_rnn=2, dim=dim, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
              cond_dim=86, spk_dim=6)
@@ -174,8 +175,8 @@ def test_generate_bf16_mode_against_oracle(dim, B):
     n_cond = 2
     cond = torch.rand(B, n_cond, 86)
     spk = torch.randint(0, 6, (B,))
-    audio, samples, logp = S.Generator(m, cuda=True, mode=S.MODE_BF16)(B, 0, cond, spk, seed=5, return_samples=True,
-                                                                        return_logp=True)
+    audio, samples, logp = S.Generator(m, cuda=True, mode=mode)(B, 0, cond, spk, seed=5, return_samples=True,
+                                                                return_logp=True)
     assert int(samples.min()) >= 0 and int(samples.max()) <= 255
     seq = torch.cat([torch.full((B, 80), 128, dtype=torch.long), samples.long()], 1)
     w = O.unpack_state_dict(sd, O.Config(**c))
