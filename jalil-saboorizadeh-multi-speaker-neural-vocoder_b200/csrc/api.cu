@@ -304,25 +304,6 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
 // Generator.__call__  (model.py:445-520): one CUDA graph per top-tier period (lookback samples), replayed n_cond
 // times.  fp32 mode: FFMA GEMMs.  bf16 mode: the same schedule with every H-wide contraction on tcgen05 (gemm_umma).
 // ------------------------------------------------------------------------------------------------
-namespace srnn {
-struct MlpPersistParams {   // must match mlp_persist.cu
-    int B, H, FS, nsteps, pos0, lookback, Lseq, T;
-    const int* step_base;
-    uint8_t* seq;
-    const float* c0;
-    const __nv_bfloat16* tbl;
-    const float* b_hid;
-    const float* b_out;
-    __nv_bfloat16* x1;
-    float* part;
-    unsigned* ctr;
-    const float* uniforms;
-    float* logp_out;
-};
-int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
-                       cudaStream_t st);
-}  // namespace srnn
-
 static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_cond, const float* cond, int cond_rows,
                           const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
                           float* logp_out, cudaStream_t user) {

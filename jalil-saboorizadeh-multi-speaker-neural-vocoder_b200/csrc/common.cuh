@@ -144,7 +144,23 @@ int add_int(int* p, int v, cudaStream_t st);
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
               const float* bias, const float* addend, int ld_add, float* out_f32, __nv_bfloat16* out_bf16,
               int ld_out, int relu, int bm, int bn, cudaStream_t st);
-struct MlpPersistParams;
+// persistent fused sample-level kernel (mlp_persist.cu)
+struct MlpPersistParams {
+    int B, H, FS, nsteps, pos0, lookback, Lseq, T;
+    const int* step_base;
+    uint8_t* seq;                 // (B, Lseq) quantised samples (read + written)
+    const float* c0;              // tier-0 output (B, FS*H): conditioning of sample phase p at [b][p*H + f]
+    const __nv_bfloat16* tbl;     // (FS, 256, H) folded embedding-o-conv table
+    const float* b_hid;
+    const float* b_out;
+    __nv_bfloat16* x1;            // (RG*32, H) exchange buffer
+    float* part;                  // (RG, NS, 32, 256) split-K partial logits
+    unsigned* ctr;                // (RG) group-barrier counters, zeroed by the launcher
+    const float* uniforms;        // (T, B)
+    float* logp_out;              // (B, T, 256) or null
+};
+int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
+                       cudaStream_t st);
 size_t mlp_persist_smem(int H);
 bool mlp_persist_supported(int H, int FS, int B, int n_sms);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,

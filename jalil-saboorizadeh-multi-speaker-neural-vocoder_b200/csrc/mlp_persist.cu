@@ -25,22 +25,6 @@
 namespace srnn {
 
 using namespace ptx;
-int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
-
-struct MlpPersistParams {
-    int B, H, FS, nsteps, pos0, lookback, Lseq, T;
-    const int* step_base;
-    uint8_t* seq;                 // (B, Lseq) quantised samples (read + written)
-    const float* c0;              // tier-0 output (B, FS*H): conditioning of sample phase p at [b][p*H + f]
-    const __nv_bfloat16* tbl;     // (FS, 256, H) folded embedding-o-conv table
-    const float* b_hid;
-    const float* b_out;
-    __nv_bfloat16* x1;            // (RG*32, H) exchange buffer
-    float* part;                  // (RG, NS, 32, 256) split-K partial logits
-    unsigned* ctr;                // (RG) group-barrier counters, zero at launch
-    const float* uniforms;        // (T, B)
-    float* logp_out;              // (B, T, 256) or null
-};
 
 constexpr int MP_THREADS = 320;
 constexpr int MP_MAX_STAGES = 8;

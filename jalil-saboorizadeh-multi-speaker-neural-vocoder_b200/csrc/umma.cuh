@@ -7,6 +7,8 @@
 #include <stdint.h>
 
 namespace srnn {
+// host: bf16 row-major (rows x cols, ld elements) -> 2-D tensor map, {64, box_rows} box, 128-byte swizzle (gemm_umma.cu)
+int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
