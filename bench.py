@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("SRNN_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("SRNN_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16", "bf16_graph"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--n-cond", type=int, default=100, help="conditioner frames (x80 samples) per step")
     ap.add_argument("--ref-n-cond", type=int, default=2)
@@ -147,7 +147,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode = {"fp32": S.MODE_FP32, "bf16": S.MODE_BF16}.get(args.mode)
+    mode = {"fp32": S.MODE_FP32, "bf16": S.MODE_BF16, "bf16_graph": S.MODE_BF16_GRAPH}.get(args.mode)
     if mode is None:
         mode = S.MODE_BF16 if getattr(S.package, "HAS_BF16", False) else S.MODE_FP32
     lib = S._lib.load()
@@ -215,7 +215,7 @@ def main():
         "metric": "generated samples/sec", "value": value, "unit": "samples/s", "x_realtime_16k": value / SAMPLE_RATE,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
+        "dtype": "f32" if mode == S.MODE_FP32 else "bf16", "data": "synthetic",
         "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond 86, weight-norm",
                    "batch_per_gpu": B, "total_batch": B * world, "samples_per_utterance": T,
                    "l2": "192 MiB flush write between timed iterations", "us_per_sample_step": 1e6 * secs / args.steps / T},
