@@ -1,6 +1,7 @@
 // C-ABI entry points (include/srnn_b200.h): context, weight packing, Predictor.forward, Generator.__call__.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace srnn {
 
@@ -363,6 +364,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     const int bn_tier = B <= 32 ? 32 : 64;     // batch-row tile of the tier GEMMs (UMMA M = 128 features)
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
+    long long* trace = nullptr;
+    if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 10));
     const bool use_graph = !persist;   // the persistent kernel is a cooperative launch; it is issued directly
     const long long before = g_launches.load();
     if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -413,7 +416,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 mp.B = B; mp.H = H; mp.FS = FS0; mp.nsteps = FS0; mp.pos0 = pos; mp.lookback = lookback;
                 mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
                 mp.tbl = ctx->tbl16; mp.b_hid = ctx->b_hid; mp.b_out = ctx->b_out; mp.x1 = X1h; mp.part = part;
-                mp.ctr = gctr; mp.uniforms = uniforms; mp.logp_out = logp_out;
+                mp.ctr = gctr; mp.uniforms = uniforms; mp.logp_out = logp_out; mp.trace = trace;
                 SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
                 continue;
             }
@@ -453,6 +456,19 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         for (int p = 0; p < n_cond; ++p) SRNN_TRY(body());
     }
     SRNN_TRY(dequant_audio(seq, Lseq, lookback, ctx->lut, samples_out, audio_out, B, T, st));   // model.py:520
+    if (trace) {   // debugging aid: average phase durations (SM cycles) of CTA 0 over the last persistent launch
+        SRNN_CUDA(cudaStreamSynchronize(st));
+        static const char* names[9] = {"wait P", "x1 slice", "barrier A", "TMA+MMA1", "epilogue1", "MMA2", "epilogue2",
+                                       "barrier B", "reduce+sample"};
+        double acc[9] = {0}, tot = 0;
+        for (int k = 2; k < FS0; ++k)
+            for (int j = 0; j < 9; ++j) acc[j] += (double)(trace[k * 10 + j + 1] - trace[k * 10 + j]);
+        for (int k = 3; k < FS0; ++k) tot += (double)(trace[k * 10] - trace[(k - 1) * 10]);
+        fprintf(stderr, "[srnn trace] k_mlp_persist CTA0 cycles/step:");
+        for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%.0f", names[j], acc[j] / (FS0 - 2));
+        fprintf(stderr, " | step=%.0f\n", tot / (FS0 - 3));
+        cudaFree(trace);
+    }
     SRNN_CUDA(cudaEventRecord(ev_out, st));
     SRNN_CUDA(cudaStreamWaitEvent(user, ev_out, 0));
     // the graph/stream objects can be released once the work is enqueued; CUDA defers destruction until completion

@@ -158,6 +158,7 @@ struct MlpPersistParams {
     unsigned* ctr;                // (RG) group-barrier counters, zeroed by the launcher
     const float* uniforms;        // (T, B)
     float* logp_out;              // (B, T, 256) or null
+    long long* trace;             // optional (nsteps, 10) clock64 stamps of CTA 0 (SRNN_TRACE=1), else null
 };
 int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
                        cudaStream_t st);

@@ -43,11 +43,9 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target, int tidE) {
     named_bar_sync(1, 128);
     if (tidE == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");   // publishes the CTA's writes
         while (ld_acquire_gpu(ctr) < target) {
         }
-        __threadfence();
     }
     named_bar_sync(1, 128);
 }
@@ -61,6 +59,11 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
         f[2 * i + 1] = t.y;
     }
 }
+
+#define MP_TRACE(slot)                                                                   \
+    do {                                                                                 \
+        if (p.trace && blockIdx.x == 0 && tidE == 0) p.trace[k * 10 + (slot)] = clock64(); \
+    } while (0)
 
 __global__ void __launch_bounds__(MP_THREADS, 1)
 k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWo,
@@ -193,7 +196,9 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         for (int k = 0; k < p.nsteps; ++k) {
             const int i = i0 + k;
             // ---- E1: x1 = relu(P + Tbl[FS-1][newest sample]) for the owned rows -> global X1 ----
+            MP_TRACE(0);
             mbar_wait(&p_ready[k & 1], (k >> 1) & 1);
+            MP_TRACE(1);
             {
                 const int qn = sQ[rl * 32 + ((i - 1) & 31)];
                 const uint4* tp = reinterpret_cast<const uint4*>(p.tbl + ((size_t)(FS - 1) * SRNN_Q + qn) * H + f0);
@@ -216,7 +221,9 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 xp[1] = make_uint4(o[4], o[5], o[6], o[7]);
             }
             // ---- group barrier A: the whole X1 of this row group is in global memory ----
+            MP_TRACE(2);
             group_barrier(ctr, (++bar_no) * NS, tidE);
+            MP_TRACE(3);
             if (tidE == 0) {
                 mbar_arrive(&p_free[k & 1]);              // P[k&1] consumed (all E threads passed the barrier above)
                 fence_proxy_async_all();                  // generic-proxy global writes -> visible to TMA reads
@@ -224,6 +231,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             }
             // ---- epilogue 1: D1 (+bias, ReLU) -> bf16 swizzled B operand in smem ----
             mbar_wait(bar_d1, k & 1);
+            MP_TRACE(4);
             tc_fence_after();
             {
                 float v0[16], v1[16];
@@ -247,8 +255,10 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             fence_proxy_async_smem();                     // generic smem writes -> visible to the UMMA operand reads
             named_bar_sync(1, 128);
             if (tidE == 0) mbar_arrive(x2_ready);
+            MP_TRACE(5);
             // ---- epilogue 2: split-K partial logits -> global Part[rg][sl][row][256] ----
             mbar_wait(bar_d2, k & 1);
+            MP_TRACE(6);
             tc_fence_after();
             {
                 float* dst = p.part + ((size_t)(rg * NS + sl) * 32) * SRNN_Q + 32 * q4 + lane;
@@ -266,7 +276,9 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             }
             tc_fence_before();
             // ---- group barrier B: all slices' partial logits are in global memory ----
+            MP_TRACE(7);
             group_barrier(ctr, (++bar_no) * NS, tidE);
+            MP_TRACE(8);
             // ---- reduce + log-softmax + defined sampler for the owned rows ----
             for (int r2 = warp - 2; r2 < RPC; r2 += 4) {
                 const int n = sl * RPC + r2, bb = row0 + r2;
@@ -276,10 +288,22 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     const float4 a0 = __ldg(bo), a1 = __ldg(bo + 1);
                     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
                 }
-                for (int s2 = 0; s2 < NS; ++s2) {
-                    const float4* pp = reinterpret_cast<const float4*>(p.part + ((size_t)(rg * NS + s2) * 32 + n) * SRNN_Q + lane * 8);
-                    const float4 a0 = __ldcg(pp), a1 = __ldcg(pp + 1);
-                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                for (int s0 = 0; s0 < NS; s0 += 8) {     // 8 slices (16 independent 16-byte loads) in flight at a time
+                    float4 a[8][2];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int s2 = (s0 + u < NS) ? s0 + u : NS - 1;
+                        const float4* pp = reinterpret_cast<const float4*>(p.part + ((size_t)(rg * NS + s2) * 32 + n) * SRNN_Q + lane * 8);
+                        a[u][0] = __ldcg(pp);
+                        a[u][1] = __ldcg(pp + 1);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {         // fixed summation order: slice 0, 1, 2, ...
+                        if (s0 + u < NS) {
+                            v[0] += a[u][0].x; v[1] += a[u][0].y; v[2] += a[u][0].z; v[3] += a[u][0].w;
+                            v[4] += a[u][1].x; v[5] += a[u][1].y; v[6] += a[u][1].z; v[7] += a[u][1].w;
+                        }
+                    }
                 }
                 float m = v[0];
 #pragma unroll
@@ -316,6 +340,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 __threadfence_block();
                 *q_count = k + 1;
             }
+            MP_TRACE(9);
         }
     } else {
         // ===================== G warps: prefetch P_g = c0 + taps 0..FS-2 for step g =====================
@@ -342,7 +367,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 }
             }
             const uint8_t* qrow = sQ + rl * 32;
-#pragma unroll 4
+#pragma unroll 8
             for (int j = 0; j < FS - 1; ++j) {
                 const int qj = qrow[(i - FS + j) & 31];
                 const uint4* tp = reinterpret_cast<const uint4*>(p.tbl + ((size_t)j * SRNN_Q + qj) * H + f0);
