@@ -28,6 +28,13 @@ using namespace ptx;
 
 constexpr int MP_THREADS = 320;
 constexpr int MP_MAX_STAGES = 8;
+// Back-to-back tcgen05.mma that accumulate into the SAME TMEM tile serialise on the accumulator (~150 cycles each,
+// measured), which dominates with N = 32 columns.  The K loop is therefore spread round-robin over NACC1 independent
+// accumulators that the epilogue sums.  Two M=64 accumulators share a column range (lanes 0-15 / 16-31 of each
+// quadrant, the "interleaved" M=64 TMEM layout), so one 32-lane tcgen05.ld fetches two of them.
+constexpr int MP_NACC1 = 8;                      // hidden GEMM accumulators (4 column ranges of 32)
+constexpr int MP_D2_COL = (MP_NACC1 / 2) * 32;   // output GEMM: 2 tiles x 2 accumulators x 32 columns
+constexpr uint32_t MP_TMEM_COLS = 512;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -70,6 +77,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
               const __grid_constant__ CUtensorMap tmX1, const MlpPersistParams p) {
     const int H = p.H, KB = H >> 6, NS = H >> 6, RPC = 32 / NS, FS = p.FS;
     const int NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
+    const int nacc = KB * 4 < MP_NACC1 ? KB * 4 : MP_NACC1;   // hidden-GEMM accumulators actually used (even)
     const int rg = blockIdx.x / NS, sl = blockIdx.x % NS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -81,7 +89,9 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     uint8_t* sX2 = sRing + (size_t)NSTG * 4096;           // 32 rows x 128 B
     float* sP = (float*)(sX2 + 4096);                     // 2 x 2048 fp32
     uint8_t* sQ = (uint8_t*)(sP + 4096);                  // 32 owned rows x 32-entry sample ring
-    uint64_t* bars = (uint64_t*)(sQ + 1024);
+    float* sU = (float*)(sQ + 1024);                      // this step's uniform of every owned row (prefetched)
+    float* sLogit = sU + 32;                              // RPC owned rows x 256 reduced logits
+    uint64_t* bars = (uint64_t*)(sLogit + (size_t)RPC * SRNN_Q);
     uint64_t* w_ready = bars + 0;
     uint64_t* full = bars + 1;                            // [MP_MAX_STAGES]
     uint64_t* empty = full + MP_MAX_STAGES;               // [MP_MAX_STAGES]
@@ -117,7 +127,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         *q_count = 0;
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<128>(tmem_slot);
+    if (warp == 1) tmem_alloc<MP_TMEM_COLS>(tmem_slot);
     // owned rows' sample ring: the FS most recent samples before i0 (written by earlier launches / the q_zero prefix)
     for (int e = threadIdx.x; e < RPC * 32; e += MP_THREADS) {
         const int rl = e >> 5, w = e & 31;
@@ -131,7 +141,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 32;
+    const uint32_t tm_d1 = tmem, tm_d2 = tmem + MP_D2_COL;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -168,7 +178,11 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     const uint64_t da = umma_desc_sw128(smem_u32(sWh + (size_t)kb * 8192));
                     const uint64_t db = umma_desc_sw128(smem_u32(sRing + (size_t)s * 4096));
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_bf16(tm_d1, da + 2 * kk, db + 2 * kk, idesc1, (kb | kk) != 0);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int j = kb * 4 + kk, a = j % nacc;               // round-robin over the accumulators
+                        const uint32_t d = tm_d1 + ((uint32_t)((a & 1) * 16) << 16) + (uint32_t)(a >> 1) * 32;
+                        umma_bf16(d, da + 2 * kk, db + 2 * kk, idesc1, j >= nacc);
+                    }
                     umma_commit(&empty[s]);
                 }
                 umma_commit(bar_d1);
@@ -179,7 +193,8 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 for (int t2 = 0; t2 < 2; ++t2) {
                     const uint64_t da2 = umma_desc_sw128(smem_u32(sWo + t2 * 16384));
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_bf16(tm_d2 + 32 * t2, da2 + 2 * kk, db2 + 2 * kk, idesc2, kk != 0);
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tm_d2 + 64 * t2 + 32 * (kk & 1), da2 + 2 * kk, db2 + 2 * kk, idesc2, kk >= 2);
                 }
                 umma_commit(bar_d2);
             }
@@ -197,6 +212,10 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             const int i = i0 + k;
             // ---- E1: x1 = relu(P + Tbl[FS-1][newest sample]) for the owned rows -> global X1 ----
             MP_TRACE(0);
+            if (tidE < RPC) {                             // prefetch this step's uniforms off the serial path
+                const int bb = row0 + tidE;
+                sU[tidE] = bb < p.B ? __ldg(p.uniforms + (size_t)(i - p.lookback) * p.B + bb) : 0.f;
+            }
             mbar_wait(&p_ready[k & 1], (k >> 1) & 1);
             MP_TRACE(1);
             {
@@ -237,6 +256,22 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 float v0[16], v1[16];
                 tmem_ld16(tm_d1 + ((uint32_t)(32 * q4) << 16), v0);
                 tmem_ld16(tm_d1 + ((uint32_t)(32 * q4) << 16) + 16, v1);
+#pragma unroll 1
+                for (int c = 1; c < nacc / 2; ++c) {
+                    float w0[16], w1[16];
+                    tmem_ld16(tm_d1 + ((uint32_t)(32 * q4) << 16) + 32 * c, w0);
+                    tmem_ld16(tm_d1 + ((uint32_t)(32 * q4) << 16) + 32 * c + 16, w1);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        v0[n] += w0[n];
+                        v1[n] += w1[n];
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < 16; ++n) {            // lanes 16-31 hold the odd accumulators of the same features
+                    v0[n] += __shfl_down_sync(0xffffffffu, v0[n], 16);
+                    v1[n] += __shfl_down_sync(0xffffffffu, v1[n], 16);
+                }
                 if (lane < 16) {
                     const int f = 16 * q4 + lane;         // feature inside the slice = K index of the output GEMM
                     const float bv = p.b_hid[sl * 64 + f];
@@ -264,13 +299,15 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 float* dst = p.part + ((size_t)(rg * NS + sl) * 32) * SRNN_Q + 32 * q4 + lane;
 #pragma unroll
                 for (int t2 = 0; t2 < 2; ++t2) {
-                    float v0[16], v1[16];
-                    tmem_ld16(tm_d2 + 32 * t2 + ((uint32_t)(32 * q4) << 16), v0);
-                    tmem_ld16(tm_d2 + 32 * t2 + ((uint32_t)(32 * q4) << 16) + 16, v1);
+                    float v0[16], v1[16], w0[16], w1[16];
+                    tmem_ld16(tm_d2 + 64 * t2 + ((uint32_t)(32 * q4) << 16), v0);
+                    tmem_ld16(tm_d2 + 64 * t2 + ((uint32_t)(32 * q4) << 16) + 16, v1);
+                    tmem_ld16(tm_d2 + 64 * t2 + 32 + ((uint32_t)(32 * q4) << 16), w0);
+                    tmem_ld16(tm_d2 + 64 * t2 + 32 + ((uint32_t)(32 * q4) << 16) + 16, w1);
 #pragma unroll
                     for (int n = 0; n < 16; ++n) {
-                        dst[(size_t)n * SRNN_Q + t2 * 128] = v0[n];
-                        dst[(size_t)(n + 16) * SRNN_Q + t2 * 128] = v1[n];
+                        dst[(size_t)n * SRNN_Q + t2 * 128] = v0[n] + w0[n];
+                        dst[(size_t)(n + 16) * SRNN_Q + t2 * 128] = v1[n] + w1[n];
                     }
                 }
             }
@@ -279,31 +316,39 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             MP_TRACE(7);
             group_barrier(ctr, (++bar_no) * NS, tidE);
             MP_TRACE(8);
-            // ---- reduce + log-softmax + defined sampler for the owned rows ----
+            // ---- reduce the NS split-K partials of the owned rows (all 128 E threads, every load in flight) ----
+            {
+                const int per_row = SRNN_Q / 4;                                   // 64 threads cover one row's 256 logits
+                for (int e = tidE; e < RPC * per_row; e += 128) {
+                    const int r2 = e / per_row, o4 = (e % per_row) * 4;
+                    const int n = sl * RPC + r2;
+                    const float* src = p.part + ((size_t)(rg * NS) * 32 + n) * SRNN_Q + o4;
+                    float4 acc = __ldg(reinterpret_cast<const float4*>(p.b_out + o4));
+                    for (int s0 = 0; s0 < NS; s0 += 16) {
+                        float4 a[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const int s2 = (s0 + u < NS) ? s0 + u : NS - 1;
+                            a[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)s2 * 32 * SRNN_Q));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u)                              // fixed summation order: slice 0, 1, 2, ...
+                            if (s0 + u < NS) {
+                                acc.x += a[u].x; acc.y += a[u].y; acc.z += a[u].z; acc.w += a[u].w;
+                            }
+                    }
+                    *reinterpret_cast<float4*>(sLogit + r2 * SRNN_Q + o4) = acc;
+                }
+            }
+            named_bar_sync(1, 128);
+            // ---- log-softmax + defined sampler, one warp per owned row ----
             for (int r2 = warp - 2; r2 < RPC; r2 += 4) {
-                const int n = sl * RPC + r2, bb = row0 + r2;
+                const int bb = row0 + r2;
                 float v[8];
                 {
-                    const float4* bo = reinterpret_cast<const float4*>(p.b_out + lane * 8);
-                    const float4 a0 = __ldg(bo), a1 = __ldg(bo + 1);
+                    const float4* lp = reinterpret_cast<const float4*>(sLogit + r2 * SRNN_Q + lane * 8);
+                    const float4 a0 = lp[0], a1 = lp[1];
                     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-                }
-                for (int s0 = 0; s0 < NS; s0 += 8) {     // 8 slices (16 independent 16-byte loads) in flight at a time
-                    float4 a[8][2];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int s2 = (s0 + u < NS) ? s0 + u : NS - 1;
-                        const float4* pp = reinterpret_cast<const float4*>(p.part + ((size_t)(rg * NS + s2) * 32 + n) * SRNN_Q + lane * 8);
-                        a[u][0] = __ldcg(pp);
-                        a[u][1] = __ldcg(pp + 1);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {         // fixed summation order: slice 0, 1, 2, ...
-                        if (s0 + u < NS) {
-                            v[0] += a[u][0].x; v[1] += a[u][0].y; v[2] += a[u][0].z; v[3] += a[u][0].w;
-                            v[4] += a[u][1].x; v[5] += a[u][1].y; v[6] += a[u][1].z; v[7] += a[u][1].w;
-                        }
-                    }
                 }
                 float m = v[0];
 #pragma unroll
@@ -325,7 +370,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = expf(v[j]);
-                    const float u = __ldg(p.uniforms + (size_t)t * p.B + bb);
+                    const float u = sU[r2];
                     const int idx = sampler_warp(v, u, lane);
                     if (lane == 0) {
                         p.seq[(size_t)bb * p.Lseq + i] = (uint8_t)idx;
@@ -386,12 +431,13 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<128>(tmem);
+    if (warp == 1) tmem_dealloc<MP_TMEM_COLS>(tmem);
 }
 
 size_t mlp_persist_smem(int H) {
     const int KB = H / 64, NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
-    return (size_t)KB * 8192 + 32768 + (size_t)NSTG * 4096 + 4096 + 16384 + 1024 + 512 + 1024;
+    const int RPC = 32 / (H / 64);
+    return (size_t)KB * 8192 + 32768 + (size_t)NSTG * 4096 + 4096 + 16384 + 1024 + 128 + (size_t)RPC * 1024 + 512 + 1024;
 }
 
 bool mlp_persist_supported(int H, int FS, int B, int n_sms) {
