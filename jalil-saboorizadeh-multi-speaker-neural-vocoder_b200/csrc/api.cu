@@ -365,7 +365,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
     long long* trace = nullptr;
-    if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 10));
+    if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 64));
     const bool use_graph = !persist;   // the persistent kernel is a cooperative launch; it is issued directly
     const long long before = g_launches.load();
     if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -461,9 +461,21 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         static const char* names[9] = {"wait P", "x1 slice", "barrier A", "TMA+MMA1", "epilogue1", "MMA2", "epilogue2",
                                        "barrier B", "reduce+sample"};
         double acc[9] = {0}, tot = 0;
-        for (int k = 2; k < FS0; ++k)
-            for (int j = 0; j < 9; ++j) acc[j] += (double)(trace[k * 10 + j + 1] - trace[k * 10 + j]);
-        for (int k = 3; k < FS0; ++k) tot += (double)(trace[k * 10] - trace[(k - 1) * 10]);
+        double w[5] = {0};
+        for (int k = 2; k < FS0; ++k) {
+            for (int j = 0; j < 9; ++j) acc[j] += (double)(trace[k * 64 + j + 1] - trace[k * 64 + j]);
+            for (int j = 0; j < 5; ++j) w[j] += (double)(trace[k * 64 + 10 + j] - trace[k * 64 + 3]);
+        }
+        for (int k = 3; k < FS0; ++k) tot += (double)(trace[k * 64] - trace[(k - 1) * 64]);
+        fprintf(stderr, "[srnn trace] since barrier A: W0 woke=%.0f W0 issued all=%.0f W1 full[0]=%.0f W1 full[7]=%.0f W1 last MMA issued=%.0f\n",
+                w[0] / (FS0 - 2), w[1] / (FS0 - 2), w[2] / (FS0 - 2), w[3] / (FS0 - 2), w[4] / (FS0 - 2));
+        {
+            const int k = FS0 - 1;
+            fprintf(stderr, "[srnn trace] W1 per k-block (wait start, wait end) since barrier A, last step:");
+            for (int kb = 0; kb < 16 && kb < H / 64; ++kb)
+                fprintf(stderr, " [%lld,%lld]", trace[k * 64 + 16 + 2 * kb] - trace[k * 64 + 3], trace[k * 64 + 17 + 2 * kb] - trace[k * 64 + 3]);
+            fprintf(stderr, "\n");
+        }
         fprintf(stderr, "[srnn trace] k_mlp_persist CTA0 cycles/step:");
         for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%.0f", names[j], acc[j] / (FS0 - 2));
         fprintf(stderr, " | step=%.0f\n", tot / (FS0 - 3));

@@ -87,7 +87,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps UMMA operands in uniform regs)
 
     if (warp == 0) {
         if (lane == 0) {
