@@ -16,10 +16,12 @@
 //              owner rows: logits = b_out + sum_slices Part; log-softmax; defined sampler -> seq      [CUDA cores]
 //   The (FS-1)-tap part of the gather for the NEXT step (P) is prefetched by 4 dedicated warps during the GEMMs, so
 //   only one table row per utterance is on the serial path.
-// Warp roles (320 threads): 0..3 = gather/"G" warps, 4..7 = epilogue/"E" warps, 8 = TMA producer,
-// 9 = TMEM alloc + MMA issuer.  The SM's issue arbiter favours the highest warp id, so the two single-thread
-// latency-critical roles sit on top and every wait in the bulk warps is an mbarrier try_wait (hardware back-off),
-// never a hot shared-memory spin.
+// Warp roles (416 threads): 0..3 = gather/"G" warps, 4..7 = epilogue/"E" warps, 8 = TMA producer,
+// 9..12 = MMA issuers (warp 9 also owns the TMEM allocation).  One thread can only issue a small-tile tcgen05.mma
+// every ~45-90 cycles (measured, tools/umma_probe*.cu), far above the 16-cycle tensor floor of an M=64,N=32 tile, so
+// the K loop is split over FOUR issuing threads, each with private accumulators (k-block kb belongs to issuer kb%4).
+// The SM's issue arbiter favours the highest warp id, so the single-thread latency-critical roles sit on top and
+// every wait in the bulk warps is an mbarrier try_wait (hardware back-off), never a hot shared-memory spin.
 #include "common.cuh"
 #include "sampler.cuh"
 #include "umma.cuh"
@@ -28,7 +30,8 @@ namespace srnn {
 
 using namespace ptx;
 
-constexpr int MP_THREADS = 320;
+constexpr int MP_THREADS = 416;
+constexpr int MP_ISSUERS = 4;
 constexpr int MP_MAX_STAGES = 8;
 // Back-to-back tcgen05.mma that accumulate into the SAME TMEM tile serialise on the accumulator (~150 cycles each,
 // measured), which dominates with N = 32 columns.  The K loop is therefore spread round-robin over NACC1 independent
@@ -79,7 +82,8 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
               const __grid_constant__ CUtensorMap tmX1, const MlpPersistParams p) {
     const int H = p.H, KB = H >> 6, NS = H >> 6, RPC = 32 / NS, FS = p.FS;
     const int NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
-    const int nacc = KB * 4 < MP_NACC1 ? KB * 4 : MP_NACC1;   // hidden-GEMM accumulators actually used (even)
+    const int nissue = KB < MP_ISSUERS ? KB : MP_ISSUERS;     // MMA-issuing threads in use
+    const int nacc = 2 * nissue;                              // hidden-GEMM accumulators in use (2 per issuer)
     const int rg = blockIdx.x / NS, sl = blockIdx.x % NS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -119,9 +123,9 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             mbar_init(&empty[s], 1);
         }
         mbar_init(x1_ready, 1);
-        mbar_init(bar_d1, 1);
+        mbar_init(bar_d1, nissue);
         mbar_init(x2_ready, 1);
-        mbar_init(bar_d2, 1);
+        mbar_init(bar_d2, nissue);
         mbar_init(&p_ready[0], 128);
         mbar_init(&p_ready[1], 128);
         mbar_init(&p_free[0], 1);
@@ -170,50 +174,50 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 if (p.trace && blockIdx.x == 0) p.trace[k * 64 + 11] = clock64();
             }
         }
-    } else if (warp == 9) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+    } else if (warp >= 9) {
+        // ===================== MMA issuers (one thread each) =====================
+        const int w = warp - 9;
+        if (lane == 0 && w < nissue) {
             constexpr uint32_t idesc1 = umma_idesc_bf16(64, 32);
             constexpr uint32_t idesc2 = umma_idesc_bf16(128, 32);
             mbar_wait(w_ready, 0);
-            int it = 0;
             const uint64_t dA0 = umma_desc_sw128(smem_u32(sWh));      // + kb * (8192 >> 4)
             const uint64_t dB0 = umma_desc_sw128(smem_u32(sRing));    // + stage * (4096 >> 4)
-            const uint32_t acc_mask = (uint32_t)nacc - 1;             // nacc is 4 or 8
             const uint64_t dWo0 = umma_desc_sw128(smem_u32(sWo));     // + tile * (16384 >> 4)
             const uint64_t db2 = umma_desc_sw128(smem_u32(sX2));
+            const uint32_t d1a = tm_d1 + (uint32_t)w * 32;            // this issuer's two interleaved M=64 accumulators
+            const uint32_t d1b = d1a + (16u << 16);
             for (int k = 0; k < p.nsteps; ++k) {
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                for (int kb = w; kb < KB; kb += MP_ISSUERS) {
+                    const int it = k * KB + kb;
                     const int s = it & stg_mask;
                     const uint32_t ph = (it >> stg_shift) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint64_t da = dA0 + (uint64_t)(kb * 512);
                     const uint64_t db = dB0 + (uint64_t)(s * 256);
-                    const uint32_t accum = (uint32_t)(kb * 4) >= (uint32_t)nacc;
-                    const uint32_t abase = (uint32_t)(kb * 4) & acc_mask;     // 0 or 4: accumulators abase .. abase+3
-                    const uint32_t d0 = tm_d1 + (abase >> 1) * 32;            // a>>1 column range, a&1 lane half
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(d0 + (uint32_t)(kk >> 1) * 32 + ((uint32_t)((kk & 1) * 16) << 16), da + 2 * kk, db + 2 * kk,
-                                  idesc1, accum);
+                    const uint32_t acc = kb >= MP_ISSUERS;
+                    umma_bf16(d1a, da, db, idesc1, acc);
+                    umma_bf16(d1b, da + 2, db + 2, idesc1, acc);
+                    umma_bf16(d1a, da + 4, db + 4, idesc1, 1);
+                    umma_bf16(d1b, da + 6, db + 6, idesc1, 1);
                     umma_commit(&empty[s]);
                 }
                 umma_commit(bar_d1);
-                if (p.trace && blockIdx.x == 0) p.trace[k * 64 + 14] = clock64();
+                if (p.trace && blockIdx.x == 0 && w == 0) p.trace[k * 64 + 14] = clock64();
                 mbar_wait(x2_ready, k & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int t2 = 0; t2 < 2; ++t2) {
-                    const uint64_t da2 = dWo0 + (uint64_t)(t2 * 1024);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tm_d2 + 64 * t2 + 32 * (kk & 1), da2 + 2 * kk, db2 + 2 * kk, idesc2, kk >= 2);
+                for (int c = w; c < 4; c += nissue) {                 // (output tile, K half) -> its own accumulator
+                    const int t2 = c >> 1, h2 = c & 1;
+                    const uint64_t da2 = dWo0 + (uint64_t)(t2 * 1024) + (uint64_t)(h2 * 4);
+                    const uint32_t d2 = tm_d2 + 64 * t2 + 32 * h2;
+                    umma_bf16(d2, da2, db2 + (uint64_t)(h2 * 4), idesc2, 0);
+                    umma_bf16(d2, da2 + 2, db2 + (uint64_t)(h2 * 4) + 2, idesc2, 1);
                 }
                 umma_commit(bar_d2);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===================== E warps: per-row work, epilogues, group barriers =====================
         const int tidE = threadIdx.x - 128;
         const int q4 = warp & 3;                          // TMEM lane quadrant this warp may access
@@ -398,7 +402,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             if (tidE == 0) mbar_arrive(&q_ready[k & 1]);
             MP_TRACE(9);
         }
-    } else {
+    } else if (warp < 4) {
         // ===================== G warps: prefetch P_g = c0 + taps 0..FS-2 for step g =====================
         const int tidG = threadIdx.x;
         const int flat = tidG * 16;
