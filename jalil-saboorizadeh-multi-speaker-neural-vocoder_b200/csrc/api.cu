@@ -122,6 +122,7 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
         for (int i = 0; i < c.n_tiers; ++i) {
             TierPacked& t = ctx->tiers[i];
             SRNN_TRY(ctx->weights.alloc((void**)&t.w_in, sizeof(float) * H * t.kin));
+            SRNN_TRY(ctx->weights.alloc((void**)&t.w_in_t, sizeof(float) * H * t.kin));
             SRNN_TRY(ctx->weights.alloc((void**)&t.b_in, sizeof(float) * H));
             for (int l = 0; l < L; ++l) {
                 SRNN_TRY(ctx->weights.alloc((void**)&t.w_ih[l], sizeof(float) * 3 * H * H));
@@ -189,6 +190,7 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
             SRNN_TRY(wn_fold(tp.input_expand, t.w_in, H, t.n, st));
             SRNN_TRY(copy_f32(tp.input_expand.bias, t.b_in, H, st));
         }
+        SRNN_TRY(transpose_f32(t.w_in, t.w_in_t, H, t.kin, st));
         for (int l = 0; l < L; ++l) {
             if (!tp.weight_ih[l] || !tp.weight_hh[l] || !tp.bias_ih[l] || !tp.bias_hh[l]) return fail(SRNN_ERR_ARG, "tier %d: missing GRU layer %d", i, l);
             SRNN_TRY(copy_f32(tp.weight_ih[l], t.w_ih[l], (size_t)3 * H * H, st));
@@ -361,12 +363,14 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             SRNN_TRY(bcast_rows(ctx->tiers[i].h0 + (size_t)l * H, hid[i] + (size_t)l * B * H, B, H, st));
         if (bf16) SRNN_TRY(f32_to_bf16_pad(hid[i], NL * B, H, H, hid16[i], NL * B, H, st));
     }
-    const int bn_tier = B <= 32 ? 32 : 64;     // batch-row tile of the tier GEMMs (UMMA M = 128 features)
+    // batch-row tile of the tier GEMMs (UMMA M = 128 features): one thread issues a tcgen05.mma every ~45+ cycles, so
+    // only N = 256 tiles (128-cycle tensor floor) keep the tensor pipe rather than the issue slot busy
+    const int bn_tier = B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256));
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
     long long* trace = nullptr;
     if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 64));
-    const bool use_graph = !persist;   // the persistent kernel is a cooperative launch; it is issued directly
+    bool use_graph = !getenv("SRNN_NO_GRAPH");
     const long long before = g_launches.load();
     if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
@@ -374,8 +378,6 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             for (int i = NT - 1; i >= 0; --i) {
                 const TierPacked& t = ctx->tiers[i];
                 if (pos % t.n) continue;                                             // model.py:465
-                SRNN_TRY(frame_input(seq, Lseq, pos - t.n, step_base, t.n, B, 1, cond, 0, cond_rows, n_cond, spk,
-                                     c.cond_dim, c.spk_dim, ctx->lut, A[i], t.kin, t.top, st));
                 const float* upper = nullptr;
                 int up_ld = 0;
                 if (!t.top) {                                                        // model.py:491-495
@@ -383,18 +385,19 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     upper = OUT[i + 1] + (size_t)((pos / t.n) % u.fs) * H;
                     up_ld = u.fs * H;
                 }
-                SRNN_TRY(gemm_f32(B, H, t.kin, A[i], t.kin, t.w_in, t.kin, t.b_in, upper, up_ld, 0, X[i], H, st,
-                                  bf16 ? X16[i] : nullptr));
+                SRNN_TRY(tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
+                                        c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
+                                        H, t.kin, t.top, st));
                 const float* in = X[i];
                 const bf* in16 = X16[i];
                 for (int l = 0; l < NL; ++l) {
                     float* h = hid[i] + (size_t)l * B * H;
                     bf* h16 = hid16[i] + (size_t)l * B * H;
-                    if (bf16) {
-                        SRNN_TRY(gemm_umma(t.w_ih16[l], 3 * H, in16, B, H, H, H, t.b_ih[l], nullptr, 0, GI[i], nullptr,
-                                           3 * H, 0, 128, bn_tier, st));
-                        SRNN_TRY(gemm_umma(t.w_hh16[l], 3 * H, h16, B, H, H, H, t.b_hh[l], nullptr, 0, GH[i], nullptr,
-                                           3 * H, 0, 128, bn_tier, st));
+                    if (bf16) {      // gi = W_ih x + b_ih and gh = W_hh h + b_hh side by side in one launch
+                        GemmOperands ops[2] = {
+                            {t.w_ih16[l], in16, t.b_ih[l], nullptr, GI[i], nullptr, 3 * H, H, H, 0, 3 * H, 0},
+                            {t.w_hh16[l], h16, t.b_hh[l], nullptr, GH[i], nullptr, 3 * H, H, H, 0, 3 * H, 0}};
+                        SRNN_TRY(gemm_umma_multi(ops, 2, B, H, 128, bn_tier, st));
                     } else {
                         SRNN_TRY(gemm_f32(B, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
                         SRNN_TRY(gemm_f32(B, 3 * H, H, h, H, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
@@ -443,16 +446,28 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         const int rc = body();
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         const long long nodes = g_launches.load() - before;
-        if (rc != SRNN_OK) {
+        if (rc != SRNN_OK && !persist) {
             if (graph) cudaGraphDestroy(graph);
             cudaStreamDestroy(st);
             return rc;
         }
-        if (ce != cudaSuccess) return fail(SRNN_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-        SRNN_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-        for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(exec, st));
-        g_launches.fetch_add(nodes * (long long)(n_cond - 1));
-    } else {
+        if (rc != SRNN_OK) ce = cudaErrorStreamCaptureUnsupported;   // the cooperative launch refused to be captured
+        if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (ce == cudaSuccess) {
+            for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(exec, st));
+            g_launches.fetch_add(nodes * (long long)(n_cond - 1));
+        } else {
+            // e.g. a driver that cannot put the cooperative persistent kernel into a graph: issue the launches directly
+            cudaGetLastError();
+            g_launches.fetch_sub(nodes);
+            if (graph) cudaGraphDestroy(graph);
+            graph = nullptr;
+            exec = nullptr;
+            use_graph = false;
+            if (getenv("SRNN_TRACE")) fprintf(stderr, "[srnn] graph path unavailable (%s); direct launches\n", cudaGetErrorString(ce));
+        }
+    }
+    if (!use_graph) {
         for (int p = 0; p < n_cond; ++p) SRNN_TRY(body());
     }
     SRNN_TRY(dequant_audio(seq, Lseq, lookback, ctx->lut, samples_out, audio_out, B, T, st));   // model.py:520

@@ -50,6 +50,7 @@ struct TierPacked {
     int kin = 0;       // K of the input GEMM: n (+ cond_dim + spk_dim on the top tier)
     bool top = false;
     float* w_in = nullptr;    // (H, kin)   [input_expand | cond_expand | spk_expand . E^T]
+    float* w_in_t = nullptr;  // (kin, H)   transpose of w_in for the fused generation-time input kernel
     float* b_in = nullptr;    // (H)        summed biases
     float* w_ih[SRNN_MAX_RNN] = {};   // (3H, H)
     float* w_hh[SRNN_MAX_RNN] = {};
@@ -118,6 +119,11 @@ int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, i
                 const void* cond, int cond_is_f64, int cond_rows, int cond_frames,
                 const int64_t* spk, int cond_dim, int spk_dim, const float* lut, float* A, int kin, bool top,
                 cudaStream_t st);
+int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
+                   int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, int spk_dim, const float* lut,
+                   const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
+                   __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st);
+int transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t st);
 // GRU cell tail (model.py:244): h' from gi (+bias already in), gh (+bias already in), h
 int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
               float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st,
@@ -164,6 +170,16 @@ int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out1
                        cudaStream_t st);
 size_t mlp_persist_smem(int H);
 bool mlp_persist_supported(int H, int FS, int B, int n_sms);
+struct GemmOperands {
+    const __nv_bfloat16* W;       // (n_feat, K) weights, the UMMA A operand
+    const __nv_bfloat16* act;     // (n_rows, K) activations, the UMMA B operand
+    const float* bias;            // (n_feat) or null
+    const float* addend;          // (n_rows, ld_add) or null
+    float* out_f32;               // (n_rows, ld_out) or null
+    __nv_bfloat16* out_bf16;      // (n_rows, ld_out) or null
+    int n_feat, ld_w, ld_act, ld_add, ld_out, relu;
+};
+int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);
 

@@ -55,13 +55,28 @@ struct GemmSmem {
     static constexpr int TOTAL = UMMA_STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// one launch can carry two independent problems that share the activation row count and K (blockIdx.z selects):
+// the GRU input projection gi = W_ih x and the recurrent projection gh = W_hh h of one layer run side by side.
+struct alignas(64) GemmProb {
+    CUtensorMap tmA, tmB;
+    const float* bias;
+    const float* addend;
+    float* out_f32;
+    __nv_bfloat16* out_bf16;
+    int n_feat, ld_add, ld_out, relu;
+};
+struct alignas(64) GemmArgs {
+    GemmProb p[2];
+    int n_rows, K;
+};
+
 template <int BM, int BN>
 __global__ void __launch_bounds__(192, 1)
-k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int n_feat, int n_rows,
-            int K, const float* __restrict__ bias, const float* __restrict__ addend, int ld_add,
-            float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ld_out, int relu) {
+k_gemm_umma(const __grid_constant__ GemmArgs args) {
     using S = GemmSmem<BM, BN>;
     constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+    const GemmProb& P = args.p[blockIdx.z];
+    const int n_feat = P.n_feat, n_rows = args.n_rows;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + UMMA_STAGES * S::STAGE);
@@ -71,11 +86,12 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int KB = K / 64;
+    const int KB = args.K / 64;
+    if (m0 >= n_feat) return;                      // the two problems of a launch may differ in feature count
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmA);
-        prefetch_tmap(&tmB);
+        prefetch_tmap(&P.tmA);
+        prefetch_tmap(&P.tmB);
         for (int s = 0; s < UMMA_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -96,20 +112,21 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint32_t ph = (kb / UMMA_STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], S::STAGE);
-                tma_load_2d(smem + s * S::STAGE, &tmA, &full[s], kb * 64, m0);
-                tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &tmB, &full[s], kb * 64, n0);
+                tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], kb * 64, m0);
+                tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], kb * 64, n0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            const uint64_t d0 = umma_desc_sw128(smem_u32(smem));
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % UMMA_STAGES;
                 const uint32_t ph = (kb / UMMA_STAGES) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_u32(smem + s * S::STAGE));
-                const uint64_t db = umma_desc_sw128(smem_u32(smem + s * S::STAGE + S::A_BYTES));
+                const uint64_t da = d0 + (uint64_t)(s * (S::STAGE >> 4));
+                const uint64_t db = da + (uint64_t)(S::A_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)       // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
                     umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
@@ -120,6 +137,11 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
         // epilogue: a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
+        const float* __restrict__ bias = P.bias;
+        const float* __restrict__ addend = P.addend;
+        float* __restrict__ out_f32 = P.out_f32;
+        __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
+        const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         int m;
@@ -135,6 +157,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const float bv = (bias && m_ok) ? bias[m] : 0.f;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 16) {
+            if (n0 + c >= n_rows) break;           // warp-uniform: nothing but padding rows beyond this point
             float v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
             if (m_ok) {
@@ -158,34 +181,44 @@ k_gemm_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BM, int BN>
-static int launch_gemm_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, int n_feat, int n_rows, int K,
-                            const float* bias, const float* addend, int ld_add, float* out_f32,
-                            __nv_bfloat16* out_bf16, int ld_out, int relu, cudaStream_t st) {
+static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaStream_t st) {
     using S = GemmSmem<BM, BN>;
     static bool attr_set = false;
     if (!attr_set) {
         SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma<BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
-    dim3 grid(cdiv(n_feat, BM), cdiv(n_rows, BN));
-    SRNN_LAUNCH((k_gemm_umma<BM, BN>), grid, 192, S::TOTAL, st, tmA, tmB, n_feat, n_rows, K, bias, addend, ld_add,
-                out_f32, out_bf16, ld_out, relu);
+    dim3 grid(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nprob);
+    SRNN_LAUNCH((k_gemm_umma<BM, BN>), grid, 192, S::TOTAL, st, args);
     return SRNN_OK;
 }
 
-// out (rows, feat) = act (rows, K) . W (feat, K)^T + bias [+ addend] [relu]; W / act are bf16, K % 64 == 0.
-// bn selects the batch-row tile (16..256); bm = 128 (default) or 64.
-int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
-              const float* bias, const float* addend, int ld_add, float* out_f32, __nv_bfloat16* out_bf16,
-              int ld_out, int relu, int bm, int bn, cudaStream_t st) {
+// nprob (1 or 2) problems  out_i (rows, feat_i) = act_i (rows, K) . W_i (feat_i, K)^T + bias_i [+ addend_i] [relu];
+// W / act are bf16 with K % 64 == 0.  bn selects the batch-row tile (32..256); bm = 128 (default) or 64.
+int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st) {
     if (K % 64 || K <= 0) return fail(SRNN_ERR_ARG, "gemm_umma: K=%d must be a positive multiple of 64", K);
-    CUtensorMap tmA, tmB;
-    SRNN_TRY(make_tmap_bf16(&tmA, W, n_feat, K, ld_w, bm));
-    SRNN_TRY(make_tmap_bf16(&tmB, act, n_rows, K, ld_act, bn));
-#define SRNN_GEMM_CASE(BM_, BN_)                                                                              \
-    if (bm == BM_ && bn == BN_)                                                                               \
-        return launch_gemm_umma<BM_, BN_>(tmA, tmB, n_feat, n_rows, K, bias, addend, ld_add, out_f32, out_bf16, \
-                                          ld_out, relu, st);
+    if (nprob < 1 || nprob > 2) return fail(SRNN_ERR_ARG, "gemm_umma: 1 or 2 problems per launch");
+    GemmArgs args;
+    memset(&args, 0, sizeof(args));
+    args.n_rows = n_rows;
+    args.K = K;
+    int max_feat = 0;
+    for (int i = 0; i < nprob; ++i) {
+        const GemmOperands& o = ops[i];
+        SRNN_TRY(make_tmap_bf16(&args.p[i].tmA, o.W, o.n_feat, K, o.ld_w, bm));
+        SRNN_TRY(make_tmap_bf16(&args.p[i].tmB, o.act, n_rows, K, o.ld_act, bn));
+        args.p[i].bias = o.bias;
+        args.p[i].addend = o.addend;
+        args.p[i].out_f32 = o.out_f32;
+        args.p[i].out_bf16 = o.out_bf16;
+        args.p[i].n_feat = o.n_feat;
+        args.p[i].ld_add = o.ld_add;
+        args.p[i].ld_out = o.ld_out;
+        args.p[i].relu = o.relu;
+        if (o.n_feat > max_feat) max_feat = o.n_feat;
+    }
+#define SRNN_GEMM_CASE(BM_, BN_) \
+    if (bm == BM_ && bn == BN_) return launch_gemm_umma<BM_, BN_>(args, nprob, max_feat, st);
     SRNN_GEMM_CASE(128, 256)
     SRNN_GEMM_CASE(128, 128)
     SRNN_GEMM_CASE(128, 64)
@@ -194,6 +227,13 @@ int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int 
     SRNN_GEMM_CASE(64, 64)
 #undef SRNN_GEMM_CASE
     return fail(SRNN_ERR_UNSUPPORTED, "gemm_umma: tile %dx%d not instantiated", bm, bn);
+}
+
+int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
+              const float* bias, const float* addend, int ld_add, float* out_f32, __nv_bfloat16* out_bf16,
+              int ld_out, int relu, int bm, int bn, cudaStream_t st) {
+    GemmOperands o{W, act, bias, addend, out_f32, out_bf16, n_feat, ld_w, ld_act, ld_add, ld_out, relu};
+    return gemm_umma_multi(&o, 1, n_rows, K, bm, bn, st);
 }
 
 // ---- fp32 -> bf16 with zero padding (test hook + weight packing) ------------------------------------------------

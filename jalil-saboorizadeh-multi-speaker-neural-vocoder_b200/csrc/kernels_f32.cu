@@ -242,6 +242,61 @@ int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, i
     return SRNN_OK;
 }
 
+// generation (one frame per utterance): frame assembly fused with the input expansion
+//   X[b,:] = W_in . [lut[prev n samples] | cond | onehot(spk)] + b_in (+ upper[b,:]);  W_in^T is (kin, H) so that
+//   consecutive threads read consecutive features  (model.py:196-218 at F = 1)
+__global__ void k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
+                                 const int* __restrict__ step_base, int n, const float* __restrict__ cond,
+                                 int cond_rows, int cond_frames, const int64_t* __restrict__ spk, int cond_dim,
+                                 int spk_dim, const float* __restrict__ lut, const float* __restrict__ w_in_t,
+                                 const float* __restrict__ b_in, const float* __restrict__ upper, int up_ld,
+                                 float* __restrict__ X, __nv_bfloat16* __restrict__ X16, int H, int kin, int top) {
+    extern __shared__ float a_s[];
+    const int b = blockIdx.x;
+    const int start = start_static + (step_base ? *step_base : 0);
+    const uint8_t* s = seq + (size_t)b * seq_ld + start;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a_s[i] = lut[s[i]];
+    if (top) {
+        const int crow = cond_rows == 1 ? 0 : b;
+        const size_t cbase = ((size_t)crow * cond_frames + start / n) * cond_dim;
+        for (int i = threadIdx.x; i < cond_dim; i += blockDim.x) a_s[n + i] = cond[cbase + i];
+        const int sp = (int)spk[crow];
+        for (int i = threadIdx.x; i < spk_dim; i += blockDim.x) a_s[n + cond_dim + i] = (i == sp) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float acc = b_in[h];
+        if (upper) acc += upper[(size_t)b * up_ld + h];
+        for (int k = 0; k < kin; ++k) acc = fmaf(a_s[k], w_in_t[(size_t)k * H + h], acc);
+        X[(size_t)b * H + h] = acc;
+        if (X16) X16[(size_t)b * H + h] = __float2bfloat16(acc);
+    }
+}
+int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
+                   int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, int spk_dim, const float* lut,
+                   const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
+                   __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st) {
+    SRNN_LAUNCH(k_tier_input_gen, B, H >= 256 ? 256 : 64, kin * sizeof(float), st, seq, seq_ld, off, step_base, n, cond,
+                cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper, up_ld, X, X16, H, kin,
+                top ? 1 : 0);
+    return SRNN_OK;
+}
+
+// (rows, cols) -> (cols, rows)
+__global__ void k_transpose_f32(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    const size_t total = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i % cols);
+        dst[(size_t)c * rows + r] = src[i];
+    }
+}
+int transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t st) {
+    const size_t total = (size_t)rows * cols;
+    SRNN_LAUNCH(k_transpose_f32, (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, st, src, dst,
+                rows, cols);
+    return SRNN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // GRU cell tail: gi, gh include their biases.  r,z,n row blocks (torch nn.GRU, model.py:154-159,244)
 // ------------------------------------------------------------------------------------------------
