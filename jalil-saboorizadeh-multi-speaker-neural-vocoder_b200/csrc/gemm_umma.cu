@@ -5,9 +5,11 @@
 // features per CTA) and the ACTIVATIONS (rows x K, bf16, K-major) are the B operand (N = BN batch rows), so the
 // accumulator in TMEM is D[feature lane][batch-row column] and the big streamed operand (the weights) is read once
 // per row tile.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> coalesced stores of out[row][feature]).
+// warps 2..9 = epilogue (tcgen05.ld -> bias/ReLU -> coalesced stores of out[row][feature]); two warps share each
+// TMEM lane quadrant and split the batch-row columns between them (the epilogue, not the MMA, bounds small-K tiles).
 #include "common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace srnn {
 
@@ -46,6 +48,7 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
 }
 
 constexpr int UMMA_STAGES = 4;
+constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
 
 template <int BM, int BN>
 struct GemmSmem {
@@ -68,10 +71,44 @@ struct alignas(64) GemmProb {
 struct alignas(64) GemmArgs {
     GemmProb p[2];
     int n_rows, K;
+    long long* trace;      // development aid (SRNN_TRACE_GEMM=1): clock64 stamps of CTA (0,0,0), else null
 };
 
+// 16 accumulator columns (= 16 consecutive batch rows) of one feature -> global memory.  The flag combination is a
+// compile-time parameter: a branchy per-element epilogue (~50 SASS instructions per value) was measured to cost more
+// than the whole K loop of a 128x256 tile.
+template <bool ADD, bool RELU, bool F32, bool B16>
+__device__ __forceinline__ void epi_store16(const float (&v)[16], float bv, int nn, size_t row, int m,
+                                            const float* __restrict__ addend, int ld_add, float* __restrict__ out_f32,
+                                            __nv_bfloat16* __restrict__ out_bf16, int ld_out) {
+    float* pf = F32 ? out_f32 + row * ld_out + m : nullptr;
+    __nv_bfloat16* pb = B16 ? out_bf16 + row * ld_out + m : nullptr;
+    const float* pa = ADD ? addend + row * ld_add + m : nullptr;
+    if (nn == 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float x = v[i] + bv;
+            if (ADD) x += pa[(size_t)i * ld_add];
+            if (RELU) x = fmaxf(x, 0.f);
+            if (F32) pf[(size_t)i * ld_out] = x;
+            if (B16) pb[(size_t)i * ld_out] = __float2bfloat16(x);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < nn) {
+                float x = v[i] + bv;
+                if (ADD) x += pa[(size_t)i * ld_add];
+                if (RELU) x = fmaxf(x, 0.f);
+                if (F32) pf[(size_t)i * ld_out] = x;
+                if (B16) pb[(size_t)i * ld_out] = __float2bfloat16(x);
+            }
+        }
+    }
+}
+
 template <int BM, int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_umma(const __grid_constant__ GemmArgs args) {
     using S = GemmSmem<BM, BN>;
     constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
@@ -88,6 +125,8 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int KB = args.K / 64;
     if (m0 >= n_feat) return;                      // the two problems of a launch may differ in feature count
+    long long* tr = (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? args.trace : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = clock64();
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&P.tmA);
@@ -111,6 +150,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
                 const int s = kb % UMMA_STAGES;
                 const uint32_t ph = (kb / UMMA_STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                if (tr && kb < 24) tr[8 + kb] = clock64();
                 mbar_expect_tx(&full[s], S::STAGE);
                 tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], kb * 64, m0);
                 tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], kb * 64, n0);
@@ -124,6 +164,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
                 const int s = kb % UMMA_STAGES;
                 const uint32_t ph = (kb / UMMA_STAGES) & 1;
                 mbar_wait(&full[s], ph);
+                if (tr && kb < 24) tr[32 + kb] = clock64();
                 tc_fence_after();
                 const uint64_t da = d0 + (uint64_t)(s * (S::STAGE >> 4));
                 const uint64_t db = da + (uint64_t)(S::A_BYTES >> 4);
@@ -135,14 +176,17 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
             umma_commit(tmem_full);
         }
     } else {
-        // epilogue: a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        // epilogue: a warp may only touch TMEM lanes 32*(warp%4) .. +31; warps 2..5 take the even 16-column chunks,
+        // warps 6..9 the odd ones
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const float* __restrict__ bias = P.bias;
         const float* __restrict__ addend = P.addend;
         float* __restrict__ out_f32 = P.out_f32;
         __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
         const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
         mbar_wait(tmem_full, 0);
+        if (tr && threadIdx.x == 64) tr[1] = clock64();
         tc_fence_after();
         int m;
         bool lane_ok;
@@ -156,25 +200,32 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         const bool m_ok = lane_ok && m < n_feat;
         const float bv = (bias && m_ok) ? bias[m] : 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
+        for (int c = 16 * half; c < BN; c += 32) {
             if (n0 + c >= n_rows) break;           // warp-uniform: nothing but padding rows beyond this point
             float v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
-            if (m_ok) {
+            if (!m_ok) continue;
+            const int nn = n_rows - (n0 + c) < 16 ? n_rows - (n0 + c) : 16;
+            const size_t row = (size_t)(n0 + c);
+            if (!addend && !relu && out_f32 && !out_bf16)          // GRU projections, upsampling, logits
+                epi_store16<false, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+            else if (!addend && relu && !out_f32 && out_bf16)      // MLP hidden layer feeding the next GEMM
+                epi_store16<false, true, false, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+            else {                                                 // generic (test hook)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int n = n0 + c + i;
-                    if (n < n_rows) {
-                        float x = v[i] + bv;
-                        if (addend) x += addend[(size_t)n * ld_add + m];
+                    float x = v[i] + bv;
+                    if (i < nn) {
+                        if (addend) x += addend[(row + i) * ld_add + m];
                         if (relu) x = fmaxf(x, 0.f);
-                        if (out_f32) out_f32[(size_t)n * ld_out + m] = x;
-                        if (out_bf16) out_bf16[(size_t)n * ld_out + m] = __float2bfloat16(x);
+                        if (out_f32) out_f32[(row + i) * ld_out + m] = x;
+                        if (out_bf16) out_bf16[(row + i) * ld_out + m] = __float2bfloat16(x);
                     }
                 }
             }
         }
     }
+    if (tr && threadIdx.x == 64) tr[2] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TCOLS>(tmem_d);
@@ -189,7 +240,7 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
         attr_set = true;
     }
     dim3 grid(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nprob);
-    SRNN_LAUNCH((k_gemm_umma<BM, BN>), grid, 192, S::TOTAL, st, args);
+    SRNN_LAUNCH((k_gemm_umma<BM, BN>), grid, GEMM_THREADS, S::TOTAL, st, args);
     return SRNN_OK;
 }
 
@@ -217,8 +268,15 @@ int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int b
         args.p[i].relu = o.relu;
         if (o.n_feat > max_feat) max_feat = o.n_feat;
     }
+    static long long* g_trace = nullptr;
+    if (getenv("SRNN_TRACE_GEMM")) {
+        if (!g_trace) cudaMallocManaged((void**)&g_trace, sizeof(long long) * 64);
+        if (g_trace) memset(g_trace, 0, sizeof(long long) * 64);
+        args.trace = g_trace;
+    }
+    int rc = SRNN_ERR_UNSUPPORTED;
 #define SRNN_GEMM_CASE(BM_, BN_) \
-    if (bm == BM_ && bn == BN_) return launch_gemm_umma<BM_, BN_>(args, nprob, max_feat, st);
+    if (bm == BM_ && bn == BN_) rc = launch_gemm_umma<BM_, BN_>(args, nprob, max_feat, st);
     SRNN_GEMM_CASE(128, 256)
     SRNN_GEMM_CASE(128, 128)
     SRNN_GEMM_CASE(128, 64)
@@ -226,7 +284,18 @@ int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int b
     SRNN_GEMM_CASE(64, 32)
     SRNN_GEMM_CASE(64, 64)
 #undef SRNN_GEMM_CASE
-    return fail(SRNN_ERR_UNSUPPORTED, "gemm_umma: tile %dx%d not instantiated", bm, bn);
+    if (rc == SRNN_ERR_UNSUPPORTED) return fail(SRNN_ERR_UNSUPPORTED, "gemm_umma: tile %dx%d not instantiated", bm, bn);
+    if (rc == SRNN_OK && args.trace) {
+        cudaStreamSynchronize(st);
+        const long long t0 = g_trace[0];
+        fprintf(stderr, "[gemm trace %dx%d K=%d] mma done=%lld epilogue done=%lld | producer issue:", bm, bn, K,
+                g_trace[1] - t0, g_trace[2] - t0);
+        for (int kb = 0; kb < K / 64 && kb < 24; ++kb) fprintf(stderr, " %lld", g_trace[8 + kb] - t0);
+        fprintf(stderr, " | consumer full:");
+        for (int kb = 0; kb < K / 64 && kb < 24; ++kb) fprintf(stderr, " %lld", g_trace[32 + kb] - t0);
+        fprintf(stderr, "\n");
+    }
+    return rc;
 }
 
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
