@@ -107,8 +107,8 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     uint64_t* bar_d2 = x2_ready + 1;
     uint64_t* p_ready = bar_d2 + 1;                       // [2]
     uint64_t* p_free = p_ready + 2;                       // [2]
-    uint64_t* q_ready = p_free + 2;                       // [2] sample of an even / odd step has been drawn
-    uint32_t* tmem_slot = (uint32_t*)(q_ready + 2);
+    uint64_t* q_ready = p_free + 2;                       // [3] sample of step k has been drawn (barrier k % 3)
+    uint32_t* tmem_slot = (uint32_t*)(q_ready + 3);
 
     const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
     const int row0 = rg * 32 + sl * RPC;                  // first owned row (global utterance index)
@@ -132,6 +132,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         mbar_init(&p_free[1], 1);
         mbar_init(&q_ready[0], 1);
         mbar_init(&q_ready[1], 1);
+        mbar_init(&q_ready[2], 1);
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc<MP_TMEM_COLS>(tmem_slot);
@@ -162,7 +163,13 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             tma_load_2d(sWo + 16384, &tmWo, w_ready, sl * 64, 128);
             int it = 0;
             for (int k = 0; k < p.nsteps; ++k) {
-                mbar_wait(x1_ready, k & 1);
+                {   // group barrier A, waiting side: arrivals so far = (2k+1) * NS once every slice has published X1
+                    const unsigned target = (unsigned)(2 * k + 1) * (unsigned)NS;
+                    const unsigned* ctr = p.ctr + rg;
+                    while (ld_acquire_gpu(ctr) < target) {
+                    }
+                    fence_proxy_async_all();              // other CTAs' generic-proxy global writes -> visible to TMA reads
+                }
                 if (p.trace && blockIdx.x == 0) p.trace[k * 64 + 10] = clock64();
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it & stg_mask;
@@ -237,12 +244,17 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             mbar_wait(&p_ready[k & 1], (k >> 1) & 1);
             MP_TRACE(1);
             {
-                const int qn = sQ[rl * 32 + ((i - 1) & 31)];
+                const int qn = sQ[rl * 32 + ((i - 1) & 31)], qm = sQ[rl * 32 + ((i - 2) & 31)];
                 const uint4* tp = reinterpret_cast<const uint4*>(p.tbl + ((size_t)(FS - 1) * SRNN_Q + qn) * H + f0);
-                const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
-                float tv[16];
+                const uint4* tq = reinterpret_cast<const uint4*>(p.tbl + ((size_t)(FS - 2) * SRNN_Q + qm) * H + f0);
+                const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tq), t3 = __ldg(tq + 1);
+                float tv[16], tw[16];
                 bf16x8_to_f32(t0, tv);
                 bf16x8_to_f32(t1, tv + 8);
+                bf16x8_to_f32(t2, tw);
+                bf16x8_to_f32(t3, tw + 8);
+#pragma unroll
+                for (int v = 0; v < 16; ++v) tv[v] += tw[v];
                 const float4* pp = reinterpret_cast<const float4*>(sP + (k & 1) * 2048 + flat);
                 uint32_t o[8];
 #pragma unroll
@@ -259,13 +271,15 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             }
             // ---- group barrier A: the whole X1 of this row group is in global memory ----
             MP_TRACE(2);
-            group_barrier(ctr, (++bar_no) * NS, tidE);
-            MP_TRACE(3);
+            // E warps only ARRIVE (release); the TMA thread is the one that waits for the other slices' arrivals, so the
+            // wake-up hand-off between two warps is off the serial path.  X1 is not rewritten before barrier B.
+            named_bar_sync(1, 128);
+            ++bar_no;
             if (tidE == 0) {
-                mbar_arrive(&p_free[k & 1]);              // P[k&1] consumed (all E threads passed the barrier above)
-                fence_proxy_async_all();                  // generic-proxy global writes -> visible to TMA reads
-                mbar_arrive(x1_ready);
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
+                mbar_arrive(&p_free[k & 1]);              // P[k&1] consumed by every E thread
             }
+            MP_TRACE(3);
             // ---- epilogue 1: D1 (+bias, ReLU) -> bf16 swizzled B operand in smem ----
             mbar_wait(bar_d1, k & 1);
             MP_TRACE(4);
@@ -399,11 +413,11 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 }
             }
             named_bar_sync(1, 128);                       // sample i of every owned row is in sQ
-            if (tidE == 0) mbar_arrive(&q_ready[k & 1]);
+            if (tidE == 0) mbar_arrive(&q_ready[k % 3]);
             MP_TRACE(9);
         }
     } else if (warp < 4) {
-        // ===================== G warps: prefetch P_g = c0 + taps 0..FS-2 for step g =====================
+        // ===================== G warps: prefetch P_g = c0 + taps 0..FS-3 for step g (two steps of slack) ==========
         const int tidG = threadIdx.x;
         const int flat = tidG * 16;
         const int rl = flat / H, f0 = flat % H;
@@ -411,12 +425,10 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         const int bc = b < p.B ? b : p.B - 1;             // clamp: padded rows compute garbage that is never used
         for (int g = 0; g < p.nsteps; ++g) {
             const int i = i0 + g;
-            if (g >= 2) {
-                // sample i-2 (tap FS-2) has been drawn.  Two barriers by step parity: E can be at most one step past
-                // the awaited one, which would alias the phase parity of a single barrier.
-                mbar_wait(&q_ready[g & 1], ((g >> 1) - 1) & 1);
-                mbar_wait(&p_free[g & 1], ((g >> 1) - 1) & 1);
-            }
+            if (g >= 3)   // sample i-3 (tap FS-3, the newest one this prefetch uses) has been drawn.  Three barriers by
+                          // step % 3: E can be up to two steps past the awaited one, which would alias a phase parity.
+                mbar_wait(&q_ready[g % 3], (g / 3 - 1) & 1);
+            if (g >= 2) mbar_wait(&p_free[g & 1], ((g >> 1) - 1) & 1);
             float acc[16];
             {
                 const float4* cp = reinterpret_cast<const float4*>(p.c0 + (size_t)bc * FS * H + (size_t)(i % FS) * H + f0);
@@ -427,8 +439,8 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 }
             }
             const uint8_t* qrow = sQ + rl * 32;
-#pragma unroll 8
-            for (int j = 0; j < FS - 1; ++j) {
+#pragma unroll 6
+            for (int j = 0; j < FS - 2; ++j) {
                 const int qj = qrow[(i - FS + j) & 31];
                 const uint4* tp = reinterpret_cast<const uint4*>(p.tbl + ((size_t)j * SRNN_Q + qj) * H + f0);
                 const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
