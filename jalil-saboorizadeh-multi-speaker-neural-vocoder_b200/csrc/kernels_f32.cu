@@ -264,19 +264,29 @@ __global__ void k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, in
         for (int i = threadIdx.x; i < spk_dim; i += blockDim.x) a_s[n + cond_dim + i] = (i == sp) ? 1.f : 0.f;
     }
     __syncthreads();
-    for (int h = threadIdx.x; h < H; h += blockDim.x) {
-        float acc = b_in[h];
-        if (upper) acc += upper[(size_t)b * up_ld + h];
-        for (int k = 0; k < kin; ++k) acc = fmaf(a_s[k], w_in_t[(size_t)k * H + h], acc);
-        X[(size_t)b * H + h] = acc;
-        if (X16) X16[(size_t)b * H + h] = __float2bfloat16(acc);
+    const int h = blockIdx.y * blockDim.x + threadIdx.x;          // one feature per thread, 4 independent FMA chains
+    if (h >= H) return;
+    float acc0 = b_in[h], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (upper) acc0 += upper[(size_t)b * up_ld + h];
+    const float* w = w_in_t + h;
+    int k = 0;
+    for (; k + 4 <= kin; k += 4) {
+        acc0 = fmaf(a_s[k], w[(size_t)k * H], acc0);
+        acc1 = fmaf(a_s[k + 1], w[(size_t)(k + 1) * H], acc1);
+        acc2 = fmaf(a_s[k + 2], w[(size_t)(k + 2) * H], acc2);
+        acc3 = fmaf(a_s[k + 3], w[(size_t)(k + 3) * H], acc3);
     }
+    for (; k < kin; ++k) acc0 = fmaf(a_s[k], w[(size_t)k * H], acc0);
+    const float acc = (acc0 + acc1) + (acc2 + acc3);
+    X[(size_t)b * H + h] = acc;
+    if (X16) X16[(size_t)b * H + h] = __float2bfloat16(acc);
 }
 int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
                    int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, int spk_dim, const float* lut,
                    const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
                    __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st) {
-    SRNN_LAUNCH(k_tier_input_gen, B, H >= 256 ? 256 : 64, kin * sizeof(float), st, seq, seq_ld, off, step_base, n, cond,
+    const int threads = H >= 256 ? 256 : 64;
+    SRNN_LAUNCH(k_tier_input_gen, dim3(B, cdiv(H, threads)), threads, kin * sizeof(float), st, seq, seq_ld, off, step_base, n, cond,
                 cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper, up_ld, X, X16, H, kin,
                 top ? 1 : 0);
     return SRNN_OK;
