@@ -343,7 +343,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         X1h = b.take<bf>((size_t)RG * 32 * H);
         X2h = b.take<bf>((size_t)B * H);
         part = b.take<float>(persist ? (size_t)RG * NS * 32 * Q : 1);
-        gctr = b.take<unsigned>(RG);
+        gctr = b.take<unsigned>(2 * RG);
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
     }
     // private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
