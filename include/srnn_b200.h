@@ -114,6 +114,11 @@ SRNN_API int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t
                      int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
                      float* logp_out, int32_t mode, void* stream);
 
+/* sequence_nll_loss_bits (nn.py:66-70): loss_out (1 device float) = -mean_r logp[r, target[r]] * log2(e), rows = B*T;
+ * deterministic two-stage reduction. */
+SRNN_API int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, int32_t rows, float* loss_out,
+                                void* stream);
+
 /* ---- Generator.__call__ (model.py:445-520) ---------------------------------------------------- */
 /* cond (cond_rows, n_cond, cond_dim) fp32 with cond_rows == 1 (reference form: one conditioner for all
  * sequences, model.py:484-487) or == B (per-utterance extension); spk (cond_rows) int64;

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "srnn_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
     "srnn_predict_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "srnn_nll_loss_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "srnn_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "srnn_sample_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -233,74 +233,143 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // Predictor.forward  (model.py:357-436)
 // ------------------------------------------------------------------------------------------------
+// lay the forward buffers out in the context scratch (two-pass bump allocation); returns the bytes used
+static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback;
+    const int Lseq = lookback + T - 1;
+    const bool bf16 = mode != SRNN_MODE_FP32;
+    typedef __nv_bfloat16 bf;
+    FwdPlan& P = ctx->fwd;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump b(pass ? ctx->ws : nullptr);
+        P.seq = b.take<uint8_t>((size_t)B * Lseq);
+        for (int i = 0; i < NT; ++i) {
+            const TierPacked& t = ctx->tiers[i];
+            const size_t M = (size_t)B * (T / t.n);
+            P.A[i] = b.take<float>(M * t.kin);
+            P.X[i] = b.take<float>(M * H);
+            P.X16[i] = b.take<bf>(bf16 ? M * H : 1);
+            for (int l = 0; l < NL; ++l) {
+                P.GI[i][l] = b.take<float>(M * 3 * H);
+                P.GH[i][l] = b.take<float>(M * 3 * H);
+                P.Y[i][l] = b.take<float>(M * H);
+                P.Y16[i][l] = b.take<bf>(bf16 ? M * H : 1);
+            }
+            P.H0[i] = b.take<float>((size_t)NL * B * H);
+            P.H016[i] = b.take<bf>(bf16 ? (size_t)NL * B * H : 1);
+            P.UP[i] = b.take<float>(M * t.fs * H);
+        }
+        P.X1 = b.take<float>(bf16 ? 1 : (size_t)B * T * H);
+        P.X2 = b.take<float>(bf16 ? 1 : (size_t)B * T * H);
+        P.X1h = b.take<bf>(bf16 ? (size_t)B * T * H : 1);
+        P.X2h = b.take<bf>(bf16 ? (size_t)B * T * H : 1);
+        P.bytes = b.off;
+        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
+    }
+    P.B = B;
+    P.T = T;
+    P.mode = mode;
+    return SRNN_OK;
+}
+
+static inline int pick_bn(int rows) { return rows <= 32 ? 32 : (rows <= 64 ? 64 : (rows <= 128 ? 128 : 256)); }
+
 int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_seq, const void* cond,
                      int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
                      float* logp_out, int32_t mode, void* stream) {
     SRNN_TRY(check_ready(ctx));
     if (!input_seq || !cond || !spk || !hidden_io || !logp_out) return fail(SRNN_ERR_ARG, "null argument");
     if (B < 1 || T < 1 || T % ctx->lookback) return fail(SRNN_ERR_ARG, "T=%d must be a positive multiple of lookback=%d", T, ctx->lookback);
-    if (mode != SRNN_MODE_FP32) return fail(SRNN_ERR_UNSUPPORTED, "predict_fwd: mode %d not available", mode);
+    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16) return fail(SRNN_ERR_UNSUPPORTED, "predict_fwd: mode %d not available", mode);
+    if (mode == SRNN_MODE_BF16 && !ctx->has_bf16)
+        return fail(SRNN_ERR_UNSUPPORTED, "bf16 tensor-core mode needs dim %% 64 == 0 (dim=%d)", ctx->H);
     cudaStream_t st = (cudaStream_t)stream;
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback;
     const int Lseq = lookback + T - 1;
+    const bool bf16 = mode == SRNN_MODE_BF16;
+    ctx->fwd.valid = false;
+    SRNN_TRY(plan_forward(ctx, B, T, mode));
+    FwdPlan& P = ctx->fwd;
 
-    uint8_t* seq = nullptr;
-    float *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS], *Y0[SRNN_MAX_TIERS],
-        *Y1[SRNN_MAX_TIERS], *UP[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr;
-    for (int pass = 0; pass < 2; ++pass) {
-        Bump b(pass ? ctx->ws : nullptr);
-        seq = b.take<uint8_t>((size_t)B * Lseq);
-        for (int i = 0; i < NT; ++i) {
-            const TierPacked& t = ctx->tiers[i];
-            const size_t M = (size_t)B * (T / t.n);
-            A[i] = b.take<float>(M * t.kin);
-            X[i] = b.take<float>(M * H);
-            GI[i] = b.take<float>(M * 3 * H);
-            GH[i] = b.take<float>((size_t)B * 3 * H);
-            Y0[i] = b.take<float>(M * H);
-            Y1[i] = b.take<float>(M * H);
-            UP[i] = b.take<float>(M * t.fs * H);
-        }
-        X1 = b.take<float>((size_t)B * T * H);
-        X2 = b.take<float>((size_t)B * T * H);
-        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
-    }
-    SRNN_TRY(i64_to_u8(input_seq, seq, (size_t)B * Lseq, st));
+    SRNN_TRY(i64_to_u8(input_seq, P.seq, (size_t)B * Lseq, st));
     const float* upper = nullptr;
     for (int i = NT - 1; i >= 0; --i) {                                     // model.py:378 top tier first
         const TierPacked& t = ctx->tiers[i];
         const int F = T / t.n, M = B * F;
         if (!hidden_io[i]) return fail(SRNN_ERR_ARG, "hidden_io[%d] is null", i);
-        SRNN_TRY(frame_input(seq, Lseq, lookback - t.n, nullptr, t.n, B, F, cond, cond_is_f64, B, T / lookback, spk,
-                             c.cond_dim, c.spk_dim, ctx->lut, A[i], t.kin, t.top, st));
-        SRNN_TRY(gemm_f32(M, H, t.kin, A[i], t.kin, t.w_in, t.kin, t.b_in, upper, H, 0, X[i], H, st));
-        const float* in = X[i];
-        float* Y = nullptr;
+        SRNN_TRY(frame_input(P.seq, Lseq, lookback - t.n, nullptr, t.n, B, F, cond, cond_is_f64, B, T / lookback, spk,
+                             c.cond_dim, c.spk_dim, ctx->lut, P.A[i], t.kin, t.top, st));
+        SRNN_TRY(gemm_f32(M, H, t.kin, P.A[i], t.kin, t.w_in, t.kin, t.b_in, upper, H, 0, P.X[i], H, st,
+                          bf16 ? P.X16[i] : nullptr));
+        const float* in = P.X[i];
+        const __nv_bfloat16* in16 = P.X16[i];
         for (int l = 0; l < NL; ++l) {
-            Y = (l & 1) ? Y1[i] : Y0[i];
+            float* Y = P.Y[i][l];
+            __nv_bfloat16* Y16 = P.Y16[i][l];
             float* hid = hidden_io[i] + (size_t)l * B * H;
-            if ((reset_mask >> i) & 1) SRNN_TRY(bcast_rows(t.h0 + (size_t)l * H, hid, B, H, st));   // model.py:222-228
-            SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
+            float* h0 = P.H0[i] + (size_t)l * B * H;                        // the initial state this pass used (for BPTT)
+            __nv_bfloat16* h016 = P.H016[i] + (size_t)l * B * H;
+            if ((reset_mask >> i) & 1) SRNN_TRY(bcast_rows(t.h0 + (size_t)l * H, h0, B, H, st));   // model.py:222-228
+            else SRNN_TRY(copy_f32(hid, h0, (size_t)B * H, st));
+            float* GI = P.GI[i][l];
+            float* GH = P.GH[i][l];
+            if (bf16) {
+                SRNN_TRY(f32_to_bf16_pad(h0, B, H, H, h016, B, H, st));
+                SRNN_TRY(gemm_umma(t.w_ih16[l], 3 * H, in16, M, H, H, H, t.b_ih[l], nullptr, 0, GI, nullptr, 3 * H, 0, 128,
+                                   pick_bn(M), st));
+            } else {
+                SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI, 3 * H, st));
+            }
             for (int f = 0; f < F; ++f) {
-                const float* hp = f ? Y + (size_t)(f - 1) * H : hid;
+                const float* hp = f ? Y + (size_t)(f - 1) * H : h0;
                 const int hp_ld = f ? F * H : H;
-                SRNN_TRY(gemm_f32(B, 3 * H, H, hp, hp_ld, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
-                SRNN_TRY(gru_gates(GI[i] + (size_t)f * 3 * H, F * 3 * H, GH[i], 3 * H, hp, hp_ld, Y + (size_t)f * H,
-                                   F * H, f == F - 1 ? hid : nullptr, B, H, st));   // carry: model.py:348
+                float* gh = GH + (size_t)f * 3 * H;
+                if (bf16) {
+                    const __nv_bfloat16* hp16 = f ? Y16 + (size_t)(f - 1) * H : h016;
+                    SRNN_TRY(gemm_umma(t.w_hh16[l], 3 * H, hp16, B, H, H, hp_ld, t.b_hh[l], nullptr, 0, gh, nullptr,
+                                       F * 3 * H, 0, 128, pick_bn(B), st));
+                } else {
+                    SRNN_TRY(gemm_f32(B, 3 * H, H, hp, hp_ld, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, gh, F * 3 * H, st));
+                }
+                SRNN_TRY(gru_gates(GI + (size_t)f * 3 * H, F * 3 * H, gh, F * 3 * H, hp, hp_ld, Y + (size_t)f * H, F * H,
+                                   f == F - 1 ? hid : nullptr, B, H, st, bf16 ? Y16 + (size_t)f * H : nullptr,
+                                   F * H));                                 // carry: model.py:348
             }
             in = Y;
+            in16 = Y16;
         }
-        SRNN_TRY(gemm_f32(M, t.fs * H, H, Y, H, t.w_up, H, t.b_up, nullptr, 0, 0, UP[i], t.fs * H, st));
-        upper = UP[i];
+        if (bf16)
+            SRNN_TRY(gemm_umma(t.w_up16, t.fs * H, in16, M, H, H, H, t.b_up, nullptr, 0, P.UP[i], nullptr, t.fs * H, 0, 128,
+                               pick_bn(M), st));
+        else
+            SRNN_TRY(gemm_f32(M, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, P.UP[i], t.fs * H, st));
+        upper = P.UP[i];
     }
     // sample-level MLP  (model.py:422-436, 308-325)
-    const int FS0 = ctx->FS0;
-    SRNN_TRY(mlp_gather(seq, Lseq, lookback - FS0, nullptr, ctx->tbl, upper, (long long)T * H, H, X1, B, T, H, FS0, st));
-    SRNN_TRY(gemm_f32(B * T, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
-    SRNN_TRY(gemm_f32(B * T, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st));
-    SRNN_TRY(logsoftmax_rows(logp_out, B * T, st));
+    const int FS0 = ctx->FS0, R = B * T;
+    if (bf16) {
+        SRNN_TRY(mlp_gather_bf16(P.seq, Lseq, lookback - FS0, nullptr, ctx->tbl16, upper, (long long)T * H, H, P.X1h, B, T, H,
+                                 FS0, st));
+        SRNN_TRY(gemm_umma(ctx->w_hid16, H, P.X1h, R, H, H, H, ctx->b_hid, nullptr, 0, nullptr, P.X2h, H, 1, 128, pick_bn(R), st));
+        SRNN_TRY(gemm_umma(ctx->w_out16, Q, P.X2h, R, H, H, H, ctx->b_out, nullptr, 0, logp_out, nullptr, Q, 0, 128, pick_bn(R), st));
+    } else {
+        SRNN_TRY(mlp_gather(P.seq, Lseq, lookback - FS0, nullptr, ctx->tbl, upper, (long long)T * H, H, P.X1, B, T, H, FS0, st));
+        SRNN_TRY(gemm_f32(R, H, H, P.X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, P.X2, H, st));
+        SRNN_TRY(gemm_f32(R, Q, H, P.X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st));
+    }
+    SRNN_TRY(logsoftmax_rows(logp_out, R, st));
+    P.valid = true;
     return SRNN_OK;
+}
+
+// mean NLL in bits of log-probabilities against targets (nn.py:66-70); loss_out = one device float
+int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, int32_t rows, float* loss_out, void* stream) {
+    if (!ctx || !logp || !target || !loss_out || rows < 1) return fail(SRNN_ERR_ARG, "bad argument");
+    static const int NP = 256;
+    if (!ctx->loss_partial) SRNN_TRY(ctx->weights.alloc((void**)&ctx->loss_partial, sizeof(float) * NP));
+    return nll_bits(logp, target, rows, ctx->loss_partial, NP, loss_out, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

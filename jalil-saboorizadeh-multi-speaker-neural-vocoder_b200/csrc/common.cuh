@@ -73,8 +73,34 @@ struct Arena {
 
 }  // namespace srnn
 
+namespace srnn {
+// Buffers of the last teacher-forced forward pass (inside the context's scratch): the saved activations of the
+// backward pass.  Row index of frame-level tensors = b*F + f; of sample-level tensors = b*T + t.
+struct FwdPlan {
+    bool valid = false;
+    int B = 0, T = 0, mode = 0;
+    uint8_t* seq = nullptr;                                   // (B, lookback+T-1)
+    float* A[SRNN_MAX_TIERS] = {};                            // (M, kin) assembled tier inputs
+    float* X[SRNN_MAX_TIERS] = {};                            // (M, H) GRU layer-0 input
+    __nv_bfloat16* X16[SRNN_MAX_TIERS] = {};
+    float* GI[SRNN_MAX_TIERS][SRNN_MAX_RNN] = {};             // (M, 3H) W_ih x + b_ih
+    float* GH[SRNN_MAX_TIERS][SRNN_MAX_RNN] = {};             // (M, 3H) W_hh h_{t-1} + b_hh
+    float* Y[SRNN_MAX_TIERS][SRNN_MAX_RNN] = {};              // (M, H) layer outputs h_t
+    __nv_bfloat16* Y16[SRNN_MAX_TIERS][SRNN_MAX_RNN] = {};
+    float* H0[SRNN_MAX_TIERS] = {};                           // (n_rnn, B, H) initial hidden state used
+    __nv_bfloat16* H016[SRNN_MAX_TIERS] = {};
+    float* UP[SRNN_MAX_TIERS] = {};                           // (M, fs*H) upsampled conditioning for the tier below
+    float* X1 = nullptr;                                      // (B*T, H) relu(gather + c0)        [fp32 mode]
+    float* X2 = nullptr;                                      // (B*T, H) relu(hidden)             [fp32 mode]
+    __nv_bfloat16* X1h = nullptr;                             // bf16 mode
+    __nv_bfloat16* X2h = nullptr;
+    size_t bytes = 0;
+};
+}  // namespace srnn
+
 struct srnn_ctx {
     srnn_config cfg{};
+    srnn::FwdPlan fwd;
     int lookback = 0;
     int H = 0, Q = SRNN_Q, FS0 = 0;
     bool packed = false;
@@ -85,6 +111,7 @@ struct srnn_ctx {
     float* w_out = nullptr;   // (Q, H)
     float* b_out = nullptr;
     float* lut = nullptr;     // (Q) 2*dequantize(q)
+    float* loss_partial = nullptr;
     bool has_bf16 = false;    // tcgen05 path available (H % 64 == 0)
     __nv_bfloat16* tbl16 = nullptr;
     __nv_bfloat16* w_hid16 = nullptr;
@@ -127,7 +154,9 @@ int transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t
 // GRU cell tail (model.py:244): h' from gi (+bias already in), gh (+bias already in), h
 int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
               float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st,
-              __nv_bfloat16* h16 = nullptr);
+              __nv_bfloat16* h16 = nullptr, int h16_ld = 0);
+int nll_bits(const float* logp, const int64_t* target, int rows, float* partial, int n_partial, float* out,
+             cudaStream_t st);
 int bcast_rows(const float* src, float* dst, int B, int H, cudaStream_t st);
 // x1[r,:] = relu(sum_j Tbl[j][seq[b, off + t + j]] + upper[r,:])
 int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, const float* tbl,

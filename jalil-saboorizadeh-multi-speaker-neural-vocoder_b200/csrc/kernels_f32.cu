@@ -312,7 +312,7 @@ int transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gru_gates(const float* __restrict__ gi, int gi_ld, const float* __restrict__ gh, int gh_ld,
                             const float* __restrict__ h_prev, int hp_ld, float* __restrict__ h_out, int ho_ld,
-                            float* __restrict__ h_out2, int H, __nv_bfloat16* __restrict__ h16) {
+                            float* __restrict__ h_out2, int H, __nv_bfloat16* __restrict__ h16, int h16_ld) {
     const int b = blockIdx.y;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= H) return;
@@ -325,12 +325,12 @@ __global__ void k_gru_gates(const float* __restrict__ gi, int gi_ld, const float
     const float hn = (1.f - z) * nn + z * hp;
     h_out[(size_t)b * ho_ld + u] = hn;
     if (h_out2) h_out2[(size_t)b * H + u] = hn;
-    if (h16) h16[(size_t)b * H + u] = __float2bfloat16(hn);
+    if (h16) h16[(size_t)b * h16_ld + u] = __float2bfloat16(hn);
 }
 int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,
-              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st, __nv_bfloat16* h16) {
+              float* h_out, int ho_ld, float* h_out2, int B, int H, cudaStream_t st, __nv_bfloat16* h16, int h16_ld) {
     SRNN_LAUNCH(k_gru_gates, dim3(cdiv(H, 128), B), 128, 0, st, gi, gi_ld, gh, gh_ld, h_prev, hp_ld, h_out, ho_ld,
-                h_out2, H, h16);
+                h_out2, H, h16, h16_ld ? h16_ld : H);
     return SRNN_OK;
 }
 
@@ -483,6 +483,35 @@ int dequant_audio(const uint8_t* seq, int seq_ld, int off, const float* lut, uin
     int gx = cdiv(T, 256);
     if (gx > 1024) gx = 1024;
     SRNN_LAUNCH(k_dequant_audio, dim3(gx, B), 256, 0, st, seq, seq_ld, off, lut, samples, audio, T);
+    return SRNN_OK;
+}
+
+// mean NLL in bits (nn.py:66-70): -mean_r logp[r, target[r]] * log2(e); fixed-order two-stage reduction
+__global__ void k_nll_partial(const float* __restrict__ logp, const int64_t* __restrict__ target, int rows,
+                              float* __restrict__ partial) {
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
+        s -= logp[(size_t)r * SRNN_Q + (int)(target[r] & 0xff)];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void k_nll_final(const float* __restrict__ partial, int n, int rows, float* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += partial[i];
+        *out = s / (float)rows * 1.4426950408889634f;
+    }
+}
+int nll_bits(const float* logp, const int64_t* target, int rows, float* partial, int n_partial, float* out,
+             cudaStream_t st) {
+    SRNN_LAUNCH(k_nll_partial, n_partial, 256, 0, st, logp, target, rows, partial);
+    SRNN_LAUNCH(k_nll_final, 1, 32, 0, st, partial, n_partial, rows, out);
     return SRNN_OK;
 }
 

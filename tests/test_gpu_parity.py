@@ -188,3 +188,44 @@ def test_generate_bf16_mode_against_oracle(dim, B, mode):
     with torch.no_grad():
         tf32 = p(seq[:, :-1], True, cond, spk.reshape(B, 1), None, None)
     logp_gate(tf32.cpu().numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("dim,B,T", [(64, 3, 160), (128, 5, 240), (256, 130, 80)])
+def test_predict_bf16_mode_against_oracle(dim, B, T):
+    torch.manual_seed(dim + 1)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=dim, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c)
+    p = S.Predictor(m, mode=S.MODE_BF16)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    x = torch.randint(0, 256, (B, 80 + 2 * T - 1))
+    cond = torch.rand(B, 2 * T // 80, 86, dtype=torch.float64)
+    spk = torch.randint(0, 6, (B, 1))
+    w = O.unpack_state_dict(sd, O.Config(**c))
+    ref_p = O.Predictor(w)
+    with torch.no_grad():
+        for i in range(2):                          # two consecutive chunks: the bf16 path carries hidden state too
+            xs = x[:, i * T: i * T + 80 + T - 1].contiguous()
+            cs = cond[:, i * (T // 80): (i + 1) * (T // 80)].contiguous()
+            ref = ref_p.forward(xs, i == 0, cs, spk)
+            got = p(xs, i == 0, cs, spk, None, None).cpu()
+            d = (ref - got).abs()
+            assert float(d.max()) <= BF16_MAX_ABS and float(d.mean()) <= BF16_MEAN_ABS, (i, float(d.max()), float(d.mean()))
+
+
+def test_nll_loss_bits_hook(golden):
+    m, p = build(golden)
+    x, y, c = golden.chunk(0)
+    spk = torch.from_numpy(golden["spk"])
+    with torch.no_grad():
+        logp = p(x, True, c, spk, None, None)
+    loss = torch.empty(1, device="cuda")
+    tgt = y.cuda().contiguous()
+    L.check(L.load().srnn_nll_loss_bits(m._ensure_packed(), logp.data_ptr(), tgt.data_ptr(), int(tgt.numel()),
+                                        loss.data_ptr(), stream()))
+    assert abs(float(loss.item()) - float(golden["tf/loss0"])) < 1e-4
