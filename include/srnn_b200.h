@@ -114,6 +114,21 @@ SRNN_API int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t
                      int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
                      float* logp_out, int32_t mode, void* stream);
 
+/* Backward of the last srnn_predict_fwd on this context (what torch autograd does for the reference at
+ * trainer/__init__.py:103): logp = that call's output (B,T,Q), dlogp = dL/dlogp, params = the raw tensors given to
+ * srnn_pack_weights, grads = the same struct pointing at WRITABLE gradient buffers of identical shapes (null entries
+ * are skipped; non-null ones are overwritten).  Hidden-state carries are detached (model.py:348): h0 receives a
+ * gradient only for tiers that started from it in that forward pass, zeros otherwise (torch-0.4 zero_grad semantics,
+ * SURVEY App. C #12).  Available for SRNN_MODE_FP32 forward passes. */
+SRNN_API int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* params,
+                              const srnn_params* grads, void* stream);
+
+/* optim.py:10-13 element-wise clamp of every gradient to [-clamp, clamp] fused with torch.optim.Adam's update
+ * (train.py:238: betas (0.9, 0.999), eps 1e-8, no weight decay) over `count` tensors in one launch; step = 1, 2, ... */
+SRNN_API int srnn_clamp_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                                  float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2,
+                                  float eps, int32_t step, float clamp, void* stream);
+
 /* sequence_nll_loss_bits (nn.py:66-70): loss_out (1 device float) = -mean_r logp[r, target[r]] * log2(e), rows = B*T;
  * deterministic two-stage reduction. */
 SRNN_API int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, int32_t rows, float* loss_out,

@@ -44,6 +44,10 @@ _SIGNATURES = {
     "srnn_pack_weights": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p]),
     "srnn_predict_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "srnn_predict_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.POINTER(Params), C.c_void_p]),
+    "srnn_clamp_adam_step": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_int32, C.c_float, C.c_void_p]),
     "srnn_nll_loss_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "srnn_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -265,7 +265,9 @@ static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
         P.X1h = b.take<bf>(bf16 ? (size_t)B * T * H : 1);
         P.X2h = b.take<bf>(bf16 ? (size_t)B * T * H : 1);
         P.bytes = b.off;
-        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
+        // the backward pass works in the scratch right behind the saved activations: reserve it now, because growing the
+        // scratch later would free them
+        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off + (bf16 ? 0 : backward_scratch_bytes(ctx, B, T))));
     }
     P.B = B;
     P.T = T;
@@ -360,8 +362,38 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
         SRNN_TRY(gemm_f32(R, Q, H, P.X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st));
     }
     SRNN_TRY(logsoftmax_rows(logp_out, R, st));
+    P.reset_mask = reset_mask;
+    P.cond = cond;
+    P.cond_is_f64 = cond_is_f64;
+    P.spk = spk;
     P.valid = true;
     return SRNN_OK;
+}
+
+// Backward of srnn_predict_fwd (the autograd the reference gets from torch, trainer/__init__.py:103).  Must follow the
+// forward call it differentiates on the same context.  logp = that call's output, dlogp = dL/dlogp (B,T,Q);
+// params = the same raw tensors given to srnn_pack_weights; grads = same struct of WRITABLE gradient buffers
+// (entries may be null to skip).  Every non-null gradient is overwritten, not accumulated.
+int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* params,
+                     const srnn_params* grads, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    if (!logp || !dlogp || !params || !grads) return fail(SRNN_ERR_ARG, "null argument");
+    if (!ctx->fwd.valid) return fail(SRNN_ERR_STATE, "srnn_predict_bwd needs a preceding srnn_predict_fwd on this context");
+    if (ctx->fwd.mode != SRNN_MODE_FP32) return fail(SRNN_ERR_UNSUPPORTED, "backward is available for SRNN_MODE_FP32 forward passes");
+    const int rc = predict_bwd_f32(ctx, logp, dlogp, params, grads, (cudaStream_t)stream);
+    ctx->fwd.valid = false;
+    return rc;
+}
+
+// optim.py:10-13 (element-wise clamp of every gradient to [-clamp, clamp]) fused with torch.optim.Adam's update
+// (train.py:238; no weight decay / amsgrad) over `count` tensors in one launch.  step = 1, 2, ... (bias correction).
+int srnn_clamp_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2, float eps,
+                         int32_t step, float clamp, void* stream) {
+    if (count < 0 || (count && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes))) return fail(SRNN_ERR_ARG, "bad argument");
+    if (step < 1) return fail(SRNN_ERR_ARG, "step must be >= 1");
+    return clamp_adam(count, params, grads, exp_avg, exp_avg_sq, (const long long*)sizes, lr, beta1, beta2, eps, step, clamp,
+                      (cudaStream_t)stream);
 }
 
 // mean NLL in bits of log-probabilities against targets (nn.py:66-70); loss_out = one device float

@@ -1,0 +1,592 @@
+// Teacher-forced backward pass (the autograd of Predictor.forward, trainer/__init__.py:99-103) and the fused
+// clamp + Adam update (optim.py:4-21 + torch.optim.Adam, train.py:238-241).
+//
+// This is the fp32 (SRNN_MODE_FP32) implementation: every contraction is an FFMA tile GEMM with arbitrary operand
+// strides, so the three GEMM forms of back-propagation (dIn = dOut.W, dW = dOut^T.In, and the forward form) share one
+// kernel.  The embedding-o-conv fold of the forward pass is differentiated exactly: dTbl is a bucketed row sum of
+// dpre1 by sample value (deterministic, no atomics), then folded back onto W_in and E.
+#include "common.cuh"
+
+namespace srnn {
+
+// ------------------------------------------------------------------------------------------------
+// C[m,n] = sum_k A(m,k) * B(n,k) (+ add[m,n]);  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]
+// ------------------------------------------------------------------------------------------------
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+__global__ void __launch_bounds__(256)
+k_gemm_f32_strided(int M, int N, int K, const float* __restrict__ A, long long sam, long long sak,
+                   const float* __restrict__ B, long long sbn, long long sbk, const float* add, int ldadd, float* C,
+                   int ldc) {
+    __shared__ float As[SBK][SBM + 4];
+    __shared__ float Bs[SBK][SBN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += SBK) {
+        for (int i = tid; i < SBM * SBK; i += 256) {
+            int r, c;
+            if (sak == 1) { r = i / SBK; c = i % SBK; } else { c = i / SBM; r = i % SBM; }   // walk the unit-stride index fastest
+            const int gm = m0 + r, gk = k0 + c;
+            As[c][r] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+        }
+        for (int i = tid; i < SBN * SBK; i += 256) {
+            int r, c;
+            if (sbk == 1) { r = i / SBK; c = i % SBK; } else { c = i / SBN; r = i % SBN; }
+            const int gn = n0 + r, gk = k0 + c;
+            Bs[c][r] = (gn < N && gk < K) ? B[gn * sbn + gk * sbk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SBK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (add) v += add[(size_t)gm * ldadd + gn];
+            C[(size_t)gm * ldc + gn] = v;
+        }
+    }
+}
+
+static int gemm_s(int M, int N, int K, const float* A, long long sam, long long sak, const float* B, long long sbn,
+                  long long sbk, const float* add, int ldadd, float* C, int ldc, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return SRNN_OK;
+    dim3 grid(cdiv(N, SBN), cdiv(M, SBM));
+    SRNN_LAUNCH(k_gemm_f32_strided, grid, 256, 0, st, M, N, K, A, sam, sak, B, sbn, sbk, add, ldadd, C, ldc);
+    return SRNN_OK;
+}
+// dIn (rows, K) = dOut (rows, N) . W (N, K)  [+ add]
+static int gemm_dx(int rows, int Kdim, int Ndim, const float* dOut, int ld_do, const float* W, int ld_w, const float* add,
+                   int ldadd, float* dIn, int ld_di, cudaStream_t st) {
+    return gemm_s(rows, Kdim, Ndim, dOut, ld_do, 1, W, 1, ld_w, add, ldadd, dIn, ld_di, st);
+}
+// dW (N, K) = dOut (rows, N)^T . In (rows, K)
+static int gemm_dw(int Ndim, int Kdim, int rows, const float* dOut, int ld_do, const float* In, int ld_in, float* dW,
+                   int ld_dw, cudaStream_t st) {
+    return gemm_s(Ndim, Kdim, rows, dOut, 1, ld_do, In, 1, ld_in, nullptr, 0, dW, ld_dw, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise / reduction kernels
+// ------------------------------------------------------------------------------------------------
+// log_softmax backward, one warp per 256-wide row: dlogits = dlogp - exp(logp) * sum(dlogp)
+__global__ void k_logsoftmax_bwd(const float* __restrict__ dlogp, const float* __restrict__ logp, float* __restrict__ dlogits,
+                                 int rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const size_t o = (size_t)row * SRNN_Q + lane * 8;
+    float g[8], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = dlogp[o + i]; s += g[i]; }
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dlogits[o + i] = g[i] - expf(logp[o + i]) * s;
+}
+
+__global__ void k_relu_mask(const float* __restrict__ dx, const float* __restrict__ x, float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = x[i] > 0.f ? dx[i] : 0.f;
+}
+
+// column sums of X (rows, cols, ld): stage 1 -> partial[chunk][col], stage 2 -> out[col] (fixed order)
+constexpr int CS_CHUNKS = 64;
+__global__ void k_colsum_partial(const float* __restrict__ X, int rows, int cols, int ld, float* __restrict__ partial) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    const int per = (rows + CS_CHUNKS - 1) / CS_CHUNKS;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += X[(size_t)r * ld + col];
+    partial[(size_t)blockIdx.y * cols + col] = s;
+}
+__global__ void k_colsum_final(const float* __restrict__ partial, int cols, float* __restrict__ out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    float s = 0.f;
+    for (int c = 0; c < CS_CHUNKS; ++c) s += partial[(size_t)c * cols + col];
+    out[col] = s;
+}
+static int colsum(const float* X, int rows, int cols, int ld, float* partial, float* out, cudaStream_t st) {
+    SRNN_LAUNCH(k_colsum_partial, dim3(cdiv(cols, 128), CS_CHUNKS), 128, 0, st, X, rows, cols, ld, partial);
+    SRNN_LAUNCH(k_colsum_final, cdiv(cols, 128), 128, 0, st, partial, cols, out);
+    return SRNN_OK;
+}
+
+// out = a + b (+ c)
+__global__ void k_add3(const float* a, const float* b, const float* c, float* out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dTbl[j][q][h] = sum over rows r=(b,t) with seq[b, off + t + j] == q of dpre1[r][h]   (bucketed, deterministic)
+// grid (H/64, FS, DT_CHUNKS), 64 threads (one feature each), smem table [256][64]
+// ------------------------------------------------------------------------------------------------
+constexpr int DT_CHUNKS = 4;
+__global__ void __launch_bounds__(64)
+k_dtbl_partial(const uint8_t* __restrict__ seq, int seq_ld, int off, const float* __restrict__ dpre1, int B, int T, int H,
+               float* __restrict__ partial /* (DT_CHUNKS, FS, Q, H) */, int FS) {
+    extern __shared__ float tab[];        // [256][64]
+    const int h = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y, ch = blockIdx.z;
+    for (int i = threadIdx.x; i < SRNN_Q * 64; i += 64) tab[i] = 0.f;
+    __syncthreads();
+    const int R = B * T, per = (R + DT_CHUNKS - 1) / DT_CHUNKS;
+    const int r0 = ch * per, r1 = min(R, r0 + per);
+    if (h < H) {
+        for (int r = r0; r < r1; ++r) {
+            const int b = r / T, t = r % T;
+            const int q = seq[(size_t)b * seq_ld + off + t + j];
+            tab[q * 64 + threadIdx.x] += dpre1[(size_t)r * H + h];
+        }
+        for (int q = 0; q < SRNN_Q; ++q)
+            partial[(((size_t)ch * FS + j) * SRNN_Q + q) * H + h] = tab[q * 64 + threadIdx.x];
+    }
+}
+__global__ void k_dtbl_final(const float* __restrict__ partial, size_t n, float* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < DT_CHUNKS; ++c) s += partial[(size_t)c * n + i];
+        out[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU cell backward for one frame (all utterances): recomputes r, z, n from the saved projections
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gru_bwd_gates(const float* __restrict__ gi, const float* __restrict__ gh, int g_ld,
+                                const float* __restrict__ h_prev, int hp_ld, const float* __restrict__ dy, int dy_ld,
+                                const float* __restrict__ dh_carry, float* __restrict__ dgi, float* __restrict__ dgh,
+                                float* __restrict__ dh_prev, int H) {
+    const int b = blockIdx.y;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= H) return;
+    const float* gir = gi + (size_t)b * g_ld;
+    const float* ghr = gh + (size_t)b * g_ld;
+    const float r = 1.f / (1.f + expf(-(gir[u] + ghr[u])));
+    const float z = 1.f / (1.f + expf(-(gir[H + u] + ghr[H + u])));
+    const float ghn = ghr[2 * H + u];
+    const float n = tanhf(gir[2 * H + u] + r * ghn);
+    const float hp = h_prev[(size_t)b * hp_ld + u];
+    float dh = dy[(size_t)b * dy_ld + u];
+    if (dh_carry) dh += dh_carry[(size_t)b * H + u];
+    const float dn = dh * (1.f - z);
+    const float dz = dh * (hp - n);
+    const float dpn = dn * (1.f - n * n);
+    const float dr = dpn * ghn;
+    const float dpr = dr * r * (1.f - r);
+    const float dpz = dz * z * (1.f - z);
+    float* dgir = dgi + (size_t)b * g_ld;
+    float* dghr = dgh + (size_t)b * g_ld;
+    dgir[u] = dpr;          dghr[u] = dpr;
+    dgir[H + u] = dpz;      dghr[H + u] = dpz;
+    dgir[2 * H + u] = dpn;  dghr[2 * H + u] = dpn * r;
+    dh_prev[(size_t)b * H + u] = dh * z;
+}
+
+// Hprev[(b,f), :] = f ? Y[(b,f-1), :] : h0[b, :]   (the recurrent input of every frame, for dW_hh)
+__global__ void k_build_hprev(const float* __restrict__ Y, const float* __restrict__ h0, float* __restrict__ hp, int F, int H) {
+    const int r = blockIdx.x, b = r / F, f = r % F;
+    const float* src = f ? Y + (size_t)(r - 1) * H : h0 + (size_t)b * H;
+    for (int u = threadIdx.x; u < H; u += blockDim.x) hp[(size_t)r * H + u] = src[u];
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-norm backward per row: w = g v/||v||  =>  dg = <dw, v>/||v||,  dv = g/||v|| (dw - v <dw,v>/||v||^2)
+// (plain weight: dweight = dw)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_wn_bwd(const float* __restrict__ dw, const float* __restrict__ g, const float* __restrict__ v,
+                         float* __restrict__ dweight, float* __restrict__ dg, float* __restrict__ dv, int cols) {
+    const int r = blockIdx.x;
+    const float* dwr = dw + (size_t)r * cols;
+    if (dweight) {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) dweight[(size_t)r * cols + c] = dwr[c];
+        return;
+    }
+    __shared__ float red0[32], red1[32];
+    __shared__ float s_vv, s_dv;
+    const float* vr = v + (size_t)r * cols;
+    float vv = 0.f, dvv = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        vv = fmaf(vr[c], vr[c], vv);
+        dvv = fmaf(dwr[c], vr[c], dvv);
+    }
+    for (int o = 16; o; o >>= 1) {
+        vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        dvv += __shfl_xor_sync(0xffffffffu, dvv, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red0[threadIdx.x >> 5] = vv; red1[threadIdx.x >> 5] = dvv; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float a = threadIdx.x < (blockDim.x >> 5) ? red0[threadIdx.x] : 0.f;
+        float b = threadIdx.x < (blockDim.x >> 5) ? red1[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (threadIdx.x == 0) { s_vv = a; s_dv = b; }
+    }
+    __syncthreads();
+    const float nrm = sqrtf(s_vv), gg = g[r];
+    if (threadIdx.x == 0 && dg) dg[r] = s_dv / nrm;
+    if (dv) {
+        const float sc = gg / nrm, proj = s_dv / s_vv;
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) dv[(size_t)r * cols + c] = sc * (dwr[c] - vr[c] * proj);
+    }
+}
+static int wn_bwd(const float* dw, const srnn_conv_params& p, const srnn_conv_params& g, int rows, int cols, cudaStream_t st) {
+    float* dweight = (float*)g.weight;
+    float* dg = (float*)g.weight_g;
+    float* dv = (float*)g.weight_v;
+    if (p.weight) {
+        if (!dweight) return SRNN_OK;
+        SRNN_LAUNCH(k_wn_bwd, rows, 256, 0, st, dw, nullptr, nullptr, dweight, nullptr, nullptr, cols);
+    } else {
+        if (!dg && !dv) return SRNN_OK;
+        SRNN_LAUNCH(k_wn_bwd, rows, 256, 0, st, dw, p.weight_g, p.weight_v, nullptr, dg, dv, cols);
+    }
+    return SRNN_OK;
+}
+
+// dW_up packed ((j*H+o), c) -> conv_t gradient layout (c, o, j); packed bias gradient (j*H+o) -> (o, j)
+__global__ void k_unpack_up_grad(const float* __restrict__ dwp, const float* __restrict__ dbp, float* __restrict__ dwf,
+                                 float* __restrict__ dbias, int H, int k) {
+    const int row = blockIdx.x;           // j*H + o
+    const int j = row / H, o = row % H;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) dwf[((size_t)c * H + o) * k + j] = dwp[(size_t)row * H + c];
+    if (threadIdx.x == 0 && dbias) dbias[o * k + j] = dbp[row];
+}
+
+// top tier: gradient of the K-concatenated matrix (H, n + cond_dim + spk_dim) -> its three sources
+__global__ void k_unpack_top_in(const float* __restrict__ dcomb, float* __restrict__ d_in, float* __restrict__ d_c,
+                                float* __restrict__ d_s /* (H, spk_dim) wrt folded spk_expand */, const float* __restrict__ emb,
+                                int n, int cond_dim, int spk_dim) {
+    const int h = blockIdx.x, kin = n + cond_dim + spk_dim;
+    const float* r = dcomb + (size_t)h * kin;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d_in[(size_t)h * n + i] = r[i];
+    for (int i = threadIdx.x; i < cond_dim; i += blockDim.x) d_c[(size_t)h * cond_dim + i] = r[n + i];
+    for (int e = threadIdx.x; e < spk_dim; e += blockDim.x) {      // comb[h,s] = sum_e w_s[h,e] E[s,e]
+        float a = 0.f;
+        for (int s = 0; s < spk_dim; ++s) a = fmaf(r[n + cond_dim + s], emb[s * spk_dim + e], a);
+        d_s[(size_t)h * spk_dim + e] = a;
+    }
+}
+// dEmb[s,e] = sum_h dcomb[h, n+cond_dim+s] * w_s[h,e]
+__global__ void k_spk_emb_grad(const float* __restrict__ dcomb, const float* __restrict__ w_s, float* __restrict__ demb,
+                               int H, int kin, int off, int spk_dim) {
+    const int s = blockIdx.x / spk_dim, e = blockIdx.x % spk_dim;
+    __shared__ float red[128];
+    float a = 0.f;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) a = fmaf(dcomb[(size_t)h * kin + off + s], w_s[(size_t)h * spk_dim + e], a);
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 64; o; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) demb[s * spk_dim + e] = red[0];
+}
+
+// (FS, H, Q) -> (H, Q, FS)
+__global__ void k_untranspose_mlp_in(const float* __restrict__ wt, float* __restrict__ w, int H, int Q, int FS) {
+    const int h = blockIdx.x, j = blockIdx.y;
+    for (int e = threadIdx.x; e < Q; e += blockDim.x) w[((size_t)h * Q + e) * FS + j] = wt[((size_t)j * H + h) * Q + e];
+}
+
+static inline int gsz(size_t n) { return (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256); }
+
+// ------------------------------------------------------------------------------------------------
+// orchestration
+// ------------------------------------------------------------------------------------------------
+struct Bump2 {
+    char* base;
+    size_t off;
+    Bump2(void* b, size_t o) : base((char*)b), off(o) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T) {
+    const srnn_config& c = ctx->cfg;
+    const size_t H = ctx->H, Q = ctx->Q, R = (size_t)B * T, FS0 = ctx->FS0;
+    size_t maxM = 0, maxfs = 1, maxkin = 1;
+    for (int i = 0; i < c.n_tiers; ++i) {
+        const size_t M = (size_t)B * (T / ctx->tiers[i].n);
+        if (M > maxM) maxM = M;
+        if ((size_t)ctx->tiers[i].fs > maxfs) maxfs = ctx->tiers[i].fs;
+        if ((size_t)ctx->tiers[i].kin > maxkin) maxkin = ctx->tiers[i].kin;
+    }
+    size_t f = R * Q + 2 * R * H                                // dlogits, dA, dB
+               + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H   // dY ping/pong, dX, dGI, dGH, carries
+               + maxfs * H * H * 2 + maxfs * H + H * maxkin + H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin)   // weight-grad staging
+               + (DT_CHUNKS + 1) * FS0 * Q * H + 2 * FS0 * H * Q            // dTbl partials + final, dWm_t, dWm
+               + (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + Q + 4096;
+    return f * sizeof(float) + 64 * 256;
+}
+
+int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
+                    cudaStream_t st) {
+    const FwdPlan& F = ctx->fwd;
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
+    const int B = F.B, T = F.T, R = B * T, Lseq = lookback + T - 1;
+    if (F.bytes + backward_scratch_bytes(ctx, B, T) > ctx->ws_bytes)
+        return fail(SRNN_ERR_STATE, "backward scratch was not reserved by the forward pass");
+    int maxfs = 1, maxkin = 1;
+    size_t maxM = 0;
+    for (int i = 0; i < NT; ++i) {
+        const size_t M = (size_t)B * (T / ctx->tiers[i].n);
+        if (M > maxM) maxM = M;
+        if (ctx->tiers[i].fs > maxfs) maxfs = ctx->tiers[i].fs;
+        if (ctx->tiers[i].kin > maxkin) maxkin = ctx->tiers[i].kin;
+    }
+    Bump2 b(ctx->ws, F.bytes);
+    float* dlogits = b.take<float>((size_t)R * Q);
+    float* dA = b.take<float>((size_t)R * H);
+    float* dB = b.take<float>((size_t)R * H);
+    float* dYa = b.take<float>(maxM * H);
+    float* dYb = b.take<float>(maxM * H);
+    float* dXbuf[2] = {b.take<float>(maxM * H), nullptr};
+    float* dGI = b.take<float>(maxM * 3 * H);
+    float* dGH = b.take<float>(maxM * 3 * H);
+    float* dhc0 = b.take<float>((size_t)B * H);
+    float* dhc1 = b.take<float>((size_t)B * H);
+    float* dWup = b.take<float>((size_t)maxfs * H * H);
+    float* dwf = b.take<float>((size_t)maxfs * H * H);
+    float* dbup = b.take<float>((size_t)maxfs * H);
+    float* dWin = b.take<float>((size_t)H * maxkin);
+    float* wsf = b.take<float>((size_t)H * c.spk_dim);
+    const size_t stg = (size_t)H * (H > maxkin ? H : maxkin);
+    float* t_in = b.take<float>(stg);
+    float* t_c = b.take<float>(stg);
+    float* t_s = b.take<float>(stg);
+    float* dTblP = b.take<float>((size_t)DT_CHUNKS * FS0 * Q * H);
+    float* dTbl = b.take<float>((size_t)FS0 * Q * H);
+    float* dWmt = b.take<float>((size_t)FS0 * H * Q);
+    float* dWm = b.take<float>((size_t)FS0 * H * Q);
+    float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
+    float* dbtmp = b.take<float>((size_t)3 * H);
+    float* dWo = b.take<float>((size_t)Q * H);
+    float* wmf = dWm;   // folded mlp-input weights (H,Q,FS0) are rebuilt into dWm's storage before it is needed (see below)
+    (void)wmf;
+
+    // ---- log_softmax backward ----
+    SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
+    // ---- output layer: logits = x2 W_o^T + b_o ----
+    SRNN_TRY(gemm_dw(Q, H, R, dlogits, Q, F.X2, H, dWo, H, st));
+    SRNN_TRY(wn_bwd(dWo, P->mlp_output, G->mlp_output, Q, H, st));
+    if (G->mlp_output.bias) SRNN_TRY(colsum(dlogits, R, Q, Q, csp, (float*)G->mlp_output.bias, st));
+    SRNN_TRY(gemm_dx(R, H, Q, dlogits, Q, ctx->w_out, H, nullptr, 0, dA, H, st));               // dx2
+    SRNN_LAUNCH(k_relu_mask, gsz((size_t)R * H), 256, 0, st, dA, F.X2, dA, (size_t)R * H);        // dpre2
+    // ---- hidden layer ----
+    SRNN_TRY(gemm_dw(H, H, R, dA, H, F.X1, H, t_in, H, st));
+    SRNN_TRY(wn_bwd(t_in, P->mlp_hidden, G->mlp_hidden, H, H, st));
+    if (G->mlp_hidden.bias) SRNN_TRY(colsum(dA, R, H, H, csp, (float*)G->mlp_hidden.bias, st));
+    SRNN_TRY(gemm_dx(R, H, H, dA, H, ctx->w_hid, H, nullptr, 0, dB, H, st));                    // dx1
+    SRNN_LAUNCH(k_relu_mask, gsz((size_t)R * H), 256, 0, st, dB, F.X1, dB, (size_t)R * H);        // dpre1 = dc0
+    // ---- folded table: dTbl, then back onto W_in (H,Q,FS) and E (Q,Q) ----
+    {
+        static bool dt_attr = false;
+        if (!dt_attr) {
+            SRNN_CUDA(cudaFuncSetAttribute(k_dtbl_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, SRNN_Q * 64 * (int)sizeof(float)));
+            dt_attr = true;
+        }
+        SRNN_LAUNCH(k_dtbl_partial, dim3(cdiv(H, 64), FS0, DT_CHUNKS), 64, SRNN_Q * 64 * sizeof(float), st, F.seq, Lseq,
+                    lookback - FS0, dB, B, T, H, dTblP, FS0);
+        const size_t n = (size_t)FS0 * Q * H;
+        SRNN_LAUNCH(k_dtbl_final, gsz(n), 256, 0, st, dTblP, n, dTbl);
+        // folded W_in^T per tap (FS,H,Q) is rebuilt into dTblP's storage (no longer needed)
+        float* wm_fold = dTblP;                       // (H, Q, FS)
+        float* wm_t = dTblP + (size_t)H * Q * FS0;    // (FS, H, Q)
+        SRNN_TRY(wn_fold(P->mlp_input, wm_fold, H, Q * FS0, st));
+        SRNN_TRY(transpose_mlp_in(wm_fold, wm_t, H, Q, FS0, st));
+        float* dE = (float*)G->embedding;
+        for (int j = 0; j < FS0; ++j) {
+            const float* dT = dTbl + (size_t)j * Q * H;            // (Q, H)
+            // dWm_t[j] (H, Q=e) = sum_q dT[q, h] * E[q, e]
+            SRNN_TRY(gemm_s(H, Q, Q, dT, 1, H, P->embedding, 1, Q, nullptr, 0, dWmt + (size_t)j * H * Q, Q, st));
+            // dE (Q, e) += sum_h dT[q, h] * wm_t[j][h, e]
+            if (dE) SRNN_TRY(gemm_s(Q, Q, H, dT, H, 1, wm_t + (size_t)j * H * Q, 1, Q, j ? dE : nullptr, Q, dE, Q, st));
+        }
+        SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
+        SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
+    }
+    // ---- frame tiers, lowest first: each receives dUP (M, fs*H) from below ----
+    const float* dUP = dB;                            // tier 0's upsampled output is the MLP conditioning c0
+    int xb = 0;
+    for (int i = 0; i < NT; ++i) {
+        const TierPacked& t = ctx->tiers[i];
+        const srnn_tier_params& tp = P->tiers[i];
+        const srnn_tier_params& tg = G->tiers[i];
+        const int Fr = T / t.n, M = B * Fr;
+        // upsampling: UP = Y_last W_up^T + b_up
+        const float* Ylast = F.Y[i][NL - 1];
+        SRNN_TRY(gemm_dw(t.fs * H, H, M, dUP, t.fs * H, Ylast, H, dWup, H, st));
+        SRNN_TRY(colsum(dUP, M, t.fs * H, t.fs * H, csp, dbup, st));
+        SRNN_LAUNCH(k_unpack_up_grad, t.fs * H, 128, 0, st, dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs);
+        SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
+        float* dY = dYa;
+        float* dYn = dYb;
+        SRNN_TRY(gemm_dx(M, H, t.fs * H, dUP, t.fs * H, t.w_up, H, nullptr, 0, dY, H, st));
+        // GRU layers, last first (BPTT inside each)
+        for (int l = NL - 1; l >= 0; --l) {
+            const float* GI = F.GI[i][l];
+            const float* GH = F.GH[i][l];
+            const float* Y = F.Y[i][l];
+            const float* h0 = F.H0[i] + (size_t)l * B * H;
+            float* carry = nullptr;
+            float* cnext = dhc0;
+            for (int f = Fr - 1; f >= 0; --f) {
+                const float* hp = f ? Y + (size_t)(f - 1) * H : h0;
+                const int hp_ld = f ? Fr * H : H;
+                float* part = (cnext == dhc0) ? dhc1 : dhc0;      // dh*z lands here, the GEMM adds dGH.W_hh into cnext
+                SRNN_LAUNCH(k_gru_bwd_gates, dim3(cdiv(H, 128), B), 128, 0, st, GI + (size_t)f * 3 * H, GH + (size_t)f * 3 * H,
+                            Fr * 3 * H, hp, hp_ld, dY + (size_t)f * H, Fr * H, carry, dGI + (size_t)f * 3 * H,
+                            dGH + (size_t)f * 3 * H, part, H);
+                // dh_{f-1} = dh*z + dGH_f . W_hh
+                SRNN_TRY(gemm_s(B, H, 3 * H, dGH + (size_t)f * 3 * H, (long long)Fr * 3 * H, 1, t.w_hh[l], 1, H, part, H, cnext, H, st));
+                carry = cnext;
+                cnext = part;
+            }
+            // carry = dL/dh_{-1} (B,H): gradient of the learned initial state when this pass started from it
+            float* dh0 = (float*)tg.h0;
+            if (dh0) {
+                if ((F.reset_mask >> i) & 1) SRNN_TRY(colsum(carry, B, H, H, csp, dh0 + (size_t)l * H, st));
+                else SRNN_CUDA(cudaMemsetAsync(dh0 + (size_t)l * H, 0, sizeof(float) * H, st));   // carried state is detached
+            }
+            // recurrent weights: dW_hh = dGH^T . Hprev, rows (b,f) with Hprev = h_{f-1}
+            float* dWhh = (float*)tg.weight_hh[l];
+            if (dWhh) {
+                SRNN_LAUNCH(k_build_hprev, M, 128, 0, st, Y, h0, dYn, Fr, H);      // dYn is free until `din` below
+                SRNN_TRY(gemm_dw(3 * H, H, M, dGH, 3 * H, dYn, H, dWhh, H, st));
+            }
+            if (tg.bias_hh[l]) SRNN_TRY(colsum(dGH, M, 3 * H, 3 * H, csp, (float*)tg.bias_hh[l], st));
+            // input weights
+            const float* in = l ? F.Y[i][l - 1] : F.X[i];
+            if (tg.weight_ih[l]) SRNN_TRY(gemm_dw(3 * H, H, M, dGI, 3 * H, in, H, (float*)tg.weight_ih[l], H, st));
+            if (tg.bias_ih[l]) SRNN_TRY(colsum(dGI, M, 3 * H, 3 * H, csp, (float*)tg.bias_ih[l], st));
+            // gradient wrt this layer's input = dY of the layer below (or dX)
+            float* din = l ? dYn : dXbuf[0];
+            SRNN_TRY(gemm_dx(M, H, 3 * H, dGI, 3 * H, t.w_ih[l], H, nullptr, 0, din, H, st));
+            if (l) { float* tmp = dY; dY = dYn; dYn = tmp; }
+        }
+        float* dX = dXbuf[0];
+        // input expansion: X = A W_in^T + b_in (+ upper)
+        SRNN_TRY(gemm_dw(H, t.kin, M, dX, H, F.A[i], t.kin, dWin, t.kin, st));
+        SRNN_TRY(colsum(dX, M, H, H, csp, dbtmp, st));
+        if (t.top) {
+            SRNN_TRY(wn_fold(tp.spk_expand, wsf, H, c.spk_dim, st));
+            SRNN_LAUNCH(k_unpack_top_in, H, 128, 0, st, dWin, t_in, t_c, t_s, tp.spk_embedding, t.n, c.cond_dim, c.spk_dim);
+            SRNN_TRY(wn_bwd(t_in, tp.input_expand, tg.input_expand, H, t.n, st));
+            SRNN_TRY(wn_bwd(t_c, tp.cond_expand, tg.cond_expand, H, c.cond_dim, st));
+            SRNN_TRY(wn_bwd(t_s, tp.spk_expand, tg.spk_expand, H, c.spk_dim, st));
+            if (tg.spk_embedding)
+                SRNN_LAUNCH(k_spk_emb_grad, c.spk_dim * c.spk_dim, 128, 0, st, dWin, wsf, (float*)tg.spk_embedding, H, t.kin,
+                            t.n + c.cond_dim, c.spk_dim);
+            if (tg.input_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.input_expand.bias, H, st));
+            if (tg.cond_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.cond_expand.bias, H, st));
+            if (tg.spk_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.spk_expand.bias, H, st));
+        } else {
+            SRNN_TRY(wn_bwd(dWin, tp.input_expand, tg.input_expand, H, t.n, st));
+            if (tg.input_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.input_expand.bias, H, st));
+            // d upper = dX: same memory viewed as (M_{i+1}, fs_{i+1}*H).  Keep it alive while the tier above runs.
+            SRNN_TRY(copy_f32(dX, dA, (size_t)M * H, st));     // dA (R*H floats) is free by now
+            dUP = dA;
+        }
+        (void)xb;
+    }
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused element-wise clamp to [-1, 1] + Adam over up to 64 tensors in one launch
+// ------------------------------------------------------------------------------------------------
+constexpr int ADAM_MAX = 64, ADAM_CHUNK = 4096;
+struct AdamArgs {
+    float* p[ADAM_MAX];
+    const float* g[ADAM_MAX];
+    float* m[ADAM_MAX];
+    float* v[ADAM_MAX];
+    int first_chunk[ADAM_MAX + 1];
+    long long n[ADAM_MAX];
+    int count;
+    float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, clamp;
+};
+__global__ void k_clamp_adam(const __grid_constant__ AdamArgs a) {
+    int t = 0;
+    while (t + 1 < a.count && (int)blockIdx.x >= a.first_chunk[t + 1]) ++t;
+    const long long base = (long long)((int)blockIdx.x - a.first_chunk[t]) * ADAM_CHUNK;
+    float* __restrict__ p = a.p[t];
+    const float* __restrict__ g = a.g[t];
+    float* __restrict__ m = a.m[t];
+    float* __restrict__ v = a.v[t];
+    for (int i = threadIdx.x; i < ADAM_CHUNK; i += blockDim.x) {
+        const long long idx = base + i;
+        if (idx >= a.n[t]) break;
+        float gg = fminf(fmaxf(g[idx], -a.clamp), a.clamp);                 // optim.py:10-13 hardtanh
+        const float mm = a.beta1 * m[idx] + (1.f - a.beta1) * gg;
+        const float vv = a.beta2 * v[idx] + (1.f - a.beta2) * gg * gg;
+        m[idx] = mm;
+        v[idx] = vv;
+        p[idx] -= a.lr_over_bc1 * mm / (sqrtf(vv) * a.inv_sqrt_bc2 + a.eps);
+    }
+}
+
+int clamp_adam(int count, float* const* params, const float* const* grads, float* const* m, float* const* v,
+               const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st) {
+    for (int s0 = 0; s0 < count; s0 += ADAM_MAX) {
+        AdamArgs a;
+        memset(&a, 0, sizeof(a));
+        const int cnt = count - s0 < ADAM_MAX ? count - s0 : ADAM_MAX;
+        int chunks = 0;
+        for (int i = 0; i < cnt; ++i) {
+            a.p[i] = params[s0 + i];
+            a.g[i] = grads[s0 + i];
+            a.m[i] = m[s0 + i];
+            a.v[i] = v[s0 + i];
+            a.n[i] = sizes[s0 + i];
+            a.first_chunk[i] = chunks;
+            chunks += (int)((sizes[s0 + i] + ADAM_CHUNK - 1) / ADAM_CHUNK);
+        }
+        a.first_chunk[cnt] = chunks;
+        a.count = cnt;
+        const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+        a.lr_over_bc1 = (float)(lr / bc1);
+        a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+        a.beta1 = beta1;
+        a.beta2 = beta2;
+        a.eps = eps;
+        a.clamp = clamp;
+        if (chunks) SRNN_LAUNCH(k_clamp_adam, chunks, 256, 0, st, a);
+    }
+    return SRNN_OK;
+}
+
+}  // namespace srnn

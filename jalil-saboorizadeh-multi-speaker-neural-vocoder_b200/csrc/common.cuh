@@ -78,7 +78,10 @@ namespace srnn {
 // backward pass.  Row index of frame-level tensors = b*F + f; of sample-level tensors = b*T + t.
 struct FwdPlan {
     bool valid = false;
-    int B = 0, T = 0, mode = 0;
+    int B = 0, T = 0, mode = 0, reset_mask = 0;
+    const void* cond = nullptr;   // caller's conditioner / speaker tensors of that pass (must stay alive until backward)
+    int cond_is_f64 = 0;
+    const int64_t* spk = nullptr;
     uint8_t* seq = nullptr;                                   // (B, lookback+T-1)
     float* A[SRNN_MAX_TIERS] = {};                            // (M, kin) assembled tier inputs
     float* X[SRNN_MAX_TIERS] = {};                            // (M, H) GRU layer-0 input
@@ -174,6 +177,13 @@ int sample_rows(const float* p, const float* u, int rows, int* idx, cudaStream_t
 int dequant_audio(const uint8_t* seq, int seq_ld, int off, const float* lut, uint8_t* samples, float* audio,
                   int B, int T, cudaStream_t st);
 int add_int(int* p, int v, cudaStream_t st);
+
+// ---- backward pass + optimizer (backward.cu) --------------------------------------------------------
+size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T);
+int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
+                    cudaStream_t st);
+int clamp_adam(int count, float* const* params, const float* const* grads, float* const* m, float* const* v,
+               const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st);
 
 // ---- tcgen05 / TMA kernels (gemm_umma.cu) ------------------------------------------------------------
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,

@@ -57,14 +57,17 @@ class _Conv(tnn.Module):
         if bias_len is not None:
             self.bias = tnn.Parameter(torch.zeros(bias_len))
 
-    def c_params(self, bias=None):
+    def c_params(self, bias=None, ptr=None):
+        """``ptr`` maps a parameter tensor to the device pointer to bind (its data by default, its gradient buffer for
+        the backward pass; None skips the entry)."""
+        ptr = ptr or (lambda t: t.data_ptr())
         p = L.ConvParams()
         if hasattr(self, "weight"):
-            p.weight = self.weight.data_ptr()
+            p.weight = ptr(self.weight)
         else:
-            p.weight_g, p.weight_v = self.weight_g.data_ptr(), self.weight_v.data_ptr()
+            p.weight_g, p.weight_v = ptr(self.weight_g), ptr(self.weight_v)
         b = bias if bias is not None else getattr(self, "bias", None)
-        p.bias = b.data_ptr() if b is not None else None
+        p.bias = ptr(b) if b is not None else None
         return p
 
 
@@ -212,6 +215,30 @@ class SampleRNN(tnn.Module):
     def _tensors(self):
         return list(self.parameters()) + list(self.buffers())
 
+    def _c_params(self, ptr=None):
+        """srnn_params over the parameter tensors (``ptr`` = tensor -> device pointer or None, see _Conv.c_params)."""
+        ptr = ptr or (lambda t: t.data_ptr())
+        P = L.Params()
+        for i, rnn in enumerate(self.frame_level_rnns):
+            tp = P.tiers[i]
+            tp.h0 = ptr(rnn.h0)
+            tp.input_expand = rnn.input_expand.c_params(ptr=ptr)
+            if rnn.cond_expand is not None:
+                tp.cond_expand = rnn.cond_expand.c_params(ptr=ptr)
+                tp.spk_embedding = ptr(rnn.spk_embedding.weight)
+                tp.spk_expand = rnn.spk_expand.c_params(ptr=ptr)
+            for l in range(self.n_rnn):
+                tp.weight_ih[l] = ptr(getattr(rnn.rnn, f"weight_ih_l{l}"))
+                tp.weight_hh[l] = ptr(getattr(rnn.rnn, f"weight_hh_l{l}"))
+                tp.bias_ih[l] = ptr(getattr(rnn.rnn, f"bias_ih_l{l}"))
+                tp.bias_hh[l] = ptr(getattr(rnn.rnn, f"bias_hh_l{l}"))
+            tp.upsampling = rnn.upsampling.conv_t.c_params(bias=rnn.upsampling.bias, ptr=ptr)
+        mlp = self.sample_level_mlp
+        P.embedding = ptr(mlp.embedding.weight)
+        P.mlp_input, P.mlp_hidden, P.mlp_output = (mlp.input.c_params(ptr=ptr), mlp.hidden.c_params(ptr=ptr),
+                                                   mlp.output.c_params(ptr=ptr))
+        return P
+
     def _ensure_packed(self):
         """Re-snapshot the parameters into kernel layouts when any of them changed (in-place or re-allocated)."""
         ctx = self._context()
@@ -222,24 +249,7 @@ class SampleRNN(tnn.Module):
         key = tuple((t.data_ptr(), t._version) for t in ts)
         if key == self._packed_key:
             return ctx
-        P = L.Params()
-        for i, rnn in enumerate(self.frame_level_rnns):
-            tp = P.tiers[i]
-            tp.h0 = rnn.h0.data_ptr()
-            tp.input_expand = rnn.input_expand.c_params()
-            if rnn.cond_expand is not None:
-                tp.cond_expand = rnn.cond_expand.c_params()
-                tp.spk_embedding = rnn.spk_embedding.weight.data_ptr()
-                tp.spk_expand = rnn.spk_expand.c_params()
-            for l in range(self.n_rnn):
-                tp.weight_ih[l] = getattr(rnn.rnn, f"weight_ih_l{l}").data_ptr()
-                tp.weight_hh[l] = getattr(rnn.rnn, f"weight_hh_l{l}").data_ptr()
-                tp.bias_ih[l] = getattr(rnn.rnn, f"bias_ih_l{l}").data_ptr()
-                tp.bias_hh[l] = getattr(rnn.rnn, f"bias_hh_l{l}").data_ptr()
-            tp.upsampling = rnn.upsampling.conv_t.c_params(bias=rnn.upsampling.bias)
-        mlp = self.sample_level_mlp
-        P.embedding = mlp.embedding.weight.data_ptr()
-        P.mlp_input, P.mlp_hidden, P.mlp_output = mlp.input.c_params(), mlp.hidden.c_params(), mlp.output.c_params()
+        P = self._c_params()
         with torch.cuda.device(self._ctx_device):
             L.check(L.load().srnn_pack_weights(ctx, C.byref(P), _stream()))
         self._packed_key = key
@@ -294,11 +304,27 @@ class _PredictFn(torch.autograd.Function):
             L.check(L.load().srnn_predict_fwd(h, B, T, seq.data_ptr(), cond.data_ptr(),
                                               int(cond.dtype == torch.float64), spk.data_ptr(), ptrs, mask,
                                               out.data_ptr(), mode, _stream()))
+        ctx.model, ctx.params, ctx.mode = model, params, mode
+        ctx.keep = (seq, cond, spk)                # the library reads them again in the backward pass
+        ctx.save_for_backward(out)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise NotImplementedError("srnn_predict_bwd is not part of this build yet (teacher-forced backward)")
+        """srnn_predict_bwd: gradients of every parameter that was passed to forward (trainer/__init__.py:103)."""
+        model, params = ctx.model, ctx.params
+        if ctx.mode != L.MODE_FP32:
+            raise NotImplementedError("the backward pass is available for MODE_FP32 forward passes")
+        (logp,) = ctx.saved_tensors
+        dev = model._ctx_device
+        grads = {id(p): torch.empty_like(p) for p in params}
+        G = model._c_params(ptr=lambda t: grads[id(t)].data_ptr() if id(t) in grads else None)
+        P = model._c_params()
+        dlogp = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            L.check(L.load().srnn_predict_bwd(model._ctx, logp.data_ptr(), dlogp.data_ptr(), C.byref(P), C.byref(G),
+                                              _stream()))
+        return (None, None, None, None, None) + tuple(grads[id(p)] for p in params)
 
 
 class Predictor(Runner, tnn.Module):

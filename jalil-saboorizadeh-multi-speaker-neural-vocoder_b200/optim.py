@@ -1,0 +1,83 @@
+"""Host mirror of the reference training-step semantics: ``optim.gradient_clipping(torch.optim.Adam(...))``
+(optim.py:4-21, train.py:238-241) as ONE fused CUDA launch (srnn_clamp_adam_step) over all parameter tensors.
+
+    opt = ClampAdam(predictor.parameters(), lr=1e-3)
+    opt.zero_grad(); loss = opt.step(closure)          # closure = forward + loss + backward, as trainer/__init__.py:99-112
+
+``zero_grad`` keeps zero tensors (torch-0.4 semantics the reference relies on: a parameter that received no gradient,
+e.g. ``h0`` on a non-reset batch, still gets an Adam update from its momentum).
+With ``torch.distributed`` initialised, ``step`` averages the gradients over ranks (one all-reduce on a flat bucket) BEFORE
+the clamp, so an N-GPU run equals a single-GPU run at N times the batch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class ClampAdam:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, process_group=None, model=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.betas, self.eps, self.clamp = lr, betas, eps, clamp
+        self.step_count = 0
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.process_group = process_group
+        self.model = model                  # the SampleRNN whose packed weights must be refreshed after an update
+        self.param_groups = [{"params": self.params, "lr": lr}]       # enough for torch LR schedulers' read access
+
+    def zero_grad(self):
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            else:
+                p.grad.zero_()
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+        dist.all_reduce(flat, group=self.process_group)
+        flat /= dist.get_world_size(self.process_group)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        self._allreduce()
+        self.step_count += 1
+        n = len(self.params)
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        sizes = (C.c_int64 * n)(*[p.numel() for p in self.params])
+        lr = self.param_groups[0]["lr"]
+        dev = self.params[0].device
+        with torch.cuda.device(dev):
+            L.check(L.load().srnn_clamp_adam_step(n, arr([p.data for p in self.params]), arr([p.grad for p in self.params]),
+                                                  arr(self.exp_avg), arr(self.exp_avg_sq), sizes, lr, self.betas[0],
+                                                  self.betas[1], self.eps, self.step_count, self.clamp,
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # the library updated the parameters behind torch's back: make SampleRNN re-pack them on the next forward
+        if self.model is not None:
+            self.model._packed_key = None
+        else:
+            with torch.no_grad():
+                for p in self.params:
+                    p.add_(0)                       # bumps the tensor version that SampleRNN._ensure_packed watches
+        return loss
+
+
+def sequence_nll_loss_bits(logp, target, model=None):
+    """nn.py:66-70 through the fused CUDA reduction when no gradient is needed; autograd-friendly torch expression
+    otherwise (the gradient of the loss w.r.t. the log-probs is a constant scatter, there is nothing to fuse)."""
+    import math
+    Q = logp.shape[-1]
+    picked = logp.reshape(-1, Q).gather(1, target.reshape(-1, 1).long().to(logp.device))
+    return -picked.mean() * math.log(math.e, 2)
