@@ -120,6 +120,83 @@ def run_reference(args, rank, world):
     }))
 
 
+def run_train(args, rank, world, local):
+    """Secondary line (BASELINE.json configs[2], "C3"): teacher-forced training step = forward + NLL(bits) + backward +
+    gradient all-reduce (N>1) + fused clamp/Adam, batch 128 x T 1040 per GPU, synthetic tokens/conditioners."""
+    import torch
+    import torch.distributed as dist
+    import srnn_b200 as S
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mode = S.MODE_BF16 if args.mode == "bf16" else S.MODE_FP32
+    lib = S._lib.load()
+    torch.manual_seed(77977)
+    model = S.SampleRNN(**C2).to(dev)
+    pred = S.Predictor(model, mode=mode)
+    opt = S.ClampAdam(pred.parameters(), lr=1e-4, model=model)
+    B, T = args.train_batch, args.train_T
+    g = torch.Generator().manual_seed(100 + rank)
+    data = torch.randint(0, 256, (B, 80 + T * (args.steps + args.warmup) + T), generator=g).to(dev)
+    cond = torch.rand(B, (T // 80) * (args.steps + args.warmup + 1) + 1, 86, generator=g).to(dev)
+    spk = torch.randint(0, 6, (B, 1), generator=g).to(dev)
+    losses = []
+
+    def step(i):
+        s = i * T
+        x = data[:, s: s + 80 + T - 1].contiguous()
+        y = data[:, s + 80: s + 80 + T].contiguous()
+        c = cond[:, i * (T // 80) + 1: (i + 1) * (T // 80) + 1].contiguous()
+
+        def closure():
+            out = pred(x, i == 0, c, spk, None, None)
+            loss = S.sequence_nll_loss_bits(out, y)
+            loss.backward()
+            return loss.detach()
+
+        opt.zero_grad()
+        losses.append(opt.step(closure))
+
+    for i in range(args.warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.srnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, args.warmup + args.steps):
+        step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item()) / 1e3
+    tokens = world * B * T * args.steps
+    peak_tf, _, peak_src = measured_peaks()
+    f_step = 3 * F_ALG                                          # fwd + bwd ~ 3x forward, folded form (what the kernels execute)
+    ach = tokens / secs * f_step / 1e12 / world
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training tokens/sec (teacher-forced step)", "value": tokens / secs, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
+            "config": {"workload": "C3 training step: 3-tier [20,4] SampleRNN dim 1024, batch %d x T %d per GPU, Adam lr 1e-4 "
+                                   "with element-wise gradient clamp" % (B, T), "allreduce": "mean over ranks before the clamp"},
+            "loss_bits_first_last": [float(losses[0]), float(losses[-1])],
+            "gpu_launches": int(lib.srnn_launch_count() - l0),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                         "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                         "flops_per_token": f_step, "kernel": "whole training step"},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,6 +209,10 @@ def main():
     ap.add_argument("--ref-n-cond", type=int, default=2)
     ap.add_argument("--cpu-n-cond", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="generate", choices=["generate", "train"],
+                    help="generate = the headline metric (default); train = C3 teacher-forced training step")
+    ap.add_argument("--train-batch", type=int, default=128)
+    ap.add_argument("--train-T", type=int, default=1040)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -139,6 +220,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.workload == "train":
+        return run_train(args, rank, world, local)
 
     import torch
     import torch.distributed as dist
