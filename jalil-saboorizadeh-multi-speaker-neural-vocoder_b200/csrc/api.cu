@@ -150,7 +150,14 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
                     SRNN_TRY(ctx->weights.alloc((void**)&t.w_hh16[l], sizeof(bf) * 3 * H * H));
                 }
                 SRNN_TRY(ctx->weights.alloc((void**)&t.w_up16, sizeof(bf) * (size_t)t.fs * H * H));
+                for (int l = 0; l < L; ++l) {
+                    SRNN_TRY(ctx->weights.alloc((void**)&t.w_ih16_t[l], sizeof(bf) * 3 * H * H));
+                    SRNN_TRY(ctx->weights.alloc((void**)&t.w_hh16_t[l], sizeof(bf) * 3 * H * H));
+                }
+                SRNN_TRY(ctx->weights.alloc((void**)&t.w_up16_t, sizeof(bf) * (size_t)t.fs * H * H));
             }
+            SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_hid16_t, sizeof(bf) * H * H));
+            SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_out16_t, sizeof(bf) * Q * H));
             SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_hid16, sizeof(bf) * H * H));
             SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_out16, sizeof(bf) * Q * H));
             SRNN_TRY(ctx->weights.alloc((void**)&ctx->tbl16, sizeof(bf) * (size_t)FS0 * Q * H));
@@ -221,7 +228,14 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
                 SRNN_TRY(f32_to_bf16_pad(t.w_hh[l], 3 * H, H, H, t.w_hh16[l], 3 * H, H, st));
             }
             SRNN_TRY(f32_to_bf16_pad(t.w_up, t.fs * H, H, H, t.w_up16, t.fs * H, H, st));
+            for (int l = 0; l < L; ++l) {
+                SRNN_TRY(transpose_to_bf16(t.w_ih[l], 3 * H, H, H, t.w_ih16_t[l], 3 * H, st));
+                SRNN_TRY(transpose_to_bf16(t.w_hh[l], 3 * H, H, H, t.w_hh16_t[l], 3 * H, st));
+            }
+            SRNN_TRY(transpose_to_bf16(t.w_up, t.fs * H, H, H, t.w_up16_t, t.fs * H, st));
         }
+        SRNN_TRY(transpose_to_bf16(ctx->w_hid, H, H, H, ctx->w_hid16_t, H, st));
+        SRNN_TRY(transpose_to_bf16(ctx->w_out, Q, H, H, ctx->w_out16_t, Q, st));
         SRNN_TRY(f32_to_bf16_pad(ctx->w_hid, H, H, H, ctx->w_hid16, H, H, st));
         SRNN_TRY(f32_to_bf16_pad(ctx->w_out, Q, H, H, ctx->w_out16, Q, H, st));
         SRNN_TRY(f32_to_bf16_pad(ctx->tbl, FS0 * Q, H, H, ctx->tbl16, FS0 * Q, H, st));
@@ -267,7 +281,7 @@ static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
         P.bytes = b.off;
         // the backward pass works in the scratch right behind the saved activations: reserve it now, because growing the
         // scratch later would free them
-        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off + (bf16 ? 0 : backward_scratch_bytes(ctx, B, T))));
+        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off + (bf16 ? backward_scratch_bytes_bf16(ctx, B, T) : backward_scratch_bytes(ctx, B, T))));
     }
     P.B = B;
     P.T = T;
@@ -379,8 +393,8 @@ int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     SRNN_TRY(check_ready(ctx));
     if (!logp || !dlogp || !params || !grads) return fail(SRNN_ERR_ARG, "null argument");
     if (!ctx->fwd.valid) return fail(SRNN_ERR_STATE, "srnn_predict_bwd needs a preceding srnn_predict_fwd on this context");
-    if (ctx->fwd.mode != SRNN_MODE_FP32) return fail(SRNN_ERR_UNSUPPORTED, "backward is available for SRNN_MODE_FP32 forward passes");
-    const int rc = predict_bwd_f32(ctx, logp, dlogp, params, grads, (cudaStream_t)stream);
+    const int rc = ctx->fwd.mode == SRNN_MODE_FP32 ? predict_bwd_f32(ctx, logp, dlogp, params, grads, (cudaStream_t)stream)
+                                                   : predict_bwd_bf16(ctx, logp, dlogp, params, grads, (cudaStream_t)stream);
     ctx->fwd.valid = false;
     return rc;
 }

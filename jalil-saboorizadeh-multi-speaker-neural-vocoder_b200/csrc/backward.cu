@@ -113,13 +113,16 @@ __global__ void k_relu_mask(const float* __restrict__ dx, const float* __restric
 
 // column sums of X (rows, cols, ld): stage 1 -> partial[chunk][col], stage 2 -> out[col] (fixed order)
 constexpr int CS_CHUNKS = 64;
-__global__ void k_colsum_partial(const float* __restrict__ X, int rows, int cols, int ld, float* __restrict__ partial) {
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T>
+__global__ void k_colsum_partial(const T* __restrict__ X, int rows, int cols, int ld, float* __restrict__ partial) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= cols) return;
     const int per = (rows + CS_CHUNKS - 1) / CS_CHUNKS;
     const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += X[(size_t)r * ld + col];
+    for (int r = r0; r < r1; ++r) s += to_f(X[(size_t)r * ld + col]);
     partial[(size_t)blockIdx.y * cols + col] = s;
 }
 __global__ void k_colsum_final(const float* __restrict__ partial, int cols, float* __restrict__ out) {
@@ -129,8 +132,9 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int cols, floa
     for (int c = 0; c < CS_CHUNKS; ++c) s += partial[(size_t)c * cols + col];
     out[col] = s;
 }
-static int colsum(const float* X, int rows, int cols, int ld, float* partial, float* out, cudaStream_t st) {
-    SRNN_LAUNCH(k_colsum_partial, dim3(cdiv(cols, 128), CS_CHUNKS), 128, 0, st, X, rows, cols, ld, partial);
+template <typename T>
+static int colsum(const T* X, int rows, int cols, int ld, float* partial, float* out, cudaStream_t st) {
+    SRNN_LAUNCH((k_colsum_partial<T>), dim3(cdiv(cols, 128), CS_CHUNKS), 128, 0, st, X, rows, cols, ld, partial);
     SRNN_LAUNCH(k_colsum_final, cdiv(cols, 128), 128, 0, st, partial, cols, out);
     return SRNN_OK;
 }
@@ -146,8 +150,9 @@ __global__ void k_add3(const float* a, const float* b, const float* c, float* ou
 // grid (H/64, FS, DT_CHUNKS), 64 threads (one feature each), smem table [256][64]
 // ------------------------------------------------------------------------------------------------
 constexpr int DT_CHUNKS = 4;
+template <typename T1>
 __global__ void __launch_bounds__(64)
-k_dtbl_partial(const uint8_t* __restrict__ seq, int seq_ld, int off, const float* __restrict__ dpre1, int B, int T, int H,
+k_dtbl_partial(const uint8_t* __restrict__ seq, int seq_ld, int off, const T1* __restrict__ dpre1, int B, int T, int H,
                float* __restrict__ partial /* (DT_CHUNKS, FS, Q, H) */, int FS) {
     extern __shared__ float tab[];        // [256][64]
     const int h = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y, ch = blockIdx.z;
@@ -159,7 +164,7 @@ k_dtbl_partial(const uint8_t* __restrict__ seq, int seq_ld, int off, const float
         for (int r = r0; r < r1; ++r) {
             const int b = r / T, t = r % T;
             const int q = seq[(size_t)b * seq_ld + off + t + j];
-            tab[q * 64 + threadIdx.x] += dpre1[(size_t)r * H + h];
+            tab[q * 64 + threadIdx.x] += to_f(dpre1[(size_t)r * H + h]);
         }
         for (int q = 0; q < SRNN_Q; ++q)
             partial[(((size_t)ch * FS + j) * SRNN_Q + q) * H + h] = tab[q * 64 + threadIdx.x];
@@ -179,7 +184,8 @@ __global__ void k_dtbl_final(const float* __restrict__ partial, size_t n, float*
 __global__ void k_gru_bwd_gates(const float* __restrict__ gi, const float* __restrict__ gh, int g_ld,
                                 const float* __restrict__ h_prev, int hp_ld, const float* __restrict__ dy, int dy_ld,
                                 const float* __restrict__ dh_carry, float* __restrict__ dgi, float* __restrict__ dgh,
-                                float* __restrict__ dh_prev, int H) {
+                                float* __restrict__ dh_prev, int H, __nv_bfloat16* __restrict__ dgi16 = nullptr,
+                                __nv_bfloat16* __restrict__ dgh16 = nullptr) {
     const int b = blockIdx.y;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= H) return;
@@ -203,6 +209,13 @@ __global__ void k_gru_bwd_gates(const float* __restrict__ gi, const float* __res
     dgir[u] = dpr;          dghr[u] = dpr;
     dgir[H + u] = dpz;      dghr[H + u] = dpz;
     dgir[2 * H + u] = dpn;  dghr[2 * H + u] = dpn * r;
+    if (dgi16) {
+        __nv_bfloat16* a = dgi16 + (size_t)b * g_ld;
+        __nv_bfloat16* c = dgh16 + (size_t)b * g_ld;
+        a[u] = __float2bfloat16(dpr);          c[u] = __float2bfloat16(dpr);
+        a[H + u] = __float2bfloat16(dpz);      c[H + u] = __float2bfloat16(dpz);
+        a[2 * H + u] = __float2bfloat16(dpn);  c[2 * H + u] = __float2bfloat16(dpn * r);
+    }
     dh_prev[(size_t)b * H + u] = dh * z;
 }
 
@@ -415,10 +428,10 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     {
         static bool dt_attr = false;
         if (!dt_attr) {
-            SRNN_CUDA(cudaFuncSetAttribute(k_dtbl_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, SRNN_Q * 64 * (int)sizeof(float)));
+            SRNN_CUDA(cudaFuncSetAttribute(k_dtbl_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SRNN_Q * 64 * (int)sizeof(float)));
             dt_attr = true;
         }
-        SRNN_LAUNCH(k_dtbl_partial, dim3(cdiv(H, 64), FS0, DT_CHUNKS), 64, SRNN_Q * 64 * sizeof(float), st, F.seq, Lseq,
+        SRNN_LAUNCH(k_dtbl_partial<float>, dim3(cdiv(H, 64), FS0, DT_CHUNKS), 64, SRNN_Q * 64 * sizeof(float), st, F.seq, Lseq,
                     lookback - FS0, dB, B, T, H, dTblP, FS0);
         const size_t n = (size_t)FS0 * Q * H;
         SRNN_LAUNCH(k_dtbl_final, gsz(n), 256, 0, st, dTblP, n, dTbl);
@@ -521,6 +534,233 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
             dUP = dA;
         }
         (void)xb;
+    }
+    return SRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 / tcgen05 backward (SRNN_MODE_BF16 forward passes): same chain rule as predict_bwd_f32, with every
+// H-wide contraction on the tensor cores through gemm_umma_multi:
+//   dIn (rows, K)  = dOut (rows, N) . W (N, K)   : A operand = W^T (K, N) bf16 (packed once), B = dOut bf16
+//   dW  (N, K)     = dOut^T . In                 : A = In^T (K, rows_p), B = dOut^T (N, rows_p), rows zero-padded to 64
+// The transposed operands are produced by a tiled transpose+convert kernel (their HBM traffic is a few percent of the
+// GEMM time at C3).  Element-wise pieces (GRU cell, masks, reductions) stay fp32.
+// ------------------------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf;
+static inline int rup64(long long x) { return (int)((x + 63) / 64 * 64); }
+static inline int pick_bn2(int rows) { return rows <= 32 ? 32 : (rows <= 64 ? 64 : (rows <= 128 ? 128 : 256)); }
+
+static int tc_dx(int rows, int Kin, int Nout, const bf* dOut16, int ld_do, const bf* Wt16, const float* addend, int ld_add,
+                 float* outf, bf* outb, const bf* mask, int ld_out, cudaStream_t st) {
+    GemmOperands o{Wt16, dOut16, nullptr, addend, outf, outb, Kin, Nout, ld_do, ld_add, ld_out, 0, mask};
+    return gemm_umma_multi(&o, 1, rows, Nout, 128, pick_bn2(rows), st);
+}
+static int tc_dw(int Nout, int Kin, int Kp, const bf* InT, const bf* dOutT, float* dW, cudaStream_t st) {
+    GemmOperands o{InT, dOutT, nullptr, nullptr, dW, nullptr, Kin, Kp, Kp, 0, Kin, 0, nullptr};
+    return gemm_umma_multi(&o, 1, Nout, Kp, 128, pick_bn2(Nout), st);
+}
+
+size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T) {
+    const srnn_config& c = ctx->cfg;
+    const size_t H = ctx->H, Q = ctx->Q, R = (size_t)B * T, Rp = rup64(R), FS0 = ctx->FS0;
+    size_t maxM = 0, maxfs = 1, maxkin = 1;
+    for (int i = 0; i < c.n_tiers; ++i) {
+        const size_t M = (size_t)B * (T / ctx->tiers[i].n);
+        if (M > maxM) maxM = M;
+        if ((size_t)ctx->tiers[i].fs > maxfs) maxfs = ctx->tiers[i].fs;
+        if ((size_t)ctx->tiers[i].kin > maxkin) maxkin = ctx->tiers[i].kin;
+    }
+    const size_t Mp = rup64(maxM);
+    size_t f32 = R * Q + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H + 2 * maxfs * H * H + maxfs * H + H * maxkin +
+                 H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin) + (DT_CHUNKS + 1) * FS0 * Q * H + 2 * FS0 * H * Q +
+                 (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + 3 * H * H;
+    size_t b16 = R * Q + Q * Rp + 2 * H * Rp + 2 * R * H                     // D16, D16t, TA, TB, DP2, DP1
+                 + maxfs * H * Mp + 3 * H * Mp + 2 * 3 * H * Mp + 2 * maxM * 3 * H + 2 * maxM * H;   // tier transposes + copies
+    return f32 * sizeof(float) + b16 * sizeof(bf) + 96 * 256;
+}
+
+int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
+                     cudaStream_t st) {
+    const FwdPlan& F = ctx->fwd;
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
+    const int B = F.B, T = F.T, R = B * T, Rp = rup64(R), Lseq = lookback + T - 1;
+    if (F.bytes + backward_scratch_bytes_bf16(ctx, B, T) > ctx->ws_bytes)
+        return fail(SRNN_ERR_STATE, "backward scratch was not reserved by the forward pass");
+    int maxfs = 1, maxkin = 1;
+    size_t maxM = 0;
+    for (int i = 0; i < NT; ++i) {
+        const size_t M = (size_t)B * (T / ctx->tiers[i].n);
+        if (M > maxM) maxM = M;
+        if (ctx->tiers[i].fs > maxfs) maxfs = ctx->tiers[i].fs;
+        if (ctx->tiers[i].kin > maxkin) maxkin = ctx->tiers[i].kin;
+    }
+    const size_t Mpmax = rup64(maxM);
+    Bump2 b(ctx->ws, F.bytes);
+    float* dlogits = b.take<float>((size_t)R * Q);
+    float* dYa = b.take<float>(maxM * H);
+    float* dYb = b.take<float>(maxM * H);
+    float* dXf = b.take<float>(maxM * H);
+    float* dGI = b.take<float>(maxM * 3 * H);
+    float* dGH = b.take<float>(maxM * 3 * H);
+    float* dhc0 = b.take<float>((size_t)B * H);
+    float* dhc1 = b.take<float>((size_t)B * H);
+    float* dWup = b.take<float>((size_t)maxfs * H * H);
+    float* dwf = b.take<float>((size_t)maxfs * H * H);
+    float* dbup = b.take<float>((size_t)maxfs * H);
+    float* dWin = b.take<float>((size_t)H * maxkin);
+    float* wsf = b.take<float>((size_t)H * c.spk_dim);
+    const size_t stg = (size_t)H * (H > maxkin ? H : maxkin);
+    float* t_in = b.take<float>(stg);
+    float* t_c = b.take<float>(stg);
+    float* t_s = b.take<float>(stg);
+    float* dTblP = b.take<float>((size_t)DT_CHUNKS * FS0 * Q * H);
+    float* dTbl = b.take<float>((size_t)FS0 * Q * H);
+    float* dWmt = b.take<float>((size_t)FS0 * H * Q);
+    float* dWm = b.take<float>((size_t)FS0 * H * Q);
+    float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
+    float* dbtmp = b.take<float>((size_t)3 * H);
+    float* dWo = b.take<float>((size_t)Q * H);
+    float* dWtmp = b.take<float>((size_t)3 * H * H);
+    bf* D16 = b.take<bf>((size_t)R * Q);
+    bf* D16t = b.take<bf>((size_t)Q * Rp);
+    bf* TA = b.take<bf>((size_t)H * Rp);
+    bf* TB = b.take<bf>((size_t)H * Rp);
+    bf* DP2 = b.take<bf>((size_t)R * H);
+    bf* DP1 = b.take<bf>((size_t)R * H);
+    bf* dUPt = b.take<bf>((size_t)maxfs * H * Mpmax);
+    bf* Yt = b.take<bf>((size_t)H * Mpmax);
+    bf* HPt = b.take<bf>((size_t)H * Mpmax);
+    bf* INt = b.take<bf>((size_t)H * Mpmax);
+    bf* dGIt = b.take<bf>((size_t)3 * H * Mpmax);
+    bf* dGHt = b.take<bf>((size_t)3 * H * Mpmax);
+    bf* dGI16 = b.take<bf>(maxM * 3 * H);
+    bf* dGH16 = b.take<bf>(maxM * 3 * H);
+    bf* HP16 = b.take<bf>(maxM * H);
+    bf* DX16 = b.take<bf>(maxM * H);
+
+    // ---- log_softmax backward; bf16 copies of dlogits in both orientations ----
+    SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
+    SRNN_TRY(f32_to_bf16_pad(dlogits, R, Q, Q, D16, R, Q, st));
+    SRNN_TRY(transpose_to_bf16(dlogits, R, Q, Q, D16t, Rp, st));
+    // ---- output layer ----
+    SRNN_TRY(transpose_to_bf16(F.X2h, R, H, H, TA, Rp, st));                                   // x2^T
+    SRNN_TRY(tc_dw(Q, H, Rp, TA, D16t, dWo, st));
+    SRNN_TRY(wn_bwd(dWo, P->mlp_output, G->mlp_output, Q, H, st));
+    if (G->mlp_output.bias) SRNN_TRY(colsum(dlogits, R, Q, Q, csp, (float*)G->mlp_output.bias, st));
+    SRNN_TRY(tc_dx(R, H, Q, D16, Q, ctx->w_out16_t, nullptr, 0, nullptr, DP2, F.X2h, H, st));   // dpre2 = dx2 * (x2 > 0)
+    // ---- hidden layer ----
+    SRNN_TRY(transpose_to_bf16(F.X1h, R, H, H, TA, Rp, st));                                   // x1^T
+    SRNN_TRY(transpose_to_bf16(DP2, R, H, H, TB, Rp, st));                                     // dpre2^T
+    SRNN_TRY(tc_dw(H, H, Rp, TA, TB, dWtmp, st));
+    SRNN_TRY(wn_bwd(dWtmp, P->mlp_hidden, G->mlp_hidden, H, H, st));
+    if (G->mlp_hidden.bias) SRNN_TRY(colsum(DP2, R, H, H, csp, (float*)G->mlp_hidden.bias, st));
+    SRNN_TRY(tc_dx(R, H, H, DP2, H, ctx->w_hid16_t, nullptr, 0, nullptr, DP1, F.X1h, H, st));   // dpre1 = dc0
+    // ---- folded table ----
+    {
+        static bool dt_attr = false;
+        if (!dt_attr) {
+            SRNN_CUDA(cudaFuncSetAttribute(k_dtbl_partial<bf>, cudaFuncAttributeMaxDynamicSharedMemorySize, SRNN_Q * 64 * (int)sizeof(float)));
+            dt_attr = true;
+        }
+        SRNN_LAUNCH(k_dtbl_partial<bf>, dim3(cdiv(H, 64), FS0, DT_CHUNKS), 64, SRNN_Q * 64 * sizeof(float), st, F.seq, Lseq,
+                    lookback - FS0, DP1, B, T, H, dTblP, FS0);
+        const size_t n = (size_t)FS0 * Q * H;
+        SRNN_LAUNCH(k_dtbl_final, gsz(n), 256, 0, st, dTblP, n, dTbl);
+        float* wm_fold = dTblP;
+        float* wm_t = dTblP + (size_t)H * Q * FS0;
+        SRNN_TRY(wn_fold(P->mlp_input, wm_fold, H, Q * FS0, st));
+        SRNN_TRY(transpose_mlp_in(wm_fold, wm_t, H, Q, FS0, st));
+        float* dE = (float*)G->embedding;
+        for (int j = 0; j < FS0; ++j) {
+            const float* dT = dTbl + (size_t)j * Q * H;
+            SRNN_TRY(gemm_s(H, Q, Q, dT, 1, H, P->embedding, 1, Q, nullptr, 0, dWmt + (size_t)j * H * Q, Q, st));
+            if (dE) SRNN_TRY(gemm_s(Q, Q, H, dT, H, 1, wm_t + (size_t)j * H * Q, 1, Q, j ? dE : nullptr, Q, dE, Q, st));
+        }
+        SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
+        SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
+    }
+    // ---- frame tiers, lowest first ----
+    const bf* dUP = DP1;
+    for (int i = 0; i < NT; ++i) {
+        const TierPacked& t = ctx->tiers[i];
+        const srnn_tier_params& tp = P->tiers[i];
+        const srnn_tier_params& tg = G->tiers[i];
+        const int Fr = T / t.n, M = B * Fr, Mp = rup64(M), NU = t.fs * H;
+        // upsampling
+        SRNN_TRY(transpose_to_bf16(dUP, M, NU, NU, dUPt, Mp, st));
+        SRNN_TRY(transpose_to_bf16(F.Y16[i][NL - 1], M, H, H, Yt, Mp, st));
+        SRNN_TRY(tc_dw(NU, H, Mp, Yt, dUPt, dWup, st));
+        SRNN_TRY(colsum(dUP, M, NU, NU, csp, dbup, st));
+        SRNN_LAUNCH(k_unpack_up_grad, NU, 128, 0, st, dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs);
+        SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
+        float* dY = dYa;
+        float* dYn = dYb;
+        SRNN_TRY(tc_dx(M, H, NU, dUP, NU, t.w_up16_t, nullptr, 0, dY, nullptr, nullptr, H, st));
+        for (int l = NL - 1; l >= 0; --l) {
+            const float* GI = F.GI[i][l];
+            const float* GH = F.GH[i][l];
+            const float* Y = F.Y[i][l];
+            const float* h0 = F.H0[i] + (size_t)l * B * H;
+            float* carry = nullptr;
+            float* cnext = dhc0;
+            for (int f = Fr - 1; f >= 0; --f) {
+                const float* hp = f ? Y + (size_t)(f - 1) * H : h0;
+                const int hp_ld = f ? Fr * H : H;
+                float* part = (cnext == dhc0) ? dhc1 : dhc0;
+                SRNN_LAUNCH(k_gru_bwd_gates, dim3(cdiv(H, 128), B), 128, 0, st, GI + (size_t)f * 3 * H, GH + (size_t)f * 3 * H,
+                            Fr * 3 * H, hp, hp_ld, dY + (size_t)f * H, Fr * H, carry, dGI + (size_t)f * 3 * H,
+                            dGH + (size_t)f * 3 * H, part, H, dGI16 + (size_t)f * 3 * H, dGH16 + (size_t)f * 3 * H);
+                // dh_{f-1} = dh*z + dGH_f . W_hh      (tensor cores, fp32 addend)
+                SRNN_TRY(tc_dx(B, H, 3 * H, dGH16 + (size_t)f * 3 * H, Fr * 3 * H, t.w_hh16_t[l], part, H, cnext, nullptr,
+                               nullptr, H, st));
+                carry = cnext;
+                cnext = part;
+            }
+            float* dh0 = (float*)tg.h0;
+            if (dh0) {
+                if ((F.reset_mask >> i) & 1) SRNN_TRY(colsum(carry, B, H, H, csp, dh0 + (size_t)l * H, st));
+                else SRNN_CUDA(cudaMemsetAsync(dh0 + (size_t)l * H, 0, sizeof(float) * H, st));
+            }
+            SRNN_TRY(transpose_to_bf16(dGH, M, 3 * H, 3 * H, dGHt, Mp, st));
+            SRNN_TRY(transpose_to_bf16(dGI, M, 3 * H, 3 * H, dGIt, Mp, st));
+            if (tg.weight_hh[l]) {
+                SRNN_LAUNCH(k_build_hprev, M, 128, 0, st, Y, h0, dYn, Fr, H);
+                SRNN_TRY(transpose_to_bf16(dYn, M, H, H, HPt, Mp, st));
+                SRNN_TRY(tc_dw(3 * H, H, Mp, HPt, dGHt, (float*)tg.weight_hh[l], st));
+            }
+            if (tg.bias_hh[l]) SRNN_TRY(colsum(dGH, M, 3 * H, 3 * H, csp, (float*)tg.bias_hh[l], st));
+            if (tg.weight_ih[l]) {
+                if (l) SRNN_TRY(transpose_to_bf16(F.Y16[i][l - 1], M, H, H, INt, Mp, st));
+                else SRNN_TRY(transpose_to_bf16(F.X16[i], M, H, H, INt, Mp, st));
+                SRNN_TRY(tc_dw(3 * H, H, Mp, INt, dGIt, (float*)tg.weight_ih[l], st));
+            }
+            if (tg.bias_ih[l]) SRNN_TRY(colsum(dGI, M, 3 * H, 3 * H, csp, (float*)tg.bias_ih[l], st));
+            float* din = l ? dYn : dXf;
+            SRNN_TRY(tc_dx(M, H, 3 * H, dGI16, 3 * H, t.w_ih16_t[l], nullptr, 0, din, nullptr, nullptr, H, st));
+            if (l) { float* tmp = dY; dY = dYn; dYn = tmp; }
+        }
+        // input expansion (K = kin is small: fp32 FFMA)
+        SRNN_TRY(gemm_dw(H, t.kin, M, dXf, H, F.A[i], t.kin, dWin, t.kin, st));
+        SRNN_TRY(colsum(dXf, M, H, H, csp, dbtmp, st));
+        if (t.top) {
+            SRNN_TRY(wn_fold(tp.spk_expand, wsf, H, c.spk_dim, st));
+            SRNN_LAUNCH(k_unpack_top_in, H, 128, 0, st, dWin, t_in, t_c, t_s, tp.spk_embedding, t.n, c.cond_dim, c.spk_dim);
+            SRNN_TRY(wn_bwd(t_in, tp.input_expand, tg.input_expand, H, t.n, st));
+            SRNN_TRY(wn_bwd(t_c, tp.cond_expand, tg.cond_expand, H, c.cond_dim, st));
+            SRNN_TRY(wn_bwd(t_s, tp.spk_expand, tg.spk_expand, H, c.spk_dim, st));
+            if (tg.spk_embedding)
+                SRNN_LAUNCH(k_spk_emb_grad, c.spk_dim * c.spk_dim, 128, 0, st, dWin, wsf, (float*)tg.spk_embedding, H, t.kin,
+                            t.n + c.cond_dim, c.spk_dim);
+            if (tg.input_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.input_expand.bias, H, st));
+            if (tg.cond_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.cond_expand.bias, H, st));
+            if (tg.spk_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.spk_expand.bias, H, st));
+        } else {
+            SRNN_TRY(wn_bwd(dWin, tp.input_expand, tg.input_expand, H, t.n, st));
+            if (tg.input_expand.bias) SRNN_TRY(copy_f32(dbtmp, (float*)tg.input_expand.bias, H, st));
+            SRNN_TRY(f32_to_bf16_pad(dXf, M, H, H, DX16, M, H, st));     // d upper for the tier above, (M_{i+1}, fs_{i+1}*H)
+            dUP = DX16;
+        }
     }
     return SRNN_OK;
 }

@@ -63,6 +63,10 @@ struct TierPacked {
     __nv_bfloat16* w_ih16[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_hh16[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_up16 = nullptr;
+    // transposed bf16 copies (H, 3H) / (H, fs*H): the A operands of the dIn = dOut . W GEMMs of the backward pass
+    __nv_bfloat16* w_ih16_t[SRNN_MAX_RNN] = {};
+    __nv_bfloat16* w_hh16_t[SRNN_MAX_RNN] = {};
+    __nv_bfloat16* w_up16_t = nullptr;
 };
 
 struct Arena {
@@ -119,6 +123,8 @@ struct srnn_ctx {
     __nv_bfloat16* tbl16 = nullptr;
     __nv_bfloat16* w_hid16 = nullptr;
     __nv_bfloat16* w_out16 = nullptr;
+    __nv_bfloat16* w_hid16_t = nullptr;   // (H, H) transposed
+    __nv_bfloat16* w_out16_t = nullptr;   // (H, Q) transposed
     srnn::Arena weights;      // freed on destroy
     // grow-only scratch for predict / generate
     void* ws = nullptr;
@@ -182,6 +188,9 @@ int add_int(int* p, int v, cudaStream_t st);
 size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T);
 int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
                     cudaStream_t st);
+size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T);
+int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
+                     cudaStream_t st);
 int clamp_adam(int count, float* const* params, const float* const* grads, float* const* m, float* const* v,
                const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st);
 
@@ -217,7 +226,10 @@ struct GemmOperands {
     float* out_f32;               // (n_rows, ld_out) or null
     __nv_bfloat16* out_bf16;      // (n_rows, ld_out) or null
     int n_feat, ld_w, ld_act, ld_add, ld_out, relu;
+    const __nv_bfloat16* mask;    // optional (n_rows, ld_out): keep the value where mask > 0 (ReLU backward), bf16 output
 };
+int transpose_to_bf16(const float* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
+int transpose_to_bf16(const __nv_bfloat16* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);

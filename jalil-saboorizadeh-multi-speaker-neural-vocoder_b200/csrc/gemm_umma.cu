@@ -66,6 +66,7 @@ struct alignas(64) GemmProb {
     const float* addend;
     float* out_f32;
     __nv_bfloat16* out_bf16;
+    const __nv_bfloat16* mask;     // optional (rows, ld_out) bf16: the value is kept where mask > 0, else 0 (ReLU backward)
     int n_feat, ld_add, ld_out, relu;
 };
 struct alignas(64) GemmArgs {
@@ -77,32 +78,24 @@ struct alignas(64) GemmArgs {
 // 16 accumulator columns (= 16 consecutive batch rows) of one feature -> global memory.  The flag combination is a
 // compile-time parameter: a branchy per-element epilogue (~50 SASS instructions per value) was measured to cost more
 // than the whole K loop of a 128x256 tile.
-template <bool ADD, bool RELU, bool F32, bool B16>
+template <bool ADD, bool RELU, bool F32, bool B16, bool MASK = false>
 __device__ __forceinline__ void epi_store16(const float (&v)[16], float bv, int nn, size_t row, int m,
                                             const float* __restrict__ addend, int ld_add, float* __restrict__ out_f32,
-                                            __nv_bfloat16* __restrict__ out_bf16, int ld_out) {
+                                            __nv_bfloat16* __restrict__ out_bf16, int ld_out,
+                                            const __nv_bfloat16* __restrict__ mask = nullptr) {
     float* pf = F32 ? out_f32 + row * ld_out + m : nullptr;
     __nv_bfloat16* pb = B16 ? out_bf16 + row * ld_out + m : nullptr;
     const float* pa = ADD ? addend + row * ld_add + m : nullptr;
-    if (nn == 16) {
+    const __nv_bfloat16* pm = MASK ? mask + row * ld_out + m : nullptr;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 16; ++i) {
+        if (nn == 16 || i < nn) {
             float x = v[i] + bv;
             if (ADD) x += pa[(size_t)i * ld_add];
             if (RELU) x = fmaxf(x, 0.f);
+            if (MASK) x = __bfloat162float(pm[(size_t)i * ld_out]) > 0.f ? x : 0.f;
             if (F32) pf[(size_t)i * ld_out] = x;
             if (B16) pb[(size_t)i * ld_out] = __float2bfloat16(x);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < nn) {
-                float x = v[i] + bv;
-                if (ADD) x += pa[(size_t)i * ld_add];
-                if (RELU) x = fmaxf(x, 0.f);
-                if (F32) pf[(size_t)i * ld_out] = x;
-                if (B16) pb[(size_t)i * ld_out] = __float2bfloat16(x);
-            }
         }
     }
 }
@@ -184,6 +177,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         const float* __restrict__ addend = P.addend;
         float* __restrict__ out_f32 = P.out_f32;
         __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
+        const __nv_bfloat16* __restrict__ mask = P.mask;
         const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
         mbar_wait(tmem_full, 0);
         if (tr && threadIdx.x == 64) tr[1] = clock64();
@@ -207,10 +201,14 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
             if (!m_ok) continue;
             const int nn = n_rows - (n0 + c) < 16 ? n_rows - (n0 + c) : 16;
             const size_t row = (size_t)(n0 + c);
-            if (!addend && !relu && out_f32 && !out_bf16)          // GRU projections, upsampling, logits
+            if (mask)                                              // ReLU backward: dpre = dx where the forward value > 0
+                epi_store16<false, false, false, true, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out, mask);
+            else if (!addend && !relu && out_f32 && !out_bf16)     // GRU projections, upsampling, logits, weight gradients
                 epi_store16<false, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
             else if (!addend && relu && !out_f32 && out_bf16)      // MLP hidden layer feeding the next GEMM
                 epi_store16<false, true, false, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+            else if (addend && !relu && out_f32 && !out_bf16)      // BPTT carry: dh*z + dGH.W_hh
+                epi_store16<true, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
             else {                                                 // generic (test hook)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -262,6 +260,7 @@ int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int b
         args.p[i].addend = o.addend;
         args.p[i].out_f32 = o.out_f32;
         args.p[i].out_bf16 = o.out_bf16;
+        args.p[i].mask = o.mask;
         args.p[i].n_feat = o.n_feat;
         args.p[i].ld_add = o.ld_add;
         args.p[i].ld_out = o.ld_out;
@@ -301,7 +300,7 @@ int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int b
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,
               const float* bias, const float* addend, int ld_add, float* out_f32, __nv_bfloat16* out_bf16,
               int ld_out, int relu, int bm, int bn, cudaStream_t st) {
-    GemmOperands o{W, act, bias, addend, out_f32, out_bf16, n_feat, ld_w, ld_act, ld_add, ld_out, relu};
+    GemmOperands o{W, act, bias, addend, out_f32, out_bf16, n_feat, ld_w, ld_act, ld_add, ld_out, relu, nullptr};
     return gemm_umma_multi(&o, 1, n_rows, K, bm, bn, st);
 }
 
@@ -322,6 +321,36 @@ int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloa
     if (grid < 1) grid = 1;
     SRNN_LAUNCH(k_f32_to_bf16_pad, grid, 256, 0, st, src, rows, cols, ld_src, dst, rows_p, cols_p);
     return SRNN_OK;
+}
+
+// src (rows, cols; fp32 or bf16; leading dimension ld_src) -> dst (cols, ld_dst) bf16 with dst[c][r] = src[r][c];
+// columns rows..ld_dst-1 of dst are zero-filled (K padding of the transposed operand)
+template <typename T>
+__global__ void k_transpose_to_bf16(const T* __restrict__ src, int rows, int cols, long long ld_src,
+                                    __nv_bfloat16* __restrict__ dst, int ld_dst) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? (float)src[(size_t)r * ld_src + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < ld_dst) dst[(size_t)c * ld_dst + r] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+template <typename T>
+static int transpose_to_bf16_t(const T* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st) {
+    dim3 grid(cdiv(ld_dst, 32), cdiv(cols, 32));
+    SRNN_LAUNCH((k_transpose_to_bf16<T>), grid, dim3(32, 8), 0, st, src, rows, cols, ld_src, dst, ld_dst);
+    return SRNN_OK;
+}
+int transpose_to_bf16(const float* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st) {
+    return transpose_to_bf16_t(src, rows, cols, ld_src, dst, ld_dst, st);
+}
+int transpose_to_bf16(const __nv_bfloat16* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st) {
+    return transpose_to_bf16_t(src, rows, cols, ld_src, dst, ld_dst, st);
 }
 
 }  // namespace srnn

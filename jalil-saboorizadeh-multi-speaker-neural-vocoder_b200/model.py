@@ -313,8 +313,6 @@ class _PredictFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         """srnn_predict_bwd: gradients of every parameter that was passed to forward (trainer/__init__.py:103)."""
         model, params = ctx.model, ctx.params
-        if ctx.mode != L.MODE_FP32:
-            raise NotImplementedError("the backward pass is available for MODE_FP32 forward passes")
         (logp,) = ctx.saved_tensors
         dev = model._ctx_device
         grads = {id(p): torch.empty_like(p) for p in params}

@@ -74,3 +74,40 @@ def test_clamp_adam_against_oracle_formula():
         ref = O.clamp_adam_step(ref, grads, st, lr=1e-2)
     for i, q in enumerate(ps):
         np.testing.assert_allclose(q.detach().cpu().numpy(), ref[str(i)].numpy(), atol=2e-6)
+
+
+@pytest.mark.parametrize("dim,B,T", [(64, 3, 160), (128, 5, 80)])
+def test_bf16_backward_against_oracle(dim, B, T):
+    """tcgen05 training path: gradients within bf16 accuracy of the fp32 oracle (relative L2 per tensor)."""
+    torch.manual_seed(dim + 7)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=dim, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c)
+    p = S.Predictor(m, mode=S.MODE_BF16)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    x = torch.randint(0, 256, (B, 80 + T - 1))
+    y = torch.randint(0, 256, (B, T))
+    cond = torch.rand(B, T // 80, 86, dtype=torch.float64)
+    spk = torch.randint(0, 6, (B, 1))
+    loss_ref, grads, _, _ = O.loss_and_grads(sd, O.Config(**c), None, x, True, cond, spk, y)
+    out = p(x, True, cond, spk, None, None)
+    loss = S.sequence_nll_loss_bits(out, y)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref)) < 0.02
+    worst = 0.0
+    for k, q in p.named_parameters():
+        ref = grads[k].numpy().astype(np.float64)
+        got = q.grad.detach().cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all(), k
+        nref = np.linalg.norm(ref)
+        if nref < 1e-7:
+            continue
+        rel = np.linalg.norm(got - ref) / nref
+        worst = max(worst, rel)
+        assert rel < 0.06, (k, rel)
+    assert worst > 0          # something was actually compared
