@@ -88,6 +88,8 @@ static int gemm_dw(int Ndim, int Kdim, int rows, const float* dOut, int ld_do, c
     return gemm_s(Ndim, Kdim, rows, dOut, 1, ld_do, In, 1, ld_in, nullptr, 0, dW, ld_dw, st);
 }
 
+static inline int gsz(size_t n) { return (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256); }
+
 // ------------------------------------------------------------------------------------------------
 // element-wise / reduction kernels
 // ------------------------------------------------------------------------------------------------
@@ -146,37 +148,119 @@ __global__ void k_add3(const float* a, const float* b, const float* c, float* ou
 }
 
 // ------------------------------------------------------------------------------------------------
-// dTbl[j][q][h] = sum over rows r=(b,t) with seq[b, off + t + j] == q of dpre1[r][h]   (bucketed, deterministic)
-// grid (H/64, FS, DT_CHUNKS), 64 threads (one feature each), smem table [256][64]
+// dTbl[j][q][h] = sum over rows r=(b,t) with seq[b, off + t + j] == q of dpre1[r][h]
+// The bucket of a window position (b, pi) does not depend on the tap: position pi with value q feeds tap j with row
+// t = pi - j.  So the window positions are counting-sorted by value ONCE (ascending position order, deterministic), and a
+// block per (value, feature chunk, segment) walks its positions, reading for each the FS consecutive rows
+// dpre1[b, pi-FS+1 .. pi] into FS register accumulators: no atomics, no shared-memory table, coalesced row reads.
 // ------------------------------------------------------------------------------------------------
-constexpr int DT_CHUNKS = 4;
-template <typename T1>
-__global__ void __launch_bounds__(64)
-k_dtbl_partial(const uint8_t* __restrict__ seq, int seq_ld, int off, const T1* __restrict__ dpre1, int B, int T, int H,
-               float* __restrict__ partial /* (DT_CHUNKS, FS, Q, H) */, int FS) {
-    extern __shared__ float tab[];        // [256][64]
-    const int h = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y, ch = blockIdx.z;
-    for (int i = threadIdx.x; i < SRNN_Q * 64; i += 64) tab[i] = 0.f;
+constexpr int DT_SEG = 4;      // segments per value bucket (partials summed in fixed order)
+constexpr int DT_MAXFS = 32;
+
+__global__ void k_q_count(const uint8_t* __restrict__ seq, int seq_ld, int off, int B, int W, int* __restrict__ counts) {
+    const int q = blockIdx.x;
+    __shared__ int red[256];
+    int c = 0;
+    for (int i = threadIdx.x; i < B * W; i += blockDim.x) c += seq[(size_t)(i / W) * seq_ld + off + (i % W)] == q;
+    red[threadIdx.x] = c;
     __syncthreads();
-    const int R = B * T, per = (R + DT_CHUNKS - 1) / DT_CHUNKS;
-    const int r0 = ch * per, r1 = min(R, r0 + per);
-    if (h < H) {
-        for (int r = r0; r < r1; ++r) {
-            const int b = r / T, t = r % T;
-            const int q = seq[(size_t)b * seq_ld + off + t + j];
-            tab[q * 64 + threadIdx.x] += to_f(dpre1[(size_t)r * H + h]);
-        }
-        for (int q = 0; q < SRNN_Q; ++q)
-            partial[(((size_t)ch * FS + j) * SRNN_Q + q) * H + h] = tab[q * 64 + threadIdx.x];
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[q] = red[0];
+}
+__global__ void k_q_prefix(const int* __restrict__ counts, int* __restrict__ starts) {
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int q = 0; q < SRNN_Q; ++q) { starts[q] = s; s += counts[q]; }
+        starts[SRNN_Q] = s;
     }
 }
-__global__ void k_dtbl_final(const float* __restrict__ partial, size_t n, float* __restrict__ out) {
+// ordered compaction: block q writes the window positions (b*W + pi) holding value q, ascending
+__global__ void k_q_scatter(const uint8_t* __restrict__ seq, int seq_ld, int off, int B, int W, const int* __restrict__ starts,
+                            int* __restrict__ pos) {
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int wsum[8];
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = starts[q];
+    __syncthreads();
+    for (int i0 = 0; i0 < B * W; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const bool hit = i < B * W && seq[(size_t)(i / W) * seq_ld + off + (i % W)] == q;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += wsum[w2];
+        if (hit) pos[base_s + before + __popc(bal & ((1u << lane) - 1))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w2 = 0; w2 < 8; ++w2) t += wsum[w2];
+            base_s += t;
+        }
+        __syncthreads();
+    }
+}
+// grid (Q, H/256, DT_SEG), 256 threads = 256 features
+template <typename T1>
+__global__ void __launch_bounds__(256)
+k_dtbl_accum(const int* __restrict__ pos, const int* __restrict__ starts, const T1* __restrict__ dpre1, int T, int W, int H,
+             int FS, float* __restrict__ partial /* (DT_SEG, FS, Q, H) */) {
+    const int q = blockIdx.x, h = blockIdx.y * 256 + threadIdx.x, seg = blockIdx.z;
+    const int s0 = starts[q], n = starts[q + 1] - s0;
+    const int per = (n + DT_SEG - 1) / DT_SEG;
+    const int k0 = s0 + seg * per, k1 = min(s0 + n, k0 + per);
+    float acc[DT_MAXFS];
+#pragma unroll
+    for (int j = 0; j < DT_MAXFS; ++j) acc[j] = 0.f;
+    if (h < H) {
+        for (int k = k0; k < k1; ++k) {
+            const int i = pos[k], b = i / W, pi = i % W;
+            const T1* rowbase = dpre1 + ((size_t)b * T + pi) * H + h;          // row t = pi - j  ->  rowbase - j*H
+#pragma unroll
+            for (int j = 0; j < DT_MAXFS; ++j) {
+                const int t = pi - j;
+                if (j < FS && t >= 0 && t < T) acc[j] += to_f(rowbase[-(long long)j * H]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DT_MAXFS; ++j)
+            if (j < FS) partial[(((size_t)seg * FS + j) * SRNN_Q + q) * H + h] = acc[j];
+    }
+}
+// sum the segment partials (fixed order) -> dTbl (FS,Q,H) and its per-tap transpose dTblT (FS,H,Q)
+__global__ void k_dtbl_final(const float* __restrict__ partial, int FS, int H, float* __restrict__ out, float* __restrict__ outT) {
+    const size_t n = (size_t)FS * SRNN_Q * H;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float s = 0.f;
-        for (int c = 0; c < DT_CHUNKS; ++c) s += partial[(size_t)c * n + i];
+        for (int c = 0; c < DT_SEG; ++c) s += partial[(size_t)c * n + i];
         out[i] = s;
+        const int h = (int)(i % H), q = (int)((i / H) % SRNN_Q), j = (int)(i / ((size_t)H * SRNN_Q));
+        outT[((size_t)j * H + h) * SRNN_Q + q] = s;
     }
 }
+
+template <typename T1>
+static int dtbl_compute(const uint8_t* seq, int seq_ld, int off, const T1* dpre1, int B, int T, int H, int FS, int* iwork,
+                        float* partial, float* dTbl, float* dTblT, cudaStream_t st) {
+    if (FS > DT_MAXFS) return fail(SRNN_ERR_UNSUPPORTED, "frame size %d > %d", FS, DT_MAXFS);
+    const int W = T + FS - 1;
+    int* counts = iwork;
+    int* starts = iwork + 256;
+    int* pos = iwork + 768;
+    SRNN_LAUNCH(k_q_count, SRNN_Q, 256, 0, st, seq, seq_ld, off, B, W, counts);
+    SRNN_LAUNCH(k_q_prefix, 1, 32, 0, st, counts, starts);
+    SRNN_LAUNCH(k_q_scatter, SRNN_Q, 256, 0, st, seq, seq_ld, off, B, W, starts, pos);
+    SRNN_LAUNCH((k_dtbl_accum<T1>), dim3(SRNN_Q, cdiv(H, 256), DT_SEG), 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
+    SRNN_LAUNCH(k_dtbl_final, gsz((size_t)FS * SRNN_Q * H), 256, 0, st, partial, FS, H, dTbl, dTblT);
+    return SRNN_OK;
+}
+
+// fold dTbl back onto the MLP input weights (H,Q,FS) and the embedding (Q,Q):  Tbl[j][q][h] = sum_e Wm[h,e,j] E[q,e]
+static int tbl_foldback(srnn_ctx* ctx, const srnn_params* P, const srnn_params* G, const float* dTblT, float* scratch2HQF,
+                        float* dWmt, float* dWm, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // GRU cell backward for one frame (all utterances): recomputes r, z, n from the saved projections
@@ -328,7 +412,23 @@ __global__ void k_untranspose_mlp_in(const float* __restrict__ wt, float* __rest
     for (int e = threadIdx.x; e < Q; e += blockDim.x) w[((size_t)h * Q + e) * FS + j] = wt[((size_t)j * H + h) * Q + e];
 }
 
-static inline int gsz(size_t n) { return (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256); }
+
+static int tbl_foldback(srnn_ctx* ctx, const srnn_params* P, const srnn_params* G, const float* dTblT, float* scratch2HQF,
+                        float* dWmt, float* dWm, cudaStream_t st) {
+    const int H = ctx->H, Q = ctx->Q, FS0 = ctx->FS0;
+    float* wm_fold = scratch2HQF;                       // (H, Q, FS)
+    float* wm_t = scratch2HQF + (size_t)H * Q * FS0;    // (FS, H, Q)
+    SRNN_TRY(wn_fold(P->mlp_input, wm_fold, H, Q * FS0, st));
+    SRNN_TRY(transpose_mlp_in(wm_fold, wm_t, H, Q, FS0, st));
+    // dWm_t[(j,h), e] = sum_q dTblT[(j,h), q] E[q, e]        (one GEMM over all taps)
+    SRNN_TRY(gemm_s(FS0 * H, Q, Q, dTblT, Q, 1, P->embedding, 1, Q, nullptr, 0, dWmt, Q, st));
+    // dE[q, e] = sum_{(j,h)} dTblT[(j,h), q] wm_t[(j,h), e]
+    float* dE = (float*)G->embedding;
+    if (dE) SRNN_TRY(gemm_s(Q, Q, FS0 * H, dTblT, 1, Q, wm_t, 1, Q, nullptr, 0, dE, Q, st));
+    SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
+    SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
+    return SRNN_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // orchestration
@@ -359,7 +459,7 @@ size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T) {
     size_t f = R * Q + 2 * R * H                                // dlogits, dA, dB
                + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H   // dY ping/pong, dX, dGI, dGH, carries
                + maxfs * H * H * 2 + maxfs * H + H * maxkin + H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin)   // weight-grad staging
-               + (DT_CHUNKS + 1) * FS0 * Q * H + 2 * FS0 * H * Q            // dTbl partials + final, dWm_t, dWm
+               + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0))             // dTbl partials + final, dWm_t, dWm
                + (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + Q + 4096;
     return f * sizeof(float) + 64 * 256;
 }
@@ -400,8 +500,10 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     float* t_in = b.take<float>(stg);
     float* t_c = b.take<float>(stg);
     float* t_s = b.take<float>(stg);
-    float* dTblP = b.take<float>((size_t)DT_CHUNKS * FS0 * Q * H);
+    float* dTblP = b.take<float>((size_t)DT_SEG * FS0 * Q * H);
     float* dTbl = b.take<float>((size_t)FS0 * Q * H);
+    float* dTblT = b.take<float>((size_t)FS0 * Q * H);
+    int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0));
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
     float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
@@ -425,32 +527,8 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     SRNN_TRY(gemm_dx(R, H, H, dA, H, ctx->w_hid, H, nullptr, 0, dB, H, st));                    // dx1
     SRNN_LAUNCH(k_relu_mask, gsz((size_t)R * H), 256, 0, st, dB, F.X1, dB, (size_t)R * H);        // dpre1 = dc0
     // ---- folded table: dTbl, then back onto W_in (H,Q,FS) and E (Q,Q) ----
-    {
-        static bool dt_attr = false;
-        if (!dt_attr) {
-            SRNN_CUDA(cudaFuncSetAttribute(k_dtbl_partial<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SRNN_Q * 64 * (int)sizeof(float)));
-            dt_attr = true;
-        }
-        SRNN_LAUNCH(k_dtbl_partial<float>, dim3(cdiv(H, 64), FS0, DT_CHUNKS), 64, SRNN_Q * 64 * sizeof(float), st, F.seq, Lseq,
-                    lookback - FS0, dB, B, T, H, dTblP, FS0);
-        const size_t n = (size_t)FS0 * Q * H;
-        SRNN_LAUNCH(k_dtbl_final, gsz(n), 256, 0, st, dTblP, n, dTbl);
-        // folded W_in^T per tap (FS,H,Q) is rebuilt into dTblP's storage (no longer needed)
-        float* wm_fold = dTblP;                       // (H, Q, FS)
-        float* wm_t = dTblP + (size_t)H * Q * FS0;    // (FS, H, Q)
-        SRNN_TRY(wn_fold(P->mlp_input, wm_fold, H, Q * FS0, st));
-        SRNN_TRY(transpose_mlp_in(wm_fold, wm_t, H, Q, FS0, st));
-        float* dE = (float*)G->embedding;
-        for (int j = 0; j < FS0; ++j) {
-            const float* dT = dTbl + (size_t)j * Q * H;            // (Q, H)
-            // dWm_t[j] (H, Q=e) = sum_q dT[q, h] * E[q, e]
-            SRNN_TRY(gemm_s(H, Q, Q, dT, 1, H, P->embedding, 1, Q, nullptr, 0, dWmt + (size_t)j * H * Q, Q, st));
-            // dE (Q, e) += sum_h dT[q, h] * wm_t[j][h, e]
-            if (dE) SRNN_TRY(gemm_s(Q, Q, H, dT, H, 1, wm_t + (size_t)j * H * Q, 1, Q, j ? dE : nullptr, Q, dE, Q, st));
-        }
-        SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
-        SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
-    }
+    SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, dB, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
+    SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
     // ---- frame tiers, lowest first: each receives dUP (M, fs*H) from below ----
     const float* dUP = dB;                            // tier 0's upsampled output is the MLP conditioning c0
     int xb = 0;
@@ -572,7 +650,7 @@ size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T) {
     }
     const size_t Mp = rup64(maxM);
     size_t f32 = R * Q + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H + 2 * maxfs * H * H + maxfs * H + H * maxkin +
-                 H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin) + (DT_CHUNKS + 1) * FS0 * Q * H + 2 * FS0 * H * Q +
+                 H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin) + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0))  +
                  (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + 3 * H * H;
     size_t b16 = R * Q + Q * Rp + 2 * H * Rp + 2 * R * H                     // D16, D16t, TA, TB, DP2, DP1
                  + maxfs * H * Mp + 3 * H * Mp + 2 * 3 * H * Mp + 2 * maxM * 3 * H + 2 * maxM * H;   // tier transposes + copies
@@ -614,8 +692,10 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     float* t_in = b.take<float>(stg);
     float* t_c = b.take<float>(stg);
     float* t_s = b.take<float>(stg);
-    float* dTblP = b.take<float>((size_t)DT_CHUNKS * FS0 * Q * H);
+    float* dTblP = b.take<float>((size_t)DT_SEG * FS0 * Q * H);
     float* dTbl = b.take<float>((size_t)FS0 * Q * H);
+    float* dTblT = b.take<float>((size_t)FS0 * Q * H);
+    int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0));
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
     float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
@@ -657,29 +737,8 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     if (G->mlp_hidden.bias) SRNN_TRY(colsum(DP2, R, H, H, csp, (float*)G->mlp_hidden.bias, st));
     SRNN_TRY(tc_dx(R, H, H, DP2, H, ctx->w_hid16_t, nullptr, 0, nullptr, DP1, F.X1h, H, st));   // dpre1 = dc0
     // ---- folded table ----
-    {
-        static bool dt_attr = false;
-        if (!dt_attr) {
-            SRNN_CUDA(cudaFuncSetAttribute(k_dtbl_partial<bf>, cudaFuncAttributeMaxDynamicSharedMemorySize, SRNN_Q * 64 * (int)sizeof(float)));
-            dt_attr = true;
-        }
-        SRNN_LAUNCH(k_dtbl_partial<bf>, dim3(cdiv(H, 64), FS0, DT_CHUNKS), 64, SRNN_Q * 64 * sizeof(float), st, F.seq, Lseq,
-                    lookback - FS0, DP1, B, T, H, dTblP, FS0);
-        const size_t n = (size_t)FS0 * Q * H;
-        SRNN_LAUNCH(k_dtbl_final, gsz(n), 256, 0, st, dTblP, n, dTbl);
-        float* wm_fold = dTblP;
-        float* wm_t = dTblP + (size_t)H * Q * FS0;
-        SRNN_TRY(wn_fold(P->mlp_input, wm_fold, H, Q * FS0, st));
-        SRNN_TRY(transpose_mlp_in(wm_fold, wm_t, H, Q, FS0, st));
-        float* dE = (float*)G->embedding;
-        for (int j = 0; j < FS0; ++j) {
-            const float* dT = dTbl + (size_t)j * Q * H;
-            SRNN_TRY(gemm_s(H, Q, Q, dT, 1, H, P->embedding, 1, Q, nullptr, 0, dWmt + (size_t)j * H * Q, Q, st));
-            if (dE) SRNN_TRY(gemm_s(Q, Q, H, dT, H, 1, wm_t + (size_t)j * H * Q, 1, Q, j ? dE : nullptr, Q, dE, Q, st));
-        }
-        SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
-        SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
-    }
+    SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, DP1, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
+    SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
     // ---- frame tiers, lowest first ----
     const bf* dUP = DP1;
     for (int i = 0; i < NT; ++i) {

@@ -47,7 +47,6 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
     return SRNN_OK;
 }
 
-constexpr int UMMA_STAGES = 4;
 constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
 
 template <int BM, int BN>
@@ -55,7 +54,9 @@ struct GemmSmem {
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = UMMA_STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // as many TMA stages as fit in ~192 KB (max 8): small-N tiles are latency-bound on the load pipeline, not on the MMA
+    static constexpr int NSTAGE = (196608 / STAGE) < 8 ? (196608 / STAGE) : 8;
+    static constexpr int TOTAL = NSTAGE * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 // one launch can carry two independent problems that share the activation row count and K (blockIdx.z selects):
@@ -109,6 +110,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
     const int n_feat = P.n_feat, n_rows = args.n_rows;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int UMMA_STAGES = S::NSTAGE;
     uint64_t* full = (uint64_t*)(smem + UMMA_STAGES * S::STAGE);
     uint64_t* empty = full + UMMA_STAGES;
     uint64_t* tmem_full = empty + UMMA_STAGES;
