@@ -26,6 +26,8 @@ C2 = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, u
           cond_dim=86, spk_dim=6)
 F_ALG = 6.423e6      # FLOP per generated sample per utterance, embedding-o-conv folded; what the kernels execute
 F_DENSE = 16.889e6   # the reference graph's dense work, for context
+F_MLP = 2.0 * (1024 * 1024 + 1024 * 256) + 20 * 1024   # k_mlp_persist's share of F_ALG per sample per utterance: hidden +
+                                                       # output contraction + the folded-table adds (SURVEY 8d components)
 SAMPLE_RATE = 16000
 
 
@@ -287,11 +289,37 @@ def main():
     clocks = sampler.stop() if sampler else None
     secs_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 3))
 
+    # Dominant kernel (k_mlp_persist, one launch per tier-0 frame = FS0 samples x B utterances): CUDA events around every
+    # launch on the library's generation stream, over one more (untimed-for-`value`) pass with direct launches.
+    kern = None
+    if mode == S.MODE_BF16:
+        import ctypes
+        os.environ["SRNN_TIME_KERNELS"] = "1"
+        try:
+            flush.fill_(1)
+            step_device()
+            torch.cuda.synchronize()
+            ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+            lib.srnn_timed_kernel(model._ctx, ctypes.byref(ms), ctypes.byref(n))
+            if n.value:
+                kern = (ms.value / n.value * 1e-3, n.value, ms.value * 1e-3)
+        finally:
+            del os.environ["SRNN_TIME_KERNELS"]
+
     total = world * B * T * args.steps
     value = total / secs
     e2e = total / secs_e2e
     peak_tf, peak_gbs, peak_src = measured_peaks()
-    ach = value * F_ALG / 1e12 / world                                          # per-GPU TFLOP/s, algorithmic
+    ach_step = value * F_ALG / 1e12 / world                                     # per-GPU TFLOP/s, algorithmic, whole step
+    fs0 = C2["frame_sizes"][0]
+    if kern:
+        flops_launch = F_MLP * B * fs0
+        ach, kname = flops_launch / kern[0] / 1e12, "srnn::k_mlp_persist"
+        kinfo = {"kernel": kname, "launches_timed": kern[1], "avg_launch_us": kern[0] * 1e6, "flops_per_launch": flops_launch,
+                 "share_of_step": kern[2] / (secs / args.steps),
+                 "how": "CUDA events around each launch on the generation stream (direct launches, SRNN_TIME_KERNELS)"}
+    else:
+        ach, kinfo = ach_step, {"kernel": "whole generation step (all launches of srnn_generate)"}
     h2d = cond_h.numel() * 4 + spk_h.numel() * 8 + uni_h.numel() * 4
     d2h = audio_h.numel() * 4
     line = {
@@ -308,8 +336,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                      "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
-                     "flops_per_sample": F_ALG, "achieved_dense_equiv": value * F_DENSE / 1e12 / world,
-                     "kernel": "whole generation step (all launches of srnn_generate)"},
+                     "flops_per_sample": F_ALG, "whole_step_achieved": ach_step, "whole_step_frac": ach_step / peak_tf,
+                     "achieved_dense_equiv": value * F_DENSE / 1e12 / world, **kinfo},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, dt, th = cpu_port_rate(args.cpu_n_cond, B)

@@ -154,6 +154,9 @@ SRNN_API int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream);
 /* C (M,N) = A (M,K) . B (N,K)^T + bias (N) [+ addend (M,N)] [relu]; row-major fp32; mode as above. */
 SRNN_API int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
               const float* addend, int32_t relu, float* C, int32_t mode, void* stream);
+/* Measurement hook: CUDA-event time (ms) and launch count of the persistent sample-level kernel over the last
+ * srnn_generate call made with the environment variable SRNN_TIME_KERNELS set (direct launches instead of the graph). */
+SRNN_API int srnn_timed_kernel(const srnn_ctx* ctx, double* ms, int64_t* launches);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 SRNN_API int64_t srnn_launch_count(void);
 

@@ -410,6 +410,16 @@ int srnn_clamp_adam_step(int32_t count, float* const* params, const float* const
                       (cudaStream_t)stream);
 }
 
+// Measurement hook: accumulated CUDA-event time (ms) and launch count of the persistent sample-level kernel over the last
+// srnn_generate call that ran with the environment variable SRNN_TIME_KERNELS set (which issues the launches directly
+// instead of through the CUDA graph so that events can bracket them on their stream).
+int srnn_timed_kernel(const srnn_ctx* ctx, double* ms, int64_t* launches) {
+    if (!ctx || !ms || !launches) return fail(SRNN_ERR_ARG, "null argument");
+    *ms = ctx->timed_ms;
+    *launches = ctx->timed_launches;
+    return SRNN_OK;
+}
+
 // mean NLL in bits of log-probabilities against targets (nn.py:66-70); loss_out = one device float
 int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, int32_t rows, float* loss_out, void* stream) {
     if (!ctx || !logp || !target || !loss_out || rows < 1) return fail(SRNN_ERR_ARG, "bad argument");
@@ -485,7 +495,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
     long long* trace = nullptr;
     if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 64));
-    bool use_graph = !getenv("SRNN_NO_GRAPH");
+    const bool time_kernels = persist && getenv("SRNN_TIME_KERNELS");
+    bool use_graph = !getenv("SRNN_NO_GRAPH") && !time_kernels;
+    std::vector<cudaEvent_t> tev;
     const long long before = g_launches.load();
     if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
@@ -535,7 +547,18 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
                 mp.tbl = ctx->tbl16; mp.b_hid = ctx->b_hid; mp.b_out = ctx->b_out; mp.x1 = X1h; mp.part = part;
                 mp.ctr = gctr; mp.uniforms = uniforms; mp.logp_out = logp_out; mp.trace = trace;
-                SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
+                if (time_kernels) {
+                    cudaEvent_t e0, e1;
+                    SRNN_CUDA(cudaEventCreate(&e0));
+                    SRNN_CUDA(cudaEventCreate(&e1));
+                    SRNN_CUDA(cudaEventRecord(e0, st));
+                    SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
+                    SRNN_CUDA(cudaEventRecord(e1, st));
+                    tev.push_back(e0);
+                    tev.push_back(e1);
+                } else {
+                    SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
+                }
                 continue;
             }
             if (bf16) {
@@ -586,6 +609,19 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         for (int p = 0; p < n_cond; ++p) SRNN_TRY(body());
     }
     SRNN_TRY(dequant_audio(seq, Lseq, lookback, ctx->lut, samples_out, audio_out, B, T, st));   // model.py:520
+    if (time_kernels) {   // CUDA-event duration of every persistent launch, on the stream it ran on
+        SRNN_CUDA(cudaStreamSynchronize(st));
+        double tot = 0;
+        for (size_t k = 0; k + 1 < tev.size(); k += 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[k], tev[k + 1]);
+            tot += ms;
+            cudaEventDestroy(tev[k]);
+            cudaEventDestroy(tev[k + 1]);
+        }
+        ctx->timed_ms = tot;
+        ctx->timed_launches = (long long)(tev.size() / 2);
+    }
     if (trace) {   // debugging aid: average phase durations (SM cycles) of CTA 0 over the last persistent launch
         SRNN_CUDA(cudaStreamSynchronize(st));
         static const char* names[9] = {"wait P", "x1 slice", "barrier A", "TMA+MMA1", "epilogue1", "MMA2", "epilogue2",

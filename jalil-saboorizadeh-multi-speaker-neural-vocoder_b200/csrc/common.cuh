@@ -119,6 +119,8 @@ struct srnn_ctx {
     float* b_out = nullptr;
     float* lut = nullptr;     // (Q) 2*dequantize(q)
     float* loss_partial = nullptr;
+    double timed_ms = 0;          // see srnn_timed_kernel
+    long long timed_launches = 0;
     bool has_bf16 = false;    // tcgen05 path available (H % 64 == 0)
     __nv_bfloat16* tbl16 = nullptr;
     __nv_bfloat16* w_hid16 = nullptr;
