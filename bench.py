@@ -132,7 +132,7 @@ def run_train(args, rank, world, local):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode = S.MODE_BF16 if args.mode == "bf16" else S.MODE_FP32
+    mode = S.MODE_FP32 if args.mode == "fp32" else S.MODE_BF16
     lib = S._lib.load()
     torch.manual_seed(77977)
     model = S.SampleRNN(**C2).to(dev)
