@@ -291,6 +291,15 @@ static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
 
 static inline int pick_bn(int rows) { return rows <= 32 ? 32 : (rows <= 64 ? 64 : (rows <= 128 ? 128 : 256)); }
 
+// teacher-forced contraction out (rows, n_feat) = act (rows, K) . W (n_feat, K)^T + bias [relu]: ROWS orientation (vector
+// epilogue) when there are enough rows to fill 128-row tiles, swap-AB otherwise
+static int tf_gemm(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int rows, int K, const float* bias,
+                   float* out_f32, __nv_bfloat16* out_bf16, int ld_out, int relu, cudaStream_t st) {
+    GemmOperands o{W, act, bias, nullptr, out_f32, out_bf16, n_feat, K, K, 0, ld_out, relu, nullptr};
+    if (rows >= 256 && ld_out % 8 == 0 && n_feat % 16 == 0) return gemm_umma_rows(o, rows, K, 1, nullptr, st);
+    return gemm_umma_multi(&o, 1, rows, K, 128, pick_bn(rows), st);
+}
+
 int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_seq, const void* cond,
                      int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
                      float* logp_out, int32_t mode, void* stream) {
@@ -333,8 +342,7 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
             float* GH = P.GH[i][l];
             if (bf16) {
                 SRNN_TRY(f32_to_bf16_pad(h0, B, H, H, h016, B, H, st));
-                SRNN_TRY(gemm_umma(t.w_ih16[l], 3 * H, in16, M, H, H, H, t.b_ih[l], nullptr, 0, GI, nullptr, 3 * H, 0, 128,
-                                   pick_bn(M), st));
+                SRNN_TRY(tf_gemm(t.w_ih16[l], 3 * H, in16, M, H, t.b_ih[l], GI, nullptr, 3 * H, 0, st));
             } else {
                 SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI, 3 * H, st));
             }
@@ -357,8 +365,7 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
             in16 = Y16;
         }
         if (bf16)
-            SRNN_TRY(gemm_umma(t.w_up16, t.fs * H, in16, M, H, H, H, t.b_up, nullptr, 0, P.UP[i], nullptr, t.fs * H, 0, 128,
-                               pick_bn(M), st));
+            SRNN_TRY(tf_gemm(t.w_up16, t.fs * H, in16, M, H, t.b_up, P.UP[i], nullptr, t.fs * H, 0, st));
         else
             SRNN_TRY(gemm_f32(M, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, P.UP[i], t.fs * H, st));
         upper = P.UP[i];
@@ -368,8 +375,8 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
     if (bf16) {
         SRNN_TRY(mlp_gather_bf16(P.seq, Lseq, lookback - FS0, nullptr, ctx->tbl16, upper, (long long)T * H, H, P.X1h, B, T, H,
                                  FS0, st));
-        SRNN_TRY(gemm_umma(ctx->w_hid16, H, P.X1h, R, H, H, H, ctx->b_hid, nullptr, 0, nullptr, P.X2h, H, 1, 128, pick_bn(R), st));
-        SRNN_TRY(gemm_umma(ctx->w_out16, Q, P.X2h, R, H, H, H, ctx->b_out, nullptr, 0, logp_out, nullptr, Q, 0, 128, pick_bn(R), st));
+        SRNN_TRY(tf_gemm(ctx->w_hid16, H, P.X1h, R, H, ctx->b_hid, nullptr, P.X2h, H, 1, st));
+        SRNN_TRY(tf_gemm(ctx->w_out16, Q, P.X2h, R, H, ctx->b_out, logp_out, nullptr, Q, 0, st));
     } else {
         SRNN_TRY(mlp_gather(P.seq, Lseq, lookback - FS0, nullptr, ctx->tbl, upper, (long long)T * H, H, P.X1, B, T, H, FS0, st));
         SRNN_TRY(gemm_f32(R, H, H, P.X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, P.X2, H, st));
@@ -699,18 +706,25 @@ int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, c
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == SRNN_MODE_FP32) return gemm_f32(M, N, K, A, K, B, K, bias, addend, N, relu, C, N, st);
     if ((mode & 0xff) == SRNN_MODE_BF16) {
-        // tile selector for tests: bits 8..15 = UMMA M (0 -> 128), bits 16..27 = batch-row tile (0 -> 64)
+        // tile selector for tests: bits 8..15 = UMMA M (0 -> 128), bits 16..27 = batch-row tile (0 -> 64),
+        // bit 28 = ROWS orientation (activation rows on the TMEM lanes; bits 16..27 then give the feature tile),
+        // bit 29 = split the K loop three ways (plain fp32 output only: bias/addend/relu must be absent)
         const int bm = ((mode >> 8) & 0xff) ? ((mode >> 8) & 0xff) : 128;
         const int bn = ((mode >> 16) & 0xfff) ? ((mode >> 16) & 0xfff) : 64;
+        const bool rows = (mode >> 28) & 1, split = (mode >> 29) & 1;
         const int Kp = (K + 63) / 64 * 64, Np = (N + bm - 1) / bm * bm;
         __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;
         SRNN_CUDA(cudaMallocAsync((void**)&a16, sizeof(__nv_bfloat16) * (size_t)M * Kp, st));
         SRNN_CUDA(cudaMallocAsync((void**)&w16, sizeof(__nv_bfloat16) * (size_t)Np * Kp, st));
         SRNN_TRY(f32_to_bf16_pad(A, M, K, K, a16, M, Kp, st));
         SRNN_TRY(f32_to_bf16_pad(B, N, K, K, w16, Np, Kp, st));
-        int rc = gemm_umma(w16, N, a16, M, Kp, Kp, Kp, bias, addend, N, C, nullptr, N, relu, bm, bn, st);
+        float* scratch = nullptr;
+        if (split) SRNN_CUDA(cudaMallocAsync((void**)&scratch, sizeof(float) * 3 * (size_t)M * N, st));
+        GemmOperands o{w16, a16, bias, addend, C, nullptr, N, Kp, Kp, N, N, relu, nullptr};
+        int rc = gemm_umma_ex(&o, 1, M, Kp, bm, bn, rows, split ? 3 : 1, scratch, st);
         cudaFreeAsync(a16, st);
         cudaFreeAsync(w16, st);
+        if (scratch) cudaFreeAsync(scratch, st);
         return rc;
     }
     return fail(SRNN_ERR_UNSUPPORTED, "gemm: mode %d not available", mode);

@@ -17,11 +17,18 @@ constexpr int SBM = 64, SBN = 64, SBK = 16;
 __global__ void __launch_bounds__(256)
 k_gemm_f32_strided(int M, int N, int K, const float* __restrict__ A, long long sam, long long sak,
                    const float* __restrict__ B, long long sbn, long long sbk, const float* add, int ldadd, float* C,
-                   int ldc) {
+                   int ldc, int kper) {
     __shared__ float As[SBK][SBM + 4];
     __shared__ float Bs[SBK][SBN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+    if (kper > 0) {                                // split-K: slice blockIdx.z of the K range -> partial matrix z
+        const int kbeg = blockIdx.z * kper;
+        A += (long long)kbeg * sak;
+        B += (long long)kbeg * sbk;
+        K = K - kbeg < kper ? K - kbeg : kper;
+        C += (size_t)blockIdx.z * M * ldc;
+    }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -74,8 +81,25 @@ static int gemm_s(int M, int N, int K, const float* A, long long sam, long long 
                   long long sbk, const float* add, int ldadd, float* C, int ldc, cudaStream_t st) {
     if (M <= 0 || N <= 0) return SRNN_OK;
     dim3 grid(cdiv(N, SBN), cdiv(M, SBM));
-    SRNN_LAUNCH(k_gemm_f32_strided, grid, 256, 0, st, M, N, K, A, sam, sak, B, sbn, sbk, add, ldadd, C, ldc);
+    SRNN_LAUNCH(k_gemm_f32_strided, grid, 256, 0, st, M, N, K, A, sam, sak, B, sbn, sbk, add, ldadd, C, ldc, 0);
     return SRNN_OK;
+}
+// Same contraction with the K range cut into slices (one grid.z layer each) when the M x N tile grid alone cannot fill
+// the GPU; the partial matrices land in `scratch` (splits x M x ldc floats) and are summed in fixed order.
+static int gemm_s_splitk(int M, int N, int K, const float* A, long long sam, long long sak, const float* B, long long sbn,
+                         long long sbk, float* C, int ldc, float* scratch, size_t scratch_floats, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return SRNN_OK;
+    const int tiles = cdiv(N, SBN) * cdiv(M, SBM);
+    int splits = cdiv(592, tiles);                                    // ~4 CTAs per SM
+    const size_t cap = scratch ? scratch_floats / ((size_t)M * ldc) : 0;
+    if ((size_t)splits > cap) splits = (int)cap;
+    if (splits > K / (4 * SBK)) splits = K / (4 * SBK);
+    if (splits < 2) return gemm_s(M, N, K, A, sam, sak, B, sbn, sbk, nullptr, 0, C, ldc, st);
+    int kper = cdiv(cdiv(K, splits), SBK) * SBK;
+    splits = cdiv(K, kper);
+    dim3 grid(cdiv(N, SBN), cdiv(M, SBM), splits);
+    SRNN_LAUNCH(k_gemm_f32_strided, grid, 256, 0, st, M, N, K, A, sam, sak, B, sbn, sbk, nullptr, 0, scratch, ldc, kper);
+    return sum_splits(scratch, splits, (size_t)M * ldc, (size_t)M * ldc, C, st);
 }
 // dIn (rows, K) = dOut (rows, N) . W (N, K)  [+ add]
 static int gemm_dx(int rows, int Kdim, int Ndim, const float* dOut, int ld_do, const float* W, int ld_w, const float* add,
@@ -118,26 +142,43 @@ constexpr int CS_CHUNKS = 64;
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
 template <typename T>
-__global__ void k_colsum_partial(const T* __restrict__ X, int rows, int cols, int ld, float* __restrict__ partial) {
+__global__ void k_colsum_partial(const T* __restrict__ X, int rows, int cols, int ld, float* __restrict__ partial, int per) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= cols) return;
-    const int per = (rows + CS_CHUNKS - 1) / CS_CHUNKS;
     const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += to_f(X[(size_t)r * ld + col]);
-    partial[(size_t)blockIdx.y * cols + col] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains: the loads of a row block overlap
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += to_f(X[(size_t)r * ld + col]);
+        s1 += to_f(X[(size_t)(r + 1) * ld + col]);
+        s2 += to_f(X[(size_t)(r + 2) * ld + col]);
+        s3 += to_f(X[(size_t)(r + 3) * ld + col]);
+    }
+    for (; r < r1; ++r) s0 += to_f(X[(size_t)r * ld + col]);
+    partial[(size_t)blockIdx.y * cols + col] = (s0 + s1) + (s2 + s3);
 }
-__global__ void k_colsum_final(const float* __restrict__ partial, int cols, float* __restrict__ out) {
+__global__ void k_colsum_final(const float* __restrict__ partial, int cols, int chunks, float* __restrict__ out) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= cols) return;
     float s = 0.f;
-    for (int c = 0; c < CS_CHUNKS; ++c) s += partial[(size_t)c * cols + col];
+    for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * cols + col];
     out[col] = s;
 }
+// `partial` holds CS_CHUNKS * max_cols floats (max_cols = the widest matrix of the pass): narrow matrices use the spare
+// room for more row chunks so that the grid still fills the GPU (fixed summation order either way).
+static size_t g_colsum_cap = 0;   // floats available in the partial buffer of the running pass
 template <typename T>
 static int colsum(const T* X, int rows, int cols, int ld, float* partial, float* out, cudaStream_t st) {
-    SRNN_LAUNCH((k_colsum_partial<T>), dim3(cdiv(cols, 128), CS_CHUNKS), 128, 0, st, X, rows, cols, ld, partial);
-    SRNN_LAUNCH(k_colsum_final, cdiv(cols, 128), 128, 0, st, partial, cols, out);
+    int chunks = CS_CHUNKS;
+    const int want = cdiv(1184, cdiv(cols, 128));                         // ~8 CTAs per SM
+    if (want > chunks) chunks = want;
+    if (g_colsum_cap && (size_t)chunks * cols > g_colsum_cap) chunks = (int)(g_colsum_cap / cols);
+    if (!g_colsum_cap) chunks = CS_CHUNKS;
+    if (chunks > rows) chunks = rows > 0 ? rows : 1;
+    const int per = cdiv(rows, chunks);
+    chunks = cdiv(rows, per);
+    SRNN_LAUNCH((k_colsum_partial<T>), dim3(cdiv(cols, 128), chunks), 128, 0, st, X, rows, cols, ld, partial, per);
+    SRNN_LAUNCH(k_colsum_final, cdiv(cols, 128), 128, 0, st, partial, cols, chunks, out);
     return SRNN_OK;
 }
 
@@ -424,7 +465,9 @@ static int tbl_foldback(srnn_ctx* ctx, const srnn_params* P, const srnn_params* 
     SRNN_TRY(gemm_s(FS0 * H, Q, Q, dTblT, Q, 1, P->embedding, 1, Q, nullptr, 0, dWmt, Q, st));
     // dE[q, e] = sum_{(j,h)} dTblT[(j,h), q] wm_t[(j,h), e]
     float* dE = (float*)G->embedding;
-    if (dE) SRNN_TRY(gemm_s(Q, Q, FS0 * H, dTblT, 1, Q, wm_t, 1, Q, nullptr, 0, dE, Q, st));
+    if (dE)
+        SRNN_TRY(gemm_s_splitk(Q, Q, FS0 * H, dTblT, 1, Q, wm_t, 1, Q, dE, Q, scratch2HQF + 2 * (size_t)H * Q * FS0,
+                               2 * (size_t)H * Q * FS0, st));
     SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
     SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
     return SRNN_OK;
@@ -507,6 +550,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
     float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
+    g_colsum_cap = (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H);
     float* dbtmp = b.take<float>((size_t)3 * H);
     float* dWo = b.take<float>((size_t)Q * H);
     float* wmf = dWm;   // folded mlp-input weights (H,Q,FS0) are rebuilt into dWm's storage before it is needed (see below)
@@ -590,7 +634,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
         }
         float* dX = dXbuf[0];
         // input expansion: X = A W_in^T + b_in (+ upper)
-        SRNN_TRY(gemm_dw(H, t.kin, M, dX, H, F.A[i], t.kin, dWin, t.kin, st));
+        SRNN_TRY(gemm_s_splitk(H, t.kin, M, dX, 1, H, F.A[i], 1, t.kin, dWin, t.kin, dTblP, (size_t)DT_SEG * FS0 * Q * H, st));
         SRNN_TRY(colsum(dX, M, H, H, csp, dbtmp, st));
         if (t.top) {
             SRNN_TRY(wn_fold(tp.spk_expand, wsf, H, c.spk_dim, st));
@@ -631,10 +675,21 @@ static inline int pick_bn2(int rows) { return rows <= 32 ? 32 : (rows <= 64 ? 64
 static int tc_dx(int rows, int Kin, int Nout, const bf* dOut16, int ld_do, const bf* Wt16, const float* addend, int ld_add,
                  float* outf, bf* outb, const bf* mask, int ld_out, cudaStream_t st) {
     GemmOperands o{Wt16, dOut16, nullptr, addend, outf, outb, Kin, Nout, ld_do, ld_add, ld_out, 0, mask};
+    if (rows >= 256 && ld_out % 8 == 0 && ld_add % 4 == 0) return gemm_umma_rows(o, rows, Nout, 1, nullptr, st);
     return gemm_umma_multi(&o, 1, rows, Nout, 128, pick_bn2(rows), st);
 }
-static int tc_dw(int Nout, int Kin, int Kp, const bf* InT, const bf* dOutT, float* dW, cudaStream_t st) {
+// scratch: split-K partials (the K of a weight gradient is the token count: few output tiles, very long K loops)
+static int tc_dw(int Nout, int Kin, int Kp, const bf* InT, const bf* dOutT, float* dW, float* scratch, size_t scratch_floats,
+                 cudaStream_t st) {
     GemmOperands o{InT, dOutT, nullptr, nullptr, dW, nullptr, Kin, Kp, Kp, 0, Kin, 0, nullptr};
+    if (Nout >= 128 && Kin % 8 == 0) {
+        const int tiles = cdiv(Nout, 128) * cdiv(Kin, Kin <= 128 ? 128 : 256);
+        int ks = cdiv(296, tiles);
+        const size_t cap = scratch ? scratch_floats / ((size_t)Nout * Kin) : 0;
+        if ((size_t)ks > cap) ks = (int)cap;
+        if (ks > Kp / 512) ks = Kp / 512;              // at least 8 k-blocks per split
+        return gemm_umma_rows(o, Nout, Kp, ks < 2 ? 1 : ks, scratch, st);
+    }
     return gemm_umma_multi(&o, 1, Nout, Kp, 128, pick_bn2(Nout), st);
 }
 
@@ -699,9 +754,11 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
     float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
+    g_colsum_cap = (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H);
     float* dbtmp = b.take<float>((size_t)3 * H);
     float* dWo = b.take<float>((size_t)Q * H);
     float* dWtmp = b.take<float>((size_t)3 * H * H);
+    const size_t dtblp_floats = (size_t)DT_SEG * FS0 * Q * H;   // dTblP doubles as split-K scratch outside dtbl_compute/foldback
     bf* D16 = b.take<bf>((size_t)R * Q);
     bf* D16t = b.take<bf>((size_t)Q * Rp);
     bf* TA = b.take<bf>((size_t)H * Rp);
@@ -725,14 +782,14 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     SRNN_TRY(transpose_to_bf16(dlogits, R, Q, Q, D16t, Rp, st));
     // ---- output layer ----
     SRNN_TRY(transpose_to_bf16(F.X2h, R, H, H, TA, Rp, st));                                   // x2^T
-    SRNN_TRY(tc_dw(Q, H, Rp, TA, D16t, dWo, st));
+    SRNN_TRY(tc_dw(Q, H, Rp, TA, D16t, dWo, dTblP, dtblp_floats, st));
     SRNN_TRY(wn_bwd(dWo, P->mlp_output, G->mlp_output, Q, H, st));
     if (G->mlp_output.bias) SRNN_TRY(colsum(dlogits, R, Q, Q, csp, (float*)G->mlp_output.bias, st));
     SRNN_TRY(tc_dx(R, H, Q, D16, Q, ctx->w_out16_t, nullptr, 0, nullptr, DP2, F.X2h, H, st));   // dpre2 = dx2 * (x2 > 0)
     // ---- hidden layer ----
     SRNN_TRY(transpose_to_bf16(F.X1h, R, H, H, TA, Rp, st));                                   // x1^T
     SRNN_TRY(transpose_to_bf16(DP2, R, H, H, TB, Rp, st));                                     // dpre2^T
-    SRNN_TRY(tc_dw(H, H, Rp, TA, TB, dWtmp, st));
+    SRNN_TRY(tc_dw(H, H, Rp, TA, TB, dWtmp, dTblP, dtblp_floats, st));
     SRNN_TRY(wn_bwd(dWtmp, P->mlp_hidden, G->mlp_hidden, H, H, st));
     if (G->mlp_hidden.bias) SRNN_TRY(colsum(DP2, R, H, H, csp, (float*)G->mlp_hidden.bias, st));
     SRNN_TRY(tc_dx(R, H, H, DP2, H, ctx->w_hid16_t, nullptr, 0, nullptr, DP1, F.X1h, H, st));   // dpre1 = dc0
@@ -749,7 +806,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
         // upsampling
         SRNN_TRY(transpose_to_bf16(dUP, M, NU, NU, dUPt, Mp, st));
         SRNN_TRY(transpose_to_bf16(F.Y16[i][NL - 1], M, H, H, Yt, Mp, st));
-        SRNN_TRY(tc_dw(NU, H, Mp, Yt, dUPt, dWup, st));
+        SRNN_TRY(tc_dw(NU, H, Mp, Yt, dUPt, dWup, dTblP, dtblp_floats, st));
         SRNN_TRY(colsum(dUP, M, NU, NU, csp, dbup, st));
         SRNN_LAUNCH(k_unpack_up_grad, NU, 128, 0, st, dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs);
         SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
@@ -786,13 +843,13 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
             if (tg.weight_hh[l]) {
                 SRNN_LAUNCH(k_build_hprev, M, 128, 0, st, Y, h0, dYn, Fr, H);
                 SRNN_TRY(transpose_to_bf16(dYn, M, H, H, HPt, Mp, st));
-                SRNN_TRY(tc_dw(3 * H, H, Mp, HPt, dGHt, (float*)tg.weight_hh[l], st));
+                SRNN_TRY(tc_dw(3 * H, H, Mp, HPt, dGHt, (float*)tg.weight_hh[l], dTblP, dtblp_floats, st));
             }
             if (tg.bias_hh[l]) SRNN_TRY(colsum(dGH, M, 3 * H, 3 * H, csp, (float*)tg.bias_hh[l], st));
             if (tg.weight_ih[l]) {
                 if (l) SRNN_TRY(transpose_to_bf16(F.Y16[i][l - 1], M, H, H, INt, Mp, st));
                 else SRNN_TRY(transpose_to_bf16(F.X16[i], M, H, H, INt, Mp, st));
-                SRNN_TRY(tc_dw(3 * H, H, Mp, INt, dGIt, (float*)tg.weight_ih[l], st));
+                SRNN_TRY(tc_dw(3 * H, H, Mp, INt, dGIt, (float*)tg.weight_ih[l], dTblP, dtblp_floats, st));
             }
             if (tg.bias_ih[l]) SRNN_TRY(colsum(dGI, M, 3 * H, 3 * H, csp, (float*)tg.bias_ih[l], st));
             float* din = l ? dYn : dXf;
@@ -800,7 +857,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
             if (l) { float* tmp = dY; dY = dYn; dYn = tmp; }
         }
         // input expansion (K = kin is small: fp32 FFMA)
-        SRNN_TRY(gemm_dw(H, t.kin, M, dXf, H, F.A[i], t.kin, dWin, t.kin, st));
+        SRNN_TRY(gemm_s_splitk(H, t.kin, M, dXf, 1, H, F.A[i], 1, t.kin, dWin, t.kin, dTblP, (size_t)DT_SEG * FS0 * Q * H, st));
         SRNN_TRY(colsum(dXf, M, H, H, csp, dbtmp, st));
         if (t.top) {
             SRNN_TRY(wn_fold(tp.spk_expand, wsf, H, c.spk_dim, st));

@@ -233,6 +233,10 @@ struct GemmOperands {
 int transpose_to_bf16(const float* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int transpose_to_bf16(const __nv_bfloat16* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st);
+int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, bool rows, int ksplit,
+                 float* split_scratch, cudaStream_t st);
+int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* split_scratch, cudaStream_t st);
+int sum_splits(const float* part, int splits, size_t n, size_t stride, float* out, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);
 

@@ -73,6 +73,8 @@ struct alignas(64) GemmProb {
 struct alignas(64) GemmArgs {
     GemmProb p[2];
     int n_rows, K;
+    int ksplit;            // > 1: single problem, blockIdx.z = K split; split z writes out_f32 + z * split_stride (partials)
+    long long split_stride;
     long long* trace;      // development aid (SRNN_TRACE_GEMM=1): clock64 stamps of CTA (0,0,0), else null
 };
 
@@ -101,12 +103,69 @@ __device__ __forceinline__ void epi_store16(const float (&v)[16], float bv, int 
     }
 }
 
-template <int BM, int BN>
+// ROWS orientation (activation rows on the TMEM lanes, features on the columns): one thread owns 16 CONSECUTIVE features of
+// one output row, so bias / addend / mask loads and the output stores are 16-byte vectors.
+template <bool ADD, bool RELU, bool F32, bool B16, bool MASK>
+__device__ __forceinline__ void epi_row16(const float (&v)[16], const float* __restrict__ bias, const float* __restrict__ pa,
+                                          float* __restrict__ pf, __nv_bfloat16* __restrict__ pb,
+                                          const __nv_bfloat16* __restrict__ pm) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = v[i];
+    if (bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + i);
+            x[4 * i] += b4.x; x[4 * i + 1] += b4.y; x[4 * i + 2] += b4.z; x[4 * i + 3] += b4.w;
+        }
+    }
+    if (ADD) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a4 = reinterpret_cast<const float4*>(pa)[i];
+            x[4 * i] += a4.x; x[4 * i + 1] += a4.y; x[4 * i + 2] += a4.z; x[4 * i + 3] += a4.w;
+        }
+    }
+    if (RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+    }
+    if (MASK) {
+        const uint4 m0 = reinterpret_cast<const uint4*>(pm)[0], m1 = reinterpret_cast<const uint4*>(pm)[1];
+        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {     // bf16 > 0  <=>  sign bit clear and magnitude non-zero (NaN never occurs: ReLU output)
+            const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+            if (!(lo != 0 && lo < 0x8000u)) x[2 * i] = 0.f;
+            if (!(hi != 0 && hi < 0x8000u)) x[2 * i + 1] = 0.f;
+        }
+    }
+    if (F32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(pf)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    }
+    if (B16) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+            o[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        reinterpret_cast<uint4*>(pb)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint4*>(pb)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// ROWS = false: "swap-AB" (weights = A operand on the TMEM lanes; the generation-time / per-frame orientation).
+// ROWS = true : activations = A operand (128 rows per CTA), weights = B operand (BN features): the orientation of the
+//               big teacher-forced GEMMs, whose epilogue then stores 16 consecutive features per thread.
+template <int BM, int BN, bool ROWS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_umma(const __grid_constant__ GemmArgs args) {
     using S = GemmSmem<BM, BN>;
     constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
-    const GemmProb& P = args.p[blockIdx.z];
+    const GemmProb& P = args.p[args.ksplit > 1 ? 0 : blockIdx.z];
     const int n_feat = P.n_feat, n_rows = args.n_rows;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -118,8 +177,13 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int KB = args.K / 64;
-    if (m0 >= n_feat) return;                      // the two problems of a launch may differ in feature count
+    int kb0 = 0, KB = args.K / 64;
+    if (args.ksplit > 1) {                         // this CTA's K range (every split is non-empty by construction)
+        const int per = (KB + args.ksplit - 1) / args.ksplit;
+        kb0 = blockIdx.z * per;
+        KB = KB - kb0 < per ? KB - kb0 : per;
+    }
+    if (m0 >= (ROWS ? n_rows : n_feat)) return;    // the two problems of a launch may differ in feature count
     long long* tr = (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? args.trace : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = clock64();
 
@@ -147,8 +211,8 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
                 mbar_wait(&empty[s], ph ^ 1);
                 if (tr && kb < 24) tr[8 + kb] = clock64();
                 mbar_expect_tx(&full[s], S::STAGE);
-                tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], kb * 64, m0);
-                tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], kb * 64, n0);
+                tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], (kb0 + kb) * 64, m0);
+                tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], (kb0 + kb) * 64, n0);
             }
         }
     } else if (warp == 1) {
@@ -177,13 +241,65 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         const int half = (warp - 2) >> 2;
         const float* __restrict__ bias = P.bias;
         const float* __restrict__ addend = P.addend;
-        float* __restrict__ out_f32 = P.out_f32;
+        float* __restrict__ out_f32 =
+            (P.out_f32 && args.ksplit > 1) ? P.out_f32 + (size_t)blockIdx.z * args.split_stride : P.out_f32;
         __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
         const __nv_bfloat16* __restrict__ mask = P.mask;
         const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
         mbar_wait(tmem_full, 0);
         if (tr && threadIdx.x == 64) tr[1] = clock64();
         tc_fence_after();
+        if constexpr (ROWS) {
+            const int r = m0 + 32 * q + lane;
+            const bool r_ok = r < n_rows;
+            float* __restrict__ of = out_f32;
+#pragma unroll 1
+            for (int c = 16 * half; c < BN; c += 32) {
+                const int f0 = n0 + c;
+                if (f0 >= n_feat) break;               // warp-uniform
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
+                if (!r_ok) continue;
+                const size_t o = (size_t)r * ld_out + f0;
+                const float* bp = bias ? bias + f0 : nullptr;
+                if (f0 + 16 <= n_feat) {
+                    if (mask)
+                        epi_row16<false, false, false, true, true>(v, bp, nullptr, nullptr, out_bf16 + o, mask + o);
+                    else if (!addend && !relu && of && !out_bf16)
+                        epi_row16<false, false, true, false, false>(v, bp, nullptr, of + o, nullptr, nullptr);
+                    else if (!addend && relu && !of && out_bf16)
+                        epi_row16<false, true, false, true, false>(v, bp, nullptr, nullptr, out_bf16 + o, nullptr);
+                    else if (addend && !relu && of && !out_bf16)
+                        epi_row16<true, false, true, false, false>(v, bp, addend + (size_t)r * ld_add + f0, of + o, nullptr, nullptr);
+                    else if (!addend && !relu && of && out_bf16)
+                        epi_row16<false, false, true, true, false>(v, bp, nullptr, of + o, out_bf16 + o, nullptr);
+                    else if (!addend && !relu && !of && out_bf16)
+                        epi_row16<false, false, false, true, false>(v, bp, nullptr, nullptr, out_bf16 + o, nullptr);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float x = v[i] + (bp ? bp[i] : 0.f);
+                            if (addend) x += addend[(size_t)r * ld_add + f0 + i];
+                            if (relu) x = fmaxf(x, 0.f);
+                            if (of) of[o + i] = x;
+                            if (out_bf16) out_bf16[o + i] = __float2bfloat16(x);
+                        }
+                    }
+                } else {                               // ragged feature tail
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (f0 + i < n_feat) {
+                            float x = v[i] + (bp ? bp[i] : 0.f);
+                            if (addend) x += addend[(size_t)r * ld_add + f0 + i];
+                            if (relu) x = fmaxf(x, 0.f);
+                            if (mask) x = __bfloat162float(mask[o + i]) > 0.f ? x : 0.f;
+                            if (of) of[o + i] = x;
+                            if (out_bf16) out_bf16[o + i] = __float2bfloat16(x);
+                        }
+                    }
+                }
+            }
+        } else {
         int m;
         bool lane_ok;
         if (BM == 128) {
@@ -224,6 +340,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
                 }
             }
         }
+        }   // !ROWS
     }
     if (tr && threadIdx.x == 64) tr[2] = clock64();
     tc_fence_before();
@@ -231,36 +348,74 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
     if (warp == 1) tmem_dealloc<TCOLS>(tmem_d);
 }
 
-template <int BM, int BN>
+template <int BM, int BN, bool ROWS>
 static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaStream_t st) {
     using S = GemmSmem<BM, BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma<BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma<BM, BN, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
-    dim3 grid(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nprob);
-    SRNN_LAUNCH((k_gemm_umma<BM, BN>), grid, GEMM_THREADS, S::TOTAL, st, args);
+    const int nz = args.ksplit > 1 ? args.ksplit : nprob;
+    dim3 grid = ROWS ? dim3(cdiv(args.n_rows, BM), cdiv(max_feat, BN), nz) : dim3(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nz);
+    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS>), grid, GEMM_THREADS, S::TOTAL, st, args);
+    return SRNN_OK;
+}
+
+// sum of `splits` partial matrices (fixed order) -> out
+__global__ void k_sum_splits(const float* __restrict__ part, int splits, size_t n, size_t stride, float* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += part[(size_t)z * stride + i];
+        out[i] = s;
+    }
+}
+int sum_splits(const float* part, int splits, size_t n, size_t stride, float* out, cudaStream_t st) {
+    int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+    SRNN_LAUNCH(k_sum_splits, grid < 1 ? 1 : grid, 256, 0, st, part, splits, n, stride, out);
     return SRNN_OK;
 }
 
 // nprob (1 or 2) problems  out_i (rows, feat_i) = act_i (rows, K) . W_i (feat_i, K)^T + bias_i [+ addend_i] [relu];
 // W / act are bf16 with K % 64 == 0.  bn selects the batch-row tile (32..256); bm = 128 (default) or 64.
-int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st) {
+// rows = false: swap-AB orientation, tile bm (128|64) features x bn (32..256) rows.
+// rows = true : activation rows on the lanes, tile 128 rows x bn (128|256) features (vector epilogue); needs ld_out % 8 == 0.
+// ksplit > 1 (single problem, fp32 output only): the K loop is cut into ksplit ranges, each CTA writes its partial tile
+// into split_scratch (ksplit x n_rows x ld_out floats) and a second kernel sums them in fixed order into out_f32.
+int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, bool rows, int ksplit,
+                 float* split_scratch, cudaStream_t st) {
     if (K % 64 || K <= 0) return fail(SRNN_ERR_ARG, "gemm_umma: K=%d must be a positive multiple of 64", K);
     if (nprob < 1 || nprob > 2) return fail(SRNN_ERR_ARG, "gemm_umma: 1 or 2 problems per launch");
     GemmArgs args;
     memset(&args, 0, sizeof(args));
     args.n_rows = n_rows;
     args.K = K;
+    args.ksplit = 1;
+    if (ksplit > 1) {
+        const int KB = K / 64, per = (KB + ksplit - 1) / ksplit;
+        ksplit = (KB + per - 1) / per;                 // no empty split
+    }
+    if (ksplit > 1) {
+        if (nprob != 1 || !ops[0].out_f32 || ops[0].out_bf16 || ops[0].bias || ops[0].addend || ops[0].relu || ops[0].mask ||
+            !split_scratch)
+            return fail(SRNN_ERR_ARG, "gemm_umma: split-K needs a single plain fp32-output problem and a scratch buffer");
+        args.ksplit = ksplit;
+        args.split_stride = (long long)n_rows * ops[0].ld_out;
+    }
     int max_feat = 0;
     for (int i = 0; i < nprob; ++i) {
         const GemmOperands& o = ops[i];
-        SRNN_TRY(make_tmap_bf16(&args.p[i].tmA, o.W, o.n_feat, K, o.ld_w, bm));
-        SRNN_TRY(make_tmap_bf16(&args.p[i].tmB, o.act, n_rows, K, o.ld_act, bn));
+        if (rows) {
+            if (o.ld_out % 8 || (o.addend && o.ld_add % 4)) return fail(SRNN_ERR_ARG, "gemm_umma rows: ld_out %% 8, ld_add %% 4");
+            SRNN_TRY(make_tmap_bf16(&args.p[i].tmA, o.act, n_rows, K, o.ld_act, 128));
+            SRNN_TRY(make_tmap_bf16(&args.p[i].tmB, o.W, o.n_feat, K, o.ld_w, bn));
+        } else {
+            SRNN_TRY(make_tmap_bf16(&args.p[i].tmA, o.W, o.n_feat, K, o.ld_w, bm));
+            SRNN_TRY(make_tmap_bf16(&args.p[i].tmB, o.act, n_rows, K, o.ld_act, bn));
+        }
         args.p[i].bias = o.bias;
         args.p[i].addend = o.addend;
-        args.p[i].out_f32 = o.out_f32;
+        args.p[i].out_f32 = args.ksplit > 1 ? split_scratch : o.out_f32;
         args.p[i].out_bf16 = o.out_bf16;
         args.p[i].mask = o.mask;
         args.p[i].n_feat = o.n_feat;
@@ -276,16 +431,18 @@ int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int b
         args.trace = g_trace;
     }
     int rc = SRNN_ERR_UNSUPPORTED;
-#define SRNN_GEMM_CASE(BM_, BN_) \
-    if (bm == BM_ && bn == BN_) rc = launch_gemm_umma<BM_, BN_>(args, nprob, max_feat, st);
-    SRNN_GEMM_CASE(128, 256)
-    SRNN_GEMM_CASE(128, 128)
-    SRNN_GEMM_CASE(128, 64)
-    SRNN_GEMM_CASE(128, 32)
-    SRNN_GEMM_CASE(64, 32)
-    SRNN_GEMM_CASE(64, 64)
+#define SRNN_GEMM_CASE(BM_, BN_, ROWS_) \
+    if (bm == BM_ && bn == BN_ && rows == ROWS_) rc = launch_gemm_umma<BM_, BN_, ROWS_>(args, nprob, max_feat, st);
+    SRNN_GEMM_CASE(128, 256, false)
+    SRNN_GEMM_CASE(128, 128, false)
+    SRNN_GEMM_CASE(128, 64, false)
+    SRNN_GEMM_CASE(128, 32, false)
+    SRNN_GEMM_CASE(64, 32, false)
+    SRNN_GEMM_CASE(64, 64, false)
+    SRNN_GEMM_CASE(128, 256, true)
+    SRNN_GEMM_CASE(128, 128, true)
 #undef SRNN_GEMM_CASE
-    if (rc == SRNN_ERR_UNSUPPORTED) return fail(SRNN_ERR_UNSUPPORTED, "gemm_umma: tile %dx%d not instantiated", bm, bn);
+    if (rc == SRNN_ERR_UNSUPPORTED) return fail(SRNN_ERR_UNSUPPORTED, "gemm_umma: tile %dx%d rows=%d not instantiated", bm, bn, (int)rows);
     if (rc == SRNN_OK && args.trace) {
         cudaStreamSynchronize(st);
         const long long t0 = g_trace[0];
@@ -296,7 +453,19 @@ int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int b
         for (int kb = 0; kb < K / 64 && kb < 24; ++kb) fprintf(stderr, " %lld", g_trace[32 + kb] - t0);
         fprintf(stderr, "\n");
     }
+    if (rc == SRNN_OK && args.ksplit > 1)
+        rc = sum_splits(split_scratch, args.ksplit, (size_t)n_rows * ops[0].ld_out, (size_t)args.split_stride, ops[0].out_f32, st);
     return rc;
+}
+
+int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st) {
+    return gemm_umma_ex(ops, nprob, n_rows, K, bm, bn, false, 1, nullptr, st);
+}
+
+// The big teacher-forced contractions (hundreds of rows or more): ROWS orientation, 128 x 256 (or 128 x 128) tiles.
+int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* split_scratch, cudaStream_t st) {
+    const int bn = o.n_feat <= 128 ? 128 : 256;
+    return gemm_umma_ex(&o, 1, n_rows, K, 128, bn, true, ksplit, split_scratch, st);
 }
 
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,

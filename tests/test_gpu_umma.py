@@ -34,3 +34,28 @@ def test_umma_gemm(bm, bn, shape):
     err = np.abs(got - ref.numpy()).max()
     assert np.isfinite(got).all(), "non-finite output"
     assert err < 2e-3 * K ** 0.5, "max err %g" % err
+
+
+@pytest.mark.parametrize("bn", [256, 128])
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("shape", [(256, 1024, 1024), (100, 304, 200), (300, 256, 64), (1000, 40, 640)])
+def test_umma_gemm_rows_orientation(bn, split, shape):
+    """ROWS orientation (activation rows on the TMEM lanes, vector epilogue) with and without split-K."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K + bn + split)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    Ab, Bb = A.bfloat16().double(), B.bfloat16().double()
+    ref = Ab @ Bb.t()
+    if not split:
+        ref = torch.relu(ref + bias.double() + add.double())
+    dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    mode = S.MODE_BF16 | (128 << 8) | (bn << 16) | (1 << 28) | (split << 29)
+    L.check(L.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), None if split else db.data_ptr(),
+                               None if split else da.data_ptr(), 0 if split else 1, out.data_ptr(), mode, stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all(), "non-finite output"
+    err = np.abs(got - ref.float().numpy()).max()
+    assert err < 2e-3 * K ** 0.5, "max err %g" % err
