@@ -151,6 +151,17 @@ SRNN_API int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float
 SRNN_API int srnn_sample_rows(const float* p, const float* u, int32_t rows, int32_t* idx, void* stream);
 /* out (256) fp32 = 2*dequantize(q) (model.py:385,471). */
 SRNN_API int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream);
+/* One GRU layer over F frames = `self.rnn(input, hidden)` (model.py:244; torch nn.GRU, gate row blocks r, z, n) given the
+ * input projections: gi (B*F, 3H) = W_ih x + b_ih with row b*F+f, w_hh (3H, H), b_hh (3H), h0 (B, H) ->
+ * y (B*F, H) = h_f, gh (B*F, 3H) = W_hh h_{f-1} + b_hh (kept for the backward pass), h_last (B, H) or NULL.
+ * SRNN_MODE_FP32: frame-by-frame fp32; SRNN_MODE_BF16: the persistent tcgen05 recurrence (B <= 128, H % 64 == 0). */
+SRNN_API int srnn_gru_seq_fwd(int32_t B, int32_t F, int32_t H, const float* gi, const float* w_hh, const float* b_hh,
+                              const float* h0, float* y, float* gh, float* h_last, int32_t mode, void* stream);
+/* Back-propagation through time of srnn_gru_seq_fwd (what autograd does for nn.GRU at trainer/__init__.py:103):
+ * dy (B*F, H) -> dgi, dgh (B*F, 3H) gradients of the two projections, dh0 (B, H) or NULL. */
+SRNN_API int srnn_gru_seq_bwd(int32_t B, int32_t F, int32_t H, const float* gi, const float* gh, const float* y,
+                              const float* h0, const float* w_hh, const float* dy, float* dgi, float* dgh, float* dh0,
+                              int32_t mode, void* stream);
 /* C (M,N) = A (M,K) . B (N,K)^T + bias (N) [+ addend (M,N)] [relu]; row-major fp32; mode as above. */
 SRNN_API int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
               const float* addend, int32_t relu, float* C, int32_t mode, void* stream);

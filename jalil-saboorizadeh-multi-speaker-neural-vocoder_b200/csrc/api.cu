@@ -98,6 +98,7 @@ int srnn_create(const srnn_config* cfg, srnn_ctx** out) {
     }
     c->lookback = n;
     cudaGetDevice(&c->device);
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
     *out = c;
     return SRNN_OK;
 }
@@ -345,6 +346,13 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
                 SRNN_TRY(tf_gemm(t.w_ih16[l], 3 * H, in16, M, H, t.b_ih[l], GI, nullptr, 3 * H, 0, st));
             } else {
                 SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI, 3 * H, st));
+            }
+            if (bf16 && gru_persist_supported(B, H, ctx->n_sms)) {      // all F frames of the layer in one persistent launch
+                if (!ctx->gru_ctr) SRNN_TRY(ctx->weights.alloc((void**)&ctx->gru_ctr, 256));
+                SRNN_TRY(gru_persist_fwd(B, F, H, GI, t.w_hh16[l], t.b_hh[l], h0, h016, GH, Y, Y16, hid, ctx->gru_ctr, st));
+                in = Y;
+                in16 = Y16;
+                continue;
             }
             for (int f = 0; f < F; ++f) {
                 const float* hp = f ? Y + (size_t)(f - 1) * H : h0;
@@ -698,6 +706,77 @@ int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream) {
     SRNN_TRY(check_ready(ctx));
     if (!out) return fail(SRNN_ERR_ARG, "null argument");
     return copy_f32(ctx->lut, out, ctx->Q, (cudaStream_t)stream);
+}
+
+// One GRU layer over F frames (torch nn.GRU as used at model.py:133-159,244).  FP32: the frame-by-frame fp32 schedule;
+// BF16: the persistent tcgen05 kernels of gru_persist.cu (B <= 128, H % 64 == 0).
+int srnn_gru_seq_fwd(int32_t B, int32_t F, int32_t H, const float* gi, const float* w_hh, const float* b_hh, const float* h0,
+                     float* y, float* gh, float* h_last, int32_t mode, void* stream) {
+    if (!gi || !w_hh || !b_hh || !h0 || !y || !gh) return fail(SRNN_ERR_ARG, "null argument");
+    if (B < 1 || F < 1 || H < 1) return fail(SRNN_ERR_ARG, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SRNN_MODE_FP32) {
+        for (int f = 0; f < F; ++f) {
+            const float* hp = f ? y + (size_t)(f - 1) * H : h0;
+            const int hp_ld = f ? F * H : H;
+            SRNN_TRY(gemm_f32(B, 3 * H, H, hp, hp_ld, w_hh, H, b_hh, nullptr, 0, 0, gh + (size_t)f * 3 * H, F * 3 * H, st));
+            SRNN_TRY(gru_gates(gi + (size_t)f * 3 * H, F * 3 * H, gh + (size_t)f * 3 * H, F * 3 * H, hp, hp_ld, y + (size_t)f * H,
+                               F * H, f == F - 1 ? h_last : nullptr, B, H, st));
+        }
+        return SRNN_OK;
+    }
+    if (mode != SRNN_MODE_BF16) return fail(SRNN_ERR_UNSUPPORTED, "gru_seq_fwd: mode %d not available", mode);
+    int dev = 0, n_sms = 0;
+    SRNN_CUDA(cudaGetDevice(&dev));
+    SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!gru_persist_supported(B, H, n_sms)) return fail(SRNN_ERR_UNSUPPORTED, "gru_seq_fwd bf16: needs B <= 128 and H %% 64 == 0");
+    __nv_bfloat16 *w16 = nullptr, *h16 = nullptr, *y16 = nullptr;
+    unsigned* ctr = nullptr;
+    SRNN_CUDA(cudaMallocAsync((void**)&w16, sizeof(__nv_bfloat16) * 3 * (size_t)H * H, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&h16, sizeof(__nv_bfloat16) * (size_t)B * H, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&y16, sizeof(__nv_bfloat16) * (size_t)B * F * H, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&ctr, 256, st));
+    SRNN_TRY(f32_to_bf16_pad(w_hh, 3 * H, H, H, w16, 3 * H, H, st));
+    SRNN_TRY(f32_to_bf16_pad(h0, B, H, H, h16, B, H, st));
+    int rc = gru_persist_fwd(B, F, H, gi, w16, b_hh, h0, h16, gh, y, y16, h_last, ctr, st);
+    cudaFreeAsync(w16, st);
+    cudaFreeAsync(h16, st);
+    cudaFreeAsync(y16, st);
+    cudaFreeAsync(ctr, st);
+    return rc;
+}
+
+// BPTT of srnn_gru_seq_fwd: dy (B*F, H) -> dgi, dgh (B*F, 3H), dh0 (B, H).
+int srnn_gru_seq_bwd(int32_t B, int32_t F, int32_t H, const float* gi, const float* gh, const float* y, const float* h0,
+                     const float* w_hh, const float* dy, float* dgi, float* dgh, float* dh0, int32_t mode, void* stream) {
+    if (!gi || !gh || !y || !h0 || !w_hh || !dy || !dgi || !dgh) return fail(SRNN_ERR_ARG, "null argument");
+    if (B < 1 || F < 1 || H < 1) return fail(SRNN_ERR_ARG, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SRNN_MODE_FP32) {
+        float* scratch = nullptr;
+        SRNN_CUDA(cudaMallocAsync((void**)&scratch, sizeof(float) * 2 * (size_t)B * H, st));
+        int rc = gru_seq_bwd_f32(B, F, H, gi, gh, y, h0, dy, w_hh, dgi, dgh, dh0, scratch, st);
+        cudaFreeAsync(scratch, st);
+        return rc;
+    }
+    if (mode != SRNN_MODE_BF16) return fail(SRNN_ERR_UNSUPPORTED, "gru_seq_bwd: mode %d not available", mode);
+    int dev = 0, n_sms = 0;
+    SRNN_CUDA(cudaGetDevice(&dev));
+    SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!gru_persist_supported(B, H, n_sms)) return fail(SRNN_ERR_UNSUPPORTED, "gru_seq_bwd bf16: needs B <= 128 and H %% 64 == 0");
+    __nv_bfloat16 *wt16 = nullptr, *dgi16 = nullptr, *dgh16 = nullptr;
+    unsigned* ctr = nullptr;
+    SRNN_CUDA(cudaMallocAsync((void**)&wt16, sizeof(__nv_bfloat16) * 3 * (size_t)H * H, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&dgi16, sizeof(__nv_bfloat16) * 3 * (size_t)B * F * H, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&dgh16, sizeof(__nv_bfloat16) * 3 * (size_t)B * F * H, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&ctr, 256, st));
+    SRNN_TRY(transpose_to_bf16(w_hh, 3 * H, H, H, wt16, 3 * H, st));
+    int rc = gru_persist_bwd(B, F, H, gi, gh, y, h0, dy, wt16, dgi, dgh, dgi16, dgh16, dh0, ctr, st);
+    cudaFreeAsync(wt16, st);
+    cudaFreeAsync(dgi16, st);
+    cudaFreeAsync(dgh16, st);
+    cudaFreeAsync(ctr, st);
+    return rc;
 }
 
 int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,

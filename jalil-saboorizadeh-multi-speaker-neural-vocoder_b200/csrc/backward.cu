@@ -473,6 +473,29 @@ static int tbl_foldback(srnn_ctx* ctx, const srnn_params* P, const srnn_params* 
     return SRNN_OK;
 }
 
+// BPTT of one GRU layer, frame by frame in fp32 (the SRNN_MODE_FP32 schedule; also the srnn_gru_seq_bwd test hook).
+// scratch: 2 * B * H floats.
+int gru_seq_bwd_f32(int B, int Fr, int H, const float* GI, const float* GH, const float* Y, const float* h0, const float* dY,
+                    const float* w_hh, float* dGI, float* dGH, float* dh0, float* scratch, cudaStream_t st) {
+    float* dhc0 = scratch;
+    float* dhc1 = scratch + (size_t)B * H;
+    float* carry = nullptr;
+    float* cnext = dhc0;
+    for (int f = Fr - 1; f >= 0; --f) {
+        const float* hp = f ? Y + (size_t)(f - 1) * H : h0;
+        const int hp_ld = f ? Fr * H : H;
+        float* part = (cnext == dhc0) ? dhc1 : dhc0;
+        SRNN_LAUNCH(k_gru_bwd_gates, dim3(cdiv(H, 128), B), 128, 0, st, GI + (size_t)f * 3 * H, GH + (size_t)f * 3 * H,
+                    Fr * 3 * H, hp, hp_ld, dY + (size_t)f * H, Fr * H, carry, dGI + (size_t)f * 3 * H,
+                    dGH + (size_t)f * 3 * H, part, H);
+        SRNN_TRY(gemm_s(B, H, 3 * H, dGH + (size_t)f * 3 * H, (long long)Fr * 3 * H, 1, w_hh, 1, H, part, H, cnext, H, st));
+        carry = cnext;
+        cnext = part;
+    }
+    if (dh0) SRNN_TRY(copy_f32(carry, dh0, (size_t)B * H, st));
+    return SRNN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // orchestration
 // ------------------------------------------------------------------------------------------------
@@ -820,7 +843,13 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
             const float* h0 = F.H0[i] + (size_t)l * B * H;
             float* carry = nullptr;
             float* cnext = dhc0;
-            for (int f = Fr - 1; f >= 0; --f) {
+            const bool persist = gru_persist_supported(B, H, ctx->n_sms);
+            if (persist) {                                   // BPTT over all frames of the layer in one persistent launch
+                if (!ctx->gru_ctr) SRNN_TRY(ctx->weights.alloc((void**)&ctx->gru_ctr, 256));
+                SRNN_TRY(gru_persist_bwd(B, Fr, H, GI, GH, Y, h0, dY, t.w_hh16_t[l], dGI, dGH, dGI16, dGH16, dhc0, ctx->gru_ctr, st));
+                carry = dhc0;
+            }
+            for (int f = Fr - 1; f >= 0 && !persist; --f) {
                 const float* hp = f ? Y + (size_t)(f - 1) * H : h0;
                 const int hp_ld = f ? Fr * H : H;
                 float* part = (cnext == dhc0) ? dhc1 : dhc0;

@@ -127,6 +127,8 @@ struct srnn_ctx {
     __nv_bfloat16* w_out16 = nullptr;
     __nv_bfloat16* w_hid16_t = nullptr;   // (H, H) transposed
     __nv_bfloat16* w_out16_t = nullptr;   // (H, Q) transposed
+    unsigned* gru_ctr = nullptr;  // frame-barrier counter of the persistent GRU kernels
+    int n_sms = 0;
     srnn::Arena weights;      // freed on destroy
     // grow-only scratch for predict / generate
     void* ws = nullptr;
@@ -193,6 +195,8 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
 size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T);
 int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
                      cudaStream_t st);
+int gru_seq_bwd_f32(int B, int Fr, int H, const float* GI, const float* GH, const float* Y, const float* h0, const float* dY,
+                    const float* w_hh, float* dGI, float* dGH, float* dh0, float* scratch, cudaStream_t st);
 int clamp_adam(int count, float* const* params, const float* const* grads, float* const* m, float* const* v,
                const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st);
 
@@ -233,6 +237,14 @@ struct GemmOperands {
 int transpose_to_bf16(const float* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int transpose_to_bf16(const __nv_bfloat16* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st);
+// persistent GRU recurrence over all frames of one layer (gru_persist.cu)
+bool gru_persist_supported(int B, int H, int n_sms);
+int gru_persist_fwd(int B, int F, int H, const float* GI, const __nv_bfloat16* w_hh16, const float* b_hh, const float* h0,
+                    const __nv_bfloat16* h0_16, float* GH, float* Y, __nv_bfloat16* Y16, float* h_last, unsigned* ctr,
+                    cudaStream_t st);
+int gru_persist_bwd(int B, int F, int H, const float* GI, const float* GH, const float* Y, const float* h0, const float* dY,
+                    const __nv_bfloat16* w_hh16_t, float* dGI, float* dGH, __nv_bfloat16* dGI16, __nv_bfloat16* dGH16,
+                    float* dh0, unsigned* ctr, cudaStream_t st);
 int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, bool rows, int ksplit,
                  float* split_scratch, cudaStream_t st);
 int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* split_scratch, cudaStream_t st);
