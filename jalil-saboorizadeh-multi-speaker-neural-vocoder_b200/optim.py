@@ -17,6 +17,9 @@ from . import _lib as L
 
 
 class ClampAdam:
+    """All gradients live in ONE flat fp32 bucket (``p.grad`` are views into it): ``zero_grad`` is a single memset, and the
+    data-parallel exchange is a single in-place NCCL all-reduce over NVLink with no gather/scatter copies."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, process_group=None, model=None):
         self.params = [p for p in params if p.requires_grad]
         self.lr, self.betas, self.eps, self.clamp = lr, betas, eps, clamp
@@ -26,32 +29,46 @@ class ClampAdam:
         self.process_group = process_group
         self.model = model                  # the SampleRNN whose packed weights must be refreshed after an update
         self.param_groups = [{"params": self.params, "lr": lr}]       # enough for torch LR schedulers' read access
+        self._flat = None
+        self._views = None
+
+    def _bucket(self):
+        """(Re)build the flat gradient bucket when the parameters moved (e.g. ``.cuda()`` after construction)."""
+        p0 = self.params[0]
+        if self._flat is None or self._flat.device != p0.device:
+            self._flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=p0.device)
+            self._views, off = [], 0
+            for p in self.params:
+                n = p.numel()
+                self._views.append(self._flat[off:off + n].view_as(p))
+                off += n
+        return self._flat
+
+    def _adopt(self):
+        """Make every ``p.grad`` the bucket view (autograd assigns a fresh tensor when ``p.grad`` was None)."""
+        self._bucket()
+        for p, v in zip(self.params, self._views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+            p.grad = v
 
     def zero_grad(self):
-        for p in self.params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-            else:
-                p.grad.zero_()
+        self._bucket().zero_()
+        for p, v in zip(self.params, self._views):
+            p.grad = v
 
     def _allreduce(self):
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) == 1:
             return
-        flat = torch.cat([p.grad.reshape(-1) for p in self.params])
-        dist.all_reduce(flat, group=self.process_group)
-        flat /= dist.get_world_size(self.process_group)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p))
-            off += n
+        dist.all_reduce(self._flat, group=self.process_group)         # sum over ranks, in place, one collective
+        self._flat.mul_(1.0 / dist.get_world_size(self.process_group))   # mean BEFORE the clamp (optim.py:10-13 clamps the full-batch gradient)
 
     def step(self, closure=None):
         loss = closure() if closure is not None else None
-        for p in self.params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        self._adopt()
         self._allreduce()
         self.step_count += 1
         n = len(self.params)
