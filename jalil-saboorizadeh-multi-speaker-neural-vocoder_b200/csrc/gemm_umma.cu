@@ -47,6 +47,24 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
     return SRNN_OK;
 }
 
+// Same matrix viewed as [k-block][row][64]: ONE TMA instruction fetches box_kb consecutive k-blocks of box_rows rows and lays
+// them out as box_kb consecutive {box_rows x 128 B} swizzled stages (issuing a TMA costs ~80 cycles of the producer thread).
+int make_tmap_bf16_kb(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_kb) {
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (((uintptr_t)base & 15) || (ld * 2) % 16 || cols % 64) return fail(SRNN_ERR_ARG, "tensor map: alignment");
+    cuuint64_t gdim[3] = {64, rows, cols / 64};
+    cuuint64_t gstride[2] = {ld * sizeof(__nv_bfloat16), 128};
+    cuuint32_t box[3] = {64, box_rows, box_kb};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return SRNN_OK;
+}
+
 constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
 
 template <int BM, int BN>

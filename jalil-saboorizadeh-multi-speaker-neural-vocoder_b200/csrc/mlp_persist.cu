@@ -32,7 +32,7 @@ using namespace ptx;
 
 constexpr int MP_THREADS = 416;
 constexpr int MP_ISSUERS = 4;
-constexpr int MP_MAX_STAGES = 8;
+constexpr int MP_MAX_STAGES = 16;   // one stage per k-block at H = 1024: the WHOLE X1 tile of a step is in flight at once
 // Back-to-back tcgen05.mma that accumulate into the SAME TMEM tile serialise on the accumulator (~150 cycles each,
 // measured), which dominates with N = 32 columns.  The K loop is therefore spread round-robin over NACC1 independent
 // accumulators that the epilogue sums.  Two M=64 accumulators share a column range (lanes 0-15 / 16-31 of each
@@ -50,7 +50,6 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-
 // barrier among the NS CTAs of one row group; executed by the 128 E threads (named barrier 1)
 __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target, int tidE) {
     named_bar_sync(1, 128);
@@ -81,7 +80,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1)
 k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWo,
               const __grid_constant__ CUtensorMap tmX1, const MlpPersistParams p) {
     const int H = p.H, KB = H >> 6, NS = H >> 6, RPC = 32 / NS, FS = p.FS;
-    const int NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
+    // The TMA ring holds every k-block of X1 (KB x 4 KB): with 8 stages the second half of the tile could only be
+    // requested after the first half had been consumed, i.e. two L2 round trips per step on the serial path (measured
+    // 4.4k cycles for 64 KB).  The 32 KB this costs are recovered by NOT keeping the W_out slice resident: it is re-fetched
+    // from L2 every step into the first 32 KB of the ring as soon as the hidden GEMM has consumed X1 (during epilogue 1).
+    const int NSTG = KB;
     const int nissue = KB < MP_ISSUERS ? KB : MP_ISSUERS;     // MMA-issuing threads in use
     const int nacc = 2 * nissue;                              // hidden-GEMM accumulators in use (2 per issuer)
     const int rg = blockIdx.x / NS, sl = blockIdx.x % NS;
@@ -90,9 +93,10 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sWh = smem;                                  // KB x (64 rows x 128 B)
-    uint8_t* sWo = sWh + (size_t)KB * 8192;               // 2 x (128 rows x 128 B)
-    uint8_t* sRing = sWo + 32768;                         // NSTG x (32 rows x 128 B)
-    uint8_t* sX2 = sRing + (size_t)NSTG * 4096;           // 32 rows x 128 B
+    uint8_t* sRing = sWh + (size_t)KB * 8192;             // X1: KB x (32 rows x 128 B); then W_out: 2 x (128 rows x 128 B)
+    uint8_t* sWo = sRing;                                 // (time-multiplexed with the X1 stages, at least 32 KB)
+    const size_t ring_bytes = (size_t)KB * 4096 > 32768 ? (size_t)KB * 4096 : 32768;
+    uint8_t* sX2 = sRing + ring_bytes;                    // 32 rows x 128 B
     float* sP = (float*)(sX2 + 4096);                     // 2 x 2048 fp32
     uint8_t* sQ = (uint8_t*)(sP + 4096);                  // 32 owned rows x 32-entry sample ring
     float* sU = (float*)(sQ + 1024);                      // this step's uniform of every owned row (prefetched)
@@ -101,7 +105,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     uint64_t* w_ready = bars + 0;
     uint64_t* full = bars + 1;                            // [MP_MAX_STAGES]
     uint64_t* empty = full + MP_MAX_STAGES;               // [MP_MAX_STAGES]
-    uint64_t* x1_ready = empty + MP_MAX_STAGES;
+    uint64_t* x1_ready = empty + MP_MAX_STAGES;           // (re-used as "W_out slice landed" barrier)
     uint64_t* bar_d1 = x1_ready + 1;
     uint64_t* x2_ready = bar_d1 + 1;
     uint64_t* bar_d2 = x2_ready + 1;
@@ -152,17 +156,19 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     // every tcgen05.mma of the single issuing thread in an ELECT/R2UR.BROADCAST loop
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tm_d1 = tmem, tm_d2 = tmem + MP_D2_COL;
-    const int stg_mask = NSTG - 1, stg_shift = 31 - __clz(NSTG);   // NSTG is a power of two
+    (void)NSTG;
+    const int ngrp = KB < MP_ISSUERS ? KB : MP_ISSUERS;       // X1 arrives in ngrp TMA boxes of gsz k-blocks (KB is a power of two)
+    const int gsz = KB / ngrp, gshift = 31 - __clz(gsz);
 
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(w_ready, (uint32_t)(KB * 8192 + 32768));
+            mbar_expect_tx(w_ready, (uint32_t)(KB * 8192));
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(sWh + (size_t)kb * 8192, &tmWh, w_ready, kb * 64, sl * 64);
-            tma_load_2d(sWo, &tmWo, w_ready, sl * 64, 0);
-            tma_load_2d(sWo + 16384, &tmWo, w_ready, sl * 64, 128);
-            int it = 0;
             for (int k = 0; k < p.nsteps; ++k) {
+                // the ring is free again once the output GEMM of the previous step has read W_out (which also implies that
+                // its hidden GEMM is done with the X1 stages)
+                if (k) mbar_wait(bar_d2, (k - 1) & 1);
                 {   // group barrier A, waiting side: arrivals so far = (2k+1) * NS once every slice has published X1
                     const unsigned target = (unsigned)(2 * k + 1) * (unsigned)NS;
                     const unsigned* ctr = p.ctr + rg;
@@ -171,14 +177,15 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     fence_proxy_async_all();              // other CTAs' generic-proxy global writes -> visible to TMA reads
                 }
                 if (p.trace && blockIdx.x == 0) p.trace[k * 64 + 10] = clock64();
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it & stg_mask;
-                    const uint32_t ph = (it >> stg_shift) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], 4096);
-                    tma_load_2d(sRing + (size_t)s * 4096, &tmX1, &full[s], kb * 64, rg * 32);
+                for (int g = 0; g < ngrp; ++g) {          // ngrp TMA instructions of gsz k-blocks each
+                    mbar_expect_tx(&full[g], (uint32_t)gsz * 4096);
+                    tma_load_3d(sRing + (size_t)g * gsz * 4096, &tmX1, &full[g], 0, rg * 32, g * gsz);
                 }
                 if (p.trace && blockIdx.x == 0) p.trace[k * 64 + 11] = clock64();
+                mbar_wait(bar_d1, k & 1);                 // hidden GEMM complete: X1 stages consumed
+                mbar_expect_tx(x1_ready, 32768);
+                tma_load_2d(sWo, &tmWo, x1_ready, sl * 64, 0);
+                tma_load_2d(sWo + 16384, &tmWo, x1_ready, sl * 64, 128);
             }
         }
     } else if (warp >= 9) {
@@ -196,23 +203,20 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             const uint32_t d1b = d1a + (16u << 16);
             for (int k = 0; k < p.nsteps; ++k) {
                 for (int kb = w; kb < KB; kb += MP_ISSUERS) {
-                    const int it = k * KB + kb;
-                    const int s = it & stg_mask;
-                    const uint32_t ph = (it >> stg_shift) & 1;
-                    mbar_wait(&full[s], ph);
+                    mbar_wait(&full[kb >> gshift], k & 1);
                     tc_fence_after();
                     const uint64_t da = dA0 + (uint64_t)(kb * 512);
-                    const uint64_t db = dB0 + (uint64_t)(s * 256);
+                    const uint64_t db = dB0 + (uint64_t)(kb * 256);
                     const uint32_t acc = kb >= MP_ISSUERS;
                     umma_bf16(d1a, da, db, idesc1, acc);
                     umma_bf16(d1b, da + 2, db + 2, idesc1, acc);
                     umma_bf16(d1a, da + 4, db + 4, idesc1, 1);
                     umma_bf16(d1b, da + 6, db + 6, idesc1, 1);
-                    umma_commit(&empty[s]);
                 }
                 umma_commit(bar_d1);
                 if (p.trace && blockIdx.x == 0 && w == 0) p.trace[k * 64 + 14] = clock64();
                 mbar_wait(x2_ready, k & 1);
+                mbar_wait(x1_ready, k & 1);               // this step's W_out slice has landed in the ring
                 tc_fence_after();
                 for (int c = w; c < 4; c += nissue) {                 // (output tile, K half) -> its own accumulator
                     const int t2 = c >> 1, h2 = c & 1;
@@ -466,14 +470,16 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
 }
 
 size_t mlp_persist_smem(int H) {
-    const int KB = H / 64, NSTG = KB < MP_MAX_STAGES ? KB : MP_MAX_STAGES;
+    const int KB = H / 64;
     const int RPC = 32 / (H / 64);
-    return (size_t)KB * 8192 + 32768 + (size_t)NSTG * 4096 + 4096 + 16384 + 1024 + 128 + (size_t)RPC * 1024 + 512 + 1024;
+    const size_t ring = (size_t)KB * 4096 > 32768 ? (size_t)KB * 4096 : 32768;
+    return (size_t)KB * 8192 + ring + 4096 + 16384 + 1024 + 128 + (size_t)RPC * 1024 + 512 + 1024;
 }
 
 bool mlp_persist_supported(int H, int FS, int B, int n_sms) {
     if (H % 64 || H > 1024) return false;
     const int NS = H / 64;
+    if (NS & (NS - 1)) return false;                       // k-block groups of the X1 TMA boxes assume a power of two
     if (32 % NS) return false;
     if (FS < 2 || FS > 31) return false;
     const int RG = (B + 31) / 32;
@@ -487,7 +493,8 @@ int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out1
     CUtensorMap tmWh, tmWo, tmX1;
     SRNN_TRY(make_tmap_bf16(&tmWh, w_hid16, H, H, H, 64));
     SRNN_TRY(make_tmap_bf16(&tmWo, w_out16, SRNN_Q, H, H, 128));
-    SRNN_TRY(make_tmap_bf16(&tmX1, p.x1, (uint64_t)RG * 32, H, H, 32));
+    const int KBh = H / 64, ngrp = KBh < MP_ISSUERS ? KBh : MP_ISSUERS;
+    SRNN_TRY(make_tmap_bf16_kb(&tmX1, p.x1, (uint64_t)RG * 32, H, H, 32, KBh / ngrp));
     const size_t smem = mlp_persist_smem(H);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
