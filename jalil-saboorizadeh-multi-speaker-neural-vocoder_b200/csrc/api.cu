@@ -448,7 +448,7 @@ int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, 
 // times.  fp32 mode: FFMA GEMMs.  bf16 mode: the same schedule with every H-wide contraction on tcgen05 (gemm_umma).
 // ------------------------------------------------------------------------------------------------
 static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_cond, const float* cond, int cond_rows,
-                          const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
+                          const int64_t* spk, const float* uniforms, int u_ld, uint8_t* samples_out, float* audio_out,
                           float* logp_out, cudaStream_t user) {
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
@@ -561,7 +561,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 mp.B = B; mp.H = H; mp.FS = FS0; mp.nsteps = FS0; mp.pos0 = pos; mp.lookback = lookback;
                 mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
                 mp.tbl = ctx->tbl16; mp.b_hid = ctx->b_hid; mp.b_out = ctx->b_out; mp.x1 = X1h; mp.part = part;
-                mp.ctr = gctr; mp.uniforms = uniforms; mp.logp_out = logp_out; mp.trace = trace;
+                mp.ctr = gctr; mp.uniforms = uniforms; mp.u_ld = u_ld; mp.logp_out = logp_out; mp.trace = trace;
                 if (time_kernels) {
                     cudaEvent_t e0, e1;
                     SRNN_CUDA(cudaEventCreate(&e0));
@@ -587,7 +587,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 SRNN_TRY(gemm_f32(B, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
                 SRNN_TRY(gemm_f32(B, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, LG, Q, st));
             }
-            SRNN_TRY(softmax_sample(LG, uniforms, B, seq, Lseq, pos, lookback, step_base, logp_out,
+            SRNN_TRY(softmax_sample(LG, uniforms, u_ld, seq, Lseq, pos, lookback, step_base, logp_out,
                                     (long long)T * Q, B, st));                       // model.py:514-517
         }
         SRNN_TRY(add_int(step_base, lookback, st));
@@ -688,7 +688,28 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
         int n_sms = 0;
         SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
         const bool persist = mode == SRNN_MODE_BF16 && mlp_persist_supported(ctx->H, ctx->FS0, B, n_sms);
-        return generate_graph(ctx, bf16, persist, B, n_cond, cond, cond_rows, spk, uniforms, samples_out, audio_out,
+        // Batches beyond what the persistent sample-level kernel can keep co-resident (RG * NS CTAs <= SMs: 288 utterances at
+        // dim 1024): up to three balanced utterance chunks run back to back through the persistent path (utterances are
+        // independent), which beats the one-GEMM-launch-per-contraction schedule until ~1000 utterances (measured, C4 sweep).
+        if (mode == SRNN_MODE_BF16 && !persist && mlp_persist_supported(ctx->H, ctx->FS0, 32, n_sms)) {
+            const int NS = ctx->H / 64, max_chunk = (n_sms / NS) * 32;
+            const int chunks = (B + max_chunk - 1) / max_chunk;
+            if (chunks <= 3) {
+                const int per = ((B + chunks - 1) / chunks + 31) / 32 * 32;
+                const size_t T = (size_t)n_cond * ctx->lookback;
+                for (int b0 = 0; b0 < B; b0 += per) {
+                    const int Bc = B - b0 < per ? B - b0 : per;
+                    const bool own = cond_rows == B;
+                    SRNN_TRY(generate_graph(ctx, true, true, Bc, n_cond, cond + (own ? (size_t)b0 * n_cond * ctx->cfg.cond_dim : 0),
+                                            own ? Bc : 1, spk + (own ? b0 : 0), uniforms + b0, B,
+                                            samples_out ? samples_out + (size_t)b0 * T : nullptr,
+                                            audio_out ? audio_out + (size_t)b0 * T : nullptr,
+                                            logp_out ? logp_out + (size_t)b0 * T * SRNN_Q : nullptr, (cudaStream_t)stream));
+                }
+                return SRNN_OK;
+            }
+        }
+        return generate_graph(ctx, bf16, persist, B, n_cond, cond, cond_rows, spk, uniforms, B, samples_out, audio_out,
                               logp_out, (cudaStream_t)stream);
     }
     return fail(SRNN_ERR_UNSUPPORTED, "generate: mode %d not available", mode);

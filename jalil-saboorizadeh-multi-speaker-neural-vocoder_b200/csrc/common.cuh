@@ -216,7 +216,8 @@ struct MlpPersistParams {
     __nv_bfloat16* x1;            // (RG*32, H) exchange buffer
     float* part;                  // (RG, NS, 32, 256) split-K partial logits
     unsigned* ctr;                // (RG) group-barrier counters, zeroed by the launcher
-    const float* uniforms;        // (T, B)
+    const float* uniforms;        // (T, u_ld): row t holds the uniforms of step t, utterance b at column b
+    int u_ld;
     float* logp_out;              // (B, T, 256) or null
     long long* trace;             // optional (nsteps, 10) clock64 stamps of CTA 0 (SRNN_TRACE=1), else null
 };

@@ -240,14 +240,14 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         // the owned rows' uniforms are fetched one step ahead (a DRAM miss would otherwise sit on the serial path)
         const int ub = row0 + tidE;
         const bool u_mine = tidE < RPC && ub < p.B;
-        float u_next = u_mine ? __ldg(p.uniforms + (size_t)(i0 - p.lookback) * p.B + ub) : 0.f;
+        float u_next = u_mine ? __ldg(p.uniforms + (size_t)(i0 - p.lookback) * p.u_ld + ub) : 0.f;
         for (int k = 0; k < p.nsteps; ++k) {
             const int i = i0 + k;
             // ---- E1: x1 = relu(P + Tbl[FS-1][newest sample]) for the owned rows -> global X1 ----
             MP_TRACE(0);
             if (tidE < RPC) {
                 sU[tidE] = u_next;
-                if (u_mine && k + 1 < p.nsteps) u_next = __ldg(p.uniforms + (size_t)(i + 1 - p.lookback) * p.B + ub);
+                if (u_mine && k + 1 < p.nsteps) u_next = __ldg(p.uniforms + (size_t)(i + 1 - p.lookback) * p.u_ld + ub);
             }
             mbar_wait(&p_ready[k & 1], (k >> 1) & 1);
             MP_TRACE(1);
