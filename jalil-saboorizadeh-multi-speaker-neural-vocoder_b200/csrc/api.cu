@@ -506,13 +506,28 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // batch-row tile of the tier GEMMs (UMMA M = 128 features): one thread issues a tcgen05.mma every ~45+ cycles, so
     // only N = 256 tiles (128-cycle tensor floor) keep the tensor pipe rather than the issue slot busy
     const int bn_tier = B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256));
+    // With more than 128 utterances a 128-row tile doubles the CTA count (measured: 19.8 -> 16.3 us for the gi+gh launch at
+    // B = 256) as long as the grid still fits one wave of SMs; the tier-2 upsampling (160 feature tiles) keeps 256-row tiles.
+    auto bn_for = [&](int n_feat, int nprob) {
+        if (bn_tier < 256) return bn_tier;
+        return cdiv(n_feat, 128) * cdiv(B, 128) * nprob <= ctx->n_sms ? 128 : 256;
+    };
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
     long long* trace = nullptr;
     if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 64));
     const bool time_kernels = persist && getenv("SRNN_TIME_KERNELS");
-    bool use_graph = !getenv("SRNN_NO_GRAPH") && !time_kernels;
+    const bool time_tiers = getenv("SRNN_TIME_TIERS") != nullptr;   // development aid: per-kernel durations of the tier steps
+    bool use_graph = !getenv("SRNN_NO_GRAPH") && !time_kernels && !time_tiers;
     std::vector<cudaEvent_t> tev;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* name) {
+        if (!time_tiers) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.push_back({name, e});
+    };
     const long long before = g_launches.load();
     if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
@@ -527,9 +542,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     upper = OUT[i + 1] + (size_t)((pos / t.n) % u.fs) * H;
                     up_ld = u.fs * H;
                 }
+                mark(t.top ? "(start top)" : "(start)");
                 SRNN_TRY(tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
                                         c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
                                         H, t.kin, t.top, st));
+                mark(t.top ? "input top" : "input");
                 const float* in = X[i];
                 const bf* in16 = X16[i];
                 for (int l = 0; l < NL; ++l) {
@@ -539,20 +556,23 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                         GemmOperands ops[2] = {
                             {t.w_ih16[l], in16, t.b_ih[l], nullptr, GI[i], nullptr, 3 * H, H, H, 0, 3 * H, 0},
                             {t.w_hh16[l], h16, t.b_hh[l], nullptr, GH[i], nullptr, 3 * H, H, H, 0, 3 * H, 0}};
-                        SRNN_TRY(gemm_umma_multi(ops, 2, B, H, 128, bn_tier, st));
+                        SRNN_TRY(gemm_umma_multi(ops, 2, B, H, 128, bn_for(3 * H, 2), st));
                     } else {
                         SRNN_TRY(gemm_f32(B, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
                         SRNN_TRY(gemm_f32(B, 3 * H, H, h, H, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
                     }
+                    mark("gi+gh gemm");
                     SRNN_TRY(gru_gates(GI[i], 3 * H, GH[i], 3 * H, h, H, h, H, nullptr, B, H, st, bf16 ? h16 : nullptr));
+                    mark("gates");
                     in = h;
                     in16 = h16;
                 }
                 if (bf16)
                     SRNN_TRY(gemm_umma(t.w_up16, t.fs * H, in16, B, H, H, H, t.b_up, nullptr, 0, OUT[i], nullptr,
-                                       t.fs * H, 0, 128, bn_tier, st));
+                                       t.fs * H, 0, 128, bn_for(t.fs * H, 1), st));
                 else
                     SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
+                mark(t.top ? "upsample top" : "upsample");
             }
             const float* up0 = OUT[0] + (size_t)(pos % FS0) * H;                     // model.py:504-513
             if (persist) {
@@ -624,6 +644,23 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         for (int p = 0; p < n_cond; ++p) SRNN_TRY(body());
     }
     SRNN_TRY(dequant_audio(seq, Lseq, lookback, ctx->lut, samples_out, audio_out, B, T, st));   // model.py:520
+    if (time_tiers && !marks.empty()) {
+        SRNN_CUDA(cudaStreamSynchronize(st));
+        std::vector<std::pair<const char*, std::pair<double, int>>> agg;
+        for (size_t k = 1; k < marks.size(); ++k) {
+            if (marks[k].first[0] == '(') continue;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
+            bool found = false;
+            for (auto& a : agg)
+                if (!strcmp(a.first, marks[k].first)) { a.second.first += ms; a.second.second++; found = true; }
+            if (!found) agg.push_back({marks[k].first, {ms, 1}});
+        }
+        fprintf(stderr, "[srnn tiers] avg us per kernel:");
+        for (auto& a : agg) fprintf(stderr, " %s=%.1f (n=%d)", a.first, 1e3 * a.second.first / a.second.second, a.second.second);
+        fprintf(stderr, "\n");
+        for (auto& m2 : marks) cudaEventDestroy(m2.second);
+    }
     if (time_kernels) {   // CUDA-event duration of every persistent launch, on the stream it ran on
         SRNN_CUDA(cudaStreamSynchronize(st));
         double tot = 0;

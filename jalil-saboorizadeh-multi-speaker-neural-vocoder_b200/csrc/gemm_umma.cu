@@ -91,6 +91,7 @@ struct alignas(64) GemmProb {
 struct alignas(64) GemmArgs {
     GemmProb p[2];
     int n_rows, K;
+    int nstage;            // TMA ring depth in use (<= GemmSmem::NSTAGE): a shallow ring lets two CTAs share an SM
     int ksplit;            // > 1: single problem, blockIdx.z = K split; split z writes out_f32 + z * split_stride (partials)
     long long split_stride;
     long long* trace;      // development aid (SRNN_TRACE_GEMM=1): clock64 stamps of CTA (0,0,0), else null
@@ -179,7 +180,7 @@ __device__ __forceinline__ void epi_row16(const float (&v)[16], const float* __r
 // ROWS = true : activations = A operand (128 rows per CTA), weights = B operand (BN features): the orientation of the
 //               big teacher-forced GEMMs, whose epilogue then stores 16 consecutive features per thread.
 template <int BM, int BN, bool ROWS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, BN <= 256 ? 2 : 1)
 k_gemm_umma(const __grid_constant__ GemmArgs args) {
     using S = GemmSmem<BM, BN>;
     constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
@@ -187,7 +188,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
     const int n_feat = P.n_feat, n_rows = args.n_rows;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int UMMA_STAGES = S::NSTAGE;
+    const int UMMA_STAGES = args.nstage;
     uint64_t* full = (uint64_t*)(smem + UMMA_STAGES * S::STAGE);
     uint64_t* empty = full + UMMA_STAGES;
     uint64_t* tmem_full = empty + UMMA_STAGES;
@@ -223,9 +224,10 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
 
     if (warp == 0) {
         if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % UMMA_STAGES;
-                const uint32_t ph = (kb / UMMA_STAGES) & 1;
+                if (kb) { if (++s == UMMA_STAGES) { s = 0; ph ^= 1; } }
                 mbar_wait(&empty[s], ph ^ 1);
                 if (tr && kb < 24) tr[8 + kb] = clock64();
                 mbar_expect_tx(&full[s], S::STAGE);
@@ -237,9 +239,10 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             const uint64_t d0 = umma_desc_sw128(smem_u32(smem));
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % UMMA_STAGES;
-                const uint32_t ph = (kb / UMMA_STAGES) & 1;
+                if (kb) { if (++s == UMMA_STAGES) { s = 0; ph ^= 1; } }
                 mbar_wait(&full[s], ph);
                 if (tr && kb < 24) tr[32 + kb] = clock64();
                 tc_fence_after();
@@ -366,6 +369,8 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
     if (warp == 1) tmem_dealloc<TCOLS>(tmem_d);
 }
 
+static int g_gemm_sms = -1;
+static constexpr int TCOLS_OF(int bn) { return bn < 32 ? 32 : bn; }
 template <int BM, int BN, bool ROWS>
 static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaStream_t st) {
     using S = GemmSmem<BM, BN>;
@@ -376,7 +381,18 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
     }
     const int nz = args.ksplit > 1 ? args.ksplit : nprob;
     dim3 grid = ROWS ? dim3(cdiv(args.n_rows, BM), cdiv(max_feat, BN), nz) : dim3(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nz);
-    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS>), grid, GEMM_THREADS, S::TOTAL, st, args);
+    // Ring depth: the deepest that fits one CTA per SM, unless the grid is a little larger than one wave of SMs -- then a
+    // shallow ring (<= 110 KB) lets two CTAs share an SM, so the whole grid is resident at once and one CTA's epilogue
+    // overlaps the other's loads (the generation-time upsampling GEMM has 160 tiles on 148 SMs).
+    GemmArgs a = args;
+    a.nstage = S::NSTAGE;
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    const int shallow = (110 * 1024 - 1280) / S::STAGE;
+    if (g_gemm_sms > 0 && ctas > g_gemm_sms && ctas <= 2 * g_gemm_sms && shallow >= 2 && TCOLS_OF(BN) <= 256 &&
+        !getenv("SRNN_GEMM_DEEP_RING"))
+        a.nstage = shallow < S::NSTAGE ? shallow : S::NSTAGE;
+    const size_t smem = (size_t)a.nstage * S::STAGE + 1024 + 256;
+    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS>), grid, GEMM_THREADS, smem, st, a);
     return SRNN_OK;
 }
 
@@ -404,6 +420,11 @@ int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, 
                  float* split_scratch, cudaStream_t st) {
     if (K % 64 || K <= 0) return fail(SRNN_ERR_ARG, "gemm_umma: K=%d must be a positive multiple of 64", K);
     if (nprob < 1 || nprob > 2) return fail(SRNN_ERR_ARG, "gemm_umma: 1 or 2 problems per launch");
+    if (g_gemm_sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_gemm_sms = 0;
+    }
     GemmArgs args;
     memset(&args, 0, sizeof(args));
     args.n_rows = n_rows;

@@ -245,50 +245,72 @@ int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, i
 // generation (one frame per utterance): frame assembly fused with the input expansion
 //   X[b,:] = W_in . [lut[prev n samples] | cond | onehot(spk)] + b_in (+ upper[b,:]);  W_in^T is (kin, H) so that
 //   consecutive threads read consecutive features  (model.py:196-218 at F = 1)
-__global__ void k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
+constexpr int TIG_RB = 8;       // utterances per CTA: every weight element loaded from L2 feeds TIG_RB FMAs
+__global__ void __launch_bounds__(256)
+k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
                                  const int* __restrict__ step_base, int n, const float* __restrict__ cond,
                                  int cond_rows, int cond_frames, const int64_t* __restrict__ spk, int cond_dim,
                                  int spk_dim, const float* __restrict__ lut, const float* __restrict__ w_in_t,
                                  const float* __restrict__ b_in, const float* __restrict__ upper, int up_ld,
-                                 float* __restrict__ X, __nv_bfloat16* __restrict__ X16, int H, int kin, int top) {
-    extern __shared__ float a_s[];
-    const int b = blockIdx.x;
+                                 float* __restrict__ X, __nv_bfloat16* __restrict__ X16, int B, int H, int kin, int top) {
+    extern __shared__ float a_s[];                                   // [kin][TIG_RB]: the assembled frames of TIG_RB utterances
+    const int b0 = blockIdx.x * TIG_RB;
     const int start = start_static + (step_base ? *step_base : 0);
-    const uint8_t* s = seq + (size_t)b * seq_ld + start;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a_s[i] = lut[s[i]];
-    if (top) {
-        const int crow = cond_rows == 1 ? 0 : b;
-        const size_t cbase = ((size_t)crow * cond_frames + start / n) * cond_dim;
-        for (int i = threadIdx.x; i < cond_dim; i += blockDim.x) a_s[n + i] = cond[cbase + i];
-        const int sp = (int)spk[crow];
-        for (int i = threadIdx.x; i < spk_dim; i += blockDim.x) a_s[n + cond_dim + i] = (i == sp) ? 1.f : 0.f;
+    for (int e = threadIdx.x; e < kin * TIG_RB; e += blockDim.x) {
+        const int r = e % TIG_RB, i = e / TIG_RB;
+        const int b = b0 + r < B ? b0 + r : B - 1;
+        float v;
+        if (i < n) {
+            v = lut[seq[(size_t)b * seq_ld + start + i]];
+        } else {
+            const int crow = cond_rows == 1 ? 0 : b;
+            if (i < n + cond_dim) v = cond[((size_t)crow * cond_frames + start / n) * cond_dim + (i - n)];
+            else v = ((i - n - cond_dim) == (int)spk[crow]) ? 1.f : 0.f;
+        }
+        a_s[e] = v;
     }
     __syncthreads();
-    const int h = blockIdx.y * blockDim.x + threadIdx.x;          // one feature per thread, 4 independent FMA chains
+    const int h = blockIdx.y * blockDim.x + threadIdx.x;          // one feature per thread, TIG_RB independent FMA chains
     if (h >= H) return;
-    float acc0 = b_in[h], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    if (upper) acc0 += upper[(size_t)b * up_ld + h];
-    const float* w = w_in_t + h;
-    int k = 0;
-    for (; k + 4 <= kin; k += 4) {
-        acc0 = fmaf(a_s[k], w[(size_t)k * H], acc0);
-        acc1 = fmaf(a_s[k + 1], w[(size_t)(k + 1) * H], acc1);
-        acc2 = fmaf(a_s[k + 2], w[(size_t)(k + 2) * H], acc2);
-        acc3 = fmaf(a_s[k + 3], w[(size_t)(k + 3) * H], acc3);
+    float acc[TIG_RB];
+    const float bias = b_in[h];
+#pragma unroll
+    for (int r = 0; r < TIG_RB; ++r) {
+        acc[r] = bias;
+        if (upper && b0 + r < B) acc[r] += upper[(size_t)(b0 + r) * up_ld + h];
     }
-    for (; k < kin; ++k) acc0 = fmaf(a_s[k], w[(size_t)k * H], acc0);
-    const float acc = (acc0 + acc1) + (acc2 + acc3);
-    X[(size_t)b * H + h] = acc;
-    if (X16) X16[(size_t)b * H + h] = __float2bfloat16(acc);
+    const float* w = w_in_t + h;
+    for (int k0 = 0; k0 < kin; k0 += 16) {                        // 16 weight loads in flight per thread (L2 latency bound)
+        float wv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) wv[u] = k0 + u < kin ? __ldg(w + (size_t)(k0 + u) * H) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (k0 + u < kin) {
+                const float4 a0 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB);
+                const float4 a1 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB + 4);
+                acc[0] = fmaf(a0.x, wv[u], acc[0]); acc[1] = fmaf(a0.y, wv[u], acc[1]);
+                acc[2] = fmaf(a0.z, wv[u], acc[2]); acc[3] = fmaf(a0.w, wv[u], acc[3]);
+                acc[4] = fmaf(a1.x, wv[u], acc[4]); acc[5] = fmaf(a1.y, wv[u], acc[5]);
+                acc[6] = fmaf(a1.z, wv[u], acc[6]); acc[7] = fmaf(a1.w, wv[u], acc[7]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TIG_RB; ++r) {
+        if (b0 + r >= B) break;
+        X[(size_t)(b0 + r) * H + h] = acc[r];
+        if (X16) X16[(size_t)(b0 + r) * H + h] = __float2bfloat16(acc[r]);
+    }
 }
 int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
                    int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, int spk_dim, const float* lut,
                    const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
                    __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st) {
     const int threads = H >= 256 ? 256 : 64;
-    SRNN_LAUNCH(k_tier_input_gen, dim3(B, cdiv(H, threads)), threads, kin * sizeof(float), st, seq, seq_ld, off, step_base, n, cond,
-                cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper, up_ld, X, X16, H, kin,
-                top ? 1 : 0);
+    SRNN_LAUNCH(k_tier_input_gen, dim3(cdiv(B, TIG_RB), cdiv(H, threads)), threads, (size_t)kin * TIG_RB * sizeof(float), st, seq,
+                seq_ld, off, step_base, n, cond, cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper,
+                up_ld, X, X16, B, H, kin, top ? 1 : 0);
     return SRNN_OK;
 }
 
