@@ -848,7 +848,23 @@ int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, c
         // bit 29 = split the K loop three ways (plain fp32 output only: bias/addend/relu must be absent)
         const int bm = ((mode >> 8) & 0xff) ? ((mode >> 8) & 0xff) : 128;
         const int bn = ((mode >> 16) & 0xfff) ? ((mode >> 16) & 0xfff) : 64;
-        const bool rows = (mode >> 28) & 1, split = (mode >> 29) & 1;
+        const bool rows = (mode >> 28) & 1, split = (mode >> 29) & 1, mnmaj = (mode >> 30) & 1;
+        if (mnmaj) {   // bit 30: C = A . B^T through the MN-major kernel: operands handed over as A^T (K, M) and B^T (K, N)
+            if (bias || addend || relu || N % 8) return fail(SRNN_ERR_ARG, "gemm hook (MN-major): plain output, N %% 8 == 0");
+            const int Mp = (M + 7) / 8 * 8, Np8 = (N + 7) / 8 * 8;
+            __nv_bfloat16 *at = nullptr, *bt = nullptr;
+            float* scratch = nullptr;
+            SRNN_CUDA(cudaMallocAsync((void**)&at, sizeof(__nv_bfloat16) * (size_t)K * Mp, st));
+            SRNN_CUDA(cudaMallocAsync((void**)&bt, sizeof(__nv_bfloat16) * (size_t)K * Np8, st));
+            if (split) SRNN_CUDA(cudaMallocAsync((void**)&scratch, sizeof(float) * 3 * (size_t)M * N, st));
+            SRNN_TRY(transpose_to_bf16(A, M, K, K, at, Mp, st));
+            SRNN_TRY(transpose_to_bf16(B, N, K, K, bt, Np8, st));
+            int rc = gemm_umma_tn(at, Mp, bt, Np8, M, N, K, C, N, split ? 3 : 1, scratch, st);
+            cudaFreeAsync(at, st);
+            cudaFreeAsync(bt, st);
+            if (scratch) cudaFreeAsync(scratch, st);
+            return rc;
+        }
         const int Kp = (K + 63) / 64 * 64, Np = (N + bm - 1) / bm * bm;
         __nv_bfloat16 *a16 = nullptr, *w16 = nullptr;
         SRNN_CUDA(cudaMallocAsync((void**)&a16, sizeof(__nv_bfloat16) * (size_t)M * Kp, st));

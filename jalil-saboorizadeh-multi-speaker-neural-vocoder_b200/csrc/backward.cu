@@ -198,18 +198,51 @@ __global__ void k_add3(const float* a, const float* b, const float* c, float* ou
 constexpr int DT_SEG = 4;      // segments per value bucket (partials summed in fixed order)
 constexpr int DT_MAXFS = 32;
 
-__global__ void k_q_count(const uint8_t* __restrict__ seq, int seq_ld, int off, int B, int W, int* __restrict__ counts) {
-    const int q = blockIdx.x;
-    __shared__ int red[256];
-    int c = 0;
-    for (int i = threadIdx.x; i < B * W; i += blockDim.x) c += seq[(size_t)(i / W) * seq_ld + off + (i % W)] == q;
-    red[threadIdx.x] = c;
-    __syncthreads();
-    for (int o = 128; o; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
+// Counting sort of the window positions by sample value, ascending position inside every bucket (deterministic):
+// each WARP owns a chunk of QS_CHUNK consecutive positions.  Pass 1: per-chunk histograms; pass 2: scans (per value over the
+// chunks, then over the values); pass 3: every warp re-walks its chunk and writes each position at its final rank.
+constexpr int QS_CHUNK = 512;
+__device__ __forceinline__ int qs_value(const uint8_t* __restrict__ seq, int seq_ld, int off, int W, int i) {
+    return seq[(size_t)(i / W) * seq_ld + off + (i % W)];
+}
+__global__ void __launch_bounds__(128)
+k_qs_hist(const uint8_t* __restrict__ seq, int seq_ld, int off, int N, int W, int nchunk, int* __restrict__ hist /* (Q, nchunk) */) {
+    __shared__ int cnt[4][SRNN_Q];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + w;
+    for (int q = lane; q < SRNN_Q; q += 32) cnt[w][q] = 0;
+    __syncwarp();
+    if (c < nchunk) {
+        const int i0 = c * QS_CHUNK;
+        for (int r = 0; r < QS_CHUNK; r += 32) {
+            const int i = i0 + r + lane;
+            const int v = i < N ? qs_value(seq, seq_ld, off, W, i) : -1;
+            const unsigned m = __match_any_sync(0xffffffffu, v);
+            if (v >= 0 && lane == __ffs(m) - 1) cnt[w][v] += __popc(m);
+            __syncwarp();
+        }
+        for (int q = lane; q < SRNN_Q; q += 32) hist[(size_t)q * nchunk + c] = cnt[w][q];
     }
-    if (threadIdx.x == 0) counts[q] = red[0];
+}
+// block q: exclusive scan of hist[q][:] in place, total -> counts[q]
+__global__ void k_qs_scan_chunks(int* __restrict__ hist, int nchunk, int* __restrict__ counts) {
+    const int q = blockIdx.x;
+    __shared__ int part[256];
+    int* row = hist + (size_t)q * nchunk;
+    const int per = (nchunk + 255) / 256;
+    const int c0 = threadIdx.x * per, c1 = min(nchunk, c0 + per);
+    int s = 0;
+    for (int c = c0; c < c1; ++c) s += row[c];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < 256; ++t) { const int v = part[t]; part[t] = run; run += v; }
+        counts[q] = run;
+    }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int c = c0; c < c1; ++c) { const int v = row[c]; row[c] = run; run += v; }
 }
 __global__ void k_q_prefix(const int* __restrict__ counts, int* __restrict__ starts) {
     if (threadIdx.x == 0) {
@@ -218,58 +251,67 @@ __global__ void k_q_prefix(const int* __restrict__ counts, int* __restrict__ sta
         starts[SRNN_Q] = s;
     }
 }
-// ordered compaction: block q writes the window positions (b*W + pi) holding value q, ascending
-__global__ void k_q_scatter(const uint8_t* __restrict__ seq, int seq_ld, int off, int B, int W, const int* __restrict__ starts,
-                            int* __restrict__ pos) {
-    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int wsum[8];
-    __shared__ int base_s;
-    if (threadIdx.x == 0) base_s = starts[q];
-    __syncthreads();
-    for (int i0 = 0; i0 < B * W; i0 += 256) {
-        const int i = i0 + threadIdx.x;
-        const bool hit = i < B * W && seq[(size_t)(i / W) * seq_ld + off + (i % W)] == q;
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) wsum[warp] = __popc(bal);
-        __syncthreads();
-        int before = 0;
-        for (int w2 = 0; w2 < warp; ++w2) before += wsum[w2];
-        if (hit) pos[base_s + before + __popc(bal & ((1u << lane) - 1))] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w2 = 0; w2 < 8; ++w2) t += wsum[w2];
-            base_s += t;
-        }
-        __syncthreads();
+__global__ void __launch_bounds__(128)
+k_qs_scatter(const uint8_t* __restrict__ seq, int seq_ld, int off, int N, int W, int nchunk, const int* __restrict__ hist,
+             const int* __restrict__ starts, int* __restrict__ pos) {
+    __shared__ int run[4][SRNN_Q];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 4 + w;
+    if (c >= nchunk) return;
+    for (int q = lane; q < SRNN_Q; q += 32) run[w][q] = starts[q] + hist[(size_t)q * nchunk + c];
+    __syncwarp();
+    const int i0 = c * QS_CHUNK;
+    for (int r = 0; r < QS_CHUNK; r += 32) {
+        const int i = i0 + r + lane;
+        const int v = i < N ? qs_value(seq, seq_ld, off, W, i) : -1;
+        const unsigned m = __match_any_sync(0xffffffffu, v);
+        if (v >= 0) pos[run[w][v] + __popc(m & ((1u << lane) - 1))] = i;
+        __syncwarp();
+        if (v >= 0 && lane == __ffs(m) - 1) run[w][v] += __popc(m);
+        __syncwarp();
     }
 }
-// grid (Q, H/256, DT_SEG), 256 threads = 256 features
-template <typename T1>
-__global__ void __launch_bounds__(256)
+// grid (Q, ceil(H/1024), DT_SEG), 256 threads x 4 consecutive features (one 8-byte bf16 / 16-byte fp32 load per row)
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T1, int FSMAX>
+__global__ void __launch_bounds__(256, 2)
 k_dtbl_accum(const int* __restrict__ pos, const int* __restrict__ starts, const T1* __restrict__ dpre1, int T, int W, int H,
              int FS, float* __restrict__ partial /* (DT_SEG, FS, Q, H) */) {
-    const int q = blockIdx.x, h = blockIdx.y * 256 + threadIdx.x, seg = blockIdx.z;
+    const int q = blockIdx.x, h = blockIdx.y * 1024 + threadIdx.x * 4, seg = blockIdx.z;
     const int s0 = starts[q], n = starts[q + 1] - s0;
     const int per = (n + DT_SEG - 1) / DT_SEG;
     const int k0 = s0 + seg * per, k1 = min(s0 + n, k0 + per);
-    float acc[DT_MAXFS];
+    if (h >= H) return;
+    float acc[FSMAX][4];
 #pragma unroll
-    for (int j = 0; j < DT_MAXFS; ++j) acc[j] = 0.f;
-    if (h < H) {
-        for (int k = k0; k < k1; ++k) {
-            const int i = pos[k], b = i / W, pi = i % W;
-            const T1* rowbase = dpre1 + ((size_t)b * T + pi) * H + h;          // row t = pi - j  ->  rowbase - j*H
+    for (int j = 0; j < FSMAX; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int k = k0; k < k1; ++k) {
+        const int i = pos[k], b = i / W, pi = i % W;
+        const T1* rowbase = dpre1 + ((size_t)b * T + pi) * H + h;          // row t = pi - j  ->  rowbase - j*H
 #pragma unroll
-            for (int j = 0; j < DT_MAXFS; ++j) {
-                const int t = pi - j;
-                if (j < FS && t >= 0 && t < T) acc[j] += to_f(rowbase[-(long long)j * H]);
+        for (int j = 0; j < FSMAX; ++j) {
+            const int t = pi - j;
+            if (j < FS && t >= 0 && t < T) {
+                float v[4];
+                ld4(rowbase - (long long)j * H, v);
+                acc[j][0] += v[0]; acc[j][1] += v[1]; acc[j][2] += v[2]; acc[j][3] += v[3];
             }
         }
-#pragma unroll
-        for (int j = 0; j < DT_MAXFS; ++j)
-            if (j < FS) partial[(((size_t)seg * FS + j) * SRNN_Q + q) * H + h] = acc[j];
     }
+#pragma unroll
+    for (int j = 0; j < FSMAX; ++j)
+        if (j < FS)
+            *reinterpret_cast<float4*>(partial + (((size_t)seg * FS + j) * SRNN_Q + q) * H + h) =
+                make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 // sum the segment partials (fixed order) -> dTbl (FS,Q,H) and its per-tap transpose dTblT (FS,H,Q)
 __global__ void k_dtbl_final(const float* __restrict__ partial, int FS, int H, float* __restrict__ out, float* __restrict__ outT) {
@@ -287,14 +329,22 @@ template <typename T1>
 static int dtbl_compute(const uint8_t* seq, int seq_ld, int off, const T1* dpre1, int B, int T, int H, int FS, int* iwork,
                         float* partial, float* dTbl, float* dTblT, cudaStream_t st) {
     if (FS > DT_MAXFS) return fail(SRNN_ERR_UNSUPPORTED, "frame size %d > %d", FS, DT_MAXFS);
-    const int W = T + FS - 1;
+    const int W = T + FS - 1, N = B * W, nchunk = cdiv(N, QS_CHUNK);
+    if (H % 4) return fail(SRNN_ERR_UNSUPPORTED, "dim %d must be a multiple of 4", H);
     int* counts = iwork;
     int* starts = iwork + 256;
     int* pos = iwork + 768;
-    SRNN_LAUNCH(k_q_count, SRNN_Q, 256, 0, st, seq, seq_ld, off, B, W, counts);
+    int* hist = iwork + 1024 + (size_t)B * (T + FS);           // (Q, nchunk)
+    SRNN_LAUNCH(k_qs_hist, cdiv(nchunk, 4), 128, 0, st, seq, seq_ld, off, N, W, nchunk, hist);
+    SRNN_LAUNCH(k_qs_scan_chunks, SRNN_Q, 256, 0, st, hist, nchunk, counts);
     SRNN_LAUNCH(k_q_prefix, 1, 32, 0, st, counts, starts);
-    SRNN_LAUNCH(k_q_scatter, SRNN_Q, 256, 0, st, seq, seq_ld, off, B, W, starts, pos);
-    SRNN_LAUNCH((k_dtbl_accum<T1>), dim3(SRNN_Q, cdiv(H, 256), DT_SEG), 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
+    SRNN_LAUNCH(k_qs_scatter, cdiv(nchunk, 4), 128, 0, st, seq, seq_ld, off, N, W, nchunk, hist, starts, pos);
+    const dim3 grid(SRNN_Q, cdiv(H, 1024), DT_SEG);          // FSMAX = accumulator rows held in registers
+    if (FS <= 4) SRNN_LAUNCH((k_dtbl_accum<T1, 4>), grid, 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
+    else if (FS <= 8) SRNN_LAUNCH((k_dtbl_accum<T1, 8>), grid, 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
+    else if (FS <= 16) SRNN_LAUNCH((k_dtbl_accum<T1, 16>), grid, 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
+    else if (FS <= 20) SRNN_LAUNCH((k_dtbl_accum<T1, 20>), grid, 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
+    else SRNN_LAUNCH((k_dtbl_accum<T1, DT_MAXFS>), grid, 256, 0, st, pos, starts, dpre1, T, W, H, FS, partial);
     SRNN_LAUNCH(k_dtbl_final, gsz((size_t)FS * SRNN_Q * H), 256, 0, st, partial, FS, H, dTbl, dTblT);
     return SRNN_OK;
 }
@@ -525,7 +575,7 @@ size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T) {
     size_t f = R * Q + 2 * R * H                                // dlogits, dA, dB
                + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H   // dY ping/pong, dX, dGI, dGH, carries
                + maxfs * H * H * 2 + maxfs * H + H * maxkin + H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin)   // weight-grad staging
-               + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0))             // dTbl partials + final, dWm_t, dWm
+               + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2))             // dTbl partials + final, dWm_t, dWm
                + (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + Q + 4096;
     return f * sizeof(float) + 64 * 256;
 }
@@ -569,7 +619,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     float* dTblP = b.take<float>((size_t)DT_SEG * FS0 * Q * H);
     float* dTbl = b.take<float>((size_t)FS0 * Q * H);
     float* dTblT = b.take<float>((size_t)FS0 * Q * H);
-    int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0));
+    int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2));
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
     float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
@@ -728,7 +778,7 @@ size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T) {
     }
     const size_t Mp = rup64(maxM);
     size_t f32 = R * Q + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H + 2 * maxfs * H * H + maxfs * H + H * maxkin +
-                 H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin) + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0))  +
+                 H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin) + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2))  +
                  (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + 3 * H * H;
     size_t b16 = R * Q + Q * Rp + 2 * H * Rp + 2 * R * H                     // D16, D16t, TA, TB, DP2, DP1
                  + maxfs * H * Mp + 3 * H * Mp + 2 * 3 * H * Mp + 2 * maxM * 3 * H + 2 * maxM * H;   // tier transposes + copies
@@ -773,7 +823,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     float* dTblP = b.take<float>((size_t)DT_SEG * FS0 * Q * H);
     float* dTbl = b.take<float>((size_t)FS0 * Q * H);
     float* dTblT = b.take<float>((size_t)FS0 * Q * H);
-    int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0));
+    int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2));
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
     float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));

@@ -179,7 +179,10 @@ __device__ __forceinline__ void epi_row16(const float (&v)[16], const float* __r
 // ROWS = false: "swap-AB" (weights = A operand on the TMEM lanes; the generation-time / per-frame orientation).
 // ROWS = true : activations = A operand (128 rows per CTA), weights = B operand (BN features): the orientation of the
 //               big teacher-forced GEMMs, whose epilogue then stores 16 consecutive features per thread.
-template <int BM, int BN, bool ROWS>
+// MNMAJ = true (ROWS only): both operands are given TRANSPOSED in memory -- tmA over X (K_total x M_total) and tmB over
+//               Y (K_total x N_total), row-major -- and out = X^T . Y: the weight-gradient GEMMs dW = dOut^T . In read
+//               dOut and In as they are, no transposed copies.
+template <int BM, int BN, bool ROWS, bool MNMAJ = false>
 __global__ void __launch_bounds__(GEMM_THREADS, BN <= 256 ? 2 : 1)
 k_gemm_umma(const __grid_constant__ GemmArgs args) {
     using S = GemmSmem<BM, BN>;
@@ -231,14 +234,24 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
                 mbar_wait(&empty[s], ph ^ 1);
                 if (tr && kb < 24) tr[8 + kb] = clock64();
                 mbar_expect_tx(&full[s], S::STAGE);
-                tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], (kb0 + kb) * 64, m0);
-                tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], (kb0 + kb) * 64, n0);
+                if constexpr (MNMAJ) {     // boxes of {64 MN elements, 64 K rows}: one per 64-wide MN chunk
+#pragma unroll
+                    for (int c = 0; c < BM / 64; ++c)
+                        tma_load_2d(smem + s * S::STAGE + c * 8192, &P.tmA, &full[s], m0 + c * 64, (kb0 + kb) * 64);
+#pragma unroll
+                    for (int c = 0; c < BN / 64; ++c)
+                        tma_load_2d(smem + s * S::STAGE + S::A_BYTES + c * 8192, &P.tmB, &full[s], n0 + c * 64, (kb0 + kb) * 64);
+                } else {
+                    tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], (kb0 + kb) * 64, m0);
+                    tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], (kb0 + kb) * 64, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            const uint64_t d0 = umma_desc_sw128(smem_u32(smem));
+            constexpr uint32_t idesc = MNMAJ ? umma_idesc_bf16_mn(BM, BN) : umma_idesc_bf16(BM, BN);
+            const uint64_t d0 = MNMAJ ? umma_desc_sw128_mn(smem_u32(smem), 8192) : umma_desc_sw128(smem_u32(smem));
+            constexpr int KSTEP = MNMAJ ? 128 : 2;   // descriptor advance per K = 16: 16 K rows x 128 B, or 32 B inside the row
             int s = 0;
             uint32_t ph = 0;
             for (int kb = 0; kb < KB; ++kb) {
@@ -250,7 +263,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
                 const uint64_t db = da + (uint64_t)(S::A_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)       // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
-                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_bf16(tmem_d, da + KSTEP * k, db + KSTEP * k, idesc, (kb | k) != 0);
                 umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
             }
             umma_commit(tmem_full);
@@ -371,12 +384,12 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
 
 static int g_gemm_sms = -1;
 static constexpr int TCOLS_OF(int bn) { return bn < 32 ? 32 : bn; }
-template <int BM, int BN, bool ROWS>
+template <int BM, int BN, bool ROWS, bool MNMAJ = false>
 static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaStream_t st) {
     using S = GemmSmem<BM, BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma<BM, BN, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        SRNN_CUDA(cudaFuncSetAttribute((k_gemm_umma<BM, BN, ROWS, MNMAJ>), cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         attr_set = true;
     }
     const int nz = args.ksplit > 1 ? args.ksplit : nprob;
@@ -392,7 +405,7 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
         !getenv("SRNN_GEMM_DEEP_RING"))
         a.nstage = shallow < S::NSTAGE ? shallow : S::NSTAGE;
     const size_t smem = (size_t)a.nstage * S::STAGE + 1024 + 256;
-    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS>), grid, GEMM_THREADS, smem, st, a);
+    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS, MNMAJ>), grid, GEMM_THREADS, smem, st, a);
     return SRNN_OK;
 }
 
@@ -499,6 +512,42 @@ int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, 
 
 int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st) {
     return gemm_umma_ex(ops, nprob, n_rows, K, bm, bn, false, 1, nullptr, st);
+}
+
+// out (M, N) fp32 = X^T . Y with X (Ktot, M; ld_x) and Y (Ktot, N; ld_y) bf16 row-major: both operands MN-major, read in place.
+// Ktot needs no padding (TMA zero-fills the tail k-block).  Optional split-K as in gemm_umma_ex.
+int gemm_umma_tn(const __nv_bfloat16* X, int ld_x, const __nv_bfloat16* Y, int ld_y, int M, int N, int Ktot, float* out,
+                 int ld_out, int ksplit, float* split_scratch, cudaStream_t st) {
+    if (ld_out % 8 || M < 1 || N < 1 || Ktot < 1) return fail(SRNN_ERR_ARG, "gemm_umma_tn: bad shape");
+    if (g_gemm_sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_gemm_sms = 0;
+    }
+    const int bn = N <= 128 ? 128 : 256;
+    const int Kp = (Ktot + 63) / 64 * 64;
+    GemmArgs args;
+    memset(&args, 0, sizeof(args));
+    args.n_rows = M;
+    args.K = Kp;
+    args.ksplit = 1;
+    if (ksplit > 1) {
+        const int KB = Kp / 64, per = (KB + ksplit - 1) / ksplit;
+        ksplit = (KB + per - 1) / per;
+    }
+    if (ksplit > 1) {
+        if (!split_scratch) return fail(SRNN_ERR_ARG, "gemm_umma_tn: split-K needs scratch");
+        args.ksplit = ksplit;
+        args.split_stride = (long long)M * ld_out;
+    }
+    SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, X, Ktot, M, ld_x, 64));
+    SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, Y, Ktot, N, ld_y, 64));
+    args.p[0].out_f32 = args.ksplit > 1 ? split_scratch : out;
+    args.p[0].n_feat = N;
+    args.p[0].ld_out = ld_out;
+    int rc = bn == 128 ? launch_gemm_umma<128, 128, true, true>(args, 1, N, st) : launch_gemm_umma<128, 256, true, true>(args, 1, N, st);
+    if (rc == SRNN_OK && args.ksplit > 1) rc = sum_splits(split_scratch, args.ksplit, (size_t)M * ld_out, (size_t)args.split_stride, out, st);
+    return rc;
 }
 
 // The big teacher-forced contractions (hundreds of rows or more): ROWS orientation, 128 x 256 (or 128 x 128) tiles.

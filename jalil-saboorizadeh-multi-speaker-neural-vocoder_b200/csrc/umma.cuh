@@ -103,11 +103,26 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// MN-major bf16 operand tile (the contraction index is the SLOW dimension in memory: operand = X^T of a row-major X):
+// a TMA box {64 MN elements, 64 K rows} with the 128-byte swizzle lands as 64 K-rows of 128 bytes; 64-element MN chunks
+// follow each other `chunk_bytes` apart.  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units
+// (cute/atom/mma_traits_sm100.hpp): LBO = distance between MN chunks, SBO = distance between groups of 8 K rows = 1024 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t chunk_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((chunk_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor, kind::f16: D = fp32 (bits 4-5 = 1), A = B = bf16 (bits 7-9 = 1, 10-12 = 1), both K-major
 // (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with both operands MN-major (bits 15 and 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
 // D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

@@ -59,3 +59,22 @@ def test_umma_gemm_rows_orientation(bn, split, shape):
     assert np.isfinite(got).all(), "non-finite output"
     err = np.abs(got - ref.float().numpy()).max()
     assert err < 2e-3 * K ** 0.5, "max err %g" % err
+
+
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("shape", [(256, 1024, 1024), (100, 304, 200), (300, 256, 64), (1000, 40, 650), (128, 128, 133120 // 8)])
+def test_umma_gemm_mn_major_operands(split, shape):
+    """Both operands MN-major (given as A^T, B^T in memory): the transposed-copy-free weight-gradient form dW = dOut^T . In."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K + split)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    ref = (A.bfloat16().double() @ B.bfloat16().double().t()).float()
+    dA, dB = A.cuda(), B.cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    mode = S.MODE_BF16 | (1 << 30) | (split << 29)
+    L.check(L.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), None, None, 0, out.data_ptr(), mode, stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all(), "non-finite output"
+    err = np.abs(got - ref.numpy()).max()
+    assert err < 2e-3 * K ** 0.5, "max err %g" % err
