@@ -766,6 +766,25 @@ static int tc_dw(int Nout, int Kin, int Kp, const bf* InT, const bf* dOutT, floa
     return gemm_umma_multi(&o, 1, Nout, Kp, 128, pick_bn2(Nout), st);
 }
 
+// dW (Nout, Kin) = dOut^T . In with dOut (rows, Nout) and In (rows, Kin) bf16 row-major read IN PLACE (MN-major UMMA operands):
+// no transposed copies.  Split-K as in tc_dw.
+static int tc_dw_tn(int Nout, int Kin, int rows, const bf* dOut16, int ld_do, const bf* In16, int ld_in, float* dW, float* scratch,
+                    size_t scratch_floats, cudaStream_t st) {
+    const int tiles = cdiv(Nout, 128) * cdiv(Kin, Kin <= 128 ? 128 : 256);
+    int ks = cdiv(296, tiles);
+    const size_t cap = scratch ? scratch_floats / ((size_t)Nout * Kin) : 0;
+    if ((size_t)ks > cap) ks = (int)cap;
+    if (ks > rows / 512) ks = rows / 512;                  // at least 8 k-blocks per split
+    return gemm_umma_tn(dOut16, ld_do, In16, ld_in, Nout, Kin, rows, dW, Kin, ks < 2 ? 1 : ks, scratch, st);
+}
+// HP16[(b,f), :] = f ? Y16[(b,f-1), :] : h0_16[b, :]   (bf16 recurrent input of every frame, for dW_hh)
+__global__ void k_build_hprev16(const bf* __restrict__ Y16, const bf* __restrict__ h0, bf* __restrict__ hp, int F, int H) {
+    const int r = blockIdx.x, b = r / F, f = r % F;
+    const uint4* src = reinterpret_cast<const uint4*>(f ? Y16 + (size_t)(r - 1) * H : h0 + (size_t)b * H);
+    uint4* dst = reinterpret_cast<uint4*>(hp + (size_t)r * H);
+    for (int u = threadIdx.x; u < H / 8; u += blockDim.x) dst[u] = src[u];
+}
+
 size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T) {
     const srnn_config& c = ctx->cfg;
     const size_t H = ctx->H, Q = ctx->Q, R = (size_t)B * T, Rp = rup64(R), FS0 = ctx->FS0;
@@ -780,8 +799,8 @@ size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T) {
     size_t f32 = R * Q + 3 * maxM * H + 2 * maxM * 3 * H + 2 * (size_t)B * H + 2 * maxfs * H * H + maxfs * H + H * maxkin +
                  H * (size_t)c.spk_dim + 3 * H * (H > maxkin ? H : maxkin) + (DT_SEG + 2) * FS0 * Q * H + 2 * FS0 * H * Q + (1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2))  +
                  (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H) + 3 * H + Q * H + 3 * H * H;
-    size_t b16 = R * Q + Q * Rp + 2 * H * Rp + 2 * R * H                     // D16, D16t, TA, TB, DP2, DP1
-                 + maxfs * H * Mp + 3 * H * Mp + 2 * 3 * H * Mp + 2 * maxM * 3 * H + 2 * maxM * H;   // tier transposes + copies
+    size_t b16 = R * Q + 2 * R * H                                            // D16, DP2, DP1
+                 + 2 * maxM * 3 * H + 2 * maxM * H + 64;                       // dGI16, dGH16, HP16, DX16
     return f32 * sizeof(float) + b16 * sizeof(bf) + 96 * 256;
 }
 
@@ -833,17 +852,8 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     float* dWtmp = b.take<float>((size_t)3 * H * H);
     const size_t dtblp_floats = (size_t)DT_SEG * FS0 * Q * H;   // dTblP doubles as split-K scratch outside dtbl_compute/foldback
     bf* D16 = b.take<bf>((size_t)R * Q);
-    bf* D16t = b.take<bf>((size_t)Q * Rp);
-    bf* TA = b.take<bf>((size_t)H * Rp);
-    bf* TB = b.take<bf>((size_t)H * Rp);
     bf* DP2 = b.take<bf>((size_t)R * H);
     bf* DP1 = b.take<bf>((size_t)R * H);
-    bf* dUPt = b.take<bf>((size_t)maxfs * H * Mpmax);
-    bf* Yt = b.take<bf>((size_t)H * Mpmax);
-    bf* HPt = b.take<bf>((size_t)H * Mpmax);
-    bf* INt = b.take<bf>((size_t)H * Mpmax);
-    bf* dGIt = b.take<bf>((size_t)3 * H * Mpmax);
-    bf* dGHt = b.take<bf>((size_t)3 * H * Mpmax);
     bf* dGI16 = b.take<bf>(maxM * 3 * H);
     bf* dGH16 = b.take<bf>(maxM * 3 * H);
     bf* HP16 = b.take<bf>(maxM * H);
@@ -852,17 +862,13 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     // ---- log_softmax backward; bf16 copies of dlogits in both orientations ----
     SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
     SRNN_TRY(f32_to_bf16_pad(dlogits, R, Q, Q, D16, R, Q, st));
-    SRNN_TRY(transpose_to_bf16(dlogits, R, Q, Q, D16t, Rp, st));
     // ---- output layer ----
-    SRNN_TRY(transpose_to_bf16(F.X2h, R, H, H, TA, Rp, st));                                   // x2^T
-    SRNN_TRY(tc_dw(Q, H, Rp, TA, D16t, dWo, dTblP, dtblp_floats, st));
+    SRNN_TRY(tc_dw_tn(Q, H, R, D16, Q, F.X2h, H, dWo, dTblP, dtblp_floats, st));
     SRNN_TRY(wn_bwd(dWo, P->mlp_output, G->mlp_output, Q, H, st));
     if (G->mlp_output.bias) SRNN_TRY(colsum(dlogits, R, Q, Q, csp, (float*)G->mlp_output.bias, st));
     SRNN_TRY(tc_dx(R, H, Q, D16, Q, ctx->w_out16_t, nullptr, 0, nullptr, DP2, F.X2h, H, st));   // dpre2 = dx2 * (x2 > 0)
     // ---- hidden layer ----
-    SRNN_TRY(transpose_to_bf16(F.X1h, R, H, H, TA, Rp, st));                                   // x1^T
-    SRNN_TRY(transpose_to_bf16(DP2, R, H, H, TB, Rp, st));                                     // dpre2^T
-    SRNN_TRY(tc_dw(H, H, Rp, TA, TB, dWtmp, dTblP, dtblp_floats, st));
+    SRNN_TRY(tc_dw_tn(H, H, R, DP2, H, F.X1h, H, dWtmp, dTblP, dtblp_floats, st));
     SRNN_TRY(wn_bwd(dWtmp, P->mlp_hidden, G->mlp_hidden, H, H, st));
     if (G->mlp_hidden.bias) SRNN_TRY(colsum(DP2, R, H, H, csp, (float*)G->mlp_hidden.bias, st));
     SRNN_TRY(tc_dx(R, H, H, DP2, H, ctx->w_hid16_t, nullptr, 0, nullptr, DP1, F.X1h, H, st));   // dpre1 = dc0
@@ -877,9 +883,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
         const srnn_tier_params& tg = G->tiers[i];
         const int Fr = T / t.n, M = B * Fr, Mp = rup64(M), NU = t.fs * H;
         // upsampling
-        SRNN_TRY(transpose_to_bf16(dUP, M, NU, NU, dUPt, Mp, st));
-        SRNN_TRY(transpose_to_bf16(F.Y16[i][NL - 1], M, H, H, Yt, Mp, st));
-        SRNN_TRY(tc_dw(NU, H, Mp, Yt, dUPt, dWup, dTblP, dtblp_floats, st));
+        SRNN_TRY(tc_dw_tn(NU, H, M, dUP, NU, F.Y16[i][NL - 1], H, dWup, dTblP, dtblp_floats, st));
         SRNN_TRY(colsum(dUP, M, NU, NU, csp, dbup, st));
         SRNN_LAUNCH(k_unpack_up_grad, NU, 128, 0, st, dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs);
         SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
@@ -917,19 +921,14 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
                 if ((F.reset_mask >> i) & 1) SRNN_TRY(colsum(carry, B, H, H, csp, dh0 + (size_t)l * H, st));
                 else SRNN_CUDA(cudaMemsetAsync(dh0 + (size_t)l * H, 0, sizeof(float) * H, st));
             }
-            SRNN_TRY(transpose_to_bf16(dGH, M, 3 * H, 3 * H, dGHt, Mp, st));
-            SRNN_TRY(transpose_to_bf16(dGI, M, 3 * H, 3 * H, dGIt, Mp, st));
             if (tg.weight_hh[l]) {
-                SRNN_LAUNCH(k_build_hprev, M, 128, 0, st, Y, h0, dYn, Fr, H);
-                SRNN_TRY(transpose_to_bf16(dYn, M, H, H, HPt, Mp, st));
-                SRNN_TRY(tc_dw(3 * H, H, Mp, HPt, dGHt, (float*)tg.weight_hh[l], dTblP, dtblp_floats, st));
+                SRNN_LAUNCH(k_build_hprev16, M, 128, 0, st, F.Y16[i][l], F.H016[i] + (size_t)l * B * H, HP16, Fr, H);
+                SRNN_TRY(tc_dw_tn(3 * H, H, M, dGH16, 3 * H, HP16, H, (float*)tg.weight_hh[l], dTblP, dtblp_floats, st));
             }
             if (tg.bias_hh[l]) SRNN_TRY(colsum(dGH, M, 3 * H, 3 * H, csp, (float*)tg.bias_hh[l], st));
-            if (tg.weight_ih[l]) {
-                if (l) SRNN_TRY(transpose_to_bf16(F.Y16[i][l - 1], M, H, H, INt, Mp, st));
-                else SRNN_TRY(transpose_to_bf16(F.X16[i], M, H, H, INt, Mp, st));
-                SRNN_TRY(tc_dw(3 * H, H, Mp, INt, dGIt, (float*)tg.weight_ih[l], dTblP, dtblp_floats, st));
-            }
+            if (tg.weight_ih[l])
+                SRNN_TRY(tc_dw_tn(3 * H, H, M, dGI16, 3 * H, l ? F.Y16[i][l - 1] : F.X16[i], H, (float*)tg.weight_ih[l], dTblP,
+                                  dtblp_floats, st));
             if (tg.bias_ih[l]) SRNN_TRY(colsum(dGI, M, 3 * H, 3 * H, csp, (float*)tg.bias_ih[l], st));
             float* din = l ? dYn : dXf;
             SRNN_TRY(tc_dx(M, H, 3 * H, dGI16, 3 * H, t.w_ih16_t[l], nullptr, 0, din, nullptr, nullptr, H, st));
