@@ -2,14 +2,17 @@
 // F frames of one GRU layer (model.py:244 `self.rnn(input, hidden)` = torch nn.GRU; its autograd for the backward kernel),
 // instead of one GEMM launch + one gate launch per frame.
 //
-// Decomposition: CTA c owns the GP_HS = 16 hidden units u0 = 16c .. u0+15 for ALL utterances (rows).  It keeps the recurrent
-// weight rows of those units resident in shared memory for the whole launch (UMMA B operand, loaded once by TMA):
+// Decomposition: CTA (c, rs) owns the GP_HS = 16 hidden units u0 = 16c .. u0+15 for the 64 utterances (rows) rs*64 .. +63
+// (the two row halves of a 128-utterance batch are independent recurrences with their own frame barrier).  It keeps the
+// recurrent weight rows of those units resident in shared memory for the whole launch (UMMA B operand, loaded once by TMA):
 //     forward : W_hh[g*H + u0 .. +16, :]  for the three gates g = r, z, n      (48 x H   bf16 = 96 KB at H = 1024)
 //     backward: W_hh^T[u0 .. +16, :]                                           (16 x 3H  bf16 = 96 KB at H = 1024)
 // and streams the recurrent activations of the frame (h_{f-1}: rows x H, resp. dGH_f: rows x 3H, bf16) through a TMA ring as
-// the UMMA A operand (M = 128 rows on the TMEM lanes).  The accumulator D[row][gate*16 + j] therefore puts r, z, n of one
-// (utterance, unit) into the SAME thread: the gate math needs no shuffles and the fp32 state h / dh lives in registers
-// across frames.  Between frames the CTAs exchange the new bf16 state through global memory (L2) behind a release/acquire
+// the UMMA A operand (M = 64 rows).  The accumulator D[row][gate*16 + j] puts r, z, n of one (utterance, unit) into the SAME
+// thread, and the fp32 state h / dh lives in registers across frames.  An M = 64 accumulator occupies lanes 0..15 of each
+// TMEM lane quadrant; a second one sits in lanes 16..31 ("interleaved"), so the four issuers' private accumulators fill
+// all 128 lanes, one shuffle exchange combines the halves, and every one of the 128 row threads does the gate math of
+// 8 units of one utterance.  Between frames the CTAs exchange the new bf16 state through global memory (L2) behind a release/acquire
 // counter barrier (all CTAs are co-resident: cooperative launch).
 // Warp roles (288 threads): 0..3 = row/epilogue warps (TMEM lane quadrant = warp), 4 = TMA producer, 5..8 = MMA issuers with
 // private accumulators (k-block kb belongs to issuer kb % 4; a single thread cannot issue small tcgen05.mma fast enough and
@@ -25,8 +28,9 @@ typedef __nv_bfloat16 bf;
 constexpr int GP_HS = 16;
 constexpr int GP_THREADS = 288;
 constexpr int GP_ISSUERS = 4;
-constexpr int GP_STAGES = 6;                  // TMA ring: 6 x (128 rows x 128 B) = 96 KB in flight per SM
-constexpr int GP_STAGE_BYTES = 128 * 128;
+constexpr int GP_ROWS = 64;                   // utterances per CTA (UMMA M)
+constexpr int GP_STAGES = 12;                 // TMA ring: 12 x (64 rows x 128 B) = 96 KB in flight per SM
+constexpr int GP_STAGE_BYTES = GP_ROWS * 128;
 constexpr uint32_t GP_TMEM_COLS = 256;
 
 __device__ __forceinline__ void gp_bar_sync(int id, int nthreads) {
@@ -42,7 +46,9 @@ __device__ __forceinline__ void gp_red_release(unsigned* p) {
 }
 __device__ __forceinline__ void gp_fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void gp_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
-__device__ __forceinline__ float gp_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU-based gate functions (ex2 + rcp): ~1e-6 absolute error, a quarter of the instructions of expf / tanhf
+__device__ __forceinline__ float gp_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float gp_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 __device__ __forceinline__ void ld16(const float* __restrict__ p, float (&v)[16]) {
 #pragma unroll
@@ -64,6 +70,39 @@ __device__ __forceinline__ void st16_bf16(bf* __restrict__ p, const float (&v)[1
     }
     reinterpret_cast<uint4*>(p)[0] = make_uint4(o[0], o[1], o[2], o[3]);
     reinterpret_cast<uint4*>(p)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* __restrict__ p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8_bf16(bf* __restrict__ p, const float (&v)[8]) {
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+// Sum of this half-warp's valid accumulators (column groups 0 and 64) for 16 consecutive columns starting at col, then
+// the halves' exchange: lanes 0..15 keep columns 0..7, lanes 16..31 columns 8..15 of (own + partner) sums.
+__device__ __forceinline__ void gp_gather8(uint32_t tlane, int col, int ncg, int hh, float (&out)[8]) {
+    float t0[16], t1[16];
+    tmem_ld16(tlane + col, t0);                     // warp-collective loads: issued by every lane, selected afterwards
+    tmem_ld16(tlane + 64 + col, t1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float lo = (ncg > 0 ? t0[i] : 0.f) + (ncg > 1 ? t1[i] : 0.f);
+        const float hi = (ncg > 0 ? t0[8 + i] : 0.f) + (ncg > 1 ? t1[8 + i] : 0.f);
+        const float mine = hh ? hi : lo;
+        const float send = hh ? lo : hi;
+        out[i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
 }
 
 struct GruFwdParams {
@@ -105,7 +144,7 @@ struct GpSmem {
 
 template <int NB, bool FWD>
 __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUtensorMap* tmA, uint8_t* sRing, uint64_t* full,
-                                            uint64_t* empty, const unsigned* ctr, int F, int KB, int K, int NS) {
+                                            uint64_t* empty, const unsigned* ctr, int F, int KB, int K, int NS, int row0) {
     int it = 0;
     for (int s = 0; s < F; ++s) {
         // forward : frame f = s reads h_{f-1} (h0 for f = 0, published before launch) -> wait for s * NS arrivals
@@ -123,7 +162,7 @@ __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUten
             const uint32_t ph = (it / GP_STAGES) & 1;
             mbar_wait(&empty[st], ph ^ 1);
             mbar_expect_tx(&full[st], GP_STAGE_BYTES);
-            tma_load_2d(sRing + (size_t)st * GP_STAGE_BYTES, tm, &full[st], col0 + kb * 64, 0);
+            tma_load_2d(sRing + (size_t)st * GP_STAGE_BYTES, tm, &full[st], col0 + kb * 64, row0);
         }
     }
 }
@@ -131,11 +170,12 @@ __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUten
 template <int NB>
 __device__ __forceinline__ void gp_issuer(int w, int nissue, uint8_t* sW, uint8_t* sRing, uint64_t* full, uint64_t* empty,
                                           uint64_t* w_ready, uint64_t* bar_d, uint32_t tmem, int F, int KB) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
+    constexpr uint32_t idesc = umma_idesc_bf16(GP_ROWS, NB);
     mbar_wait(w_ready, 0);
     const uint64_t dW0 = umma_desc_sw128(smem_u32(sW));
     const uint64_t dA0 = umma_desc_sw128(smem_u32(sRing));
-    const uint32_t dacc = tmem + (uint32_t)w * 64;
+    // issuers 0, 2 -> lanes 0..15 of every quadrant (column groups 0 / 64); issuers 1, 3 -> lanes 16..31
+    const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 64;
     for (int s = 0; s < F; ++s) {
         for (int kb = w; kb < KB; kb += GP_ISSUERS) {
             const int it = s * KB + kb;
@@ -189,7 +229,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1)
 k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH0,
                   const __grid_constant__ CUtensorMap tmY, const GruFwdParams p) {
     constexpr int NB = 3 * GP_HS;
-    const int H = p.H, F = p.F, KB = H >> 6, NS = gridDim.x;
+    const int H = p.H, F = p.F, KB = H >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,31 +261,34 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             for (int kb = 0; kb < KB; ++kb)
                 for (int g = 0; g < 3; ++g)
                     tma_load_2d(L.sW + (size_t)kb * GpSmem<NB>::W_KB_BYTES + g * (GP_HS * 128), &tmW, L.w_ready, kb * 64, g * H + u0);
-            gp_producer<NB, true>(&tmH0, &tmY, L.sRing, L.full, L.empty, p.ctr, F, KB, H, NS);
+            gp_producer<NB, true>(&tmH0, &tmY, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, H, NS, rs * GP_ROWS);
         }
     } else if (warp >= 5) {
         if (lane == 0 && warp - 5 < nissue)
             gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB);
     } else {
-        // ===================== row warps: gates, state, stores =====================
-        const int b = threadIdx.x;                           // utterance row = TMEM lane
+        // ===================== row warps: thread = (utterance row, 8 of the 16 units) =====================
+        const int hh = lane >> 4;                            // unit half: units u0 + 8*hh .. +7
+        const int b = rs * GP_ROWS + 16 * warp + (lane & 15);
         const bool ok = b < p.B;
+        const int uq = u0 + 8 * hh;
+        const int ncg = (nissue > hh) + (nissue > hh + 2);   // valid accumulators in this lane half (issuers hh, hh + 2)
         const uint32_t tlane = tmem + ((uint32_t)(32 * warp) << 16);
-        float h[16];
-        if (ok) ld16(p.h0 + (size_t)b * H + u0, h);
+        float h[8];
+        if (ok) ld8(p.h0 + (size_t)b * H + uq, h);
         else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = 0.f;
+            for (int j = 0; j < 8; ++j) h[j] = 0.f;
         }
         const size_t row_stride = (size_t)3 * H;
         for (int f = 0; f < F; ++f) {
             const size_t r = (size_t)b * F + f;
-            float gi[3][16];
+            float gi[3][8];
             if (ok) {
-                const float* gp = p.GI + r * row_stride + u0;
-                ld16(gp, gi[0]);
-                ld16(gp + H, gi[1]);
-                ld16(gp + 2 * H, gi[2]);
+                const float* gp = p.GI + r * row_stride + uq;
+                ld8(gp, gi[0]);
+                ld8(gp + H, gi[1]);
+                ld8(gp + 2 * H, gi[2]);
                 if (f + 1 < F) {                             // next frame's projections -> L2 while this frame computes
                     gp_prefetch_l2(gp + row_stride);
                     gp_prefetch_l2(gp + row_stride + H);
@@ -254,43 +297,34 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             mbar_wait(L.bar_d, f & 1);
             tc_fence_after();
-            float a[3][16];
+            float a[3][8];
 #pragma unroll
-            for (int g = 0; g < 3; ++g) tmem_ld16(tlane + 16 * g, a[g]);
-            for (int w = 1; w < nissue; ++w) {
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    float t[16];
-                    tmem_ld16(tlane + 64 * w + 16 * g, t);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) a[g][j] += t[j];
-                }
-            }
+            for (int g = 0; g < 3; ++g) gp_gather8(tlane, 16 * g, ncg, hh, a[g]);
             tc_fence_before();
             if (ok) {
-                float hn[16];
+                float hn[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    a[0][j] += L.sBias[j];
-                    a[1][j] += L.sBias[16 + j];
-                    a[2][j] += L.sBias[32 + j];
+                for (int j = 0; j < 8; ++j) {
+                    a[0][j] += L.sBias[8 * hh + j];
+                    a[1][j] += L.sBias[16 + 8 * hh + j];
+                    a[2][j] += L.sBias[32 + 8 * hh + j];
                     const float rr = gp_sigmoid(gi[0][j] + a[0][j]);
                     const float zz = gp_sigmoid(gi[1][j] + a[1][j]);
-                    const float nn = tanhf(gi[2][j] + rr * a[2][j]);
+                    const float nn = gp_tanh(gi[2][j] + rr * a[2][j]);
                     hn[j] = (1.f - zz) * nn + zz * h[j];
                     h[j] = hn[j];
                 }
-                st16_bf16(p.Y16 + r * H + u0, hn);           // first: this is what the other CTAs wait for
-                st16(p.Y + r * H + u0, hn);
-                float* ghp = p.GH + r * row_stride + u0;
-                st16(ghp, a[0]);
-                st16(ghp + H, a[1]);
-                st16(ghp + 2 * H, a[2]);
+                st8_bf16(p.Y16 + r * H + uq, hn);            // first: this is what the other CTAs wait for
+                st8(p.Y + r * H + uq, hn);
+                float* ghp = p.GH + r * row_stride + uq;
+                st8(ghp, a[0]);
+                st8(ghp + H, a[1]);
+                st8(ghp + 2 * H, a[2]);
             }
             gp_bar_sync(1, 128);
-            if (threadIdx.x == 0) gp_red_release(p.ctr);     // publishes the whole CTA's h_f slice
+            if (threadIdx.x == 0) gp_red_release(p.ctr + rs);   // publishes the whole CTA's h_f slice
         }
-        if (ok && p.h_last) st16(p.h_last + (size_t)b * H + u0, h);
+        if (ok && p.h_last) st8(p.h_last + (size_t)b * H + uq, h);
     }
     tc_fence_before();
     __syncthreads();
@@ -304,7 +338,7 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 __global__ void __launch_bounds__(GP_THREADS, 1)
 k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constant__ CUtensorMap tmG, const GruBwdParams p) {
     constexpr int NB = GP_HS;
-    const int H = p.H, F = p.F, K3 = 3 * H, KB = K3 >> 6, NS = gridDim.x;
+    const int H = p.H, F = p.F, K3 = 3 * H, KB = K3 >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -333,35 +367,38 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
             mbar_expect_tx(L.w_ready, (uint32_t)(KB * GpSmem<NB>::W_KB_BYTES));
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(L.sW + (size_t)kb * GpSmem<NB>::W_KB_BYTES, &tmWt, L.w_ready, kb * 64, u0);
-            gp_producer<NB, false>(&tmG, &tmG, L.sRing, L.full, L.empty, p.ctr, F, KB, K3, NS);
+            gp_producer<NB, false>(&tmG, &tmG, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, K3, NS, rs * GP_ROWS);
         }
     } else if (warp >= 5) {
         if (lane == 0 && warp - 5 < nissue)
             gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB);
     } else {
-        const int b = threadIdx.x;
+        const int hh = lane >> 4;
+        const int b = rs * GP_ROWS + 16 * warp + (lane & 15);
         const bool ok = b < p.B;
+        const int uq = u0 + 8 * hh;
+        const int ncg = (nissue > hh) + (nissue > hh + 2);
         const uint32_t tlane = tmem + ((uint32_t)(32 * warp) << 16);
-        float carry[16];
+        float carry[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) carry[j] = 0.f;
+        for (int j = 0; j < 8; ++j) carry[j] = 0.f;
         const size_t row_stride = (size_t)K3;
         for (int s = 0; s < F; ++s) {
             const int f = F - 1 - s;
             const size_t r = (size_t)b * F + f;
-            float dhz[16];
+            float dhz[8];
             if (ok) {
-                float gr[16], gz[16], gn[16], hr[16], hz[16], hn[16], hp[16], dy[16];
-                const float* gip = p.GI + r * row_stride + u0;
-                const float* ghp = p.GH + r * row_stride + u0;
-                ld16(gip, gr);
-                ld16(gip + H, gz);
-                ld16(gip + 2 * H, gn);
-                ld16(ghp, hr);
-                ld16(ghp + H, hz);
-                ld16(ghp + 2 * H, hn);
-                ld16(f ? p.Y + (r - 1) * H + u0 : p.h0 + (size_t)b * H + u0, hp);
-                ld16(p.dY + r * H + u0, dy);
+                float gr[8], gz[8], gn[8], hr[8], hz[8], hn[8], hp[8], dy[8];
+                const float* gip = p.GI + r * row_stride + uq;
+                const float* ghp = p.GH + r * row_stride + uq;
+                ld8(gip, gr);
+                ld8(gip + H, gz);
+                ld8(gip + 2 * H, gn);
+                ld8(ghp, hr);
+                ld8(ghp + H, hz);
+                ld8(ghp + 2 * H, hn);
+                ld8(f ? p.Y + (r - 1) * H + uq : p.h0 + (size_t)b * H + uq, hp);
+                ld8(p.dY + r * H + uq, dy);
                 if (f > 0) {                                 // the previous frame's rows -> L2 while this frame's GEMM runs
                     gp_prefetch_l2(gip - row_stride);
                     gp_prefetch_l2(gip - row_stride + H);
@@ -369,15 +406,15 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
                     gp_prefetch_l2(ghp - row_stride);
                     gp_prefetch_l2(ghp - row_stride + H);
                     gp_prefetch_l2(ghp - row_stride + 2 * H);
-                    gp_prefetch_l2(p.dY + (r - 1) * H + u0);
-                    if (f > 1) gp_prefetch_l2(p.Y + (r - 2) * H + u0);
+                    gp_prefetch_l2(p.dY + (r - 1) * H + uq);
+                    if (f > 1) gp_prefetch_l2(p.Y + (r - 2) * H + uq);
                 }
-                float o_r[16], o_z[16], o_n[16], o_nr[16];
+                float o_r[8], o_z[8], o_n[8], o_nr[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const float rr = gp_sigmoid(gr[j] + hr[j]);
                     const float zz = gp_sigmoid(gz[j] + hz[j]);
-                    const float nn = tanhf(gn[j] + rr * hn[j]);
+                    const float nn = gp_tanh(gn[j] + rr * hn[j]);
                     const float dh = dy[j] + carry[j];
                     const float dn = dh * (1.f - zz);
                     const float dz = dh * (hp[j] - nn);
@@ -389,43 +426,37 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
                     o_nr[j] = dpn * rr;
                     dhz[j] = dh * zz;
                 }
-                bf* g16 = p.dGH16 + r * row_stride + u0;     // first: the recurrent operand the other CTAs wait for
-                st16_bf16(g16, o_r);
-                st16_bf16(g16 + H, o_z);
-                st16_bf16(g16 + 2 * H, o_nr);
-                float* gh = p.dGH + r * row_stride + u0;
-                st16(gh, o_r);
-                st16(gh + H, o_z);
-                st16(gh + 2 * H, o_nr);
-                float* gi = p.dGI + r * row_stride + u0;
-                st16(gi, o_r);
-                st16(gi + H, o_z);
-                st16(gi + 2 * H, o_n);
-                bf* i16 = p.dGI16 + r * row_stride + u0;
-                st16_bf16(i16, o_r);
-                st16_bf16(i16 + H, o_z);
-                st16_bf16(i16 + 2 * H, o_n);
+                bf* g16 = p.dGH16 + r * row_stride + uq;     // first: the recurrent operand the other CTAs wait for
+                st8_bf16(g16, o_r);
+                st8_bf16(g16 + H, o_z);
+                st8_bf16(g16 + 2 * H, o_nr);
+                float* gh = p.dGH + r * row_stride + uq;
+                st8(gh, o_r);
+                st8(gh + H, o_z);
+                st8(gh + 2 * H, o_nr);
+                float* gi = p.dGI + r * row_stride + uq;
+                st8(gi, o_r);
+                st8(gi + H, o_z);
+                st8(gi + 2 * H, o_n);
+                bf* i16 = p.dGI16 + r * row_stride + uq;
+                st8_bf16(i16, o_r);
+                st8_bf16(i16 + H, o_z);
+                st8_bf16(i16 + 2 * H, o_n);
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) dhz[j] = 0.f;
+                for (int j = 0; j < 8; ++j) dhz[j] = 0.f;
             }
             gp_bar_sync(1, 128);
-            if (threadIdx.x == 0) gp_red_release(p.ctr);     // dGH_f of this CTA's units is published
+            if (threadIdx.x == 0) gp_red_release(p.ctr + rs);   // dGH_f of this CTA's units is published
             mbar_wait(L.bar_d, s & 1);
             tc_fence_after();
-            float a[16];
-            tmem_ld16(tlane, a);
-            for (int w = 1; w < nissue; ++w) {
-                float t[16];
-                tmem_ld16(tlane + 64 * w, t);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a[j] += t[j];
-            }
+            float a[8];
+            gp_gather8(tlane, 0, ncg, hh, a);
             tc_fence_before();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) carry[j] = dhz[j] + a[j];
+            for (int j = 0; j < 8; ++j) carry[j] = dhz[j] + a[j];
         }
-        if (ok && p.dh0) st16(p.dh0 + (size_t)b * H + u0, carry);
+        if (ok && p.dh0) st8(p.dh0 + (size_t)b * H + uq, carry);
     }
     tc_fence_before();
     __syncthreads();
@@ -437,18 +468,18 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
 // ---------------------------------------------------------------------------------------------------------------------
 bool gru_persist_supported(int B, int H, int n_sms) {
     if (getenv("SRNN_NO_GRU_PERSIST")) return false;
-    if (B < 1 || B > 128 || H % 64 || H < 64) return false;
-    if (H / GP_HS > n_sms) return false;                                   // all CTAs must be co-resident
+    if (B < 1 || B > 2 * GP_ROWS || H % 64 || H < 64) return false;
+    if ((H / GP_HS) * ((B + GP_ROWS - 1) / GP_ROWS) > n_sms) return false;   // all CTAs must be co-resident
     const size_t w = (size_t)(3 * H / 64) * GP_HS * 128;                   // both kernels keep 96*H bytes of weights
     return gp_smem_bytes(w) <= 227 * 1024;
 }
 
 template <typename K, typename... Args>
-static int gp_launch(K kernel, int grid, size_t smem, cudaStream_t st, unsigned* ctr, Args... args) {
+static int gp_launch(K kernel, int grid, int row_splits, size_t smem, cudaStream_t st, unsigned* ctr, Args... args) {
     SRNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SRNN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
+    SRNN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned) * 2, st));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(grid, row_splits);
     cfg.blockDim = dim3(GP_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -468,11 +499,11 @@ int gru_persist_fwd(int B, int F, int H, const float* GI, const bf* w_hh16, cons
                     float* GH, float* Y, bf* Y16, float* h_last, unsigned* ctr, cudaStream_t st) {
     CUtensorMap tmW, tmH0, tmY;
     SRNN_TRY(make_tmap_bf16(&tmW, w_hh16, (uint64_t)3 * H, H, H, GP_HS));
-    SRNN_TRY(make_tmap_bf16(&tmH0, h0_16, B, H, H, 128));
-    SRNN_TRY(make_tmap_bf16(&tmY, Y16, B, (uint64_t)F * H, (uint64_t)F * H, 128));
+    SRNN_TRY(make_tmap_bf16(&tmH0, h0_16, B, H, H, GP_ROWS));
+    SRNN_TRY(make_tmap_bf16(&tmY, Y16, B, (uint64_t)F * H, (uint64_t)F * H, GP_ROWS));
     GruFwdParams p{B, F, H, GI, GH, Y, Y16, h0, h_last, b_hh, ctr};
     const size_t smem = gp_smem_bytes((size_t)(H / 64) * 3 * GP_HS * 128);
-    return gp_launch(k_gru_persist_fwd, H / GP_HS, smem, st, ctr, tmW, tmH0, tmY, p);
+    return gp_launch(k_gru_persist_fwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmW, tmH0, tmY, p);
 }
 
 // BPTT of one GRU layer.  w_hh16_t (H, 3H) bf16 = W_hh^T.
@@ -481,10 +512,10 @@ int gru_persist_bwd(int B, int F, int H, const float* GI, const float* GH, const
                     cudaStream_t st) {
     CUtensorMap tmWt, tmG;
     SRNN_TRY(make_tmap_bf16(&tmWt, w_hh16_t, H, (uint64_t)3 * H, (uint64_t)3 * H, GP_HS));
-    SRNN_TRY(make_tmap_bf16(&tmG, dGH16, B, (uint64_t)F * 3 * H, (uint64_t)F * 3 * H, 128));
+    SRNN_TRY(make_tmap_bf16(&tmG, dGH16, B, (uint64_t)F * 3 * H, (uint64_t)F * 3 * H, GP_ROWS));
     GruBwdParams p{B, F, H, GI, GH, Y, h0, dY, dGI, dGH, dGI16, dGH16, dh0, ctr};
     const size_t smem = gp_smem_bytes((size_t)(3 * H / 64) * GP_HS * 128);
-    return gp_launch(k_gru_persist_bwd, H / GP_HS, smem, st, ctr, tmWt, tmG, p);
+    return gp_launch(k_gru_persist_bwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmWt, tmG, p);
 }
 
 }  // namespace srnn
