@@ -458,6 +458,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     int* step_base = nullptr;
     float *hid[SRNN_MAX_TIERS], *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS],
         *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
+    float* GHL[SRNN_MAX_TIERS][SRNN_MAX_RNN];      // per-layer recurrent projections of the fused-cell schedule
     bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr;
     float* part = nullptr;
     unsigned* gctr = nullptr;
@@ -473,6 +474,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             X[i] = b.take<float>((size_t)B * H);
             GI[i] = b.take<float>((size_t)B * 3 * H);
             GH[i] = b.take<float>((size_t)B * 3 * H);
+            for (int l = 0; l < NL; ++l) GHL[i][l] = b.take<float>(bf16 ? (size_t)B * 3 * H : 1);
             OUT[i] = b.take<float>((size_t)B * t.fs * H);
             hid16[i] = b.take<bf>((size_t)NL * B * H);
             X16[i] = b.take<bf>((size_t)B * H);
@@ -508,6 +510,15 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     const int bn_tier = B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256));
     // With more than 128 utterances a 128-row tile doubles the CTA count (measured: 19.8 -> 16.3 us for the gi+gh launch at
     // B = 256) as long as the grid still fits one wave of SMs; the tier-2 upsampling (160 feature tiles) keeps 256-row tiles.
+    const bool fused_cell = bf16 && gru_cell_gen_supported(H);
+    const bool skip_tiers = getenv("SRNN_SKIP_TIERS") != nullptr;   // timing experiment only (results are wrong)
+    cudaStream_t st2 = nullptr;                 // side branch of the tier steps (captured into the same graph)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (fused_cell) {
+        SRNN_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+        SRNN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        SRNN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
     auto bn_for = [&](int n_feat, int nprob) {
         if (bn_tier < 256) return bn_tier;
         return cdiv(n_feat, 128) * cdiv(B, 128) * nprob <= ctx->n_sms ? 128 : 256;
@@ -535,6 +546,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             for (int i = NT - 1; i >= 0; --i) {
                 const TierPacked& t = ctx->tiers[i];
                 if (pos % t.n) continue;                                             // model.py:465
+                if (skip_tiers) continue;
                 const float* upper = nullptr;
                 int up_ld = 0;
                 if (!t.top) {                                                        // model.py:491-495
@@ -543,13 +555,38 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     up_ld = u.fs * H;
                 }
                 mark(t.top ? "(start top)" : "(start)");
+                if (bf16 && fused_cell) {      // fork: gh of every layer runs beside the input expansion (independent of it)
+                    SRNN_CUDA(cudaEventRecord(ev_fork, st));
+                    SRNN_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+                    for (int l = 0; l < NL; l += 2) {
+                        const int np = NL - l >= 2 ? 2 : 1;
+                        GemmOperands ops[2];
+                        for (int q = 0; q < np; ++q)
+                            ops[q] = GemmOperands{t.w_hh16[l + q], hid16[i] + (size_t)(l + q) * B * H, t.b_hh[l + q], nullptr,
+                                                  GHL[i][l + q], nullptr, 3 * H, H, H, 0, 3 * H, 0, nullptr};
+                        SRNN_TRY(gemm_umma_multi(ops, np, B, H, 128, bn_for(3 * H, np), st2));
+                    }
+                    SRNN_CUDA(cudaEventRecord(ev_join, st2));
+                }
                 SRNN_TRY(tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
                                         c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
                                         H, t.kin, t.top, st));
                 mark(t.top ? "input top" : "input");
                 const float* in = X[i];
                 const bf* in16 = X16[i];
-                for (int l = 0; l < NL; ++l) {
+                if (bf16 && fused_cell) {
+                    // Fused-cell schedule: the recurrent projections gh_l = W_hh_l h_l + b_hh_l of ALL layers depend only on
+                    // the previous step's state, so they go first (two layers per launch); then one launch per layer does
+                    // gi_l = W_ih_l x + b_ih_l on tcgen05 and the gate math (k_gru_cell_gen): 1 + NL launches instead of 2 NL.
+                    SRNN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));      // join: the forked gh launch(es) below
+                    for (int l = 0; l < NL; ++l) {
+                        SRNN_TRY(gru_cell_gen(B, H, in16, t.w_ih16[l], t.b_ih[l], GHL[i][l], hid[i] + (size_t)l * B * H,
+                                              hid16[i] + (size_t)l * B * H, st));
+                        mark("cell");
+                        in16 = hid16[i] + (size_t)l * B * H;
+                    }
+                }
+                for (int l = 0; l < NL && !(bf16 && fused_cell); ++l) {
                     float* h = hid[i] + (size_t)l * B * H;
                     bf* h16 = hid16[i] + (size_t)l * B * H;
                     if (bf16) {      // gi = W_ih x + b_ih and gh = W_hh h + b_hh side by side in one launch
@@ -707,6 +744,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     SRNN_CUDA(cudaEventDestroy(ev_in));
     SRNN_CUDA(cudaEventDestroy(ev_out));
     SRNN_CUDA(cudaStreamDestroy(st));
+    if (st2) {
+        SRNN_CUDA(cudaStreamDestroy(st2));
+        SRNN_CUDA(cudaEventDestroy(ev_fork));
+        SRNN_CUDA(cudaEventDestroy(ev_join));
+    }
     return SRNN_OK;
 }
 

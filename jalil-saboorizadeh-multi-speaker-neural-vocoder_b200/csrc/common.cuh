@@ -240,6 +240,10 @@ int transpose_to_bf16(const __nv_bfloat16* src, int rows, int cols, long long ld
 int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st);
 // persistent GRU recurrence over all frames of one layer (gru_persist.cu)
 bool gru_persist_supported(int B, int H, int n_sms);
+// generation-time fused cell: gi GEMM + gate math in one launch (gru_persist.cu)
+bool gru_cell_gen_supported(int H);
+int gru_cell_gen(int B, int H, const __nv_bfloat16* x16, const __nv_bfloat16* w_ih16, const float* b_ih, const float* GH, float* h,
+                 __nv_bfloat16* h16, cudaStream_t st);
 int gru_persist_fwd(int B, int F, int H, const float* GI, const __nv_bfloat16* w_hh16, const float* b_hh, const float* h0,
                     const __nv_bfloat16* h0_16, float* GH, float* Y, __nv_bfloat16* Y16, float* h_last, unsigned* ctr,
                     cudaStream_t st);

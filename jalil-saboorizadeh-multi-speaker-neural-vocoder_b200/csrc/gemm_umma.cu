@@ -65,6 +65,25 @@ int make_tmap_bf16_kb(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
     return SRNN_OK;
 }
 
+// GRU weight matrix (3H, K) viewed as [k-block][gate][unit][64]: one TMA box = box_kb k-blocks x 3 gates x box_units units,
+// landing as box_kb consecutive {3*box_units rows x 128 B} swizzled tiles (rows ordered gate-major): the B operand of a
+// fused gate GEMM for one slice of hidden units (gru_persist.cu, k_gru_cell_gen).
+int make_tmap_bf16_gates(CUtensorMap* tm, const void* base, uint64_t H, uint64_t K, uint64_t ld, uint32_t box_units,
+                         uint32_t box_kb) {
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (((uintptr_t)base & 15) || (ld * 2) % 16 || K % 64) return fail(SRNN_ERR_ARG, "tensor map: alignment");
+    cuuint64_t gdim[4] = {64, H, 3, K / 64};
+    cuuint64_t gstride[3] = {ld * sizeof(__nv_bfloat16), H * ld * sizeof(__nv_bfloat16), 128};
+    cuuint32_t box[4] = {64, box_units, 3, box_kb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (%d)", (int)r);
+    return SRNN_OK;
+}
+
 constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
 
 template <int BM, int BN>
@@ -401,7 +420,8 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
     a.nstage = S::NSTAGE;
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const int shallow = (110 * 1024 - 1280) / S::STAGE;
-    if (g_gemm_sms > 0 && ctas > g_gemm_sms && ctas <= 2 * g_gemm_sms && shallow >= 2 && TCOLS_OF(BN) <= 256 &&
+    static const bool shallow_all = getenv("SRNN_GEMM_SHALLOW_ALL") != nullptr;
+    if (g_gemm_sms > 0 && ctas > g_gemm_sms && (ctas <= 2 * g_gemm_sms || shallow_all) && shallow >= 2 && TCOLS_OF(BN) <= 256 &&
         !getenv("SRNN_GEMM_DEEP_RING"))
         a.nstage = shallow < S::NSTAGE ? shallow : S::NSTAGE;
     const size_t smem = (size_t)a.nstage * S::STAGE + 1024 + 256;

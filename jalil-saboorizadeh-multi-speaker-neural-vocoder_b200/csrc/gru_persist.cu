@@ -464,6 +464,165 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Generation-time GRU cell: ONE launch per layer and tier step does  gi = W_ih x + b_ih  on tcgen05 AND the gate math
+// (the recurrent projection gh = W_hh h + b_hh does not depend on the new samples and is computed by an earlier launch):
+//     h' = (1 - z) n + z h,   r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r gh_n)        (model.py:244 at F = 1)
+// CTA (c, rs): 32 hidden units x 64 utterances; B operand = the r/z/n rows of W_ih for those units (96 x K, streamed by 4-D
+// TMA boxes of 4 k-blocks), A operand = x (64 rows x K).  Same interleaved M = 64 accumulators / row threads as above.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GC_US = 32;
+constexpr int GC_NB = 3 * GC_US;
+constexpr int GC_GKB = 4;                                     // k-blocks per TMA box
+constexpr int GC_RING = 2;                                    // boxes in flight
+constexpr int GC_A_BYTES = GC_GKB * GP_ROWS * 128;            // 32 KB
+constexpr int GC_W_BYTES = GC_GKB * GC_NB * 128;              // 48 KB
+constexpr int GC_GROUP_BYTES = GC_A_BYTES + GC_W_BYTES;
+
+struct GruCellParams {
+    int B, H;
+    const float* b_ih;   // (3H)
+    const float* GH;     // (B, 3H)  W_hh h + b_hh of this step
+    float* h;            // (B, H)   fp32 state, updated in place
+    bf* h16;             // (B, H)   bf16 copy of the new state
+};
+
+__global__ void __launch_bounds__(GP_THREADS, 1)
+k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const GruCellParams p) {
+    const int H = p.H, NG = (H >> 6) / GC_GKB, rs = blockIdx.y, u0 = blockIdx.x * GC_US;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sRing = smem;
+    float* sBias = (float*)(sRing + (size_t)GC_RING * GC_GROUP_BYTES);
+    uint64_t* full = (uint64_t*)(sBias + GC_NB);
+    uint64_t* empty = full + GC_RING;
+    uint64_t* bar_d = empty + GC_RING;
+    uint32_t* tmem_slot = (uint32_t*)(bar_d + 1);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmW);
+        for (int s = 0; s < GC_RING; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], GP_ISSUERS);
+        }
+        mbar_init(bar_d, GP_ISSUERS);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < GC_NB) sBias[threadIdx.x] = p.b_ih[(threadIdx.x / GC_US) * H + u0 + (threadIdx.x % GC_US)];
+    if (warp == 5) tmem_alloc<GP_TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int g = 0; g < NG; ++g) {
+                const int st = g % GC_RING;
+                const uint32_t ph = (g / GC_RING) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_expect_tx(&full[st], GC_GROUP_BYTES);
+                uint8_t* dst = sRing + (size_t)st * GC_GROUP_BYTES;
+                tma_load_3d(dst, &tmX, &full[st], 0, rs * GP_ROWS, g * GC_GKB);
+                tma_load_4d(dst + GC_A_BYTES, &tmW, &full[st], 0, u0, 0, g * GC_GKB);
+            }
+        }
+    } else if (warp >= 5) {
+        if (lane == 0) {
+            const int w = warp - 5;                                      // issuer w takes k-block w of every box
+            constexpr uint32_t idesc = umma_idesc_bf16(GP_ROWS, GC_NB);
+            const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 128;
+            for (int g = 0; g < NG; ++g) {
+                const int st = g % GC_RING;
+                const uint32_t ph = (g / GC_RING) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(sRing + (size_t)st * GC_GROUP_BYTES);
+                const uint64_t da = umma_desc_sw128(base + w * (GP_ROWS * 128));
+                const uint64_t db = umma_desc_sw128(base + GC_A_BYTES + w * (GC_NB * 128));
+                umma_bf16(dacc, da, db, idesc, g > 0);
+                umma_bf16(dacc, da + 2, db + 2, idesc, 1);
+                umma_bf16(dacc, da + 4, db + 4, idesc, 1);
+                umma_bf16(dacc, da + 6, db + 6, idesc, 1);
+                umma_commit(&empty[st]);
+            }
+            umma_commit(bar_d);
+        }
+    } else {
+        const int hh = lane >> 4;                                        // unit half: 16 of the CTA's 32 units
+        const int b = rs * GP_ROWS + 16 * warp + (lane & 15);
+        const bool ok = b < p.B;
+        const int uq = u0 + 16 * hh;
+        const uint32_t tlane = tmem + ((uint32_t)(32 * warp) << 16);
+        float gh[3][16], h[16];
+        if (ok) {
+            const float* ghp = p.GH + (size_t)b * 3 * H + uq;
+            ld16(ghp, gh[0]);
+            ld16(ghp + H, gh[1]);
+            ld16(ghp + 2 * H, gh[2]);
+            ld16(p.h + (size_t)b * H + uq, h);
+        }
+        mbar_wait(bar_d, 0);
+        tc_fence_after();
+        float gi[3][16];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            float lo[16], hi[16], t[16];
+            tmem_ld16(tlane + 32 * g, lo);
+            tmem_ld16(tlane + 32 * g + 16, hi);
+            tmem_ld16(tlane + 128 + 32 * g, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lo[j] += t[j];
+            tmem_ld16(tlane + 128 + 32 * g + 16, t);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hi[j] += t[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float mine = hh ? hi[j] : lo[j];
+                const float send = hh ? lo[j] : hi[j];
+                gi[g][j] = mine + __shfl_xor_sync(0xffffffffu, send, 16) + sBias[g * GC_US + 16 * hh + j];
+            }
+        }
+        tc_fence_before();
+        if (ok) {
+            float hn[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float rr = gp_sigmoid(gi[0][j] + gh[0][j]);
+                const float zz = gp_sigmoid(gi[1][j] + gh[1][j]);
+                const float nn = gp_tanh(gi[2][j] + rr * gh[2][j]);
+                hn[j] = (1.f - zz) * nn + zz * h[j];
+            }
+            st16(p.h + (size_t)b * H + uq, hn);
+            st16_bf16(p.h16 + (size_t)b * H + uq, hn);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc<GP_TMEM_COLS>(tmem);
+}
+
+bool gru_cell_gen_supported(int H) { return H % (64 * GC_GKB) == 0 && !getenv("SRNN_NO_GRU_CELL"); }
+
+// x16 (B, H) bf16 input of the layer, w_ih16 (3H, H), b_ih (3H), GH (B, 3H) = W_hh h + b_hh; h / h16 updated in place.
+int gru_cell_gen(int B, int H, const bf* x16, const bf* w_ih16, const float* b_ih, const float* GH, float* h, bf* h16,
+                 cudaStream_t st) {
+    CUtensorMap tmX, tmW;
+    SRNN_TRY(make_tmap_bf16_kb(&tmX, x16, B, H, H, GP_ROWS, GC_GKB));
+    SRNN_TRY(make_tmap_bf16_gates(&tmW, w_ih16, H, H, H, GC_US, GC_GKB));
+    const size_t smem = 1024 + (size_t)GC_RING * GC_GROUP_BYTES + GC_NB * 4 + 8 * (2 * GC_RING + 1) + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SRNN_CUDA(cudaFuncSetAttribute(k_gru_cell_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    GruCellParams p{B, H, b_ih, GH, h, h16};
+    SRNN_LAUNCH(k_gru_cell_gen, dim3(H / GC_US, (B + GP_ROWS - 1) / GP_ROWS), GP_THREADS, smem, st, tmX, tmW, p);
+    return SRNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 bool gru_persist_supported(int B, int H, int n_sms) {

@@ -12,6 +12,9 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
 // the same matrix as [k-block][row][64]: one TMA box = box_kb consecutive k-blocks x box_rows rows
 int make_tmap_bf16_kb(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                       uint32_t box_kb);
+// GRU weights (3H, K) as [k-block][gate][unit][64]: one box = box_kb k-blocks x 3 gates x box_units units
+int make_tmap_bf16_gates(CUtensorMap* tm, const void* base, uint64_t H, uint64_t K, uint64_t ld, uint32_t box_units,
+                         uint32_t box_kb);
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,6 +71,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 4-D tiled load (make_tmap_bf16_gates): c1 = first unit, c2 = first gate, c3 = first k-block
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 // 3-D tiled load (make_tmap_bf16_kb): c1 = row offset, c2 = first k-block
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
