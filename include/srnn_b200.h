@@ -149,6 +149,11 @@ SRNN_API int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float
 /* The defined sampler replacing Tensor.multinomial (model.py:517): p (rows, 256) fp32 unnormalised,
  * u (rows) fp32 -> idx (rows) int32.  Bit-exact with oracle/srnn_oracle.py:sample_rows. */
 SRNN_API int srnn_sample_rows(const float* p, const float* u, int32_t rows, int32_t* idx, void* stream);
+/* Training-data quantiser used by FolderDataset.__getitem__ (dataset.py:249-253): ulaw != 0 -> utils.uquantize
+ * (utils.py:33-36,48-51,58-59; the reference's out-of-range index 256 at x == 1.0 is clamped to q_levels-1),
+ * else utils.linear_quantize (utils.py:9-15, per-row min/max).  x (rows, cols) fp32 with row stride ld -> q int64. */
+SRNN_API int srnn_quantize(const float* x, int32_t rows, int32_t cols, int64_t ld, int32_t q_levels, int32_t ulaw,
+                           int64_t* q, void* stream);
 /* out (256) fp32 = 2*dequantize(q) (model.py:385,471). */
 SRNN_API int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream);
 /* One GRU layer over F frames = `self.rnn(input, hidden)` (model.py:244; torch nn.GRU, gate row blocks r, z, n) given the

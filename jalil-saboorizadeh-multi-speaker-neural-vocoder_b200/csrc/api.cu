@@ -768,12 +768,13 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
         SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
         const bool persist = mode == SRNN_MODE_BF16 && mlp_persist_supported(ctx->H, ctx->FS0, B, n_sms);
         // Batches beyond what the persistent sample-level kernel can keep co-resident (RG * NS CTAs <= SMs: 288 utterances at
-        // dim 1024): up to three balanced utterance chunks run back to back through the persistent path (utterances are
-        // independent), which beats the one-GEMM-launch-per-contraction schedule until ~1000 utterances (measured, C4 sweep).
+        // dim 1024): two balanced utterance chunks run back to back through the persistent path (utterances are independent),
+        // which beats the one-GEMM-launch-per-contraction schedule up to 576 utterances (measured at 320/512/576/864:
+        // 791/1241/1282/1285x real-time chunked vs 697/1041/1188/1325x; profiles/README.md, C4 sweep).
         if (mode == SRNN_MODE_BF16 && !persist && mlp_persist_supported(ctx->H, ctx->FS0, 32, n_sms)) {
             const int NS = ctx->H / 64, max_chunk = (n_sms / NS) * 32;
             const int chunks = (B + max_chunk - 1) / max_chunk;
-            if (chunks <= 3) {
+            if (chunks <= 2) {
                 const int per = ((B + chunks - 1) / chunks + 31) / 32 * 32;
                 const size_t T = (size_t)n_cond * ctx->lookback;
                 for (int b0 = 0; b0 < B; b0 += per) {
@@ -800,6 +801,13 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
 int srnn_sample_rows(const float* p, const float* u, int32_t rows, int32_t* idx, void* stream) {
     if (!p || !u || !idx) return fail(SRNN_ERR_ARG, "null argument");
     return sample_rows(p, u, rows, idx, (cudaStream_t)stream);
+}
+
+// Training-data quantiser (dataset.py:249-253): x (rows, cols; row stride ld) fp32 audio in [-1, 1] -> q (rows, cols) int64.
+int srnn_quantize(const float* x, int32_t rows, int32_t cols, int64_t ld, int32_t q_levels, int32_t ulaw, int64_t* q, void* stream) {
+    if (!x || !q) return fail(SRNN_ERR_ARG, "null argument");
+    if (q_levels < 2 || q_levels > 65536) return fail(SRNN_ERR_ARG, "bad q_levels");
+    return quantize_samples(x, rows, cols, ld, q_levels, ulaw, q, (cudaStream_t)stream);
 }
 
 int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream) {

@@ -149,6 +149,7 @@ int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
 int fill_u8(uint8_t* dst, uint8_t v, size_t n, cudaStream_t st);
 int build_lut(float* lut, int q_levels, int ulaw, cudaStream_t st);
 int i64_to_u8(const int64_t* src, uint8_t* dst, size_t n, cudaStream_t st);
+int quantize_samples(const float* x, int rows, int cols, long long ld, int q_levels, int ulaw, int64_t* q, cudaStream_t st);
 int pack_top_in(const float* w_in, const float* w_c, const float* w_s, const float* emb, const float* b_in,
                 const float* b_c, const float* b_s, float* w_out, float* b_out, int H, int n, int cond_dim,
                 int spk_dim, cudaStream_t st);

@@ -138,6 +138,62 @@ int i64_to_u8(const int64_t* src, uint8_t* dst, size_t n, cudaStream_t st) {
     return SRNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// quantisers of the training data path (dataset.py:249-253 -> utils.py)
+// ------------------------------------------------------------------------------------------------
+// utils.uquantize = midrise(ulaw(x)) (utils.py:33-36,48-51,58-59), same fp32 operation order as the reference:
+//   y = sign(x) * log(255 |x| + 1) / log(256);   q = long(0.5 (y + 1) * 256)      [(256 - 1e-6) is 256.0f in fp32]
+// The reference returns 256 for x == 1.0, an index outside the embedding: clamped to 255 here.
+__global__ void k_uquantize(const float* __restrict__ x, int64_t* __restrict__ q, size_t n, int q_levels) {
+    const float scale = (float)((double)q_levels - 1e-6);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const float sg = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
+        const float y = sg * logf(255.f * fabsf(v) + 1.f) / 5.5451774444795623f;
+        float t = 0.5f * (y + 1.0f);
+        t *= scale;
+        long long r = (long long)t;                        // .long(): truncation toward zero
+        r = r < 0 ? 0 : (r > q_levels - 1 ? q_levels - 1 : r);
+        q[i] = r;
+    }
+}
+// utils.linear_quantize (utils.py:9-15): per-row min/max normalisation, then (x * (q - 0.01) + 0.005).long(); one block per row
+__global__ void k_linear_quantize(const float* __restrict__ x, int64_t* __restrict__ q, int cols, long long ld, int q_levels) {
+    const float* row = x + (size_t)blockIdx.x * ld;
+    __shared__ float smin[32], smax[32];
+    float mn = INFINITY, mx = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) mn = fminf(mn, row[c]);
+    for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    mn = smin[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mn = fminf(mn, smin[w]);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, row[c] - mn);       // max AFTER the shift, as the reference
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = smax[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, smax[w]);
+    const float scale = (float)((double)q_levels - 1e-2), half = (float)(1e-2 / 2);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float t = (row[c] - mn) / mx;
+        t *= scale;
+        t += half;
+        q[(size_t)blockIdx.x * cols + c] = (long long)t;
+    }
+}
+int quantize_samples(const float* x, int rows, int cols, long long ld, int q_levels, int ulaw, int64_t* q, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return SRNN_OK;
+    if (ulaw) {
+        if (ld != cols) return fail(SRNN_ERR_ARG, "mu-law quantiser expects a contiguous tensor");
+        const size_t n = (size_t)rows * cols;
+        SRNN_LAUNCH(k_uquantize, (int)((n + 255) / 256 > 8192 ? 8192 : (n + 255) / 256), 256, 0, st, x, q, n, q_levels);
+    } else {
+        SRNN_LAUNCH(k_linear_quantize, rows, 256, 0, st, x, q, cols, ld, q_levels);
+    }
+    return SRNN_OK;
+}
+
 // lut[q] = 2 * dequantize(q)   (utils.py:18-19 linear; utils.py:39-42,54-55,62-63 mu-law; model.py:385,471 the 2x)
 __global__ void k_build_lut(float* lut, int q_levels, int ulaw) {
     const int q = threadIdx.x;
