@@ -26,6 +26,9 @@ C2 = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, u
           cond_dim=86, spk_dim=6)
 F_ALG = 6.423e6      # FLOP per generated sample per utterance, embedding-o-conv folded; what the kernels execute
 F_DENSE = 16.889e6   # the reference graph's dense work, for context
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_mlp_persist launch at B = 256 from the `ncu --set full` capture
+# summarised in profiles/r1_k_mlp_persist_ncu_full.txt (cold L2: ncu flushes caches between replays)
+NCU_TRAFFIC_MLP_PERSIST_B256 = 34.14e6 + 0.03e6
 F_MLP = 2.0 * (1024 * 1024 + 1024 * 256) + 20 * 1024   # k_mlp_persist's share of F_ALG per sample per utterance: hidden +
                                                        # output contraction + the folded-table adds (SURVEY 8d components)
 SAMPLE_RATE = 16000
@@ -208,8 +211,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("SRNN_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16", "bf16_graph"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--n-cond", type=int, default=100, help="conditioner frames (x80 samples) per step")
-    ap.add_argument("--ref-n-cond", type=int, default=2)
-    ap.add_argument("--cpu-n-cond", type=int, default=2)
+    ap.add_argument("--ref-n-cond", type=int, default=8, help="reference arm: cond frames per step (~4 s of CPU work each)")
+    ap.add_argument("--cpu-n-cond", type=int, default=24, help="cpu_baseline sample: cond frames (~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="generate", choices=["generate", "train"],
                     help="generate = the headline metric (default); train = C3 teacher-forced training step")
@@ -315,10 +318,12 @@ def main():
     if kern:
         flops_launch = F_MLP * B * fs0
         ach, kname = flops_launch / kern[0] / 1e12, "srnn::k_mlp_persist"
+        traffic = NCU_TRAFFIC_MLP_PERSIST_B256 if B == 256 else None
         kinfo = {"kernel": kname, "launches_timed": kern[1], "avg_launch_us": kern[0] * 1e6, "flops_per_launch": flops_launch,
                  "share_of_step": kern[2] / (secs / args.steps),
                  "how": "CUDA events around each launch on the generation stream (direct launches, SRNN_TIME_KERNELS)"}
     else:
+        traffic = None
         ach, kinfo = ach_step, {"kernel": "whole generation step (all launches of srnn_generate)"}
     h2d = cond_h.numel() * 4 + spk_h.numel() * 8 + uni_h.numel() * 4
     d2h = audio_h.numel() * 4
@@ -335,7 +340,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                     "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, cold L2)",
+                     "peak_source": peak_src + " bf16_tflops_sustained",
                      "flops_per_sample": F_ALG, "whole_step_achieved": ach_step, "whole_step_frac": ach_step / peak_tf,
                      "achieved_dense_equiv": value * F_DENSE / 1e12 / world, **kinfo},
     }
