@@ -119,7 +119,8 @@ def run_reference(args, rank, world):
         "x_realtime_16k": v / SAMPLE_RATE, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN dim 1024, batch %d" % args.batch, "sample": sample},
+        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond 86, weight-norm",
+                   "batch_per_gpu": args.batch, "total_batch": args.batch, "samples_per_utterance": n_cond * 80, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
