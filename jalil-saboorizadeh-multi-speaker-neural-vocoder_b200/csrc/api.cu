@@ -213,9 +213,8 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
     if (!P->embedding || !P->mlp_hidden.bias || !P->mlp_output.bias) return fail(SRNN_ERR_ARG, "missing MLP parameters");
     SRNN_TRY(wn_fold(P->mlp_input, t_mi, H, Q * FS0, st));
     SRNN_TRY(transpose_mlp_in(t_mi, t_mit, H, Q, FS0, st));
-    for (int j = 0; j < FS0; ++j)   // Tbl[j] (Q,H) = E (Q,Q) . W_in[:,:,j]^T
-        SRNN_TRY(gemm_f32(Q, H, Q, P->embedding, Q, t_mit + (size_t)j * H * Q, Q, nullptr, nullptr, 0, 0,
-                          ctx->tbl + (size_t)j * Q * H, H, st));
+    // Tbl[j] (Q,H) = E (Q,Q) . W_in[:,:,j]^T for all FS0 taps in one batched launch
+    SRNN_TRY(gemm_f32_batched(FS0, Q, H, Q, P->embedding, Q, 0, t_mit, Q, (long long)H * Q, ctx->tbl, H, (long long)Q * H, st));
     SRNN_TRY(wn_fold(P->mlp_hidden, ctx->w_hid, H, H, st));
     SRNN_TRY(copy_f32(P->mlp_hidden.bias, ctx->b_hid, H, st));
     SRNN_TRY(wn_fold(P->mlp_output, ctx->w_out, Q, H, st));

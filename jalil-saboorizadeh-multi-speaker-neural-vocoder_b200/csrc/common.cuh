@@ -144,6 +144,8 @@ int ensure_ws(srnn_ctx* ctx, size_t bytes);
 int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
              const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st,
              __nv_bfloat16* C16 = nullptr);
+int gemm_f32_batched(int batch, int M, int N, int K, const float* A, int lda, long long sA, const float* B, int ldb, long long sB,
+                     float* C, int ldc, long long sC, cudaStream_t st);
 int wn_fold(const srnn_conv_params& p, float* out, int rows, int cols, cudaStream_t st);
 int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
 int fill_u8(uint8_t* dst, uint8_t v, size_t n, cudaStream_t st);

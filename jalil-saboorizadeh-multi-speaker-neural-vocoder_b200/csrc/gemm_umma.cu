@@ -110,6 +110,8 @@ struct alignas(64) GemmProb {
 struct alignas(64) GemmArgs {
     GemmProb p[2];
     int n_rows, K;
+    int gx, gy, gz;        // tile grid (A-operand tiles, B-operand tiles, problems or K splits); CTAs stride over it
+    int nbuf;              // TMEM accumulator buffers: 2 = epilogue of tile i overlaps the main loop of tile i+1
     int nstage;            // TMA ring depth in use (<= GemmSmem::NSTAGE): a shallow ring lets two CTAs share an SM
     int ksplit;            // > 1: single problem, blockIdx.z = K split; split z writes out_f32 + z * split_stride (partials)
     long long split_stride;
@@ -201,68 +203,97 @@ __device__ __forceinline__ void epi_row16(const float (&v)[16], const float* __r
 // MNMAJ = true (ROWS only): both operands are given TRANSPOSED in memory -- tmA over X (K_total x M_total) and tmB over
 //               Y (K_total x N_total), row-major -- and out = X^T . Y: the weight-gradient GEMMs dW = dOut^T . In read
 //               dOut and In as they are, no transposed copies.
+struct TileInfo {
+    int m0, n0, kb0, KB, prob, split;
+    bool valid;
+};
+// tile index -> (A-operand tile, B-operand tile, problem / K split); the same enumeration as the former 3-D grid
+template <int BM, int BN, bool ROWS>
+__device__ __forceinline__ TileInfo tile_info(const GemmArgs& args, int tile) {
+    TileInfo t;
+    const int bx = tile % args.gx, by = (tile / args.gx) % args.gy, bz = tile / (args.gx * args.gy);
+    t.m0 = bx * BM;
+    t.n0 = by * BN;
+    t.prob = args.ksplit > 1 ? 0 : bz;
+    t.split = args.ksplit > 1 ? bz : 0;
+    t.kb0 = 0;
+    t.KB = args.K / 64;
+    if (args.ksplit > 1) {                         // this tile's K range (every split is non-empty by construction)
+        const int per = (t.KB + args.ksplit - 1) / args.ksplit;
+        t.kb0 = bz * per;
+        t.KB = t.KB - t.kb0 < per ? t.KB - t.kb0 : per;
+    }
+    t.valid = t.m0 < (ROWS ? args.n_rows : args.p[t.prob].n_feat);   // the two problems of a launch may differ in feature count
+    return t;
+}
+
 template <int BM, int BN, bool ROWS, bool MNMAJ = false>
 __global__ void __launch_bounds__(GEMM_THREADS, BN <= 256 ? 2 : 1)
 k_gemm_umma(const __grid_constant__ GemmArgs args) {
+    // PERSISTENT: CTA b processes tiles b, b + gridDim.x, ...  With args.nbuf == 2 the accumulator is double-buffered in
+    // TMEM, so the epilogue of tile i (TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1; the
+    // producer / MMA / epilogue roles only meet at mbarriers (full/empty per smem stage, full/empty per TMEM buffer).
     using S = GemmSmem<BM, BN>;
     constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
-    const GemmProb& P = args.p[args.ksplit > 1 ? 0 : blockIdx.z];
-    const int n_feat = P.n_feat, n_rows = args.n_rows;
+    const int n_rows = args.n_rows, nbuf = args.nbuf, ntiles = args.gx * args.gy * args.gz;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int UMMA_STAGES = args.nstage;
     uint64_t* full = (uint64_t*)(smem + UMMA_STAGES * S::STAGE);
     uint64_t* empty = full + UMMA_STAGES;
-    uint64_t* tmem_full = empty + UMMA_STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+    uint64_t* tmem_full = empty + UMMA_STAGES;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    int kb0 = 0, KB = args.K / 64;
-    if (args.ksplit > 1) {                         // this CTA's K range (every split is non-empty by construction)
-        const int per = (KB + args.ksplit - 1) / args.ksplit;
-        kb0 = blockIdx.z * per;
-        KB = KB - kb0 < per ? KB - kb0 : per;
-    }
-    if (m0 >= (ROWS ? n_rows : n_feat)) return;    // the two problems of a launch may differ in feature count
-    long long* tr = (args.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? args.trace : nullptr;
+    long long* tr = (args.trace && blockIdx.x == 0) ? args.trace : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = clock64();
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&P.tmA);
-        prefetch_tmap(&P.tmB);
+        prefetch_tmap(&args.p[0].tmA);
+        prefetch_tmap(&args.p[0].tmB);
         for (int s = 0; s < UMMA_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], GEMM_THREADS / 32 - 2);     // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    if (warp == 1) tmem_alloc_rt(tmem_slot, nbuf == 2 ? 2 * TCOLS : TCOLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps UMMA operands in uniform regs)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps UMMA operands in uniform regs)
 
     if (warp == 0) {
         if (lane == 0) {
-            int s = 0;
+            int s = 0, first = 1;
             uint32_t ph = 0;
-            for (int kb = 0; kb < KB; ++kb) {
-                if (kb) { if (++s == UMMA_STAGES) { s = 0; ph ^= 1; } }
-                mbar_wait(&empty[s], ph ^ 1);
-                if (tr && kb < 24) tr[8 + kb] = clock64();
-                mbar_expect_tx(&full[s], S::STAGE);
-                if constexpr (MNMAJ) {     // boxes of {64 MN elements, 64 K rows}: one per 64-wide MN chunk
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const TileInfo ti = tile_info<BM, BN, ROWS>(args, tile);
+                if (!ti.valid) continue;
+                const GemmProb& P = args.p[ti.prob];
+                const int m0 = ti.m0, n0 = ti.n0, kb0 = ti.kb0;
+                for (int kb = 0; kb < ti.KB; ++kb) {
+                    if (!first) { if (++s == UMMA_STAGES) { s = 0; ph ^= 1; } }
+                    first = 0;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (tr && tile == 0 && kb < 24) tr[8 + kb] = clock64();
+                    mbar_expect_tx(&full[s], S::STAGE);
+                    if constexpr (MNMAJ) {     // boxes of {64 MN elements, 64 K rows}: one per 64-wide MN chunk
 #pragma unroll
-                    for (int c = 0; c < BM / 64; ++c)
-                        tma_load_2d(smem + s * S::STAGE + c * 8192, &P.tmA, &full[s], m0 + c * 64, (kb0 + kb) * 64);
+                        for (int c = 0; c < BM / 64; ++c)
+                            tma_load_2d(smem + s * S::STAGE + c * 8192, &P.tmA, &full[s], m0 + c * 64, (kb0 + kb) * 64);
 #pragma unroll
-                    for (int c = 0; c < BN / 64; ++c)
-                        tma_load_2d(smem + s * S::STAGE + S::A_BYTES + c * 8192, &P.tmB, &full[s], n0 + c * 64, (kb0 + kb) * 64);
-                } else {
-                    tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], (kb0 + kb) * 64, m0);
-                    tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], (kb0 + kb) * 64, n0);
+                        for (int c = 0; c < BN / 64; ++c)
+                            tma_load_2d(smem + s * S::STAGE + S::A_BYTES + c * 8192, &P.tmB, &full[s], n0 + c * 64, (kb0 + kb) * 64);
+                    } else {
+                        tma_load_2d(smem + s * S::STAGE, &P.tmA, &full[s], (kb0 + kb) * 64, m0);
+                        tma_load_2d(smem + s * S::STAGE + S::A_BYTES, &P.tmB, &full[s], (kb0 + kb) * 64, n0);
+                    }
                 }
             }
         }
@@ -271,36 +302,54 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
             constexpr uint32_t idesc = MNMAJ ? umma_idesc_bf16_mn(BM, BN) : umma_idesc_bf16(BM, BN);
             const uint64_t d0 = MNMAJ ? umma_desc_sw128_mn(smem_u32(smem), 8192) : umma_desc_sw128(smem_u32(smem));
             constexpr int KSTEP = MNMAJ ? 128 : 2;   // descriptor advance per K = 16: 16 K rows x 128 B, or 32 B inside the row
-            int s = 0;
+            int s = 0, first = 1, tl = 0;
             uint32_t ph = 0;
-            for (int kb = 0; kb < KB; ++kb) {
-                if (kb) { if (++s == UMMA_STAGES) { s = 0; ph ^= 1; } }
-                mbar_wait(&full[s], ph);
-                if (tr && kb < 24) tr[32 + kb] = clock64();
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const TileInfo ti = tile_info<BM, BN, ROWS>(args, tile);
+                if (!ti.valid) continue;
+                const int buf = nbuf == 2 ? (tl & 1) : 0, use = nbuf == 2 ? (tl >> 1) : tl;
+                mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);        // the epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint64_t da = d0 + (uint64_t)(s * (S::STAGE >> 4));
-                const uint64_t db = da + (uint64_t)(S::A_BYTES >> 4);
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * TCOLS;
+                for (int kb = 0; kb < ti.KB; ++kb) {
+                    if (!first) { if (++s == UMMA_STAGES) { s = 0; ph ^= 1; } }
+                    first = 0;
+                    mbar_wait(&full[s], ph);
+                    if (tr && tile == 0 && kb < 24) tr[32 + kb] = clock64();
+                    tc_fence_after();
+                    const uint64_t da = d0 + (uint64_t)(s * (S::STAGE >> 4));
+                    const uint64_t db = da + (uint64_t)(S::A_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)       // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
-                    umma_bf16(tmem_d, da + KSTEP * k, db + KSTEP * k, idesc, (kb | k) != 0);
-                umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < 4; ++k)       // 4 x (K = 16 bf16 = 32 B) inside the 128-byte swizzle row
+                        umma_bf16(tmem_d, da + KSTEP * k, db + KSTEP * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+                }
+                umma_commit(&tmem_full[buf]);
+                ++tl;
             }
-            umma_commit(tmem_full);
         }
     } else {
         // epilogue: a warp may only touch TMEM lanes 32*(warp%4) .. +31; warps 2..5 take the even 16-column chunks,
         // warps 6..9 the odd ones
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileInfo ti = tile_info<BM, BN, ROWS>(args, tile);
+        if (!ti.valid) continue;
+        const GemmProb& P = args.p[ti.prob];
+        const int n_feat = P.n_feat, m0 = ti.m0, n0 = ti.n0;
+        const int buf = nbuf == 2 ? (tl & 1) : 0, use = nbuf == 2 ? (tl >> 1) : tl;
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * TCOLS;
         const float* __restrict__ bias = P.bias;
         const float* __restrict__ addend = P.addend;
         float* __restrict__ out_f32 =
-            (P.out_f32 && args.ksplit > 1) ? P.out_f32 + (size_t)blockIdx.z * args.split_stride : P.out_f32;
+            (P.out_f32 && args.ksplit > 1) ? P.out_f32 + (size_t)ti.split * args.split_stride : P.out_f32;
         __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
         const __nv_bfloat16* __restrict__ mask = P.mask;
         const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
-        mbar_wait(tmem_full, 0);
-        if (tr && threadIdx.x == 64) tr[1] = clock64();
+        mbar_wait(&tmem_full[buf], use & 1);
+        if (tr && threadIdx.x == 64 && tile == 0) tr[1] = clock64();
         tc_fence_after();
         if constexpr (ROWS) {
             const int r = m0 + 32 * q + lane;
@@ -394,11 +443,17 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
             }
         }
         }   // !ROWS
+        // this warp has read its part of the accumulator: hand the TMEM buffer back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        if (tr && threadIdx.x == 64 && tile == 0) tr[2] = clock64();
+        ++tl;
+        }   // tile loop
     }
-    if (tr && threadIdx.x == 64) tr[2] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<TCOLS>(tmem_d);
+    if (warp == 1) tmem_dealloc_rt(tmem_base, nbuf == 2 ? 2 * TCOLS : TCOLS);
 }
 
 static int g_gemm_sms = -1;
@@ -412,7 +467,7 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
         attr_set = true;
     }
     const int nz = args.ksplit > 1 ? args.ksplit : nprob;
-    dim3 grid = ROWS ? dim3(cdiv(args.n_rows, BM), cdiv(max_feat, BN), nz) : dim3(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nz);
+    const dim3 grid = ROWS ? dim3(cdiv(args.n_rows, BM), cdiv(max_feat, BN), nz) : dim3(cdiv(max_feat, BM), cdiv(args.n_rows, BN), nz);
     // Ring depth: the deepest that fits one CTA per SM, unless the grid is a little larger than one wave of SMs -- then a
     // shallow ring (<= 110 KB) lets two CTAs share an SM, so the whole grid is resident at once and one CTA's epilogue
     // overlaps the other's loads (the generation-time upsampling GEMM has 160 tiles on 148 SMs).
@@ -425,7 +480,16 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
         !getenv("SRNN_GEMM_DEEP_RING"))
         a.nstage = shallow < S::NSTAGE ? shallow : S::NSTAGE;
     const size_t smem = (size_t)a.nstage * S::STAGE + 1024 + 256;
-    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS, MNMAJ>), grid, GEMM_THREADS, smem, st, a);
+    a.gx = (int)grid.x;
+    a.gy = (int)grid.y;
+    a.gz = (int)grid.z;
+    // Deep ring = one CTA per SM: run persistent (one CTA per SM striding over the tiles) with two accumulator buffers when
+    // they fit in TMEM; shallow ring = two CTAs per SM, one tile each, one buffer (512 TMEM columns are shared by both).
+    const bool deep = a.nstage == S::NSTAGE;
+    a.nbuf = (deep && 2 * TCOLS_OF(BN) <= 512 && ctas > 1 && !getenv("SRNN_GEMM_SINGLE_BUF")) ? 2 : 1;
+    long long launch_ctas = ctas;
+    if (deep && g_gemm_sms > 0 && ctas > g_gemm_sms) launch_ctas = g_gemm_sms;
+    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS, MNMAJ>), dim3((unsigned)launch_ctas), GEMM_THREADS, smem, st, a);
     return SRNN_OK;
 }
 

@@ -14,9 +14,13 @@ constexpr int GBM = 64, GBN = 64, GBK = 16;
 __global__ void __launch_bounds__(256)
 k_gemm_f32_tn(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
               const float* __restrict__ bias, const float* __restrict__ add, int ldadd, int relu,
-              float* __restrict__ C, int ldc, __nv_bfloat16* __restrict__ C16) {
+              float* __restrict__ C, int ldc, __nv_bfloat16* __restrict__ C16, long long sA, long long sB, long long sC) {
     __shared__ float As[GBK][GBM + 4];
     __shared__ float Bs[GBK][GBN + 4];
+    A += (size_t)blockIdx.z * sA;                  // batched form: problem blockIdx.z (strides in elements)
+    B += (size_t)blockIdx.z * sB;
+    if (C) C += (size_t)blockIdx.z * sC;
+    if (C16) C16 += (size_t)blockIdx.z * sC;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
     float acc[4][4];
@@ -69,7 +73,15 @@ int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int l
              const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st, __nv_bfloat16* C16) {
     if (M <= 0 || N <= 0) return SRNN_OK;
     dim3 grid(cdiv(N, GBN), cdiv(M, GBM));
-    SRNN_LAUNCH(k_gemm_f32_tn, grid, 256, 0, st, M, N, K, A, lda, B, ldb, bias, add, ldadd, relu, C, ldc, C16);
+    SRNN_LAUNCH(k_gemm_f32_tn, grid, 256, 0, st, M, N, K, A, lda, B, ldb, bias, add, ldadd, relu, C, ldc, C16, 0LL, 0LL, 0LL);
+    return SRNN_OK;
+}
+// `batch` independent products C_z = A_z . B_z^T in one launch (element strides sA / sB / sC between problems)
+int gemm_f32_batched(int batch, int M, int N, int K, const float* A, int lda, long long sA, const float* B, int ldb, long long sB,
+                     float* C, int ldc, long long sC, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || batch <= 0) return SRNN_OK;
+    dim3 grid(cdiv(N, GBN), cdiv(M, GBM), batch);
+    SRNN_LAUNCH(k_gemm_f32_tn, grid, 256, 0, st, M, N, K, A, lda, B, ldb, nullptr, nullptr, 0, 0, C, ldc, nullptr, sA, sB, sC);
     return SRNN_OK;
 }
 
