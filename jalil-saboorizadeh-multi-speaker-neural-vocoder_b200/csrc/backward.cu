@@ -469,15 +469,6 @@ static int wn_bwd(const float* dw, const srnn_conv_params& p, const srnn_conv_pa
     return SRNN_OK;
 }
 
-// dW_up packed ((j*H+o), c) -> conv_t gradient layout (c, o, j); packed bias gradient (j*H+o) -> (o, j)
-__global__ void k_unpack_up_grad(const float* __restrict__ dwp, const float* __restrict__ dbp, float* __restrict__ dwf,
-                                 float* __restrict__ dbias, int H, int k) {
-    const int row = blockIdx.x;           // j*H + o
-    const int j = row / H, o = row % H;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) dwf[((size_t)c * H + o) * k + j] = dwp[(size_t)row * H + c];
-    if (threadIdx.x == 0 && dbias) dbias[o * k + j] = dbp[row];
-}
-
 // top tier: gradient of the K-concatenated matrix (H, n + cond_dim + spk_dim) -> its three sources
 __global__ void k_unpack_top_in(const float* __restrict__ dcomb, float* __restrict__ d_in, float* __restrict__ d_c,
                                 float* __restrict__ d_s /* (H, spk_dim) wrt folded spk_expand */, const float* __restrict__ emb,
@@ -669,7 +660,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
         const float* Ylast = F.Y[i][NL - 1];
         SRNN_TRY(gemm_dw(t.fs * H, H, M, dUP, t.fs * H, Ylast, H, dWup, H, st));
         SRNN_TRY(colsum(dUP, M, t.fs * H, t.fs * H, csp, dbup, st));
-        SRNN_LAUNCH(k_unpack_up_grad, t.fs * H, 128, 0, st, dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs);
+        SRNN_TRY(unpack_up_grad(dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs, st));
         SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
         float* dY = dYa;
         float* dYn = dYb;
@@ -896,7 +887,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
         // upsampling
         SRNN_TRY(tc_dw_tn(NU, H, M, dUP, NU, F.Y16[i][NL - 1], H, dWup, dTblP, dtblp_floats, st));
         SRNN_TRY(colsum(dUP, M, NU, NU, csp, dbup, st));
-        SRNN_LAUNCH(k_unpack_up_grad, NU, 128, 0, st, dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs);
+        SRNN_TRY(unpack_up_grad(dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs, st));
         SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
         float* dY = dYa;
         float* dYn = dYb;

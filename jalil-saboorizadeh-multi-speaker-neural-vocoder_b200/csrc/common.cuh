@@ -156,6 +156,7 @@ int pack_top_in(const float* w_in, const float* w_c, const float* w_s, const flo
                 const float* b_c, const float* b_s, float* w_out, float* b_out, int H, int n, int cond_dim,
                 int spk_dim, cudaStream_t st);
 int pack_up(const float* wf, const float* bias, float* w_up, float* b_up, int H, int k, cudaStream_t st);
+int unpack_up_grad(const float* dwp, const float* dbp, float* dwf, float* dbias, int H, int k, cudaStream_t st);
 int transpose_mlp_in(const float* w, float* wt, int H, int Q, int FS, cudaStream_t st);
 // A[b*F+f, :] = [lut[seq[b, off + f*n + i]] (i<n) | cond[crow(b), f0+f, :] | onehot(spk[crow(b)])]
 int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, int F,

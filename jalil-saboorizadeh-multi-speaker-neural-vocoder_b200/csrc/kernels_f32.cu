@@ -255,15 +255,70 @@ int pack_top_in(const float* w_in, const float* w_c, const float* w_s, const flo
 }
 
 // conv_t weight (H_in, H_out, k) [already weight-norm folded] -> (k*H_out, H_in); bias (H_out, k) -> (k*H_out)
-__global__ void k_pack_up(const float* __restrict__ wf, const float* __restrict__ bias, float* __restrict__ w_up,
-                          float* __restrict__ b_up, int H, int k) {
-    const int row = blockIdx.x;           // j*H + o
-    const int j = row / H, o = row % H;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) w_up[(size_t)row * H + c] = wf[((size_t)c * H + o) * k + j];
-    if (threadIdx.x == 0) b_up[row] = bias[o * k + j];
+// Tiled through shared memory so that BOTH sides are coalesced: a block moves the 32 input channels c0.. x UP_TO output
+// channels o0.. x all k phases; the conv_t side is contiguous in (o, j) for a fixed c, the packed side in c for a fixed (j, o).
+// PACK = true: conv_t layout -> packed;  false: packed (gradient) -> conv_t layout.
+constexpr int UP_TO = 8;
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+k_perm_up(const float* __restrict__ src, float* __restrict__ dst, int H, int k) {
+    extern __shared__ float s_up[];                            // [UP_TO * k][33]
+    const int c0 = blockIdx.x * 32, o0 = blockIdx.y * UP_TO;
+    const int n = UP_TO * k;                                   // (o_l, j) pairs of the tile, conv_t order: o_l * k + j
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (PACK) {
+        for (int cl = w; cl < 32; cl += nw) {                  // one warp per input channel: n contiguous floats
+            const int c = c0 + cl;
+            if (c >= H) continue;
+            const float* row = src + ((size_t)c * H + o0) * k;
+            for (int e = lane; e < n; e += 32)
+                if (o0 + e / k < H) s_up[e * 33 + cl] = row[e];
+        }
+        __syncthreads();
+        for (int e = w; e < n; e += nw) {                      // one warp per (o_l, j): 32 contiguous c
+            const int ol = e / k, j = e % k;
+            if (o0 + ol < H && c0 + lane < H) dst[((size_t)j * H + o0 + ol) * H + c0 + lane] = s_up[e * 33 + lane];
+        }
+    } else {
+        for (int e = w; e < n; e += nw) {
+            const int ol = e / k, j = e % k;
+            if (o0 + ol < H && c0 + lane < H) s_up[e * 33 + lane] = src[((size_t)j * H + o0 + ol) * H + c0 + lane];
+        }
+        __syncthreads();
+        for (int cl = w; cl < 32; cl += nw) {
+            const int c = c0 + cl;
+            if (c >= H) continue;
+            float* row = dst + ((size_t)c * H + o0) * k;
+            for (int e = lane; e < n; e += 32)
+                if (o0 + e / k < H) row[e] = s_up[e * 33 + cl];
+        }
+    }
+}
+// bias (H_out, k) <-> packed (k*H_out)
+__global__ void k_perm_up_bias(const float* __restrict__ src, float* __restrict__ dst, int H, int k, int pack) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * k) return;
+    const int j = i / H, o = i % H;                            // packed index i = j*H + o
+    if (pack) dst[i] = src[o * k + j];
+    else dst[o * k + j] = src[i];
+}
+static int perm_up(bool pack, const float* src, float* dst, int H, int k, cudaStream_t st) {
+    const dim3 grid(cdiv(H, 32), cdiv(H, UP_TO));
+    const size_t smem = (size_t)UP_TO * k * 33 * sizeof(float);
+    if (smem > 48 * 1024) return fail(SRNN_ERR_UNSUPPORTED, "frame size %d too large for the upsampling re-layout tile", k);
+    if (pack) SRNN_LAUNCH(k_perm_up<true>, grid, 256, smem, st, src, dst, H, k);
+    else SRNN_LAUNCH(k_perm_up<false>, grid, 256, smem, st, src, dst, H, k);
+    return SRNN_OK;
 }
 int pack_up(const float* wf, const float* bias, float* w_up, float* b_up, int H, int k, cudaStream_t st) {
-    SRNN_LAUNCH(k_pack_up, k * H, 128, 0, st, wf, bias, w_up, b_up, H, k);
+    SRNN_TRY(perm_up(true, wf, w_up, H, k, st));
+    SRNN_LAUNCH(k_perm_up_bias, cdiv(H * k, 256), 256, 0, st, bias, b_up, H, k, 1);
+    return SRNN_OK;
+}
+// packed gradients ((j*H+o), c) / (j*H+o) -> conv_t layout (c, o, j) / (o, j); dbias may be null
+int unpack_up_grad(const float* dwp, const float* dbp, float* dwf, float* dbias, int H, int k, cudaStream_t st) {
+    SRNN_TRY(perm_up(false, dwp, dwf, H, k, st));
+    if (dbias) SRNN_LAUNCH(k_perm_up_bias, cdiv(H * k, 256), 256, 0, st, dbp, dbias, H, k, 0);
     return SRNN_OK;
 }
 

@@ -315,14 +315,20 @@ class _PredictFn(torch.autograd.Function):
         model, params = ctx.model, ctx.params
         (logp,) = ctx.saved_tensors
         dev = model._ctx_device
-        grads = {id(p): torch.empty_like(p) for p in params}
+        # Gradient destinations: a fresh tensor per parameter (autograd then accumulates it into p.grad), unless the optimizer
+        # has published zeroed gradient views for this step (ClampAdam.zero_grad -> model._grad_sink): the library then
+        # writes straight into them and autograd gets None -- no 46 extra accumulate launches over 229 MB.
+        sink = getattr(model, "_grad_sink", None)
+        model._grad_sink = None
+        direct = sink is not None and all(id(p) in sink for p in params)
+        grads = {id(p): (sink[id(p)] if direct else torch.empty_like(p)) for p in params}
         G = model._c_params(ptr=lambda t: grads[id(t)].data_ptr() if id(t) in grads else None)
         P = model._c_params()
         dlogp = grad_out.to(device=dev, dtype=torch.float32).contiguous()
         with torch.cuda.device(dev):
             L.check(L.load().srnn_predict_bwd(model._ctx, logp.data_ptr(), dlogp.data_ptr(), C.byref(P), C.byref(G),
                                               _stream()))
-        return (None, None, None, None, None) + tuple(grads[id(p)] for p in params)
+        return (None, None, None, None, None) + tuple(None if direct else grads[id(p)] for p in params)
 
 
 class Predictor(Runner, tnn.Module):

@@ -58,6 +58,8 @@ class ClampAdam:
         self._bucket().zero_()
         for p, v in zip(self.params, self._views):
             p.grad = v
+        if self.model is not None:      # one backward pass may write its gradients directly into the (zeroed) views
+            self.model._grad_sink = {id(p): v for p, v in zip(self.params, self._views)}
 
     def _allreduce(self):
         import torch.distributed as dist
