@@ -902,7 +902,9 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
             const bool persist = gru_persist_supported(B, H, ctx->n_sms);
             if (persist) {                                   // BPTT over all frames of the layer in one persistent launch
                 if (!ctx->gru_ctr) SRNN_TRY(ctx->weights.alloc((void**)&ctx->gru_ctr, 256));
-                SRNN_TRY(gru_persist_bwd(B, Fr, H, GI, GH, Y, h0, dY, t.w_hh16_t[l], dGI, dGH, dGI16, dGH16, dhc0, ctx->gru_ctr, st));
+                // the kernel also sums the bias gradients, so the fp32 copies of dGI / dGH (only ever column-summed) are not written
+                SRNN_TRY(gru_persist_bwd(B, Fr, H, GI, GH, Y, h0, dY, t.w_hh16_t[l], nullptr, nullptr, dGI16, dGH16, dhc0,
+                                         ctx->gru_ctr, st, csp, (float*)tg.bias_ih[l], (float*)tg.bias_hh[l]));
                 carry = dhc0;
             }
             for (int f = Fr - 1; f >= 0 && !persist; --f) {
@@ -927,11 +929,11 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
                 SRNN_LAUNCH(k_build_hprev16, M, 128, 0, st, F.Y16[i][l], F.H016[i] + (size_t)l * B * H, HP16, Fr, H);
                 SRNN_TRY(tc_dw_tn(3 * H, H, M, dGH16, 3 * H, HP16, H, (float*)tg.weight_hh[l], dTblP, dtblp_floats, st));
             }
-            if (tg.bias_hh[l]) SRNN_TRY(colsum(dGH, M, 3 * H, 3 * H, csp, (float*)tg.bias_hh[l], st));
+            if (tg.bias_hh[l] && !persist) SRNN_TRY(colsum(dGH, M, 3 * H, 3 * H, csp, (float*)tg.bias_hh[l], st));
             if (tg.weight_ih[l])
                 SRNN_TRY(tc_dw_tn(3 * H, H, M, dGI16, 3 * H, l ? F.Y16[i][l - 1] : F.X16[i], H, (float*)tg.weight_ih[l], dTblP,
                                   dtblp_floats, st));
-            if (tg.bias_ih[l]) SRNN_TRY(colsum(dGI, M, 3 * H, 3 * H, csp, (float*)tg.bias_ih[l], st));
+            if (tg.bias_ih[l] && !persist) SRNN_TRY(colsum(dGI, M, 3 * H, 3 * H, csp, (float*)tg.bias_ih[l], st));
             float* din = l ? dYn : dXf;
             SRNN_TRY(tc_dx(M, H, 3 * H, dGI16, 3 * H, t.w_ih16_t[l], nullptr, 0, din, nullptr, nullptr, H, st));
             if (l) { float* tmp = dY; dY = dYn; dYn = tmp; }

@@ -253,7 +253,8 @@ int gru_persist_fwd(int B, int F, int H, const float* GI, const __nv_bfloat16* w
                     cudaStream_t st);
 int gru_persist_bwd(int B, int F, int H, const float* GI, const float* GH, const float* Y, const float* h0, const float* dY,
                     const __nv_bfloat16* w_hh16_t, float* dGI, float* dGH, __nv_bfloat16* dGI16, __nv_bfloat16* dGH16,
-                    float* dh0, unsigned* ctr, cudaStream_t st);
+                    float* dh0, unsigned* ctr, cudaStream_t st, float* bias_part = nullptr, float* db_ih = nullptr,
+                    float* db_hh = nullptr);
 int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, bool rows, int ksplit,
                  float* split_scratch, cudaStream_t st);
 int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* split_scratch, cudaStream_t st);

@@ -31,7 +31,11 @@ constexpr int GP_ISSUERS = 4;
 constexpr int GP_ROWS = 64;                   // utterances per CTA (UMMA M)
 constexpr int GP_STAGES = 12;                 // TMA ring: 12 x (64 rows x 128 B) = 96 KB in flight per SM
 constexpr int GP_STAGE_BYTES = GP_ROWS * 128;
-constexpr uint32_t GP_TMEM_COLS = 256;
+// TMEM map (512 columns): issuer w owns lane half (w & 1) of column group (w >> 1) * 256; inside its group it rotates over
+// GP_NACC independent accumulators 64 columns apart.  MMAs that accumulate into the SAME TMEM tile serialise on its
+// latency (~290 cycles for these tiny tiles: 48 chained MMAs per frame were 13.8k of the 23.6k cycles of a backward frame).
+constexpr uint32_t GP_TMEM_COLS = 512;
+constexpr int GP_NACC = 4;
 
 __device__ __forceinline__ void gp_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -92,21 +96,35 @@ __device__ __forceinline__ void st8_bf16(bf* __restrict__ p, const float (&v)[8]
 // Sum of this half-warp's valid accumulators (column groups 0 and 64) for 16 consecutive columns starting at col, then
 // the halves' exchange: lanes 0..15 keep columns 0..7, lanes 16..31 columns 8..15 of (own + partner) sums.
 __device__ __forceinline__ void gp_gather8(uint32_t tlane, int col, int ncg, int hh, float (&out)[8]) {
-    float t0[16], t1[16];
-    tmem_ld16(tlane + col, t0);                     // warp-collective loads: issued by every lane, selected afterwards
-    tmem_ld16(tlane + 64 + col, t1);
+    float lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) lo[i] = hi[i] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {                    // column group of issuer (hh + 2g); warp-collective loads, selected after
+        uint32_t t[GP_NACC][16];
+#pragma unroll
+        for (int a = 0; a < GP_NACC; ++a) tmem_ld16_nowait(tlane + g * 256 + a * 64 + col, t[a]);
+        tmem_ld_wait();
+        if (ncg > g) {
+#pragma unroll
+            for (int a = 0; a < GP_NACC; ++a)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    lo[i] += __uint_as_float(t[a][i]);
+                    hi[i] += __uint_as_float(t[a][8 + i]);
+                }
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float lo = (ncg > 0 ? t0[i] : 0.f) + (ncg > 1 ? t1[i] : 0.f);
-        const float hi = (ncg > 0 ? t0[8 + i] : 0.f) + (ncg > 1 ? t1[8 + i] : 0.f);
-        const float mine = hh ? hi : lo;
-        const float send = hh ? lo : hi;
+        const float mine = hh ? hi[i] : lo[i];
+        const float send = hh ? lo[i] : hi[i];
         out[i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
     }
 }
 
 struct GruFwdParams {
-    int B, F, H;
+    int B, F, H, rotate;
     const float* GI;     // (B*F, 3H)  W_ih x + b_ih of every frame (row b*F + f)
     float* GH;           // (B*F, 3H)  out: W_hh h_{f-1} + b_hh (saved for the backward pass)
     float* Y;            // (B*F, H)   out: h_f
@@ -118,18 +136,21 @@ struct GruFwdParams {
 };
 
 struct GruBwdParams {
-    int B, F, H;
+    int B, F, H, rotate;
     const float* GI;     // saved forward projections (B*F, 3H)
     const float* GH;
     const float* Y;      // (B*F, H) forward outputs; h_{f-1} = Y[b, f-1] or h0[b]
     const float* h0;     // (B, H)
     const float* dY;     // (B*F, H)  gradient w.r.t. the layer outputs
-    float* dGI;          // (B*F, 3H) out: gradient w.r.t. W_ih x + b_ih
-    float* dGH;          // (B*F, 3H) out: gradient w.r.t. W_hh h + b_hh
+    float* dGI;          // (B*F, 3H) out: gradient w.r.t. W_ih x + b_ih   (fp32 copy; may be null)
+    float* dGH;          // (B*F, 3H) out: gradient w.r.t. W_hh h + b_hh   (fp32 copy; may be null)
+    float* bias_part;    // (row halves, 4, H) out: column sums over (utterance, frame) of dpr, dpz, dpn, dpn*r = the bias
+                         //                    gradients (db_ih = r,z,n parts; db_hh = r,z,n*r parts), or null
     bf* dGI16;           // bf16 copies (operands of the weight-gradient / input-gradient GEMMs)
     bf* dGH16;           //            (and the recurrent operand of this kernel)
     float* dh0;          // (B, H)    out: dL/dh_{-1}
     unsigned* ctr;
+    long long* trace;    // development aid (SRNN_TRACE_GRU=1): clock64 stamps of CTA (0,0), 8 per frame
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -144,7 +165,8 @@ struct GpSmem {
 
 template <int NB, bool FWD>
 __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUtensorMap* tmA, uint8_t* sRing, uint64_t* full,
-                                            uint64_t* empty, const unsigned* ctr, int F, int KB, int K, int NS, int row0) {
+                                            uint64_t* empty, const unsigned* ctr, int F, int KB, int K, int NS, int row0,
+                                            int rot, long long* trace = nullptr) {
     int it = 0;
     for (int s = 0; s < F; ++s) {
         // forward : frame f = s reads h_{f-1} (h0 for f = 0, published before launch) -> wait for s * NS arrivals
@@ -155,27 +177,32 @@ __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUten
             }
             gp_fence_proxy_async();                      // other CTAs' generic-proxy writes -> visible to TMA reads
         }
+        if (trace) trace[s * 8 + 2] = clock64();
         const CUtensorMap* tm = (FWD && s == 0) ? tmA0 : tmA;
         const int col0 = FWD ? (s == 0 ? 0 : (s - 1) * K) : (F - 1 - s) * K;
+        // every CTA of a row half streams the same tiles: each starts at its own k-block (rot) so that at any moment the
+        // CTAs pull different tiles from different L2 slices instead of all hitting the same few
+        int kk = rot;
         for (int kb = 0; kb < KB; ++kb, ++it) {
             const int st = it % GP_STAGES;
             const uint32_t ph = (it / GP_STAGES) & 1;
             mbar_wait(&empty[st], ph ^ 1);
             mbar_expect_tx(&full[st], GP_STAGE_BYTES);
-            tma_load_2d(sRing + (size_t)st * GP_STAGE_BYTES, tm, &full[st], col0 + kb * 64, row0);
+            tma_load_2d(sRing + (size_t)st * GP_STAGE_BYTES, tm, &full[st], col0 + kk * 64, row0);
+            if (++kk == KB) kk = 0;
         }
     }
 }
 
 template <int NB>
 __device__ __forceinline__ void gp_issuer(int w, int nissue, uint8_t* sW, uint8_t* sRing, uint64_t* full, uint64_t* empty,
-                                          uint64_t* w_ready, uint64_t* bar_d, uint32_t tmem, int F, int KB) {
+                                          uint64_t* w_ready, uint64_t* bar_d, uint32_t tmem, int F, int KB, int rot) {
     constexpr uint32_t idesc = umma_idesc_bf16(GP_ROWS, NB);
     mbar_wait(w_ready, 0);
     const uint64_t dW0 = umma_desc_sw128(smem_u32(sW));
     const uint64_t dA0 = umma_desc_sw128(smem_u32(sRing));
     // issuers 0, 2 -> lanes 0..15 of every quadrant (column groups 0 / 64); issuers 1, 3 -> lanes 16..31
-    const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 64;
+    const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 256;
     for (int s = 0; s < F; ++s) {
         for (int kb = w; kb < KB; kb += GP_ISSUERS) {
             const int it = s * KB + kb;
@@ -184,11 +211,14 @@ __device__ __forceinline__ void gp_issuer(int w, int nissue, uint8_t* sW, uint8_
             mbar_wait(&full[st], ph);
             tc_fence_after();
             const uint64_t da = dA0 + (uint64_t)(st * (GP_STAGE_BYTES >> 4));
-            const uint64_t db = dW0 + (uint64_t)(kb * (GpSmem<NB>::W_KB_BYTES >> 4));
-            umma_bf16(dacc, da, db, idesc, kb >= GP_ISSUERS);
-            umma_bf16(dacc, da + 2, db + 2, idesc, 1);
-            umma_bf16(dacc, da + 4, db + 4, idesc, 1);
-            umma_bf16(dacc, da + 6, db + 6, idesc, 1);
+            int kw = kb + rot;                                   // the streamed tile of slot kb is k-block (kb + rot) mod KB
+            if (kw >= KB) kw -= KB;
+            const uint64_t db = dW0 + (uint64_t)(kw * (GpSmem<NB>::W_KB_BYTES >> 4));
+            const uint32_t acc = kb >= GP_ISSUERS;               // each of the four accumulators starts at this issuer's first k-block
+            umma_bf16(dacc, da, db, idesc, acc);
+            umma_bf16(dacc + 64, da + 2, db + 2, idesc, acc);
+            umma_bf16(dacc + 128, da + 4, db + 4, idesc, acc);
+            umma_bf16(dacc + 192, da + 6, db + 6, idesc, acc);
             umma_commit(&empty[st]);
         }
         umma_commit(bar_d);
@@ -232,6 +262,7 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int H = p.H, F = p.F, KB = H >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
+    const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)KB) : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
     const GpLayout L = gp_layout(smem_raw, (size_t)KB * GpSmem<NB>::W_KB_BYTES);
@@ -261,11 +292,11 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             for (int kb = 0; kb < KB; ++kb)
                 for (int g = 0; g < 3; ++g)
                     tma_load_2d(L.sW + (size_t)kb * GpSmem<NB>::W_KB_BYTES + g * (GP_HS * 128), &tmW, L.w_ready, kb * 64, g * H + u0);
-            gp_producer<NB, true>(&tmH0, &tmY, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, H, NS, rs * GP_ROWS);
+            gp_producer<NB, true>(&tmH0, &tmY, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, H, NS, rs * GP_ROWS, rot);
         }
     } else if (warp >= 5) {
         if (lane == 0 && warp - 5 < nissue)
-            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB);
+            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB, rot);
     } else {
         // ===================== row warps: thread = (utterance row, 8 of the 16 units) =====================
         const int hh = lane >> 4;                            // unit half: units u0 + 8*hh .. +7
@@ -341,6 +372,7 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
     const int H = p.H, F = p.F, K3 = 3 * H, KB = K3 >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
+    const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)KB) : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
     const GpLayout L = gp_layout(smem_raw, (size_t)KB * GpSmem<NB>::W_KB_BYTES);
@@ -367,11 +399,12 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
             mbar_expect_tx(L.w_ready, (uint32_t)(KB * GpSmem<NB>::W_KB_BYTES));
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(L.sW + (size_t)kb * GpSmem<NB>::W_KB_BYTES, &tmWt, L.w_ready, kb * 64, u0);
-            gp_producer<NB, false>(&tmG, &tmG, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, K3, NS, rs * GP_ROWS);
+            gp_producer<NB, false>(&tmG, &tmG, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, K3, NS, rs * GP_ROWS, rot,
+                                   (p.trace && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr);
         }
     } else if (warp >= 5) {
         if (lane == 0 && warp - 5 < nissue)
-            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB);
+            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB, rot);
     } else {
         const int hh = lane >> 4;
         const int b = rs * GP_ROWS + 16 * warp + (lane & 15);
@@ -379,14 +412,16 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
         const int uq = u0 + 8 * hh;
         const int ncg = (nissue > hh) + (nissue > hh + 2);
         const uint32_t tlane = tmem + ((uint32_t)(32 * warp) << 16);
-        float carry[8];
+        float carry[8], sb[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) carry[j] = 0.f;
+        for (int j = 0; j < 8; ++j) carry[j] = sb[0][j] = sb[1][j] = sb[2][j] = sb[3][j] = 0.f;
         const size_t row_stride = (size_t)K3;
+        long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ? p.trace : nullptr;
         for (int s = 0; s < F; ++s) {
             const int f = F - 1 - s;
             const size_t r = (size_t)b * F + f;
             float dhz[8];
+            if (tr) tr[s * 8 + 0] = clock64();
             if (ok) {
                 float gr[8], gz[8], gn[8], hr[8], hz[8], hn[8], hp[8], dy[8];
                 const float* gip = p.GI + r * row_stride + uq;
@@ -425,19 +460,27 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
                     o_n[j] = dpn;
                     o_nr[j] = dpn * rr;
                     dhz[j] = dh * zz;
+                    sb[0][j] += o_r[j];
+                    sb[1][j] += o_z[j];
+                    sb[2][j] += o_n[j];
+                    sb[3][j] += o_nr[j];
                 }
                 bf* g16 = p.dGH16 + r * row_stride + uq;     // first: the recurrent operand the other CTAs wait for
                 st8_bf16(g16, o_r);
                 st8_bf16(g16 + H, o_z);
                 st8_bf16(g16 + 2 * H, o_nr);
-                float* gh = p.dGH + r * row_stride + uq;
-                st8(gh, o_r);
-                st8(gh + H, o_z);
-                st8(gh + 2 * H, o_nr);
-                float* gi = p.dGI + r * row_stride + uq;
-                st8(gi, o_r);
-                st8(gi + H, o_z);
-                st8(gi + 2 * H, o_n);
+                if (p.dGH) {
+                    float* gh = p.dGH + r * row_stride + uq;
+                    st8(gh, o_r);
+                    st8(gh + H, o_z);
+                    st8(gh + 2 * H, o_nr);
+                }
+                if (p.dGI) {
+                    float* gi = p.dGI + r * row_stride + uq;
+                    st8(gi, o_r);
+                    st8(gi + H, o_z);
+                    st8(gi + 2 * H, o_n);
+                }
                 bf* i16 = p.dGI16 + r * row_stride + uq;
                 st8_bf16(i16, o_r);
                 st8_bf16(i16 + H, o_z);
@@ -446,21 +489,57 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dhz[j] = 0.f;
             }
+            if (tr) tr[s * 8 + 1] = clock64();
             gp_bar_sync(1, 128);
             if (threadIdx.x == 0) gp_red_release(p.ctr + rs);   // dGH_f of this CTA's units is published
             mbar_wait(L.bar_d, s & 1);
+            if (tr) tr[s * 8 + 3] = clock64();
             tc_fence_after();
             float a[8];
             gp_gather8(tlane, 0, ncg, hh, a);
             tc_fence_before();
 #pragma unroll
             for (int j = 0; j < 8; ++j) carry[j] = dhz[j] + a[j];
+            if (tr) tr[s * 8 + 4] = clock64();
         }
         if (ok && p.dh0) st8(p.dh0 + (size_t)b * H + uq, carry);
+        if (p.bias_part) {      // bias gradients: sum over this CTA's 64 utterances (fixed order: lanes, then warps)
+            float* sRed = reinterpret_cast<float*>(L.sRing);             // the ring is idle now: [4 warps][4][16]
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float v = sb[a][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    if ((lane & 15) == 0) sRed[(warp * 4 + a) * 16 + 8 * hh + j] = v;
+                }
+            gp_bar_sync(1, 128);
+            if (threadIdx.x < 64) {
+                const int a = threadIdx.x >> 4, u = threadIdx.x & 15;
+                const float v = (sRed[(0 * 4 + a) * 16 + u] + sRed[(1 * 4 + a) * 16 + u]) +
+                                (sRed[(2 * 4 + a) * 16 + u] + sRed[(3 * 4 + a) * 16 + u]);
+                p.bias_part[((size_t)rs * 4 + a) * H + u0 + u] = v;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc<GP_TMEM_COLS>(tmem);
+}
+
+// db_ih (3H) = [sum dpr | sum dpz | sum dpn], db_hh (3H) = [sum dpr | sum dpz | sum dpn*r] over the row halves
+__global__ void k_gru_bias_grads(const float* __restrict__ part, int nrs, int H, float* __restrict__ db_ih, float* __restrict__ db_hh) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= H) return;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < nrs; ++r)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) s[a] += part[((size_t)r * 4 + a) * H + u];
+    if (db_ih) { db_ih[u] = s[0]; db_ih[H + u] = s[1]; db_ih[2 * H + u] = s[2]; }
+    if (db_hh) { db_hh[u] = s[0]; db_hh[H + u] = s[1]; db_hh[2 * H + u] = s[3]; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -532,7 +611,8 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (lane == 0) {
             const int w = warp - 5;                                      // issuer w takes k-block w of every box
             constexpr uint32_t idesc = umma_idesc_bf16(GP_ROWS, GC_NB);
-            const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 128;
+            // two independent accumulators per issuer (128 columns apart inside its 256-column group): halves the chain
+            const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 256;
             for (int g = 0; g < NG; ++g) {
                 const int st = g % GC_RING;
                 const uint32_t ph = (g / GC_RING) & 1;
@@ -542,9 +622,9 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const uint64_t da = umma_desc_sw128(base + w * (GP_ROWS * 128));
                 const uint64_t db = umma_desc_sw128(base + GC_A_BYTES + w * (GC_NB * 128));
                 umma_bf16(dacc, da, db, idesc, g > 0);
-                umma_bf16(dacc, da + 2, db + 2, idesc, 1);
+                umma_bf16(dacc + 128, da + 2, db + 2, idesc, g > 0);
                 umma_bf16(dacc, da + 4, db + 4, idesc, 1);
-                umma_bf16(dacc, da + 6, db + 6, idesc, 1);
+                umma_bf16(dacc + 128, da + 6, db + 6, idesc, 1);
                 umma_commit(&empty[st]);
             }
             umma_commit(bar_d);
@@ -568,15 +648,21 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         float gi[3][16];
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-            float lo[16], hi[16], t[16];
-            tmem_ld16(tlane + 32 * g, lo);
-            tmem_ld16(tlane + 32 * g + 16, hi);
-            tmem_ld16(tlane + 128 + 32 * g, t);
+            float lo[16], hi[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) lo[j] += t[j];
-            tmem_ld16(tlane + 128 + 32 * g + 16, t);
+            for (int j = 0; j < 16; ++j) lo[j] = hi[j] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] += t[j];
+            for (int a = 0; a < 4; ++a) {                 // (column group, accumulator) = (a >> 1, a & 1)
+                uint32_t t0[16], t1[16];
+                tmem_ld16_nowait(tlane + (a >> 1) * 256 + (a & 1) * 128 + 32 * g, t0);
+                tmem_ld16_nowait(tlane + (a >> 1) * 256 + (a & 1) * 128 + 32 * g + 16, t1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    lo[j] += __uint_as_float(t0[j]);
+                    hi[j] += __uint_as_float(t1[j]);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float mine = hh ? hi[j] : lo[j];
@@ -660,21 +746,44 @@ int gru_persist_fwd(int B, int F, int H, const float* GI, const bf* w_hh16, cons
     SRNN_TRY(make_tmap_bf16(&tmW, w_hh16, (uint64_t)3 * H, H, H, GP_HS));
     SRNN_TRY(make_tmap_bf16(&tmH0, h0_16, B, H, H, GP_ROWS));
     SRNN_TRY(make_tmap_bf16(&tmY, Y16, B, (uint64_t)F * H, (uint64_t)F * H, GP_ROWS));
-    GruFwdParams p{B, F, H, GI, GH, Y, Y16, h0, h_last, b_hh, ctr};
+    GruFwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, GI, GH, Y, Y16, h0, h_last, b_hh, ctr};
     const size_t smem = gp_smem_bytes((size_t)(H / 64) * 3 * GP_HS * 128);
     return gp_launch(k_gru_persist_fwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmW, tmH0, tmY, p);
 }
 
 // BPTT of one GRU layer.  w_hh16_t (H, 3H) bf16 = W_hh^T.
+// dGI / dGH (fp32 copies) may be null; bias_part = scratch of 2*4*H floats when db_ih / db_hh (3H each) are wanted.
 int gru_persist_bwd(int B, int F, int H, const float* GI, const float* GH, const float* Y, const float* h0, const float* dY,
                     const bf* w_hh16_t, float* dGI, float* dGH, bf* dGI16, bf* dGH16, float* dh0, unsigned* ctr,
-                    cudaStream_t st) {
+                    cudaStream_t st, float* bias_part, float* db_ih, float* db_hh) {
     CUtensorMap tmWt, tmG;
     SRNN_TRY(make_tmap_bf16(&tmWt, w_hh16_t, H, (uint64_t)3 * H, (uint64_t)3 * H, GP_HS));
     SRNN_TRY(make_tmap_bf16(&tmG, dGH16, B, (uint64_t)F * 3 * H, (uint64_t)F * 3 * H, GP_ROWS));
-    GruBwdParams p{B, F, H, GI, GH, Y, h0, dY, dGI, dGH, dGI16, dGH16, dh0, ctr};
+    GruBwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, GI, GH, Y, h0, dY, dGI, dGH, (db_ih || db_hh) ? bias_part : nullptr,
+                   dGI16, dGH16, dh0, ctr, nullptr};
     const size_t smem = gp_smem_bytes((size_t)(3 * H / 64) * GP_HS * 128);
-    return gp_launch(k_gru_persist_bwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmWt, tmG, p);
+    if (getenv("SRNN_TRACE_GRU")) SRNN_CUDA(cudaMalloc((void**)&p.trace, sizeof(long long) * 8 * F));
+    int rc = gp_launch(k_gru_persist_bwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmWt, tmG, p);
+    if (p.trace) {      // average phase durations (SM cycles) of CTA (0,0) over the frames of this launch
+        std::vector<long long> h(8 * F);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), p.trace, sizeof(long long) * 8 * F, cudaMemcpyDeviceToHost);
+        cudaFree(p.trace);
+        double ew = 0, bar = 0, mm = 0, ep = 0, tot = 0;
+        for (int s = 1; s < F; ++s) {
+            ew += (double)(h[s * 8 + 1] - h[s * 8 + 0]);
+            bar += (double)(h[s * 8 + 2] - h[s * 8 + 1]);
+            mm += (double)(h[s * 8 + 3] - h[s * 8 + 2]);
+            ep += (double)(h[s * 8 + 4] - h[s * 8 + 3]);
+            tot += (double)(h[s * 8 + 0] - h[(s - 1) * 8 + 0]);
+        }
+        const double n = F > 1 ? F - 1 : 1;
+        fprintf(stderr, "[gru bwd trace F=%d] gates+stores=%.0f barrier(all CTAs published)=%.0f stream+MMA=%.0f tmem epilogue=%.0f | frame=%.0f cycles\n",
+                F, ew / n, bar / n, mm / n, ep / n, tot / n);
+    }
+    if (rc == SRNN_OK && p.bias_part)
+        SRNN_LAUNCH(k_gru_bias_grads, cdiv(H, 128), 128, 0, st, bias_part, (B + GP_ROWS - 1) / GP_ROWS, H, db_ih, db_hh);
+    return rc;
 }
 
 }  // namespace srnn
