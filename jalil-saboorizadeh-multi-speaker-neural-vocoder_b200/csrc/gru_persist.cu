@@ -166,7 +166,7 @@ struct GpSmem {
 template <int NB, bool FWD>
 __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUtensorMap* tmA, uint8_t* sRing, uint64_t* full,
                                             uint64_t* empty, const unsigned* ctr, int F, int KB, int K, int NS, int row0,
-                                            int rot, long long* trace = nullptr) {
+                                            int rot, int gsz, long long* trace = nullptr) {
     int it = 0;
     for (int s = 0; s < F; ++s) {
         // forward : frame f = s reads h_{f-1} (h0 for f = 0, published before launch) -> wait for s * NS arrivals
@@ -182,35 +182,39 @@ __device__ __forceinline__ void gp_producer(const CUtensorMap* tmA0, const CUten
         const int col0 = FWD ? (s == 0 ? 0 : (s - 1) * K) : (F - 1 - s) * K;
         // every CTA of a row half streams the same tiles: each starts at its own k-block (rot) so that at any moment the
         // CTAs pull different tiles from different L2 slices instead of all hitting the same few
+        // one TMA instruction fetches gsz consecutive k-blocks (3-D box) into one ring stage of gsz * 8 KB
+        const int ngrp = KB / gsz, nst = GP_STAGES / gsz;
         int kk = rot;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-            const int st = it % GP_STAGES;
-            const uint32_t ph = (it / GP_STAGES) & 1;
+        for (int g = 0; g < ngrp; ++g, ++it) {
+            const int st = it % nst;
+            const uint32_t ph = (it / nst) & 1;
             mbar_wait(&empty[st], ph ^ 1);
-            mbar_expect_tx(&full[st], GP_STAGE_BYTES);
-            tma_load_2d(sRing + (size_t)st * GP_STAGE_BYTES, tm, &full[st], col0 + kk * 64, row0);
-            if (++kk == KB) kk = 0;
+            mbar_expect_tx(&full[st], (uint32_t)gsz * GP_STAGE_BYTES);
+            tma_load_3d(sRing + (size_t)st * gsz * GP_STAGE_BYTES, tm, &full[st], 0, row0, col0 / 64 + kk);
+            kk += gsz;
+            if (kk >= KB) kk -= KB;
         }
     }
 }
 
 template <int NB>
 __device__ __forceinline__ void gp_issuer(int w, int nissue, uint8_t* sW, uint8_t* sRing, uint64_t* full, uint64_t* empty,
-                                          uint64_t* w_ready, uint64_t* bar_d, uint32_t tmem, int F, int KB, int rot) {
+                                          uint64_t* w_ready, uint64_t* bar_d, uint32_t tmem, int F, int KB, int rot, int gsz) {
     constexpr uint32_t idesc = umma_idesc_bf16(GP_ROWS, NB);
     mbar_wait(w_ready, 0);
     const uint64_t dW0 = umma_desc_sw128(smem_u32(sW));
     const uint64_t dA0 = umma_desc_sw128(smem_u32(sRing));
     // issuers 0, 2 -> lanes 0..15 of every quadrant (column groups 0 / 64); issuers 1, 3 -> lanes 16..31
     const uint32_t dacc = tmem + ((w & 1) ? (16u << 16) : 0u) + (uint32_t)(w >> 1) * 256;
+    const int ngrp = KB / gsz, nst = GP_STAGES / gsz;
     for (int s = 0; s < F; ++s) {
         for (int kb = w; kb < KB; kb += GP_ISSUERS) {
-            const int it = s * KB + kb;
-            const int st = it % GP_STAGES;
-            const uint32_t ph = (it / GP_STAGES) & 1;
+            const int g = kb / gsz, it = s * ngrp + g;
+            const int st = it % nst;
+            const uint32_t ph = (it / nst) & 1;
             mbar_wait(&full[st], ph);
             tc_fence_after();
-            const uint64_t da = dA0 + (uint64_t)(st * (GP_STAGE_BYTES >> 4));
+            const uint64_t da = dA0 + (uint64_t)((st * gsz + kb % gsz) * (GP_STAGE_BYTES >> 4));
             int kw = kb + rot;                                   // the streamed tile of slot kb is k-block (kb + rot) mod KB
             if (kw >= KB) kw -= KB;
             const uint64_t db = dW0 + (uint64_t)(kw * (GpSmem<NB>::W_KB_BYTES >> 4));
@@ -219,7 +223,7 @@ __device__ __forceinline__ void gp_issuer(int w, int nissue, uint8_t* sW, uint8_
             umma_bf16(dacc + 64, da + 2, db + 2, idesc, acc);
             umma_bf16(dacc + 128, da + 4, db + 4, idesc, acc);
             umma_bf16(dacc + 192, da + 6, db + 6, idesc, acc);
-            umma_commit(&empty[st]);
+            umma_commit(&empty[st]);                             // (a stage of gsz k-blocks collects one arrival per k-block)
         }
         umma_commit(bar_d);
     }
@@ -262,7 +266,8 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int H = p.H, F = p.F, KB = H >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
-    const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)KB) : 0;
+    const int gsz = (KB % 4 == 0) ? 4 : 1;                    // k-blocks per TMA box / ring stage
+    const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)(KB / gsz)) * gsz : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
     const GpLayout L = gp_layout(smem_raw, (size_t)KB * GpSmem<NB>::W_KB_BYTES);
@@ -274,7 +279,7 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_init(L.w_ready, 1);
         for (int s = 0; s < GP_STAGES; ++s) {
             mbar_init(&L.full[s], 1);
-            mbar_init(&L.empty[s], 1);
+            mbar_init(&L.empty[s], gsz);
         }
         mbar_init(L.bar_d, nissue);
         fence_barrier_init();
@@ -292,11 +297,11 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             for (int kb = 0; kb < KB; ++kb)
                 for (int g = 0; g < 3; ++g)
                     tma_load_2d(L.sW + (size_t)kb * GpSmem<NB>::W_KB_BYTES + g * (GP_HS * 128), &tmW, L.w_ready, kb * 64, g * H + u0);
-            gp_producer<NB, true>(&tmH0, &tmY, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, H, NS, rs * GP_ROWS, rot);
+            gp_producer<NB, true>(&tmH0, &tmY, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, H, NS, rs * GP_ROWS, rot, gsz);
         }
     } else if (warp >= 5) {
         if (lane == 0 && warp - 5 < nissue)
-            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB, rot);
+            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB, rot, gsz);
     } else {
         // ===================== row warps: thread = (utterance row, 8 of the 16 units) =====================
         const int hh = lane >> 4;                            // unit half: units u0 + 8*hh .. +7
@@ -372,7 +377,8 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
     const int H = p.H, F = p.F, K3 = 3 * H, KB = K3 >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
-    const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)KB) : 0;
+    const int gsz = (KB % 4 == 0) ? 4 : 1;                    // k-blocks per TMA box / ring stage
+    const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)(KB / gsz)) * gsz : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
     const GpLayout L = gp_layout(smem_raw, (size_t)KB * GpSmem<NB>::W_KB_BYTES);
@@ -383,7 +389,7 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
         mbar_init(L.w_ready, 1);
         for (int s = 0; s < GP_STAGES; ++s) {
             mbar_init(&L.full[s], 1);
-            mbar_init(&L.empty[s], 1);
+            mbar_init(&L.empty[s], gsz);
         }
         mbar_init(L.bar_d, nissue);
         fence_barrier_init();
@@ -399,12 +405,12 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
             mbar_expect_tx(L.w_ready, (uint32_t)(KB * GpSmem<NB>::W_KB_BYTES));
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_2d(L.sW + (size_t)kb * GpSmem<NB>::W_KB_BYTES, &tmWt, L.w_ready, kb * 64, u0);
-            gp_producer<NB, false>(&tmG, &tmG, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, K3, NS, rs * GP_ROWS, rot,
+            gp_producer<NB, false>(&tmG, &tmG, L.sRing, L.full, L.empty, p.ctr + rs, F, KB, K3, NS, rs * GP_ROWS, rot, gsz,
                                    (p.trace && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr);
         }
     } else if (warp >= 5) {
         if (lane == 0 && warp - 5 < nissue)
-            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB, rot);
+            gp_issuer<NB>(warp - 5, nissue, L.sW, L.sRing, L.full, L.empty, L.w_ready, L.bar_d, tmem, F, KB, rot, gsz);
     } else {
         const int hh = lane >> 4;
         const int b = rs * GP_ROWS + 16 * warp + (lane & 15);
@@ -744,8 +750,9 @@ int gru_persist_fwd(int B, int F, int H, const float* GI, const bf* w_hh16, cons
                     float* GH, float* Y, bf* Y16, float* h_last, unsigned* ctr, cudaStream_t st) {
     CUtensorMap tmW, tmH0, tmY;
     SRNN_TRY(make_tmap_bf16(&tmW, w_hh16, (uint64_t)3 * H, H, H, GP_HS));
-    SRNN_TRY(make_tmap_bf16(&tmH0, h0_16, B, H, H, GP_ROWS));
-    SRNN_TRY(make_tmap_bf16(&tmY, Y16, B, (uint64_t)F * H, (uint64_t)F * H, GP_ROWS));
+    const int gsz = ((H / 64) % 4 == 0) ? 4 : 1;
+    SRNN_TRY(make_tmap_bf16_kb(&tmH0, h0_16, B, H, H, GP_ROWS, gsz));
+    SRNN_TRY(make_tmap_bf16_kb(&tmY, Y16, B, (uint64_t)F * H, (uint64_t)F * H, GP_ROWS, gsz));
     GruFwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, GI, GH, Y, Y16, h0, h_last, b_hh, ctr};
     const size_t smem = gp_smem_bytes((size_t)(H / 64) * 3 * GP_HS * 128);
     return gp_launch(k_gru_persist_fwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmW, tmH0, tmY, p);
@@ -758,7 +765,8 @@ int gru_persist_bwd(int B, int F, int H, const float* GI, const float* GH, const
                     cudaStream_t st, float* bias_part, float* db_ih, float* db_hh) {
     CUtensorMap tmWt, tmG;
     SRNN_TRY(make_tmap_bf16(&tmWt, w_hh16_t, H, (uint64_t)3 * H, (uint64_t)3 * H, GP_HS));
-    SRNN_TRY(make_tmap_bf16(&tmG, dGH16, B, (uint64_t)F * 3 * H, (uint64_t)F * 3 * H, GP_ROWS));
+    const int gsz = ((3 * H / 64) % 4 == 0) ? 4 : 1;
+    SRNN_TRY(make_tmap_bf16_kb(&tmG, dGH16, B, (uint64_t)F * 3 * H, (uint64_t)F * 3 * H, GP_ROWS, gsz));
     GruBwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, GI, GH, Y, h0, dY, dGI, dGH, (db_ih || db_hh) ? bias_part : nullptr,
                    dGI16, dGH16, dh0, ctr, nullptr};
     const size_t smem = gp_smem_bytes((size_t)(3 * H / 64) * GP_HS * 128);
