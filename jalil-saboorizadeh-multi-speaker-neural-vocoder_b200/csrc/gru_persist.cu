@@ -124,7 +124,7 @@ __device__ __forceinline__ void gp_gather8(uint32_t tlane, int col, int ncg, int
 }
 
 struct GruFwdParams {
-    int B, F, H, rotate;
+    int B, F, H, rotate, gsz;
     const float* GI;     // (B*F, 3H)  W_ih x + b_ih of every frame (row b*F + f)
     float* GH;           // (B*F, 3H)  out: W_hh h_{f-1} + b_hh (saved for the backward pass)
     float* Y;            // (B*F, H)   out: h_f
@@ -136,7 +136,7 @@ struct GruFwdParams {
 };
 
 struct GruBwdParams {
-    int B, F, H, rotate;
+    int B, F, H, rotate, gsz;
     const float* GI;     // saved forward projections (B*F, 3H)
     const float* GH;
     const float* Y;      // (B*F, H) forward outputs; h_{f-1} = Y[b, f-1] or h0[b]
@@ -266,7 +266,7 @@ k_gru_persist_fwd(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int H = p.H, F = p.F, KB = H >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
-    const int gsz = (KB % 4 == 0) ? 4 : 1;                    // k-blocks per TMA box / ring stage
+    const int gsz = p.gsz;                                    // k-blocks per TMA box / ring stage
     const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)(KB / gsz)) * gsz : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
@@ -377,7 +377,7 @@ k_gru_persist_bwd(const __grid_constant__ CUtensorMap tmWt, const __grid_constan
     const int H = p.H, F = p.F, K3 = 3 * H, KB = K3 >> 6, NS = gridDim.x, rs = blockIdx.y;
     const int nissue = KB < GP_ISSUERS ? KB : GP_ISSUERS;
     const int u0 = blockIdx.x * GP_HS;
-    const int gsz = (KB % 4 == 0) ? 4 : 1;                    // k-blocks per TMA box / ring stage
+    const int gsz = p.gsz;                                    // k-blocks per TMA box / ring stage
     const int rot = p.rotate ? (int)((blockIdx.x * 5u) % (unsigned)(KB / gsz)) * gsz : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ uint8_t smem_raw[];
@@ -717,6 +717,14 @@ int gru_cell_gen(int B, int H, const bf* x16, const bf* w_ih16, const float* b_i
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
+// k-blocks per TMA box: the largest of {SRNN_GRU_GSZ or 4, 2, 1} that divides both the k-block count and the ring depth
+static int gp_box_kblocks(int KB) {
+    int want = getenv("SRNN_GRU_GSZ") ? atoi(getenv("SRNN_GRU_GSZ")) : 4;
+    for (int g = want; g > 1; --g)
+        if (KB % g == 0 && GP_STAGES % g == 0) return g;
+    return 1;
+}
+
 bool gru_persist_supported(int B, int H, int n_sms) {
     if (getenv("SRNN_NO_GRU_PERSIST")) return false;
     if (B < 1 || B > 2 * GP_ROWS || H % 64 || H < 64) return false;
@@ -750,10 +758,10 @@ int gru_persist_fwd(int B, int F, int H, const float* GI, const bf* w_hh16, cons
                     float* GH, float* Y, bf* Y16, float* h_last, unsigned* ctr, cudaStream_t st) {
     CUtensorMap tmW, tmH0, tmY;
     SRNN_TRY(make_tmap_bf16(&tmW, w_hh16, (uint64_t)3 * H, H, H, GP_HS));
-    const int gsz = ((H / 64) % 4 == 0) ? 4 : 1;
+    const int gsz = gp_box_kblocks(H / 64);
     SRNN_TRY(make_tmap_bf16_kb(&tmH0, h0_16, B, H, H, GP_ROWS, gsz));
     SRNN_TRY(make_tmap_bf16_kb(&tmY, Y16, B, (uint64_t)F * H, (uint64_t)F * H, GP_ROWS, gsz));
-    GruFwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, GI, GH, Y, Y16, h0, h_last, b_hh, ctr};
+    GruFwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, gsz, GI, GH, Y, Y16, h0, h_last, b_hh, ctr};
     const size_t smem = gp_smem_bytes((size_t)(H / 64) * 3 * GP_HS * 128);
     return gp_launch(k_gru_persist_fwd, H / GP_HS, (B + GP_ROWS - 1) / GP_ROWS, smem, st, ctr, tmW, tmH0, tmY, p);
 }
@@ -765,9 +773,9 @@ int gru_persist_bwd(int B, int F, int H, const float* GI, const float* GH, const
                     cudaStream_t st, float* bias_part, float* db_ih, float* db_hh) {
     CUtensorMap tmWt, tmG;
     SRNN_TRY(make_tmap_bf16(&tmWt, w_hh16_t, H, (uint64_t)3 * H, (uint64_t)3 * H, GP_HS));
-    const int gsz = ((3 * H / 64) % 4 == 0) ? 4 : 1;
+    const int gsz = gp_box_kblocks(3 * H / 64);
     SRNN_TRY(make_tmap_bf16_kb(&tmG, dGH16, B, (uint64_t)F * 3 * H, (uint64_t)F * 3 * H, GP_ROWS, gsz));
-    GruBwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, GI, GH, Y, h0, dY, dGI, dGH, (db_ih || db_hh) ? bias_part : nullptr,
+    GruBwdParams p{B, F, H, getenv("SRNN_GRU_NO_ROTATE") ? 0 : 1, gsz, GI, GH, Y, h0, dY, dGI, dGH, (db_ih || db_hh) ? bias_part : nullptr,
                    dGI16, dGH16, dh0, ctr, nullptr};
     const size_t smem = gp_smem_bytes((size_t)(3 * H / 64) * GP_HS * 128);
     if (getenv("SRNN_TRACE_GRU")) SRNN_CUDA(cudaMalloc((void**)&p.trace, sizeof(long long) * 8 * F));
