@@ -272,7 +272,9 @@ static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
             }
             P.H0[i] = b.take<float>((size_t)NL * B * H);
             P.H016[i] = b.take<bf>(bf16 ? (size_t)NL * B * H : 1);
-            P.UP[i] = b.take<float>(M * t.fs * H);
+            const bool up16 = bf16 && i == 0 && H % 64 == 0 && H <= 2048 && 256 % (H / 8) == 0 && !getenv("SRNN_UP_F32");   // tier 0 feeds only the table gather
+            P.UP[i] = b.take<float>(up16 ? 1 : M * t.fs * H);
+            if (i == 0) P.UP16 = up16 ? b.take<bf>(M * t.fs * H) : nullptr;
         }
         P.X1 = b.take<float>(bf16 ? 1 : (size_t)B * T * H);
         P.X2 = b.take<float>(bf16 ? 1 : (size_t)B * T * H);
@@ -372,7 +374,8 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
             in16 = Y16;
         }
         if (bf16)
-            SRNN_TRY(tf_gemm(t.w_up16, t.fs * H, in16, M, H, t.b_up, P.UP[i], nullptr, t.fs * H, 0, st));
+            SRNN_TRY(tf_gemm(t.w_up16, t.fs * H, in16, M, H, t.b_up, (i == 0 && P.UP16) ? nullptr : P.UP[i],
+                             (i == 0 && P.UP16) ? P.UP16 : nullptr, t.fs * H, 0, st));
         else
             SRNN_TRY(gemm_f32(M, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, P.UP[i], t.fs * H, st));
         upper = P.UP[i];
@@ -381,7 +384,7 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
     const int FS0 = ctx->FS0, R = B * T;
     if (bf16) {
         SRNN_TRY(mlp_gather_bf16(P.seq, Lseq, lookback - FS0, nullptr, ctx->tbl16, upper, (long long)T * H, H, P.X1h, B, T, H,
-                                 FS0, st));
+                                 FS0, st, P.UP16));
         SRNN_TRY(tf_gemm(ctx->w_hid16, H, P.X1h, R, H, ctx->b_hid, nullptr, P.X2h, H, 1, st));
         SRNN_TRY(tf_gemm(ctx->w_out16, Q, P.X2h, R, H, ctx->b_out, logp_out, nullptr, Q, 0, st));
     } else {

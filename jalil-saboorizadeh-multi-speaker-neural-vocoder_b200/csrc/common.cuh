@@ -97,6 +97,7 @@ struct FwdPlan {
     float* H0[SRNN_MAX_TIERS] = {};                           // (n_rnn, B, H) initial hidden state used
     __nv_bfloat16* H016[SRNN_MAX_TIERS] = {};
     float* UP[SRNN_MAX_TIERS] = {};                           // (M, fs*H) upsampled conditioning for the tier below
+    __nv_bfloat16* UP16 = nullptr;                            // bf16 mode: tier 0's conditioning of the MLP, stored in bf16
     float* X1 = nullptr;                                      // (B*T, H) relu(gather + c0)        [fp32 mode]
     float* X2 = nullptr;                                      // (B*T, H) relu(hidden)             [fp32 mode]
     __nv_bfloat16* X1h = nullptr;                             // bf16 mode
@@ -181,7 +182,7 @@ int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, co
                int FS, cudaStream_t st);
 int mlp_gather_bf16(const uint8_t* seq, int seq_ld, int off, const int* step_base, const __nv_bfloat16* tbl,
                     const float* upper, long long up_bstride, long long up_tstride, __nv_bfloat16* x1, int B, int T,
-                    int H, int FS, cudaStream_t st);
+                    int H, int FS, cudaStream_t st, const __nv_bfloat16* upper16 = nullptr);
 int logsoftmax_rows(float* x, int rows, cudaStream_t st);
 // generation tail: logits (B, 256) -> [logp] -> defined sampler -> seq[b, pos]
 int softmax_sample(const float* logits, const float* uniforms, int u_ld, uint8_t* seq, int seq_ld, int pos_off,

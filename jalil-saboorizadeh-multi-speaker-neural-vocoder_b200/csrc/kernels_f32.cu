@@ -528,7 +528,8 @@ int mlp_gather(const uint8_t* seq, int seq_ld, int off, const int* step_base, co
 // k_mlp_gather (conditioning first, then taps 0 .. FS-1), so the results are bit-identical to it
 __global__ void __launch_bounds__(256)
 k_mlp_gather_bf16v(const uint8_t* __restrict__ seq, int seq_ld, int start_static, const int* __restrict__ step_base,
-                   const __nv_bfloat16* __restrict__ tbl, const float* __restrict__ upper, long long up_bstride,
+                   const __nv_bfloat16* __restrict__ tbl, const float* __restrict__ upper,
+                   const __nv_bfloat16* __restrict__ upper16, long long up_bstride,
                    long long up_tstride, __nv_bfloat16* __restrict__ x1, int R, int T, int H, int FS) {
     const int tpr = H >> 3;                                  // threads per row
     const int r = blockIdx.x * (blockDim.x / tpr) + threadIdx.x / tpr;
@@ -538,7 +539,16 @@ k_mlp_gather_bf16v(const uint8_t* __restrict__ seq, int seq_ld, int start_static
     const int start = start_static + (step_base ? *step_base : 0);
     const uint8_t* s = seq + (size_t)b * seq_ld + start + t;
     float acc[8];
-    {
+    if (upper16) {       // conditioning stored in bf16 (teacher-forced tcgen05 path: halves the 545 MB tensor at C3)
+        const uint4 u = *reinterpret_cast<const uint4*>(upper16 + (size_t)b * up_bstride + (size_t)t * up_tstride + f0);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h2[i]);
+            acc[2 * i] = f.x;
+            acc[2 * i + 1] = f.y;
+        }
+    } else {
         const float4* up = reinterpret_cast<const float4*>(upper + (size_t)b * up_bstride + (size_t)t * up_tstride + f0);
         const float4 u0 = up[0], u1 = up[1];
         acc[0] = u0.x; acc[1] = u0.y; acc[2] = u0.z; acc[3] = u0.w; acc[4] = u1.x; acc[5] = u1.y; acc[6] = u1.z; acc[7] = u1.w;
@@ -572,11 +582,13 @@ k_mlp_gather_bf16v(const uint8_t* __restrict__ seq, int seq_ld, int start_static
 }
 int mlp_gather_bf16(const uint8_t* seq, int seq_ld, int off, const int* step_base, const __nv_bfloat16* tbl,
                     const float* upper, long long up_bstride, long long up_tstride, __nv_bfloat16* x1, int B, int T,
-                    int H, int FS, cudaStream_t st) {
-    if (H % 8 == 0 && H <= 2048 && 256 % (H / 8) == 0 && up_bstride % 4 == 0 && up_tstride % 4 == 0) {
+                    int H, int FS, cudaStream_t st, const __nv_bfloat16* upper16) {
+    const bool vec_ok = H % 8 == 0 && H <= 2048 && 256 % (H / 8) == 0 && up_bstride % 8 == 0 && up_tstride % 8 == 0;
+    if (upper16 && !vec_ok) return fail(SRNN_ERR_UNSUPPORTED, "bf16 conditioning needs the vectorised gather (dim %d)", H);
+    if (vec_ok) {
         const int rpb = 256 / (H / 8);
         SRNN_LAUNCH(k_mlp_gather_bf16v, cdiv((long long)B * T, rpb), 256, 0, st, seq, seq_ld, off, step_base, tbl, upper,
-                    up_bstride, up_tstride, x1, B * T, T, H, FS);
+                    upper16, up_bstride, up_tstride, x1, B * T, T, H, FS);
         return SRNN_OK;
     }
     SRNN_LAUNCH((k_mlp_gather<__nv_bfloat16, __nv_bfloat16>), B * T, H >= 256 ? 256 : 64, FS * sizeof(int), st, seq,
