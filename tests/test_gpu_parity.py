@@ -190,6 +190,42 @@ def test_generate_bf16_mode_against_oracle(dim, B, mode):
     logp_gate(tf32.cpu().numpy(), ref.numpy())
 
 
+@pytest.mark.parametrize("mode", [S.MODE_BF16, S.MODE_BF16_GRAPH])
+@pytest.mark.parametrize("cfg", [
+    dict(frame_sizes=[16], n_rnn=1, dim=128, learn_h0=True, q_levels=256, ulaw=True, weight_norm=False, cond_dim=43, spk_dim=6),   # C1 shape
+    dict(frame_sizes=[4, 2, 2], n_rnn=1, dim=64, learn_h0=False, q_levels=256, ulaw=False, weight_norm=True, cond_dim=5, spk_dim=6),
+    dict(frame_sizes=[20, 4], n_rnn=3, dim=256, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6),
+])
+def test_generate_bf16_other_architectures(cfg, mode):
+    """Single-tier (C1), three-tier / linear-quantised / buffer-h0 and three-GRU-layer models through the tcgen05 generator."""
+    torch.manual_seed(len(cfg["frame_sizes"]) * 10 + cfg["n_rnn"])
+    m = S.SampleRNN(**cfg)
+    p = S.Predictor(m)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    B, n_cond = 9, 3
+    cond = torch.rand(B, n_cond, cfg["cond_dim"])
+    spk = torch.randint(0, 6, (B,))
+    audio, samples, logp = S.Generator(m, cuda=True, mode=mode)(B, 0, cond, spk, seed=7, return_samples=True, return_logp=True)
+    lb = m.lookback
+    seq = torch.cat([torch.full((B, lb), 128, dtype=torch.long), samples.long()], 1)
+    w = O.unpack_state_dict(sd, O.Config(**cfg))
+    with torch.no_grad():
+        ref = O.Predictor(w).forward(seq[:, :-1], True, cond, spk.reshape(B, 1))
+    d = (ref - logp).abs()
+    assert float(d.max()) <= BF16_MAX_ABS and float(d.mean()) <= BF16_MEAN_ABS, (float(d.max()), float(d.mean()))
+    # teacher-forced tcgen05 forward on the same sequence
+    pb = S.Predictor(m, mode=S.MODE_BF16)
+    with torch.no_grad():
+        tf = pb(seq[:, :-1], True, cond, spk.reshape(B, 1), None, None)
+    d2 = (ref - tf.cpu()).abs()
+    assert float(d2.max()) <= BF16_MAX_ABS and float(d2.mean()) <= BF16_MEAN_ABS, (float(d2.max()), float(d2.mean()))
+
+
 def test_generate_large_batch_runs_in_independent_chunks():
     """B = 300 at dim 1024 exceeds what the persistent sample kernel keeps co-resident (288): srnn_generate then runs balanced
     utterance chunks (160 + 140) back to back.  Utterances are independent, so the result must be bit-identical to generating
