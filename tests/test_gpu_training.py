@@ -119,3 +119,42 @@ def test_bf16_backward_against_oracle(dim, B, T):
     assert rep["model.sample_level_mlp.output.weight_v"] < 0.01 and rep["model.sample_level_mlp.output.bias"] < 0.01, report
     assert worst < 0.12, sorted(report, reverse=True)[:12]
     assert float(np.median([r for r, _ in report])) < 0.08, sorted(report, reverse=True)[:12]
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(frame_sizes=[16], n_rnn=1, dim=128, learn_h0=True, q_levels=256, ulaw=True, weight_norm=False, cond_dim=43, spk_dim=6),   # C1 shape
+    dict(frame_sizes=[4, 2, 2], n_rnn=1, dim=64, learn_h0=False, q_levels=256, ulaw=False, weight_norm=True, cond_dim=5, spk_dim=6),
+    dict(frame_sizes=[20, 4], n_rnn=3, dim=256, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6),
+])
+def test_bf16_backward_other_architectures(cfg):
+    """tcgen05 training path on single-tier / three-tier / three-layer models: loss and gradients against the fp32 oracle."""
+    torch.manual_seed(17)
+    m = S.SampleRNN(**cfg)
+    p = S.Predictor(m, mode=S.MODE_BF16)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    lb = m.lookback
+    B, T = 6, 2 * lb
+    x = torch.randint(0, 256, (B, lb + T - 1))
+    y = torch.randint(0, 256, (B, T))
+    cond = torch.rand(B, T // lb, cfg["cond_dim"], dtype=torch.float64)
+    spk = torch.randint(0, 6, (B, 1))
+    loss_ref, grads, _, _ = O.loss_and_grads(sd, O.Config(**cfg), None, x, True, cond, spk, y)
+    out = p(x, True, cond, spk, None, None)
+    loss = S.sequence_nll_loss_bits(out, y)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss_ref)) < 0.02
+    rels = []
+    for k, q in p.named_parameters():
+        ref = grads[k].numpy().astype(np.float64)
+        got = q.grad.detach().cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all(), k
+        n = np.linalg.norm(ref)
+        if n > 1e-7:
+            rels.append((np.linalg.norm(got - ref) / n, k))
+    assert rels and max(rels)[0] < 0.15, sorted(rels, reverse=True)[:8]
+    assert float(np.median([r for r, _ in rels])) < 0.08, sorted(rels, reverse=True)[:8]
