@@ -156,6 +156,10 @@ SRNN_API int srnn_quantize(const float* x, int32_t rows, int32_t cols, int64_t l
                            int64_t* q, void* stream);
 /* out (256) fp32 = 2*dequantize(q) (model.py:385,471). */
 SRNN_API int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream);
+/* SampleLevelMLP.forward (model.py:308-325) with the context's packed weights: prev_samples (B, T+FS0-1) int64 in [0,Q),
+ * upper (B, T, H) fp32 conditioning from tier 0 -> logp_out (B, T, Q) fp32 log-probabilities. */
+SRNN_API int srnn_mlp_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* prev_samples, const float* upper,
+                          float* logp_out, int32_t mode, void* stream);
 /* One GRU layer over F frames = `self.rnn(input, hidden)` (model.py:244; torch nn.GRU, gate row blocks r, z, n) given the
  * input projections: gi (B*F, 3H) = W_ih x + b_ih with row b*F+f, w_hh (3H, H), b_hh (3H), h0 (B, H) ->
  * y (B*F, H) = h_f, gh (B*F, 3H) = W_hh h_{f-1} + b_hh (kept for the backward pass), h_last (B, H) or NULL.

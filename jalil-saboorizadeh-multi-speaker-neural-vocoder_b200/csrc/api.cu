@@ -818,6 +818,44 @@ int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream) {
     return copy_f32(ctx->lut, out, ctx->Q, (cudaStream_t)stream);
 }
 
+// SampleLevelMLP.forward (model.py:308-325) on the context's packed weights: prev_samples (B, T+FS0-1) int64,
+// upper (B, T, H) fp32 -> logp (B, T, 256).  Same kernels as the tail of srnn_predict_fwd.
+int srnn_mlp_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* prev_samples, const float* upper, float* logp_out,
+                 int32_t mode, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    if (!prev_samples || !upper || !logp_out || B < 1 || T < 1) return fail(SRNN_ERR_ARG, "bad argument");
+    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16) return fail(SRNN_ERR_UNSUPPORTED, "mlp_fwd: mode %d not available", mode);
+    if (mode == SRNN_MODE_BF16 && !ctx->has_bf16) return fail(SRNN_ERR_UNSUPPORTED, "bf16 mode needs dim %% 64 == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = ctx->H, Q = ctx->Q, FS0 = ctx->FS0, R = B * T, W = T + FS0 - 1;
+    uint8_t* seq = nullptr;
+    SRNN_CUDA(cudaMallocAsync((void**)&seq, (size_t)B * W, st));
+    SRNN_TRY(i64_to_u8(prev_samples, seq, (size_t)B * W, st));
+    int rc = SRNN_OK;
+    if (mode == SRNN_MODE_BF16) {
+        __nv_bfloat16 *x1 = nullptr, *x2 = nullptr;
+        SRNN_CUDA(cudaMallocAsync((void**)&x1, sizeof(__nv_bfloat16) * (size_t)R * H, st));
+        SRNN_CUDA(cudaMallocAsync((void**)&x2, sizeof(__nv_bfloat16) * (size_t)R * H, st));
+        rc = mlp_gather_bf16(seq, W, 0, nullptr, ctx->tbl16, upper, (long long)T * H, H, x1, B, T, H, FS0, st);
+        if (rc == SRNN_OK) rc = tf_gemm(ctx->w_hid16, H, x1, R, H, ctx->b_hid, nullptr, x2, H, 1, st);
+        if (rc == SRNN_OK) rc = tf_gemm(ctx->w_out16, Q, x2, R, H, ctx->b_out, logp_out, nullptr, Q, 0, st);
+        cudaFreeAsync(x1, st);
+        cudaFreeAsync(x2, st);
+    } else {
+        float *x1 = nullptr, *x2 = nullptr;
+        SRNN_CUDA(cudaMallocAsync((void**)&x1, sizeof(float) * (size_t)R * H, st));
+        SRNN_CUDA(cudaMallocAsync((void**)&x2, sizeof(float) * (size_t)R * H, st));
+        rc = mlp_gather(seq, W, 0, nullptr, ctx->tbl, upper, (long long)T * H, H, x1, B, T, H, FS0, st);
+        if (rc == SRNN_OK) rc = gemm_f32(R, H, H, x1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, x2, H, st);
+        if (rc == SRNN_OK) rc = gemm_f32(R, Q, H, x2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st);
+        cudaFreeAsync(x1, st);
+        cudaFreeAsync(x2, st);
+    }
+    if (rc == SRNN_OK) rc = logsoftmax_rows(logp_out, R, st);
+    cudaFreeAsync(seq, st);
+    return rc;
+}
+
 // One GRU layer over F frames (torch nn.GRU as used at model.py:133-159,244).  FP32: the frame-by-frame fp32 schedule;
 // BF16: the persistent tcgen05 kernels of gru_persist.cu (B <= 128, H % 64 == 0).
 int srnn_gru_seq_fwd(int32_t B, int32_t F, int32_t H, const float* gi, const float* w_hh, const float* b_hh, const float* h0,

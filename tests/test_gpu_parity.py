@@ -289,3 +289,38 @@ def test_nll_loss_bits_hook(golden):
     L.check(L.load().srnn_nll_loss_bits(m._ensure_packed(), logp.data_ptr(), tgt.data_ptr(), int(tgt.numel()),
                                         loss.data_ptr(), stream()))
     assert abs(float(loss.item()) - float(golden["tf/loss0"])) < 1e-4
+
+
+@pytest.mark.parametrize("mode", [S.MODE_FP32, S.MODE_BF16])
+def test_mlp_fwd_hook(mode):
+    """srnn_mlp_fwd = SampleLevelMLP.forward (model.py:308-325) against the oracle's dense embedding + k=FS conv form."""
+    import ctypes as C
+    torch.manual_seed(4)
+    c = dict(frame_sizes=[20, 4], n_rnn=1, dim=128, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86,
+             spk_dim=6)
+    m = S.SampleRNN(**c)
+    p = S.Predictor(m)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k:
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    h = m._ensure_packed()
+    B, T = 3, 50
+    prev = torch.randint(0, 256, (B, T + 19))
+    upper = torch.randn(B, T, 128)
+    w = O.unpack_state_dict(sd, O.Config(**c))
+    with torch.no_grad():
+        ref = O.mlp_forward(w, prev, upper)
+    out = torch.full((B, T, 256), float("nan"), device="cuda")
+    pd, ud = prev.cuda(), upper.cuda().contiguous()
+    S._lib.check(S._lib.load().srnn_mlp_fwd(h, B, T, pd.data_ptr(), ud.data_ptr(), out.data_ptr(), mode,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    got = out.cpu()
+    if mode == S.MODE_FP32:
+        logp_gate(got.numpy(), ref.numpy())
+    else:
+        d = (got - ref).abs()
+        assert float(d.max()) <= BF16_MAX_ABS and float(d.mean()) <= BF16_MEAN_ABS, (float(d.max()), float(d.mean()))
