@@ -166,9 +166,15 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int cols, int 
 }
 // `partial` holds CS_CHUNKS * max_cols floats (max_cols = the widest matrix of the pass): narrow matrices use the spare
 // room for more row chunks so that the grid still fills the GPU (fixed summation order either way).
-static size_t g_colsum_cap = 0;   // floats available in the partial buffer of the running pass
+struct ColsumScratch {
+    float* partial;
+    size_t cap;                       // floats available
+    operator float*() const { return partial; }
+};
 template <typename T>
-static int colsum(const T* X, int rows, int cols, int ld, float* partial, float* out, cudaStream_t st) {
+static int colsum(const T* X, int rows, int cols, int ld, const ColsumScratch& cs, float* out, cudaStream_t st) {
+    float* partial = cs.partial;
+    const size_t g_colsum_cap = cs.cap;
     int chunks = CS_CHUNKS;
     const int want = cdiv(1184, cdiv(cols, 128));                         // ~8 CTAs per SM
     if (want > chunks) chunks = want;
@@ -624,8 +630,8 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2));
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
-    float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
-    g_colsum_cap = (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H);
+    const size_t csp_floats = (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H);
+    const ColsumScratch csp{b.take<float>(csp_floats), csp_floats};
     float* dbtmp = b.take<float>((size_t)3 * H);
     float* dWo = b.take<float>((size_t)Q * H);
     float* wmf = dWm;   // folded mlp-input weights (H,Q,FS0) are rebuilt into dWm's storage before it is needed (see below)
@@ -847,8 +853,8 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     int* iwork = b.take<int>(1024 + (size_t)B * (T + FS0) + 256 * ((size_t)B * (T + FS0) / 512 + 2));
     float* dWmt = b.take<float>((size_t)FS0 * H * Q);
     float* dWm = b.take<float>((size_t)FS0 * H * Q);
-    float* csp = b.take<float>((size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H));
-    g_colsum_cap = (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H);
+    const size_t csp_floats = (size_t)CS_CHUNKS * (maxfs * H > 3 * H ? maxfs * H : 3 * H);
+    const ColsumScratch csp{b.take<float>(csp_floats), csp_floats};
     float* dbtmp = b.take<float>((size_t)3 * H);
     float* dWo = b.take<float>((size_t)Q * H);
     float* dWtmp = b.take<float>((size_t)3 * H * H);
