@@ -964,7 +964,9 @@ int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, c
         float* scratch = nullptr;
         if (split) SRNN_CUDA(cudaMallocAsync((void**)&scratch, sizeof(float) * 3 * (size_t)M * N, st));
         GemmOperands o{w16, a16, bias, addend, C, nullptr, N, Kp, Kp, N, N, relu, nullptr};
-        int rc = gemm_umma_ex(&o, 1, M, Kp, bm, bn, rows, split ? 3 : 1, scratch, st);
+        // ROWS without split-K goes through gemm_umma_rows, i.e. also through the CTA-pair kernel when SRNN_GEMM_PAIR selects it
+        int rc = (rows && !split && N % 8 == 0) ? gemm_umma_rows(o, M, Kp, 1, nullptr, st)
+                                                : gemm_umma_ex(&o, 1, M, Kp, bm, bn, rows, split ? 3 : 1, scratch, st);
         cudaFreeAsync(a16, st);
         cudaFreeAsync(w16, st);
         if (scratch) cudaFreeAsync(scratch, st);

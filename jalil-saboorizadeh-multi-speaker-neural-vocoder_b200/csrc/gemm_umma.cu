@@ -203,6 +203,68 @@ __device__ __forceinline__ void epi_row16(const float (&v)[16], const float* __r
 // MNMAJ = true (ROWS only): both operands are given TRANSPOSED in memory -- tmA over X (K_total x M_total) and tmB over
 //               Y (K_total x N_total), row-major -- and out = X^T . Y: the weight-gradient GEMMs dW = dOut^T . In read
 //               dOut and In as they are, no transposed copies.
+// Epilogue of one 128-row x BN-feature accumulator tile in the ROWS orientation (lane = output row, 16 consecutive features
+// per tcgen05.ld): shared by the single-CTA and the CTA-pair kernels.
+template <int BN>
+__device__ __forceinline__ void rows_epilogue(const GemmProb& P, float* __restrict__ out_f32, uint32_t tmem_d, int m0, int n0,
+                                              int n_rows, int q, int half, int lane) {
+    const int n_feat = P.n_feat;
+    const float* __restrict__ bias = P.bias;
+    const float* __restrict__ addend = P.addend;
+    __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
+    const __nv_bfloat16* __restrict__ mask = P.mask;
+    const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
+    const int r = m0 + 32 * q + lane;
+    const bool r_ok = r < n_rows;
+    float* __restrict__ of = out_f32;
+#pragma unroll 1
+    for (int c = 16 * half; c < BN; c += 32) {
+        const int f0 = n0 + c;
+        if (f0 >= n_feat) break;               // warp-uniform
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
+        if (!r_ok) continue;
+        const size_t o = (size_t)r * ld_out + f0;
+        const float* bp = bias ? bias + f0 : nullptr;
+        if (f0 + 16 <= n_feat) {
+            if (mask)
+                epi_row16<false, false, false, true, true>(v, bp, nullptr, nullptr, out_bf16 + o, mask + o);
+            else if (!addend && !relu && of && !out_bf16)
+                epi_row16<false, false, true, false, false>(v, bp, nullptr, of + o, nullptr, nullptr);
+            else if (!addend && relu && !of && out_bf16)
+                epi_row16<false, true, false, true, false>(v, bp, nullptr, nullptr, out_bf16 + o, nullptr);
+            else if (addend && !relu && of && !out_bf16)
+                epi_row16<true, false, true, false, false>(v, bp, addend + (size_t)r * ld_add + f0, of + o, nullptr, nullptr);
+            else if (!addend && !relu && of && out_bf16)
+                epi_row16<false, false, true, true, false>(v, bp, nullptr, of + o, out_bf16 + o, nullptr);
+            else if (!addend && !relu && !of && out_bf16)
+                epi_row16<false, false, false, true, false>(v, bp, nullptr, nullptr, out_bf16 + o, nullptr);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float x = v[i] + (bp ? bp[i] : 0.f);
+                    if (addend) x += addend[(size_t)r * ld_add + f0 + i];
+                    if (relu) x = fmaxf(x, 0.f);
+                    if (of) of[o + i] = x;
+                    if (out_bf16) out_bf16[o + i] = __float2bfloat16(x);
+                }
+            }
+        } else {                               // ragged feature tail
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (f0 + i < n_feat) {
+                    float x = v[i] + (bp ? bp[i] : 0.f);
+                    if (addend) x += addend[(size_t)r * ld_add + f0 + i];
+                    if (relu) x = fmaxf(x, 0.f);
+                    if (mask) x = __bfloat162float(mask[o + i]) > 0.f ? x : 0.f;
+                    if (of) of[o + i] = x;
+                    if (out_bf16) out_bf16[o + i] = __float2bfloat16(x);
+                }
+            }
+        }
+    }
+}
+
 struct TileInfo {
     int m0, n0, kb0, KB, prob, split;
     bool valid;
@@ -352,55 +414,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         if (tr && threadIdx.x == 64 && tile == 0) tr[1] = clock64();
         tc_fence_after();
         if constexpr (ROWS) {
-            const int r = m0 + 32 * q + lane;
-            const bool r_ok = r < n_rows;
-            float* __restrict__ of = out_f32;
-#pragma unroll 1
-            for (int c = 16 * half; c < BN; c += 32) {
-                const int f0 = n0 + c;
-                if (f0 >= n_feat) break;               // warp-uniform
-                float v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
-                if (!r_ok) continue;
-                const size_t o = (size_t)r * ld_out + f0;
-                const float* bp = bias ? bias + f0 : nullptr;
-                if (f0 + 16 <= n_feat) {
-                    if (mask)
-                        epi_row16<false, false, false, true, true>(v, bp, nullptr, nullptr, out_bf16 + o, mask + o);
-                    else if (!addend && !relu && of && !out_bf16)
-                        epi_row16<false, false, true, false, false>(v, bp, nullptr, of + o, nullptr, nullptr);
-                    else if (!addend && relu && !of && out_bf16)
-                        epi_row16<false, true, false, true, false>(v, bp, nullptr, nullptr, out_bf16 + o, nullptr);
-                    else if (addend && !relu && of && !out_bf16)
-                        epi_row16<true, false, true, false, false>(v, bp, addend + (size_t)r * ld_add + f0, of + o, nullptr, nullptr);
-                    else if (!addend && !relu && of && out_bf16)
-                        epi_row16<false, false, true, true, false>(v, bp, nullptr, of + o, out_bf16 + o, nullptr);
-                    else if (!addend && !relu && !of && out_bf16)
-                        epi_row16<false, false, false, true, false>(v, bp, nullptr, nullptr, out_bf16 + o, nullptr);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = v[i] + (bp ? bp[i] : 0.f);
-                            if (addend) x += addend[(size_t)r * ld_add + f0 + i];
-                            if (relu) x = fmaxf(x, 0.f);
-                            if (of) of[o + i] = x;
-                            if (out_bf16) out_bf16[o + i] = __float2bfloat16(x);
-                        }
-                    }
-                } else {                               // ragged feature tail
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (f0 + i < n_feat) {
-                            float x = v[i] + (bp ? bp[i] : 0.f);
-                            if (addend) x += addend[(size_t)r * ld_add + f0 + i];
-                            if (relu) x = fmaxf(x, 0.f);
-                            if (mask) x = __bfloat162float(mask[o + i]) > 0.f ? x : 0.f;
-                            if (of) of[o + i] = x;
-                            if (out_bf16) out_bf16[o + i] = __float2bfloat16(x);
-                        }
-                    }
-                }
-            }
+            rows_epilogue<BN>(P, out_f32, tmem_d, m0, n0, n_rows, q, half, lane);
         } else {
         int m;
         bool lane_ok;
@@ -509,6 +523,153 @@ int sum_splits(const float* part, int splits, size_t n, size_t stride, float* ou
 
 // nprob (1 or 2) problems  out_i (rows, feat_i) = act_i (rows, K) . W_i (feat_i, K)^T + bias_i [+ addend_i] [relu];
 // W / act are bf16 with K % 64 == 0.  bn selects the batch-row tile (32..256); bm = 128 (default) or 64.
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (cta_group::2) of the ROWS / K-major GEMM: the two CTAs of a 2-cluster (one TPC) execute ONE UMMA with
+// M = 256 (128 output rows per CTA) x N = 256.  Each CTA streams only its 128 activation rows and HALF of the weight tile
+// (128 feature rows) per k-block -- 32 KB instead of 48 KB -- because the tensor core of each SM reads the other half of B
+// from its peer's shared memory.  The single-CTA kernel's main loop is TMA-ingest bound (48 KB ~ 1000 cycles per k-block
+// against 512 cycles of MMA), so this is worth ~1.4x on the long-M teacher-forced GEMMs.
+//   * both CTAs run a TMA producer; the byte counts of BOTH land on the EVEN CTA's full barrier (peer-bit-masked address);
+//   * one thread of the even CTA issues tcgen05.mma.cta_group::2 and commits with .multicast::cluster to the empty / tmem_full
+//     barriers of both CTAs; the epilogue warps of both CTAs arrive on the even CTA's tmem_empty barrier;
+//   * persistent over 256 x 256 pair tiles, accumulators double-buffered in TMEM (2 x 256 columns in each CTA).
+// PTX forms follow cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp, cutlass/arch/barrier.h of the vendored CUTLASS headers.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_HALF = 16384;                 // 128 rows x 128 B
+constexpr int PAIR_STAGE = 2 * PAIR_HALF;        // A rows + B half per CTA
+constexpr int PAIR_NSTAGE = 6;
+constexpr int PAIR_SMEM = PAIR_NSTAGE * PAIR_STAGE + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
+    constexpr uint32_t TCOLS = 256;
+    const GemmProb& P = args.p[0];
+    const int n_rows = args.n_rows, KB = args.K / 64, ntiles = args.gx * args.gy;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + PAIR_NSTAGE * PAIR_STAGE);
+    uint64_t* empty = full + PAIR_NSTAGE;
+    uint64_t* tmem_full = empty + PAIR_NSTAGE;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2] (only the even CTA's are waited on)
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&P.tmA);
+        prefetch_tmap(&P.tmB);
+        for (int s = 0; s < PAIR_NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 2 * (GEMM_THREADS / 32 - 2));   // every epilogue warp of BOTH CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2_rt(tmem_slot, 2 * TCOLS);
+    tc_fence_before();
+    cluster_sync_all();                            // barriers of both CTAs initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (lane == 0) {                           // TMA producer (both CTAs)
+            int s = 0, first = 1;
+            uint32_t ph = 0;
+            for (int tile = cluster; tile < ntiles; tile += nclusters) {
+                const int m0 = (tile % args.gx) * 256 + rank * 128, nb = (tile / args.gx) * 256 + rank * 128;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (!first) { if (++s == PAIR_NSTAGE) { s = 0; ph ^= 1; } }
+                    first = 0;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * PAIR_STAGE);      // this CTA's 32 KB + the peer's 32 KB
+                    tma_load_2d_pair(smem + s * PAIR_STAGE, &P.tmA, &full[s], kb * 64, m0);
+                    tma_load_2d_pair(smem + s * PAIR_STAGE + PAIR_HALF, &P.tmB, &full[s], kb * 64, nb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {              // MMA issuer: one thread of the even CTA drives both tensor cores
+            constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+            const uint64_t d0 = umma_desc_sw128(smem_u32(smem));
+            int s = 0, first = 1, tl = 0;
+            uint32_t ph = 0;
+            for (int tile = cluster; tile < ntiles; tile += nclusters) {
+                const int buf = tl & 1, use = tl >> 1;
+                mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * TCOLS;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (!first) { if (++s == PAIR_NSTAGE) { s = 0; ph ^= 1; } }
+                    first = 0;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = d0 + (uint64_t)(s * (PAIR_STAGE >> 4));
+                    const uint64_t db = da + (uint64_t)(PAIR_HALF >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma2_commit_both(&empty[s]);
+                }
+                umma2_commit_both(&tmem_full[buf]);
+                ++tl;
+            }
+        }
+    } else {                                       // epilogue warps (both CTAs): this CTA's 128 rows x 256 features
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        int tl = 0;
+        for (int tile = cluster; tile < ntiles; tile += nclusters) {
+            const int m0 = (tile % args.gx) * 256 + rank * 128, n0 = (tile / args.gx) * 256;
+            const int buf = tl & 1, use = tl >> 1;
+            mbar_wait(&tmem_full[buf], use & 1);
+            tc_fence_after();
+            rows_epilogue<256>(P, P.out_f32, tmem_base + (uint32_t)buf * TCOLS, m0, n0, n_rows, q, half, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_even_cta(&tmem_empty[buf]);
+            ++tl;
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                            // the peer may still read this CTA's shared memory / signal its barriers
+    if (warp == 1) tmem_dealloc2_rt(tmem_base, 2 * TCOLS);
+}
+
+// out (n_rows, n_feat) = act (n_rows, K) . W (n_feat, K)^T [+bias][relu][mask] through the CTA-pair kernel
+static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, cudaStream_t st) {
+    GemmArgs args;
+    memset(&args, 0, sizeof(args));
+    args.n_rows = n_rows;
+    args.K = K;
+    args.ksplit = 1;
+    SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, n_rows, K, o.ld_act, 128));
+    SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, o.n_feat, K, o.ld_w, 128));
+    args.p[0].bias = o.bias;
+    args.p[0].addend = o.addend;
+    args.p[0].out_f32 = o.out_f32;
+    args.p[0].out_bf16 = o.out_bf16;
+    args.p[0].mask = o.mask;
+    args.p[0].n_feat = o.n_feat;
+    args.p[0].ld_add = o.ld_add;
+    args.p[0].ld_out = o.ld_out;
+    args.p[0].relu = o.relu;
+    args.gx = cdiv(n_rows, 256);
+    args.gy = cdiv(o.n_feat, 256);
+    args.gz = 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+        attr_set = true;
+    }
+    const int ntiles = args.gx * args.gy;
+    int nclusters = g_gemm_sms > 1 ? g_gemm_sms / 2 : 1;
+    if (nclusters > ntiles) nclusters = ntiles;
+    SRNN_LAUNCH(k_gemm_umma_pair, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
+    return SRNN_OK;
+}
+
 // rows = false: swap-AB orientation, tile bm (128|64) features x bn (32..256) rows.
 // rows = true : activation rows on the lanes, tile 128 rows x bn (128|256) features (vector epilogue); needs ld_out % 8 == 0.
 // ksplit > 1 (single problem, fp32 output only): the K loop is cut into ksplit ranges, each CTA writes its partial tile
@@ -636,6 +797,17 @@ int gemm_umma_tn(const __nv_bfloat16* X, int ld_x, const __nv_bfloat16* Y, int l
 
 // The big teacher-forced contractions (hundreds of rows or more): ROWS orientation, 128 x 256 (or 128 x 128) tiles.
 int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* split_scratch, cudaStream_t st) {
+    if (g_gemm_sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_gemm_sms = 0;
+    }
+    // SRNN_GEMM_PAIR: 0 = never, 1 = when there is at least a wave of pair tiles (default), 2 = always (tests)
+    static const int pair_mode = getenv("SRNN_GEMM_PAIR") ? atoi(getenv("SRNN_GEMM_PAIR")) : 1;
+    // CTA-pair kernel: long-M problems with at least a wave of 256 x 256 pair tiles
+    if (pair_mode && ksplit <= 1 && K % 64 == 0 && (o.n_feat >= 256 || pair_mode == 2) && o.ld_out % 8 == 0 && (!o.addend || o.ld_add % 4 == 0) &&
+        (pair_mode == 2 || (long long)cdiv(n_rows, 256) * cdiv(o.n_feat, 256) >= g_gemm_sms / 2))
+        return launch_gemm_pair(o, n_rows, K, st);
     const int bn = o.n_feat <= 128 ? 128 : 256;
     return gemm_umma_ex(&o, 1, n_rows, K, 128, bn, true, ksplit, split_scratch, st);
 }

@@ -78,3 +78,34 @@ def test_umma_gemm_mn_major_operands(split, shape):
     assert np.isfinite(got).all(), "non-finite output"
     err = np.abs(got - ref.numpy()).max()
     assert err < 2e-3 * K ** 0.5, "max err %g" % err
+
+
+@pytest.mark.parametrize("shape", [(256, 1024, 1024), (1000, 296, 640), (9600, 512, 256), (300, 256, 64)])
+def test_umma_gemm_cta_pair(shape, monkeypatch):
+    """cta_group::2 kernel (two SMs, one M=256 UMMA, operand halves shared through the pair's shared memory), forced on
+    for every shape through SRNN_GEMM_PAIR=2 in a fresh process so that the library's cached mode is not affected."""
+    import subprocess, sys, os, textwrap
+    M, N, K = shape
+    code = textwrap.dedent(f"""
+        import ctypes as C, numpy as np, torch, sys
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        import srnn_b200 as S
+        M, N, K = {M}, {N}, {K}
+        g = torch.Generator().manual_seed(M + N + K)
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+        bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+        ref = torch.relu(A.bfloat16().double() @ B.bfloat16().double().t() + bias.double() + add.double()).float()
+        out = torch.full((M, N), float("nan"), device="cuda")
+        dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
+        mode = S.MODE_BF16 | (128 << 8) | (256 << 16) | (1 << 28)
+        before = S._lib.load().srnn_launch_count()
+        S._lib.check(S._lib.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), db.data_ptr(), da.data_ptr(), 1,
+                                             out.data_ptr(), mode, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        err = float((out.cpu() - ref).abs().max())
+        assert np.isfinite(out.cpu().numpy()).all() and err < 2e-3 * K ** 0.5, err
+        print("ok", err)
+    """)
+    env = dict(os.environ, SRNN_GEMM_PAIR="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
