@@ -540,11 +540,14 @@ constexpr int PAIR_STAGE = 2 * PAIR_HALF;        // A rows + B half per CTA
 constexpr int PAIR_NSTAGE = 6;
 constexpr int PAIR_SMEM = PAIR_NSTAGE * PAIR_STAGE + 1024 + 256;
 
+// MNMAJ: both operands transposed in memory (weight gradients dW = dOut^T . In), as in k_gemm_umma; gz = K splits.
+template <bool MNMAJ>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
     constexpr uint32_t TCOLS = 256;
     const GemmProb& P = args.p[0];
-    const int n_rows = args.n_rows, KB = args.K / 64, ntiles = args.gx * args.gy;
+    const int n_rows = args.n_rows, KBT = args.K / 64, nxy = args.gx * args.gy, ntiles = nxy * args.gz;
+    const int kper = (KBT + args.gz - 1) / args.gz;             // k-blocks per split (every split non-empty by construction)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + PAIR_NSTAGE * PAIR_STAGE);
@@ -580,24 +583,36 @@ k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
             int s = 0, first = 1;
             uint32_t ph = 0;
             for (int tile = cluster; tile < ntiles; tile += nclusters) {
-                const int m0 = (tile % args.gx) * 256 + rank * 128, nb = (tile / args.gx) * 256 + rank * 128;
+                const int txy = tile % nxy, sp = tile / nxy;
+                const int m0 = (txy % args.gx) * 256 + rank * 128, nb = (txy / args.gx) * 256 + rank * 128;
+                const int kb0 = sp * kper, KB = KBT - kb0 < kper ? KBT - kb0 : kper;
                 for (int kb = 0; kb < KB; ++kb) {
                     if (!first) { if (++s == PAIR_NSTAGE) { s = 0; ph ^= 1; } }
                     first = 0;
                     mbar_wait(&empty[s], ph ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[s], 2 * PAIR_STAGE);      // this CTA's 32 KB + the peer's 32 KB
-                    tma_load_2d_pair(smem + s * PAIR_STAGE, &P.tmA, &full[s], kb * 64, m0);
-                    tma_load_2d_pair(smem + s * PAIR_STAGE + PAIR_HALF, &P.tmB, &full[s], kb * 64, nb);
+                    uint8_t* dst = smem + s * PAIR_STAGE;
+                    if constexpr (MNMAJ) {                                        // boxes {64 MN elements, 64 K rows}
+                        tma_load_2d_pair(dst, &P.tmA, &full[s], m0, (kb0 + kb) * 64);
+                        tma_load_2d_pair(dst + 8192, &P.tmA, &full[s], m0 + 64, (kb0 + kb) * 64);
+                        tma_load_2d_pair(dst + PAIR_HALF, &P.tmB, &full[s], nb, (kb0 + kb) * 64);
+                        tma_load_2d_pair(dst + PAIR_HALF + 8192, &P.tmB, &full[s], nb + 64, (kb0 + kb) * 64);
+                    } else {
+                        tma_load_2d_pair(dst, &P.tmA, &full[s], (kb0 + kb) * 64, m0);
+                        tma_load_2d_pair(dst + PAIR_HALF, &P.tmB, &full[s], (kb0 + kb) * 64, nb);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {              // MMA issuer: one thread of the even CTA drives both tensor cores
-            constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
-            const uint64_t d0 = umma_desc_sw128(smem_u32(smem));
+            constexpr uint32_t idesc = MNMAJ ? umma_idesc_bf16_mn(256, 256) : umma_idesc_bf16(256, 256);
+            const uint64_t d0 = MNMAJ ? umma_desc_sw128_mn(smem_u32(smem), 8192) : umma_desc_sw128(smem_u32(smem));
+            constexpr int KSTEP = MNMAJ ? 128 : 2;
             int s = 0, first = 1, tl = 0;
             uint32_t ph = 0;
             for (int tile = cluster; tile < ntiles; tile += nclusters) {
+                const int sp = tile / nxy, kb0 = sp * kper, KB = KBT - kb0 < kper ? KBT - kb0 : kper;
                 const int buf = tl & 1, use = tl >> 1;
                 mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
                 tc_fence_after();
@@ -610,7 +625,7 @@ k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
                     const uint64_t da = d0 + (uint64_t)(s * (PAIR_STAGE >> 4));
                     const uint64_t db = da + (uint64_t)(PAIR_HALF >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) umma2_bf16(tmem_d, da + KSTEP * k, db + KSTEP * k, idesc, (kb | k) != 0);
                     umma2_commit_both(&empty[s]);
                 }
                 umma2_commit_both(&tmem_full[buf]);
@@ -621,11 +636,13 @@ k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
         const int q = warp & 3, half = (warp - 2) >> 2;
         int tl = 0;
         for (int tile = cluster; tile < ntiles; tile += nclusters) {
-            const int m0 = (tile % args.gx) * 256 + rank * 128, n0 = (tile / args.gx) * 256;
+            const int txy = tile % nxy, sp = tile / nxy;
+            const int m0 = (txy % args.gx) * 256 + rank * 128, n0 = (txy / args.gx) * 256;
             const int buf = tl & 1, use = tl >> 1;
             mbar_wait(&tmem_full[buf], use & 1);
             tc_fence_after();
-            rows_epilogue<256>(P, P.out_f32, tmem_base + (uint32_t)buf * TCOLS, m0, n0, n_rows, q, half, lane);
+            float* of = (P.out_f32 && args.gz > 1) ? P.out_f32 + (size_t)sp * args.split_stride : P.out_f32;
+            rows_epilogue<256>(P, of, tmem_base + (uint32_t)buf * TCOLS, m0, n0, n_rows, q, half, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_even_cta(&tmem_empty[buf]);
@@ -637,18 +654,35 @@ k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
     if (warp == 1) tmem_dealloc2_rt(tmem_base, 2 * TCOLS);
 }
 
-// out (n_rows, n_feat) = act (n_rows, K) . W (n_feat, K)^T [+bias][relu][mask] through the CTA-pair kernel
-static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, cudaStream_t st) {
+// CTA-pair launch.  mn = false: out (n_rows, n_feat) = act (n_rows, K) . W (n_feat, K)^T [+bias][relu][mask];
+// mn = true: o.act = X (K, n_rows), o.W = Y (K, n_feat) row-major, out = X^T . Y (fp32, optional split-K into split_scratch).
+static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, bool mn, int ksplit, float* split_scratch, cudaStream_t st) {
     GemmArgs args;
     memset(&args, 0, sizeof(args));
+    const int Kp = (K + 63) / 64 * 64;
     args.n_rows = n_rows;
-    args.K = K;
+    args.K = Kp;
     args.ksplit = 1;
-    SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, n_rows, K, o.ld_act, 128));
-    SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, o.n_feat, K, o.ld_w, 128));
+    args.gz = 1;
+    if (ksplit > 1) {
+        const int KB = Kp / 64, per = (KB + ksplit - 1) / ksplit;
+        ksplit = (KB + per - 1) / per;                 // no empty split
+    }
+    if (ksplit > 1) {
+        if (!split_scratch || !o.out_f32) return fail(SRNN_ERR_ARG, "gemm pair: split-K needs scratch and an fp32 output");
+        args.gz = ksplit;
+        args.split_stride = (long long)n_rows * o.ld_out;
+    }
+    if (mn) {
+        SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, K, n_rows, o.ld_act, 64));
+        SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, K, o.n_feat, o.ld_w, 64));
+    } else {
+        SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, n_rows, K, o.ld_act, 128));
+        SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, o.n_feat, K, o.ld_w, 128));
+    }
     args.p[0].bias = o.bias;
     args.p[0].addend = o.addend;
-    args.p[0].out_f32 = o.out_f32;
+    args.p[0].out_f32 = args.gz > 1 ? split_scratch : o.out_f32;
     args.p[0].out_bf16 = o.out_bf16;
     args.p[0].mask = o.mask;
     args.p[0].n_feat = o.n_feat;
@@ -657,16 +691,18 @@ static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, cudaStream
     args.p[0].relu = o.relu;
     args.gx = cdiv(n_rows, 256);
     args.gy = cdiv(o.n_feat, 256);
-    args.gz = 1;
     static bool attr_set = false;
     if (!attr_set) {
-        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
         attr_set = true;
     }
-    const int ntiles = args.gx * args.gy;
+    const int ntiles = args.gx * args.gy * args.gz;
     int nclusters = g_gemm_sms > 1 ? g_gemm_sms / 2 : 1;
     if (nclusters > ntiles) nclusters = ntiles;
-    SRNN_LAUNCH(k_gemm_umma_pair, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
+    if (mn) SRNN_LAUNCH(k_gemm_umma_pair<true>, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
+    else SRNN_LAUNCH(k_gemm_umma_pair<false>, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
+    if (args.gz > 1) return sum_splits(split_scratch, args.gz, (size_t)n_rows * o.ld_out, (size_t)args.split_stride, o.out_f32, st);
     return SRNN_OK;
 }
 
@@ -769,6 +805,22 @@ int gemm_umma_tn(const __nv_bfloat16* X, int ld_x, const __nv_bfloat16* Y, int l
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_gemm_sms = 0;
     }
+    {
+        static const int pair_mode = getenv("SRNN_GEMM_PAIR") ? atoi(getenv("SRNN_GEMM_PAIR")) : 1;
+        // CTA-pair kernel when the 256 x 256 pair tiles (times the K splits) can fill the GPU
+        if (pair_mode && ((M >= 256 && N >= 256) || pair_mode == 2)) {
+            GemmOperands o{Y, X, nullptr, nullptr, out, nullptr, N, ld_y, ld_x, 0, ld_out, 0, nullptr};
+            int ks = ksplit;
+            if (pair_mode != 2) {      // re-derive the split for 256-wide tiles: ~2 work items per cluster
+                const int tiles = cdiv(M, 256) * cdiv(N, 256);
+                ks = cdiv(g_gemm_sms, tiles);
+                if (ks > Ktot / 512) ks = Ktot / 512;
+                if (ks > ksplit) ks = ksplit;          // the caller's split respects the capacity of split_scratch
+                if (!split_scratch) ks = 1;
+            }
+            return launch_gemm_pair(o, M, Ktot, true, ks < 2 ? 1 : ks, split_scratch, st);
+        }
+    }
     const int bn = N <= 128 ? 128 : 256;
     const int Kp = (Ktot + 63) / 64 * 64;
     GemmArgs args;
@@ -807,7 +859,7 @@ int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* 
     // CTA-pair kernel: long-M problems with at least a wave of 256 x 256 pair tiles
     if (pair_mode && ksplit <= 1 && K % 64 == 0 && (o.n_feat >= 256 || pair_mode == 2) && o.ld_out % 8 == 0 && (!o.addend || o.ld_add % 4 == 0) &&
         (pair_mode == 2 || (long long)cdiv(n_rows, 256) * cdiv(o.n_feat, 256) >= g_gemm_sms / 2))
-        return launch_gemm_pair(o, n_rows, K, st);
+        return launch_gemm_pair(o, n_rows, K, false, 1, nullptr, st);
     const int bn = o.n_feat <= 128 ? 128 : 256;
     return gemm_umma_ex(&o, 1, n_rows, K, 128, bn, true, ksplit, split_scratch, st);
 }

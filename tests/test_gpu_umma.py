@@ -80,8 +80,9 @@ def test_umma_gemm_mn_major_operands(split, shape):
     assert err < 2e-3 * K ** 0.5, "max err %g" % err
 
 
+@pytest.mark.parametrize("kind", ["kmajor", "mnmajor", "mnmajor_split"])
 @pytest.mark.parametrize("shape", [(256, 1024, 1024), (1000, 296, 640), (9600, 512, 256), (300, 256, 64)])
-def test_umma_gemm_cta_pair(shape, monkeypatch):
+def test_umma_gemm_cta_pair(shape, kind):
     """cta_group::2 kernel (two SMs, one M=256 UMMA, operand halves shared through the pair's shared memory), forced on
     for every shape through SRNN_GEMM_PAIR=2 in a fresh process so that the library's cached mode is not affected."""
     import subprocess, sys, os, textwrap
@@ -94,12 +95,18 @@ def test_umma_gemm_cta_pair(shape, monkeypatch):
         g = torch.Generator().manual_seed(M + N + K)
         A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
         bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
-        ref = torch.relu(A.bfloat16().double() @ B.bfloat16().double().t() + bias.double() + add.double()).float()
+        kind = {kind!r}
+        plain = A.bfloat16().double() @ B.bfloat16().double().t()
+        ref = (torch.relu(plain + bias.double() + add.double()) if kind == "kmajor" else plain).float()
         out = torch.full((M, N), float("nan"), device="cuda")
         dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
-        mode = S.MODE_BF16 | (128 << 8) | (256 << 16) | (1 << 28)
-        before = S._lib.load().srnn_launch_count()
-        S._lib.check(S._lib.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), db.data_ptr(), da.data_ptr(), 1,
+        if kind == "kmajor":
+            mode = S.MODE_BF16 | (128 << 8) | (256 << 16) | (1 << 28)
+            args = (db.data_ptr(), da.data_ptr(), 1)
+        else:
+            mode = S.MODE_BF16 | (1 << 30) | ((1 << 29) if kind == "mnmajor_split" else 0)
+            args = (None, None, 0)
+        S._lib.check(S._lib.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), args[0], args[1], args[2],
                                              out.data_ptr(), mode, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         torch.cuda.synchronize()
         err = float((out.cpu() - ref).abs().max())
