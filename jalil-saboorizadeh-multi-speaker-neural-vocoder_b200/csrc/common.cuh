@@ -261,6 +261,8 @@ int gemm_umma_ex(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, 
 int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* split_scratch, cudaStream_t st);
 int gemm_umma_tn(const __nv_bfloat16* X, int ld_x, const __nv_bfloat16* Y, int ld_y, int M, int N, int Ktot, float* out,
                  int ld_out, int ksplit, float* split_scratch, cudaStream_t st);
+bool gemm_umma_swap_pair_ok(int n_feat, int n_rows);
+int gemm_umma_swap_pair(const GemmOperands& o, int n_rows, int K, cudaStream_t st);
 int sum_splits(const float* part, int splits, size_t n, size_t stride, float* out, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);

@@ -265,6 +265,58 @@ __device__ __forceinline__ void rows_epilogue(const GemmProb& P, float* __restri
     }
 }
 
+// Epilogue of one BM-feature x BN-row accumulator tile in the swap-AB orientation (lane = feature, columns = batch rows).
+template <int BM, int BN>
+__device__ __forceinline__ void swap_epilogue(const GemmProb& P, float* __restrict__ out_f32, uint32_t tmem_d, int m0, int n0,
+                                              int n_rows, int q, int half, int lane) {
+    const int n_feat = P.n_feat;
+    const float* __restrict__ bias = P.bias;
+    const float* __restrict__ addend = P.addend;
+    __nv_bfloat16* __restrict__ out_bf16 = P.out_bf16;
+    const __nv_bfloat16* __restrict__ mask = P.mask;
+    const int ld_out = P.ld_out, ld_add = P.ld_add, relu = P.relu;
+    int m;
+    bool lane_ok;
+    if (BM == 128) {
+        m = m0 + 32 * q + lane;
+        lane_ok = true;
+    } else {                                   // M = 64: rows 16q..16q+15 live in lanes 0..15 of quadrant q
+        m = m0 + 16 * q + lane;
+        lane_ok = lane < 16;
+    }
+    const bool m_ok = lane_ok && m < n_feat;
+    const float bv = (bias && m_ok) ? bias[m] : 0.f;
+#pragma unroll 1
+    for (int c = 16 * half; c < BN; c += 32) {
+        if (n0 + c >= n_rows) break;           // warp-uniform: nothing but padding rows beyond this point
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
+        if (!m_ok) continue;
+        const int nn = n_rows - (n0 + c) < 16 ? n_rows - (n0 + c) : 16;
+        const size_t row = (size_t)(n0 + c);
+        if (mask)                                              // ReLU backward: dpre = dx where the forward value > 0
+            epi_store16<false, false, false, true, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out, mask);
+        else if (!addend && !relu && out_f32 && !out_bf16)     // GRU projections, upsampling, logits, weight gradients
+            epi_store16<false, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+        else if (!addend && relu && !out_f32 && out_bf16)      // MLP hidden layer feeding the next GEMM
+            epi_store16<false, true, false, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+        else if (addend && !relu && out_f32 && !out_bf16)      // BPTT carry: dh*z + dGH.W_hh
+            epi_store16<true, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+        else {                                                 // generic (test hook)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float x = v[i] + bv;
+                if (i < nn) {
+                    if (addend) x += addend[(row + i) * ld_add + m];
+                    if (relu) x = fmaxf(x, 0.f);
+                    if (out_f32) out_f32[(row + i) * ld_out + m] = x;
+                    if (out_bf16) out_bf16[(row + i) * ld_out + m] = __float2bfloat16(x);
+                }
+            }
+        }
+    }
+}
+
 struct TileInfo {
     int m0, n0, kb0, KB, prob, split;
     bool valid;
@@ -416,46 +468,7 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         if constexpr (ROWS) {
             rows_epilogue<BN>(P, out_f32, tmem_d, m0, n0, n_rows, q, half, lane);
         } else {
-        int m;
-        bool lane_ok;
-        if (BM == 128) {
-            m = m0 + 32 * q + lane;
-            lane_ok = true;
-        } else {                                   // M = 64: rows 16q..16q+15 live in lanes 0..15 of quadrant q
-            m = m0 + 16 * q + lane;
-            lane_ok = lane < 16;
-        }
-        const bool m_ok = lane_ok && m < n_feat;
-        const float bv = (bias && m_ok) ? bias[m] : 0.f;
-#pragma unroll 1
-        for (int c = 16 * half; c < BN; c += 32) {
-            if (n0 + c >= n_rows) break;           // warp-uniform: nothing but padding rows beyond this point
-            float v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + c, v);
-            if (!m_ok) continue;
-            const int nn = n_rows - (n0 + c) < 16 ? n_rows - (n0 + c) : 16;
-            const size_t row = (size_t)(n0 + c);
-            if (mask)                                              // ReLU backward: dpre = dx where the forward value > 0
-                epi_store16<false, false, false, true, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out, mask);
-            else if (!addend && !relu && out_f32 && !out_bf16)     // GRU projections, upsampling, logits, weight gradients
-                epi_store16<false, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
-            else if (!addend && relu && !out_f32 && out_bf16)      // MLP hidden layer feeding the next GEMM
-                epi_store16<false, true, false, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
-            else if (addend && !relu && out_f32 && !out_bf16)      // BPTT carry: dh*z + dGH.W_hh
-                epi_store16<true, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
-            else {                                                 // generic (test hook)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x = v[i] + bv;
-                    if (i < nn) {
-                        if (addend) x += addend[(row + i) * ld_add + m];
-                        if (relu) x = fmaxf(x, 0.f);
-                        if (out_f32) out_f32[(row + i) * ld_out + m] = x;
-                        if (out_bf16) out_bf16[(row + i) * ld_out + m] = __float2bfloat16(x);
-                    }
-                }
-            }
-        }
+            swap_epilogue<BM, BN>(P, out_f32, tmem_d, m0, n0, n_rows, q, half, lane);
         }   // !ROWS
         // this warp has read its part of the accumulator: hand the TMEM buffer back to the MMA issuer
         tc_fence_before();
@@ -541,7 +554,9 @@ constexpr int PAIR_NSTAGE = 6;
 constexpr int PAIR_SMEM = PAIR_NSTAGE * PAIR_STAGE + 1024 + 256;
 
 // MNMAJ: both operands transposed in memory (weight gradients dW = dOut^T . In), as in k_gemm_umma; gz = K splits.
-template <bool MNMAJ>
+// SWAP: swap-AB orientation (weights = A operand, 256 features per pair tile on the lanes; activations = B operand, 128 of
+// 256 batch rows per CTA): the generation-time upsampling GEMM (256 utterances x 20480 features).
+template <bool MNMAJ, bool SWAP = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
     constexpr uint32_t TCOLS = 256;
@@ -642,7 +657,8 @@ k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
             mbar_wait(&tmem_full[buf], use & 1);
             tc_fence_after();
             float* of = (P.out_f32 && args.gz > 1) ? P.out_f32 + (size_t)sp * args.split_stride : P.out_f32;
-            rows_epilogue<256>(P, of, tmem_base + (uint32_t)buf * TCOLS, m0, n0, n_rows, q, half, lane);
+            if constexpr (SWAP) swap_epilogue<128, 256>(P, of, tmem_base + (uint32_t)buf * TCOLS, m0, n0, n_rows, q, half, lane);
+            else rows_epilogue<256>(P, of, tmem_base + (uint32_t)buf * TCOLS, m0, n0, n_rows, q, half, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_even_cta(&tmem_empty[buf]);
@@ -656,7 +672,8 @@ k_gemm_umma_pair(const __grid_constant__ GemmArgs args) {
 
 // CTA-pair launch.  mn = false: out (n_rows, n_feat) = act (n_rows, K) . W (n_feat, K)^T [+bias][relu][mask];
 // mn = true: o.act = X (K, n_rows), o.W = Y (K, n_feat) row-major, out = X^T . Y (fp32, optional split-K into split_scratch).
-static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, bool mn, int ksplit, float* split_scratch, cudaStream_t st) {
+static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, bool mn, int ksplit, float* split_scratch, cudaStream_t st,
+                            bool swap = false) {
     GemmArgs args;
     memset(&args, 0, sizeof(args));
     const int Kp = (K + 63) / 64 * 64;
@@ -676,6 +693,9 @@ static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, bool mn, i
     if (mn) {
         SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, K, n_rows, o.ld_act, 64));
         SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, K, o.n_feat, o.ld_w, 64));
+    } else if (swap) {                                 // lanes = features: A = weights, B = activations
+        SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.W, o.n_feat, K, o.ld_w, 128));
+        SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.act, n_rows, K, o.ld_act, 128));
     } else {
         SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, n_rows, K, o.ld_act, 128));
         SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, o.n_feat, K, o.ld_w, 128));
@@ -689,18 +709,20 @@ static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, bool mn, i
     args.p[0].ld_add = o.ld_add;
     args.p[0].ld_out = o.ld_out;
     args.p[0].relu = o.relu;
-    args.gx = cdiv(n_rows, 256);
-    args.gy = cdiv(o.n_feat, 256);
+    args.gx = swap ? cdiv(o.n_feat, 256) : cdiv(n_rows, 256);      // pair tiles along the A operand
+    args.gy = swap ? cdiv(n_rows, 256) : cdiv(o.n_feat, 256);
     static bool attr_set = false;
     if (!attr_set) {
         SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
         SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+        SRNN_CUDA(cudaFuncSetAttribute((k_gemm_umma_pair<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
         attr_set = true;
     }
     const int ntiles = args.gx * args.gy * args.gz;
     int nclusters = g_gemm_sms > 1 ? g_gemm_sms / 2 : 1;
     if (nclusters > ntiles) nclusters = ntiles;
     if (mn) SRNN_LAUNCH(k_gemm_umma_pair<true>, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
+    else if (swap) SRNN_LAUNCH((k_gemm_umma_pair<false, true>), dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
     else SRNN_LAUNCH(k_gemm_umma_pair<false>, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
     if (args.gz > 1) return sum_splits(split_scratch, args.gz, (size_t)n_rows * o.ld_out, (size_t)args.split_stride, o.out_f32, st);
     return SRNN_OK;
@@ -862,6 +884,23 @@ int gemm_umma_rows(const GemmOperands& o, int n_rows, int K, int ksplit, float* 
         return launch_gemm_pair(o, n_rows, K, false, 1, nullptr, st);
     const int bn = o.n_feat <= 128 ? 128 : 256;
     return gemm_umma_ex(&o, 1, n_rows, K, 128, bn, true, ksplit, split_scratch, st);
+}
+
+// swap-AB through the CTA-pair kernel: worthwhile when the 256-feature pair tiles fill the clusters (>= SMs / 2 tiles) and
+// there are more than 128 batch rows (each CTA of the pair takes 128 of them)
+bool gemm_umma_swap_pair_ok(int n_feat, int n_rows) {
+    static const int pair_mode = getenv("SRNN_GEMM_PAIR") ? atoi(getenv("SRNN_GEMM_PAIR")) : 1;
+    if (g_gemm_sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_gemm_sms = 0;
+    }
+    // measured at the C2 upsampling (256 x 20480 x 1024): 31 us against 30 us for the single-CTA kernel with two CTAs per SM
+    // -- the launch is not ingest bound -- so this form is opt-in (SRNN_SWAP_PAIR=1) and kept for larger batches / tests
+    return pair_mode && getenv("SRNN_SWAP_PAIR") && n_rows > 128 && n_rows <= 256 && cdiv(n_feat, 256) >= g_gemm_sms / 2;
+}
+int gemm_umma_swap_pair(const GemmOperands& o, int n_rows, int K, cudaStream_t st) {
+    return launch_gemm_pair(o, n_rows, K, false, 1, nullptr, st, true);
 }
 
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,

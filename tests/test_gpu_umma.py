@@ -80,7 +80,7 @@ def test_umma_gemm_mn_major_operands(split, shape):
     assert err < 2e-3 * K ** 0.5, "max err %g" % err
 
 
-@pytest.mark.parametrize("kind", ["kmajor", "mnmajor", "mnmajor_split"])
+@pytest.mark.parametrize("kind", ["kmajor", "mnmajor", "mnmajor_split", "swap"])
 @pytest.mark.parametrize("shape", [(256, 1024, 1024), (1000, 296, 640), (9600, 512, 256), (300, 256, 64)])
 def test_umma_gemm_cta_pair(shape, kind):
     """cta_group::2 kernel (two SMs, one M=256 UMMA, operand halves shared through the pair's shared memory), forced on
@@ -97,11 +97,14 @@ def test_umma_gemm_cta_pair(shape, kind):
         bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
         kind = {kind!r}
         plain = A.bfloat16().double() @ B.bfloat16().double().t()
-        ref = (torch.relu(plain + bias.double() + add.double()) if kind == "kmajor" else plain).float()
+        ref = (torch.relu(plain + bias.double() + add.double()) if kind in ("kmajor", "swap") else plain).float()
         out = torch.full((M, N), float("nan"), device="cuda")
         dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
         if kind == "kmajor":
             mode = S.MODE_BF16 | (128 << 8) | (256 << 16) | (1 << 28)
+            args = (db.data_ptr(), da.data_ptr(), 1)
+        elif kind == "swap":
+            mode = S.MODE_BF16 | (128 << 8) | (256 << 16)
             args = (db.data_ptr(), da.data_ptr(), 1)
         else:
             mode = S.MODE_BF16 | (1 << 30) | ((1 << 29) if kind == "mnmajor_split" else 0)
@@ -114,5 +117,9 @@ def test_umma_gemm_cta_pair(shape, kind):
         print("ok", err)
     """)
     env = dict(os.environ, SRNN_GEMM_PAIR="2")
+    if kind == "swap":
+        if M > 256:
+            pytest.skip("swap-AB pair form takes at most 256 batch rows")
+        env["SRNN_GEMM_HOOK_SWAP_PAIR"] = "1"
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
