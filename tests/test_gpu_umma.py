@@ -123,3 +123,17 @@ def test_umma_gemm_cta_pair(shape, kind):
         env["SRNN_GEMM_HOOK_SWAP_PAIR"] = "1"
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_bf16_paths_with_cta_pair_forced():
+    """Re-run the bf16 teacher-forcing / backward parity tests with SRNN_GEMM_PAIR=2, so that the CTA-pair kernel (bf16 outputs
+    with ReLU / mask epilogues, MN-major weight gradients) serves every eligible GEMM at the small test sizes too."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SRNN_GEMM_PAIR="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(root, "tests", "test_gpu_parity.py"),
+                        os.path.join(root, "tests", "test_gpu_training.py"), "-k",
+                        "predict_bf16 or bf16_backward or other_architectures or mlp_fwd"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout, r.stdout[-500:]
