@@ -369,7 +369,6 @@ int frame_input(const uint8_t* seq, int seq_ld, int off, const int* step_base, i
 //   X[b,:] = W_in . [lut[prev n samples] | cond | onehot(spk)] + b_in (+ upper[b,:]);  W_in^T is (kin, H) so that
 //   consecutive threads read consecutive features  (model.py:196-218 at F = 1)
 constexpr int TIG_RB = 8;       // utterances per CTA: every weight element loaded from L2 feeds TIG_RB FMAs
-constexpr int TIG_KS = 4;       // K slices per CTA (the kernel is bound by the latency of its dependent L2 load batches)
 __global__ void __launch_bounds__(256)
 k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
                                  const int* __restrict__ step_base, int n, const float* __restrict__ cond,
@@ -377,8 +376,7 @@ k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
                                  int spk_dim, const float* __restrict__ lut, const float* __restrict__ w_in_t,
                                  const float* __restrict__ b_in, const float* __restrict__ upper, int up_ld,
                                  float* __restrict__ X, __nv_bfloat16* __restrict__ X16, int B, int H, int kin, int top) {
-    extern __shared__ float a_s[];                                   // [kin][TIG_RB] assembled frames, then [TIG_KS][TIG_RB][64] partials
-    float* part = a_s + (size_t)kin * TIG_RB;
+    extern __shared__ float a_s[];                                   // [kin][TIG_RB]: the assembled frames of TIG_RB utterances
     const int b0 = blockIdx.x * TIG_RB;
     const int start = start_static + (step_base ? *step_base : 0);
     for (int e = threadIdx.x; e < kin * TIG_RB; e += blockDim.x) {
@@ -395,55 +393,47 @@ k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
         a_s[e] = v;
     }
     __syncthreads();
-    const int fl = threadIdx.x & 63, ks = threadIdx.x >> 6;           // feature inside the 64-wide slab, K slice
-    const int h = blockIdx.y * 64 + fl;
-    const int kq = (kin + TIG_KS - 1) / TIG_KS, k_lo = ks * kq, k_hi = min(kin, k_lo + kq);
+    const int h = blockIdx.y * blockDim.x + threadIdx.x;          // one feature per thread, TIG_RB independent FMA chains
+    if (h >= H) return;
     float acc[TIG_RB];
+    const float bias = b_in[h];
 #pragma unroll
-    for (int r = 0; r < TIG_RB; ++r) acc[r] = 0.f;
-    if (h < H) {
-        const float* w = w_in_t + h;
-        for (int k0 = k_lo; k0 < k_hi; k0 += 16) {                    // 16 weight loads in flight per thread
-            float wv[16];
+    for (int r = 0; r < TIG_RB; ++r) {
+        acc[r] = bias;
+        if (upper && b0 + r < B) acc[r] += upper[(size_t)(b0 + r) * up_ld + h];
+    }
+    const float* w = w_in_t + h;
+    for (int k0 = 0; k0 < kin; k0 += 16) {                        // 16 weight loads in flight per thread (L2 latency bound)
+        float wv[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) wv[u] = k0 + u < k_hi ? __ldg(w + (size_t)(k0 + u) * H) : 0.f;
+        for (int u = 0; u < 16; ++u) wv[u] = k0 + u < kin ? __ldg(w + (size_t)(k0 + u) * H) : 0.f;
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                if (k0 + u < k_hi) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB);
-                    const float4 a1 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB + 4);
-                    acc[0] = fmaf(a0.x, wv[u], acc[0]); acc[1] = fmaf(a0.y, wv[u], acc[1]);
-                    acc[2] = fmaf(a0.z, wv[u], acc[2]); acc[3] = fmaf(a0.w, wv[u], acc[3]);
-                    acc[4] = fmaf(a1.x, wv[u], acc[4]); acc[5] = fmaf(a1.y, wv[u], acc[5]);
-                    acc[6] = fmaf(a1.z, wv[u], acc[6]); acc[7] = fmaf(a1.w, wv[u], acc[7]);
-                }
+        for (int u = 0; u < 16; ++u) {
+            if (k0 + u < kin) {
+                const float4 a0 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB);
+                const float4 a1 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB + 4);
+                acc[0] = fmaf(a0.x, wv[u], acc[0]); acc[1] = fmaf(a0.y, wv[u], acc[1]);
+                acc[2] = fmaf(a0.z, wv[u], acc[2]); acc[3] = fmaf(a0.w, wv[u], acc[3]);
+                acc[4] = fmaf(a1.x, wv[u], acc[4]); acc[5] = fmaf(a1.y, wv[u], acc[5]);
+                acc[6] = fmaf(a1.z, wv[u], acc[6]); acc[7] = fmaf(a1.w, wv[u], acc[7]);
             }
         }
     }
 #pragma unroll
-    for (int r = 0; r < TIG_RB; ++r) part[(ks * TIG_RB + r) * 64 + fl] = acc[r];
-    __syncthreads();
-    if (ks == 0 && h < H) {                                           // fixed summation order: bias (+ upper), slices 0..3
-        const float bias = b_in[h];
-#pragma unroll
-        for (int r = 0; r < TIG_RB; ++r) {
-            if (b0 + r >= B) break;
-            float v = bias;
-            if (upper) v += upper[(size_t)(b0 + r) * up_ld + h];
-#pragma unroll
-            for (int s2 = 0; s2 < TIG_KS; ++s2) v += part[(s2 * TIG_RB + r) * 64 + fl];
-            X[(size_t)(b0 + r) * H + h] = v;
-            if (X16) X16[(size_t)(b0 + r) * H + h] = __float2bfloat16(v);
-        }
+    for (int r = 0; r < TIG_RB; ++r) {
+        if (b0 + r >= B) break;
+        X[(size_t)(b0 + r) * H + h] = acc[r];
+        if (X16) X16[(size_t)(b0 + r) * H + h] = __float2bfloat16(acc[r]);
     }
 }
 int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
                    int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, int spk_dim, const float* lut,
                    const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
                    __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st) {
-    const size_t smem = ((size_t)kin * TIG_RB + (size_t)TIG_KS * TIG_RB * 64) * sizeof(float);
-    SRNN_LAUNCH(k_tier_input_gen, dim3(cdiv(B, TIG_RB), cdiv(H, 64)), 256, smem, st, seq, seq_ld, off, step_base, n, cond,
-                cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper, up_ld, X, X16, B, H, kin, top ? 1 : 0);
+    const int threads = H >= 256 ? 256 : 64;
+    SRNN_LAUNCH(k_tier_input_gen, dim3(cdiv(B, TIG_RB), cdiv(H, threads)), threads, (size_t)kin * TIG_RB * sizeof(float), st, seq,
+                seq_ld, off, step_base, n, cond, cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper,
+                up_ld, X, X16, B, H, kin, top ? 1 : 0);
     return SRNN_OK;
 }
 
