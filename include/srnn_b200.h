@@ -123,6 +123,11 @@ SRNN_API int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t
 SRNN_API int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* params,
                               const srnn_params* grads, void* stream);
 
+/* Data-parallel training (no counterpart in the single-GPU reference): `stream` waits until the last srnn_predict_bwd on
+ * this context has finalised every gradient below the top tier (MLP, embedding, lower tiers), so that their NCCL all-reduce
+ * can overlap the top tier's backward pass. */
+SRNN_API int srnn_bwd_wait_early(srnn_ctx* ctx, void* stream);
+
 /* optim.py:10-13 element-wise clamp of every gradient to [-clamp, clamp] fused with torch.optim.Adam's update
  * (train.py:238: betas (0.9, 0.999), eps 1e-8, no weight decay) over `count` tensors in one launch; step = 1, 2, ... */
 SRNN_API int srnn_clamp_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,

@@ -99,6 +99,7 @@ int srnn_create(const srnn_config* cfg, srnn_ctx** out) {
     c->lookback = n;
     cudaGetDevice(&c->device);
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
+    cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming);
     *out = c;
     return SRNN_OK;
 }
@@ -107,6 +108,7 @@ int srnn_destroy(srnn_ctx* ctx) {
     if (!ctx) return SRNN_OK;
     cudaDeviceSynchronize();
     ctx->weights.release();
+    if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
     if (ctx->ws) cudaFree(ctx->ws);
     delete ctx;
     return SRNN_OK;
@@ -414,6 +416,15 @@ int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const
                                                    : predict_bwd_bf16(ctx, logp, dlogp, params, grads, (cudaStream_t)stream);
     ctx->fwd.valid = false;
     return rc;
+}
+
+// Data-parallel overlap: make `stream` wait until the last srnn_predict_bwd on this context has finished every gradient that
+// does not belong to the top tier (sample-level MLP, embedding, lower tiers); the caller can then all-reduce those on
+// `stream` while the top tier's backward pass is still running on the compute stream.
+int srnn_bwd_wait_early(srnn_ctx* ctx, void* stream) {
+    if (!ctx || !ctx->ev_early) return fail(SRNN_ERR_ARG, "null context");
+    SRNN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_early, 0));
+    return SRNN_OK;
 }
 
 // optim.py:10-13 (element-wise clamp of every gradient to [-clamp, clamp]) fused with torch.optim.Adam's update

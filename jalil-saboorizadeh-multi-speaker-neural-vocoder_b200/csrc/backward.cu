@@ -654,6 +654,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     // ---- folded table: dTbl, then back onto W_in (H,Q,FS) and E (Q,Q) ----
     SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, dB, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
     SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
+    if (NT == 1 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));   // single tier: the MLP gradients are the early set
     // ---- frame tiers, lowest first: each receives dUP (M, fs*H) from below ----
     const float* dUP = dB;                            // tier 0's upsampled output is the MLP conditioning c0
     int xb = 0;
@@ -736,6 +737,9 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
             SRNN_TRY(copy_f32(dX, dA, (size_t)M * H, st));     // dA (R*H floats) is free by now
             dUP = dA;
         }
+        // every gradient below the top tier is complete: a data-parallel caller may start reducing those while the top
+        // tier's backward pass runs (srnn_bwd_wait_early)
+        if (i == NT - 2 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));
         (void)xb;
     }
     return SRNN_OK;
@@ -883,6 +887,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     // ---- folded table ----
     SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, DP1, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
     SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
+    if (NT == 1 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));
     // ---- frame tiers, lowest first ----
     const bf* dUP = DP1;
     for (int i = 0; i < NT; ++i) {
@@ -965,6 +970,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
             SRNN_TRY(f32_to_bf16_pad(dXf, M, H, H, DX16, M, H, st));     // d upper for the tier above, (M_{i+1}, fs_{i+1}*H)
             dUP = DX16;
         }
+        if (i == NT - 2 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));
     }
     return SRNN_OK;
 }

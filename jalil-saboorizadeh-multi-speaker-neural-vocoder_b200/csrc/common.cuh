@@ -129,6 +129,7 @@ struct srnn_ctx {
     __nv_bfloat16* w_hid16_t = nullptr;   // (H, H) transposed
     __nv_bfloat16* w_out16_t = nullptr;   // (H, Q) transposed
     unsigned* gru_ctr = nullptr;  // frame-barrier counter of the persistent GRU kernels
+    cudaEvent_t ev_early = nullptr;   // recorded by srnn_predict_bwd once every gradient below the top tier is final
     int n_sms = 0;
     srnn::Arena weights;      // freed on destroy
     // grow-only scratch for predict / generate

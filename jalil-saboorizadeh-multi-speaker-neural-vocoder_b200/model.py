@@ -321,6 +321,7 @@ class _PredictFn(torch.autograd.Function):
         sink = getattr(model, "_grad_sink", None)
         model._grad_sink = None
         direct = sink is not None and all(id(p) in sink for p in params)
+        model._grad_sink_used = direct
         grads = {id(p): (sink[id(p)] if direct else torch.empty_like(p)) for p in params}
         G = model._c_params(ptr=lambda t: grads[id(t)].data_ptr() if id(t) in grads else None)
         P = model._c_params()

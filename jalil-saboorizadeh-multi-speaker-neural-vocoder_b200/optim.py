@@ -22,6 +22,15 @@ class ClampAdam:
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, process_group=None, model=None):
         self.params = [p for p in params if p.requires_grad]
+        # bucket order: everything below the top tier first (its gradients are final before the top tier's backward pass
+        # runs, srnn_bwd_wait_early), the top tier's parameters last
+        self._n_early = 0
+        if model is not None:
+            late = {id(p) for p in model.frame_level_rnns[-1].parameters()}
+            early = [p for p in self.params if id(p) not in late]
+            self.params = early + [p for p in self.params if id(p) in late]
+            self._n_early = sum(p.numel() for p in early)
+        self._comm_stream = None
         self.lr, self.betas, self.eps, self.clamp = lr, betas, eps, clamp
         self.step_count = 0
         self.exp_avg = [torch.zeros_like(p) for p in self.params]
@@ -61,17 +70,35 @@ class ClampAdam:
         if self.model is not None:      # one backward pass may write its gradients directly into the (zeroed) views
             self.model._grad_sink = {id(p): v for p, v in zip(self.params, self._views)}
 
-    def _allreduce(self):
+    def _allreduce(self, overlap=False):
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) == 1:
             return
-        dist.all_reduce(self._flat, group=self.process_group)         # sum over ranks, in place, one collective
-        self._flat.mul_(1.0 / dist.get_world_size(self.process_group))   # mean BEFORE the clamp (optim.py:10-13 clamps the full-batch gradient)
+        flat, n0 = self._flat, self._n_early
+        if overlap and flat.is_cuda and 0 < n0 < flat.numel():
+            # two buckets over NVLink: the early one is reduced on a side stream as soon as the library signals that those
+            # gradients are final, i.e. while the top tier's backward pass still runs on the compute stream
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=flat.device)
+            comm = self._comm_stream
+            L.check(L.load().srnn_bwd_wait_early(self.model._ctx, C.c_void_p(comm.cuda_stream)))
+            with torch.cuda.stream(comm):
+                work = dist.all_reduce(flat[:n0], group=self.process_group, async_op=True)
+            dist.all_reduce(flat[n0:], group=self.process_group)
+            work.wait()                                                # the compute stream waits for the early bucket
+        else:
+            dist.all_reduce(flat, group=self.process_group)           # sum over ranks, in place, one collective
+        flat.mul_(1.0 / dist.get_world_size(self.process_group))      # mean BEFORE the clamp (optim.py:10-13 clamps the full-batch gradient)
 
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        # overlap is only valid when the backward pass wrote straight into the bucket (zero_grad published the sink and
+        # the pass consumed it): otherwise autograd's accumulation into p.grad happens after the early event
+        direct = self.model is not None and getattr(self.model, "_grad_sink_used", False)
+        if self.model is not None:
+            self.model._grad_sink_used = False
         self._adopt()
-        self._allreduce()
+        self._allreduce(overlap=direct)
         self.step_count += 1
         n = len(self.params)
         arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
