@@ -119,7 +119,7 @@ def run_reference(args, rank, world):
         "x_realtime_16k": v / SAMPLE_RATE, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond 86, weight-norm",
+        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond %d, weight-norm" % C2["cond_dim"],
                    "batch_per_gpu": args.batch, "total_batch": args.batch, "samples_per_utterance": n_cond * 80, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -145,7 +145,7 @@ def run_train(args, rank, world, local):
     B, T = args.train_batch, args.train_T
     g = torch.Generator().manual_seed(100 + rank)
     data = torch.randint(0, 256, (B, 80 + T * (args.steps + args.warmup) + T), generator=g).to(dev)
-    cond = torch.rand(B, (T // 80) * (args.steps + args.warmup + 1) + 1, 86, generator=g).to(dev)
+    cond = torch.rand(B, (T // 80) * (args.steps + args.warmup + 1) + 1, C2["cond_dim"], generator=g).to(dev)
     spk = torch.randint(0, 6, (B, 1), generator=g).to(dev)
     losses = []
 
@@ -217,9 +217,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="generate", choices=["generate", "train"],
                     help="generate = the headline metric (default); train = C3 teacher-forced training step")
+    ap.add_argument("--cond-dim", type=int, default=86,
+                    help="conditioner width: 86 = look-ahead (C2, default); 43 = the core of the bottle-neck variant (C5)")
     ap.add_argument("--train-batch", type=int, default=128)
     ap.add_argument("--train-T", type=int, default=1040)
     args = ap.parse_args()
+    C2["cond_dim"] = args.cond_dim
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -333,7 +336,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if mode == S.MODE_FP32 else "bf16", "data": "synthetic",
-        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond 86, weight-norm",
+        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond %d, weight-norm" % C2["cond_dim"],
                    "batch_per_gpu": B, "total_batch": B * world, "samples_per_utterance": T,
                    "l2": "192 MiB flush write between timed iterations", "us_per_sample_step": 1e6 * secs / args.steps / T},
         "e2e": {"value": e2e, "unit": "samples/s", "x_realtime_16k": e2e / SAMPLE_RATE, "h2d_bytes_per_step": h2d,
