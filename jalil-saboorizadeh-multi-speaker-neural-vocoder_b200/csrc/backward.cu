@@ -311,9 +311,28 @@ k_dtbl_accum(const int* __restrict__ pos, const int* __restrict__ starts, const 
     float acc[FSMAX][4];
 #pragma unroll
     for (int j = 0; j < FSMAX; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    int i_next = k0 < k1 ? pos[k0] : 0;
     for (int k = k0; k < k1; ++k) {
-        const int i = pos[k], b = i / W, pi = i % W;
+        const int i = i_next, b = i / W, pi = i % W;
+        if (k + 1 < k1) i_next = pos[k + 1];                               // next position's index while this one's rows load
         const T1* rowbase = dpre1 + ((size_t)b * T + pi) * H + h;          // row t = pi - j  ->  rowbase - j*H
+        if constexpr (sizeof(T1) == 2 && FSMAX % 5 == 0) {
+            if (FS == FSMAX && pi >= FS - 1 && pi < T) {                    // interior position: every tap's row exists
+#pragma unroll
+                for (int j0 = 0; j0 < FSMAX; j0 += 5) {                     // five unconditional 8-byte loads in flight, then the adds
+                    uint2 raw[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) raw[u] = *reinterpret_cast<const uint2*>(rowbase - (long long)(j0 + u) * H);
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) {
+                        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[u].x));
+                        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[u].y));
+                        acc[j0 + u][0] += a.x; acc[j0 + u][1] += a.y; acc[j0 + u][2] += c.x; acc[j0 + u][3] += c.y;
+                    }
+                }
+                continue;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < FSMAX; ++j) {
             const int t = pi - j;
