@@ -617,7 +617,14 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     in = h;
                     in16 = h16;
                 }
-                if (bf16 && gemm_umma_swap_pair_ok(t.fs * H, B)) {      // big upsampling (tier 2 at C2): CTA-pair kernel
+                if (bf16 && gemm_umma_pair_wide_ok(t.fs * H, B)) {      // big upsampling (tier 2 at C2): one wave of CTA pairs
+                    GemmOperands o{t.w_up16, in16, t.b_up, nullptr, OUT[i], nullptr, t.fs * H, H, H, 0, t.fs * H, 0, nullptr};
+                    SRNN_TRY(gemm_umma_pair_wide(o, B, H, st));
+                    if (time_tiers && getenv("SRNN_UP_TWICE")) {     // timing experiment: the same launch with its weights in L2
+                        mark("upsample (first)");
+                        SRNN_TRY(gemm_umma_pair_wide(o, B, H, st));
+                    }
+                } else if (bf16 && gemm_umma_swap_pair_ok(t.fs * H, B)) {
                     GemmOperands o{t.w_up16, in16, t.b_up, nullptr, OUT[i], nullptr, t.fs * H, H, H, 0, t.fs * H, 0, nullptr};
                     SRNN_TRY(gemm_umma_swap_pair(o, B, H, st));
                 } else if (bf16)
@@ -980,7 +987,9 @@ int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, c
         GemmOperands o{w16, a16, bias, addend, C, nullptr, N, Kp, Kp, N, N, relu, nullptr};
         // ROWS without split-K goes through gemm_umma_rows, i.e. also through the CTA-pair kernel when SRNN_GEMM_PAIR selects it;
         // SRNN_GEMM_HOOK_SWAP_PAIR routes the swap-AB form through the CTA-pair kernel (tests)
-        int rc = (!rows && !split && getenv("SRNN_GEMM_HOOK_SWAP_PAIR")) ? gemm_umma_swap_pair(o, M, Kp, st)
+        int rc = (rows && !split && N % 8 == 0 && getenv("SRNN_GEMM_HOOK_WIDE_PAIR") && gemm_umma_pair_wide_ok(N, M, true))
+                     ? gemm_umma_pair_wide(o, M, Kp, st)
+                 : (!rows && !split && getenv("SRNN_GEMM_HOOK_SWAP_PAIR")) ? gemm_umma_swap_pair(o, M, Kp, st)
                  : (rows && !split && N % 8 == 0) ? gemm_umma_rows(o, M, Kp, 1, nullptr, st)
                                                 : gemm_umma_ex(&o, 1, M, Kp, bm, bn, rows, split ? 3 : 1, scratch, st);
         cudaFreeAsync(a16, st);

@@ -264,6 +264,9 @@ int gemm_umma_tn(const __nv_bfloat16* X, int ld_x, const __nv_bfloat16* Y, int l
                  int ld_out, int ksplit, float* split_scratch, cudaStream_t st);
 bool gemm_umma_swap_pair_ok(int n_feat, int n_rows);
 int gemm_umma_swap_pair(const GemmOperands& o, int n_rows, int K, cudaStream_t st);
+// one-wave CTA-pair form with (256 + 32)-feature tiles: the generation-time upsampling of the lower tier
+bool gemm_umma_pair_wide_ok(int n_feat, int n_rows, bool force = false);
+int gemm_umma_pair_wide(const GemmOperands& o, int n_rows, int K, cudaStream_t st);
 int sum_splits(const float* part, int splits, size_t n, size_t stride, float* out, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);

@@ -84,6 +84,23 @@ int make_tmap_bf16_gates(CUtensorMap* tm, const void* base, uint64_t H, uint64_t
     return SRNN_OK;
 }
 
+// fp32 row-major output (rows x cols, leading dimension ld) -> 2-D map with a {32 floats = 128 B, box_rows} box, 128B swizzle:
+// the TMA-store epilogue of k_gemm_umma_pair_wide
+int make_tmap_f32_out(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (((uintptr_t)base & 15) || (ld * 4) % 16) return fail(SRNN_ERR_ARG, "tensor map: base/stride must be 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SRNN_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 out) failed (%d)", (int)r);
+    return SRNN_OK;
+}
+
 constexpr int GEMM_THREADS = 320;   // 2 control warps + 8 epilogue warps
 
 template <int BM, int BN>
@@ -725,6 +742,195 @@ static int launch_gemm_pair(const GemmOperands& o, int n_rows, int K, bool mn, i
     else if (swap) SRNN_LAUNCH((k_gemm_umma_pair<false, true>), dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
     else SRNN_LAUNCH(k_gemm_umma_pair<false>, dim3(2 * nclusters), GEMM_THREADS, PAIR_SMEM, st, args);
     if (args.gz > 1) return sum_splits(split_scratch, args.gz, (size_t)n_rows * o.ld_out, (size_t)args.split_stride, o.out_f32, st);
+    return SRNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ONE-WAVE CTA-pair GEMM for the generation-time upsampling (<= 256 batch rows x fs.H features, C2: 256 x 20480 x 1024).
+// With 256-feature pair tiles that problem has 80 tiles for 74 CTA pairs, i.e. a second wave for 6 of them; the per-SM TMA
+// ingest (every CTA streams all K of its 128 activation rows + its half of the weight tile) sets the duration, so the second
+// wave nearly doubles it.  Here a pair tile is 256 rows x (256 + WIDE_NX) features -- two UMMAs per K step, N = 256 and
+// N = WIDE_NX, into TMEM columns [0, 256) and [256, 256 + WIDE_NX) -- which makes 72 tiles at C2: one wave, 34 KB per CTA
+// and k-block.  One tile per cluster, single accumulator buffer.
+// With K = 1024 only, the accumulator drain is as long as the K loop if it goes through per-lane global stores (each lane owns
+// a row, 80 KB apart: 32 partial sectors per instruction; measured 2/3 of the kernel), so plain fp32 outputs take the other
+// road: TMEM -> registers (+bias) -> 128B-swizzled staging tiles in the idle TMA ring -> cp.async.bulk.tensor stores of
+// {32 features x 128 rows} boxes, one per 32-feature group as soon as the eight epilogue warps have filled it.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WIDE_NX = 32;
+constexpr int WIDE_NW = 256 + WIDE_NX;
+constexpr int WIDE_BX = WIDE_NX / 2 * 128;                 // this CTA's half of the extra weight rows
+constexpr int WIDE_STAGE = 2 * PAIR_HALF + WIDE_BX;       // 34 KB, a multiple of the 1024-byte swizzle atom
+constexpr int WIDE_NSTAGE = 6;
+constexpr int WIDE_SMEM = WIDE_NSTAGE * WIDE_STAGE + 1024 + 256 + WIDE_NW * 4 /*bias slice*/;
+static_assert(WIDE_NW / 32 * 16384 <= WIDE_NSTAGE * WIDE_STAGE, "the output staging tiles reuse the TMA ring");
+static_assert(WIDE_STAGE % 1024 == 0, "stage must keep the 1024-byte alignment of the swizzled tiles");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_umma_pair_wide(const __grid_constant__ GemmArgs args) {
+    const GemmProb& P = args.p[0];
+    const CUtensorMap* tmBX = &args.p[1].tmB;      // same weight matrix, {64, WIDE_NX / 2}-row boxes
+    const int n_rows = args.n_rows, KB = args.K / 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + WIDE_NSTAGE * WIDE_STAGE);
+    uint64_t* empty = full + WIDE_NSTAGE;
+    uint64_t* tmem_full = empty + WIDE_NSTAGE;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+    float* sbias = (float*)(smem + WIDE_NSTAGE * WIDE_STAGE + 256);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x >> 1;
+    const int m0 = (tile % args.gx) * 256 + rank * 128, n0 = (tile / args.gx) * WIDE_NW;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&P.tmA);
+        prefetch_tmap(&P.tmB);
+        prefetch_tmap(tmBX);
+        prefetch_tmap(&args.p[1].tmA);
+        for (int s = 0; s < WIDE_NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2_rt(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (lane == 0) {                           // TMA producer (both CTAs): own activation rows + own halves of the weights
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1);
+                if (rank == 0) mbar_expect_tx(&full[s], 2 * WIDE_STAGE);
+                uint8_t* dst = smem + s * WIDE_STAGE;
+                tma_load_2d_pair(dst, &P.tmA, &full[s], kb * 64, m0);
+                tma_load_2d_pair(dst + PAIR_HALF, &P.tmB, &full[s], kb * 64, n0 + rank * 128);
+                tma_load_2d_pair(dst + 2 * PAIR_HALF, tmBX, &full[s], kb * 64, n0 + 256 + rank * (WIDE_NX / 2));
+                if (++s == WIDE_NSTAGE) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, 256), idescx = umma_idesc_bf16(256, WIDE_NX);
+            const uint64_t d0 = umma_desc_sw128(smem_u32(smem));
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t da = d0 + (uint64_t)(s * (WIDE_STAGE >> 4));
+                const uint64_t db = da + (uint64_t)(PAIR_HALF >> 4), dbx = da + (uint64_t)((2 * PAIR_HALF) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma2_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma2_bf16(tmem_base + 256, da + 2 * k, dbx + 2 * k, idescx, (kb | k) != 0);
+                }
+                umma2_commit_both(&empty[s]);
+                if (++s == WIDE_NSTAGE) { s = 0; ph ^= 1; }
+            }
+            umma2_commit_both(tmem_full);
+        }
+    } else {                                       // epilogue warps (both CTAs): this CTA's 128 rows x WIDE_NW features
+        const int q = warp & 3, half = (warp - 2) >> 2, et = (int)threadIdx.x - 64;
+        const bool tma_epi = P.out_f32 && !P.out_bf16 && !P.addend && !P.mask;      // uniform
+        if (tma_epi) {                             // bias slice -> shared memory while the K loop runs
+            for (int i = et; i < WIDE_NW; i += GEMM_THREADS - 64) sbias[i] = (P.bias && n0 + i < P.n_feat) ? P.bias[n0 + i] : 0.f;
+            epi_bar_sync(1, GEMM_THREADS - 64);
+        }
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (tma_epi) {
+            const CUtensorMap* tmOut = &args.p[1].tmA;
+            const int r = 32 * q + lane, relu = P.relu;
+            const int left = P.n_feat - n0, G = left >= WIDE_NW ? WIDE_NW / 32 : (left + 31) / 32;
+            for (int g = 0; g < G; ++g) {
+                const int c = 32 * g + 16 * half;
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + c, v);
+                uint8_t* row = smem + g * 16384 + r * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 o;
+                    o.x = v[4 * j] + sbias[c + 4 * j];
+                    o.y = v[4 * j + 1] + sbias[c + 4 * j + 1];
+                    o.z = v[4 * j + 2] + sbias[c + 4 * j + 2];
+                    o.w = v[4 * j + 3] + sbias[c + 4 * j + 3];
+                    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(row + (((4 * half + j) ^ (r & 7)) << 4)) = o;      // 128B swizzle: chunk ^= row % 8
+                }
+                fence_proxy_async_smem();
+                epi_bar_sync(1, GEMM_THREADS - 64);
+                if (et == 0) {
+                    tma_store_2d(tmOut, smem + g * 16384, n0 + 32 * g, m0);
+                    bulk_commit();
+                }
+            }
+            if (et == 0) bulk_wait_read0();        // the staging tiles must outlive the bulk reads
+        } else {
+            rows_epilogue<WIDE_NW>(P, P.out_f32, tmem_base, m0, n0, n_rows, q, half, lane);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc2_rt(tmem_base, 512);
+}
+
+static void ensure_gemm_sms() {
+    if (g_gemm_sms < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&g_gemm_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_gemm_sms = 0;
+    }
+}
+// worthwhile exactly when 256-feature pair tiles need a second wave and (256 + WIDE_NX)-feature tiles do not
+bool gemm_umma_pair_wide_ok(int n_feat, int n_rows, bool force) {
+    static const int pair_mode = getenv("SRNN_GEMM_PAIR") ? atoi(getenv("SRNN_GEMM_PAIR")) : 1;
+    static const bool off = getenv("SRNN_UP_WIDE") && atoi(getenv("SRNN_UP_WIDE")) == 0;
+    ensure_gemm_sms();
+    const int nclusters = g_gemm_sms / 2;
+    if (!pair_mode || n_rows < 1 || nclusters < 1) return false;
+    const long long tiles = (long long)cdiv(n_rows, 256) * cdiv(n_feat, WIDE_NW);
+    if (force) return tiles <= nclusters;
+    return !off && n_rows > 128 && n_rows <= 256 && cdiv(n_feat, 256) > nclusters && tiles <= nclusters;
+}
+int gemm_umma_pair_wide(const GemmOperands& o, int n_rows, int K, cudaStream_t st) {
+    ensure_gemm_sms();
+    if (K % 64 || o.ld_out % 8 || (o.addend && o.ld_add % 4)) return fail(SRNN_ERR_ARG, "gemm pair (wide): K %% 64, ld_out %% 8, ld_add %% 4");
+    GemmArgs args;
+    memset(&args, 0, sizeof(args));
+    args.n_rows = n_rows;
+    args.K = K;
+    args.ksplit = 1;
+    args.gx = cdiv(n_rows, 256);
+    args.gy = cdiv(o.n_feat, WIDE_NW);
+    args.gz = 1;
+    if ((long long)args.gx * args.gy > g_gemm_sms / 2) return fail(SRNN_ERR_UNSUPPORTED, "gemm pair (wide): more tiles than CTA pairs");
+    SRNN_TRY(make_tmap_bf16(&args.p[0].tmA, o.act, n_rows, K, o.ld_act, 128));
+    SRNN_TRY(make_tmap_bf16(&args.p[0].tmB, o.W, o.n_feat, K, o.ld_w, 128));
+    SRNN_TRY(make_tmap_bf16(&args.p[1].tmB, o.W, o.n_feat, K, o.ld_w, WIDE_NX / 2));
+    if (o.out_f32 && !o.out_bf16 && !o.addend && !o.mask)
+        SRNN_TRY(make_tmap_f32_out(&args.p[1].tmA, o.out_f32, n_rows, o.n_feat, o.ld_out, 128));
+    args.p[0].bias = o.bias;
+    args.p[0].addend = o.addend;
+    args.p[0].out_f32 = o.out_f32;
+    args.p[0].out_bf16 = o.out_bf16;
+    args.p[0].mask = o.mask;
+    args.p[0].n_feat = o.n_feat;
+    args.p[0].ld_add = o.ld_add;
+    args.p[0].ld_out = o.ld_out;
+    args.p[0].relu = o.relu;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM));
+        attr_set = true;
+    }
+    SRNN_LAUNCH(k_gemm_umma_pair_wide, dim3(2 * args.gx * args.gy), GEMM_THREADS, WIDE_SMEM, st, args);
     return SRNN_OK;
 }
 

@@ -80,8 +80,9 @@ def test_umma_gemm_mn_major_operands(split, shape):
     assert err < 2e-3 * K ** 0.5, "max err %g" % err
 
 
-@pytest.mark.parametrize("kind", ["kmajor", "mnmajor", "mnmajor_split", "swap"])
-@pytest.mark.parametrize("shape", [(256, 1024, 1024), (1000, 296, 640), (9600, 512, 256), (300, 256, 64)])
+@pytest.mark.parametrize("kind", ["kmajor", "mnmajor", "mnmajor_split", "swap", "wide", "wide_tma"])
+@pytest.mark.parametrize("shape", [(256, 1024, 1024), (1000, 296, 640), (9600, 512, 256), (300, 256, 64), (256, 20480, 1024),
+                                   (200, 20480 - 40, 128)])
 def test_umma_gemm_cta_pair(shape, kind):
     """cta_group::2 kernel (two SMs, one M=256 UMMA, operand halves shared through the pair's shared memory), forced on
     for every shape through SRNN_GEMM_PAIR=2 in a fresh process so that the library's cached mode is not affected."""
@@ -97,15 +98,20 @@ def test_umma_gemm_cta_pair(shape, kind):
         bias, add = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
         kind = {kind!r}
         plain = A.bfloat16().double() @ B.bfloat16().double().t()
-        ref = (torch.relu(plain + bias.double() + add.double()) if kind in ("kmajor", "swap") else plain).float()
+        ref = (torch.relu(plain + bias.double() + add.double()) if kind in ("kmajor", "swap", "wide") else plain).float()
+        if kind == "wide_tma":      # bias + ReLU only: the TMA-store epilogue
+            ref = torch.relu(plain + bias.double()).float()
         out = torch.full((M, N), float("nan"), device="cuda")
         dA, dB, db, da = A.cuda(), B.cuda(), bias.cuda(), add.cuda()
-        if kind == "kmajor":
+        if kind in ("kmajor", "wide"):
             mode = S.MODE_BF16 | (128 << 8) | (256 << 16) | (1 << 28)
             args = (db.data_ptr(), da.data_ptr(), 1)
         elif kind == "swap":
             mode = S.MODE_BF16 | (128 << 8) | (256 << 16)
             args = (db.data_ptr(), da.data_ptr(), 1)
+        elif kind == "wide_tma":
+            mode = S.MODE_BF16 | (128 << 8) | (256 << 16) | (1 << 28)
+            args = (db.data_ptr(), None, 1)
         else:
             mode = S.MODE_BF16 | (1 << 30) | ((1 << 29) if kind == "mnmajor_split" else 0)
             args = (None, None, 0)
@@ -117,6 +123,12 @@ def test_umma_gemm_cta_pair(shape, kind):
         print("ok", err)
     """)
     env = dict(os.environ, SRNN_GEMM_PAIR="2")
+    if N > 4096 and not kind.startswith("wide"):
+        pytest.skip("upsampling-sized problems are the wide kernel's cases")
+    if kind.startswith("wide"):         # one-wave (256 + 32)-feature pair tiles: at most 74 tiles
+        if ((M + 255) // 256) * ((N + 287) // 288) > 74:
+            pytest.skip("more tiles than CTA pairs")
+        env["SRNN_GEMM_HOOK_WIDE_PAIR"] = "1"
     if kind == "swap":
         if M > 256:
             pytest.skip("swap-AB pair form takes at most 256 batch rows")
