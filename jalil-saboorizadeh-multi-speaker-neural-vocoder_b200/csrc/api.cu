@@ -536,6 +536,35 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         if (bn_tier < 256) return bn_tier;
         return cdiv(n_feat, 128) * cdiv(B, 128) * nprob <= ctx->n_sms ? 128 : 256;
     };
+    // Recurrent projections gh_l = W_hh_l h_l + b_hh_l of a tier's NEXT step depend only on the state its current step leaves
+    // behind.  With the persistent sample kernel on RG x NS CTAs (128 at C2) the remaining SMs (20) are idle for the ~180 us
+    // of a launch, so these GEMMs (96 tiles at C2) run there, capped to that many CTAs, beside the sample kernel instead of in
+    // front of the next tier step ("shadow" schedule; SRNN_NO_SHADOW_GH=1 restores the fork beside the input expansion).
+    const int spare_sms = persist ? ctx->n_sms - ((B + 31) / 32) * (H / 64) : 0;
+    const bool shadow_gh = bf16 && fused_cell && persist && spare_sms >= 8 && !skip_tiers && !getenv("SRNN_NO_SHADOW_GH");
+    cudaEvent_t ev_gh[SRNN_MAX_TIERS] = {};
+    bool gh_todo[SRNN_MAX_TIERS] = {}, gh_pending[SRNN_MAX_TIERS] = {};
+    auto launch_gh = [&](int i, cudaStream_t s, int cap) -> int {
+        const TierPacked& t = ctx->tiers[i];
+        gemm_umma_set_cta_cap(cap);
+        int rc = SRNN_OK;
+        for (int l = 0; l < NL && rc == SRNN_OK; l += 2) {
+            const int np = NL - l >= 2 ? 2 : 1;
+            GemmOperands ops[2];
+            for (int q = 0; q < np; ++q)
+                ops[q] = GemmOperands{t.w_hh16[l + q], hid16[i] + (size_t)(l + q) * B * H, t.b_hh[l + q], nullptr,
+                                      GHL[i][l + q], nullptr, 3 * H, H, H, 0, 3 * H, 0, nullptr};
+            rc = gemm_umma_multi(ops, np, B, H, 128, cap ? (B <= 128 ? bn_tier : 128) : bn_for(3 * H, np), s);
+        }
+        gemm_umma_set_cta_cap(0);
+        return rc;
+    };
+    if (shadow_gh) {
+        for (int i = 0; i < NT; ++i) {
+            SRNN_CUDA(cudaEventCreateWithFlags(&ev_gh[i], cudaEventDisableTiming));
+            SRNN_TRY(launch_gh(i, st, 0));                                           // first step: from h0, outside the graph
+        }
+    }
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
     long long* trace = nullptr;
@@ -568,7 +597,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     up_ld = u.fs * H;
                 }
                 mark(t.top ? "(start top)" : "(start)");
-                if (bf16 && fused_cell) {      // fork: gh of every layer runs beside the input expansion (independent of it)
+                if (bf16 && fused_cell && !shadow_gh) {      // fork: gh of every layer runs beside the input expansion (independent of it)
                     SRNN_CUDA(cudaEventRecord(ev_fork, st));
                     SRNN_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
                     for (int l = 0; l < NL; l += 2) {
@@ -591,7 +620,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     // Fused-cell schedule: the recurrent projections gh_l = W_hh_l h_l + b_hh_l of ALL layers depend only on
                     // the previous step's state, so they go first (two layers per launch); then one launch per layer does
                     // gi_l = W_ih_l x + b_ih_l on tcgen05 and the gate math (k_gru_cell_gen): 1 + NL launches instead of 2 NL.
-                    SRNN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));      // join: the forked gh launch(es) below
+                    if (!shadow_gh) SRNN_CUDA(cudaStreamWaitEvent(st, ev_join, 0));      // join: the forked gh launch(es) above
+                    else if (gh_pending[i]) {                            // gh of this step ran beside the previous sample launch
+                        SRNN_CUDA(cudaStreamWaitEvent(st, ev_gh[i], 0));
+                        gh_pending[i] = false;
+                    }
                     for (int l = 0; l < NL; ++l) {
                         SRNN_TRY(gru_cell_gen(B, H, in16, t.w_ih16[l], t.b_ih[l], GHL[i][l], hid[i] + (size_t)l * B * H,
                                               hid16[i] + (size_t)l * B * H, st));
@@ -633,10 +666,26 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 else
                     SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
                 mark(t.top ? "upsample top" : "upsample");
+                if (shadow_gh) gh_todo[i] = true;
             }
             const float* up0 = OUT[0] + (size_t)(pos % FS0) * H;                     // model.py:504-513
             if (persist) {
                 if (pos % FS0) continue;             // one persistent launch covers the FS0 samples of a tier-0 frame
+                if (shadow_gh) {                     // next step's recurrent projections: on the spare SMs, beside this launch
+                    bool any = false;
+                    for (int i = 0; i < NT; ++i) any = any || gh_todo[i];
+                    if (any) {
+                        SRNN_CUDA(cudaEventRecord(ev_fork, st));
+                        SRNN_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+                        for (int i = NT - 1; i >= 0; --i) {
+                            if (!gh_todo[i]) continue;
+                            SRNN_TRY(launch_gh(i, st2, spare_sms));
+                            SRNN_CUDA(cudaEventRecord(ev_gh[i], st2));
+                            gh_todo[i] = false;
+                            gh_pending[i] = true;
+                        }
+                    }
+                }
                 srnn::MlpPersistParams mp;
                 mp.B = B; mp.H = H; mp.FS = FS0; mp.nsteps = FS0; mp.pos0 = pos; mp.lookback = lookback;
                 mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
@@ -669,6 +718,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             }
             SRNN_TRY(softmax_sample(LG, uniforms, u_ld, seq, Lseq, pos, lookback, step_base, logp_out,
                                     (long long)T * Q, B, st));                       // model.py:514-517
+        }
+        for (int i = 0; i < NT; ++i) {            // join the side stream: the next period starts with every gh in place
+            if (!gh_pending[i]) continue;
+            SRNN_CUDA(cudaStreamWaitEvent(st, ev_gh[i], 0));
+            gh_pending[i] = false;
         }
         SRNN_TRY(add_int(step_base, lookback, st));
         return SRNN_OK;
@@ -767,6 +821,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     SRNN_CUDA(cudaEventDestroy(ev_in));
     SRNN_CUDA(cudaEventDestroy(ev_out));
     SRNN_CUDA(cudaStreamDestroy(st));
+    for (int i = 0; i < SRNN_MAX_TIERS; ++i)
+        if (ev_gh[i]) SRNN_CUDA(cudaEventDestroy(ev_gh[i]));
     if (st2) {
         SRNN_CUDA(cudaStreamDestroy(st2));
         SRNN_CUDA(cudaEventDestroy(ev_fork));

@@ -244,6 +244,7 @@ struct GemmOperands {
 int transpose_to_bf16(const float* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int transpose_to_bf16(const __nv_bfloat16* src, int rows, int cols, long long ld_src, __nv_bfloat16* dst, int ld_dst, cudaStream_t st);
 int gemm_umma_multi(const GemmOperands* ops, int nprob, int n_rows, int K, int bm, int bn, cudaStream_t st);
+void gemm_umma_set_cta_cap(int cap);   // > 0: following single-CTA-kernel launches of this thread use at most cap CTAs; 0 = off
 // persistent GRU recurrence over all frames of one layer (gru_persist.cu)
 bool gru_persist_supported(int B, int H, int n_sms);
 // generation-time fused cell: gi GEMM + gate math in one launch (gru_persist.cu)

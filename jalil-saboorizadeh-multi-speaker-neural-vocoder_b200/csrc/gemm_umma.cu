@@ -501,6 +501,10 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
 }
 
 static int g_gemm_sms = -1;
+// > 0: the next single-CTA launches use at most this many CTAs (persistent tile loop, deep ring) -- a GEMM that is to run on the
+// SMs another, co-resident kernel leaves free (the recurrent projections beside the persistent sample kernel)
+static thread_local int g_gemm_cta_cap = 0;
+void gemm_umma_set_cta_cap(int cap) { g_gemm_cta_cap = cap; }
 static constexpr int TCOLS_OF(int bn) { return bn < 32 ? 32 : bn; }
 template <int BM, int BN, bool ROWS, bool MNMAJ = false>
 static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaStream_t st) {
@@ -520,7 +524,8 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     const int shallow = (110 * 1024 - 1280) / S::STAGE;
     static const bool shallow_all = getenv("SRNN_GEMM_SHALLOW_ALL") != nullptr;
-    if (g_gemm_sms > 0 && ctas > g_gemm_sms && (ctas <= 2 * g_gemm_sms || shallow_all) && shallow >= 2 && TCOLS_OF(BN) <= 256 &&
+    const int cap = g_gemm_cta_cap;
+    if (!cap && g_gemm_sms > 0 && ctas > g_gemm_sms && (ctas <= 2 * g_gemm_sms || shallow_all) && shallow >= 2 && TCOLS_OF(BN) <= 256 &&
         !getenv("SRNN_GEMM_DEEP_RING"))
         a.nstage = shallow < S::NSTAGE ? shallow : S::NSTAGE;
     const size_t smem = (size_t)a.nstage * S::STAGE + 1024 + 256;
@@ -533,6 +538,7 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
     a.nbuf = (deep && 2 * TCOLS_OF(BN) <= 512 && ctas > 1 && !getenv("SRNN_GEMM_SINGLE_BUF")) ? 2 : 1;
     long long launch_ctas = ctas;
     if (deep && g_gemm_sms > 0 && ctas > g_gemm_sms) launch_ctas = g_gemm_sms;
+    if (cap > 0 && launch_ctas > cap) launch_ctas = cap;
     SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS, MNMAJ>), dim3((unsigned)launch_ctas), GEMM_THREADS, smem, st, a);
     return SRNN_OK;
 }
