@@ -525,6 +525,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // B = 256) as long as the grid still fits one wave of SMs; the tier-2 upsampling (160 feature tiles) keeps 256-row tiles.
     const bool fused_cell = bf16 && gru_cell_gen_supported(H);
     const bool skip_tiers = getenv("SRNN_SKIP_TIERS") != nullptr;   // timing experiment only (results are wrong)
+    const bool time_tiers_early = getenv("SRNN_TIME_TIERS") != nullptr;
     cudaStream_t st2 = nullptr;                 // side branch of the tier steps (captured into the same graph)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     if (fused_cell) {
@@ -542,6 +543,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // front of the next tier step ("shadow" schedule; SRNN_NO_SHADOW_GH=1 restores the fork beside the input expansion).
     const int spare_sms = persist ? ctx->n_sms - ((B + 31) / 32) * (H / 64) : 0;
     const bool shadow_gh = bf16 && fused_cell && persist && spare_sms >= 8 && !skip_tiers && !getenv("SRNN_NO_SHADOW_GH");
+    // consecutive kernels of a tier step (input expansion -> cells -> upsampling) are launched as programmatic dependents
+    const bool pdl = bf16 && fused_cell && !time_tiers_early && !getenv("SRNN_NO_PDL");
+    bool prev_tier_kernel = false;                 // the previous launch on st is one of those kernels
     cudaEvent_t ev_gh[SRNN_MAX_TIERS] = {};
     bool gh_todo[SRNN_MAX_TIERS] = {}, gh_pending[SRNN_MAX_TIERS] = {};
     auto launch_gh = [&](int i, cudaStream_t s, int cap) -> int {
@@ -584,6 +588,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     const long long before = g_launches.load();
     if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
+        prev_tier_kernel = false;
         for (int pos = 0; pos < lookback; ++pos) {                                   // i = *step_base + pos
             for (int i = NT - 1; i >= 0; --i) {
                 const TierPacked& t = ctx->tiers[i];
@@ -610,9 +615,13 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     }
                     SRNN_CUDA(cudaEventRecord(ev_join, st2));
                 }
-                SRNN_TRY(tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
-                                        c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
-                                        H, t.kin, t.top, st));
+                g_pdl = pdl && prev_tier_kernel;
+                int rc_in = tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
+                                           c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
+                                           H, t.kin, t.top, st);
+                g_pdl = 0;
+                SRNN_TRY(rc_in);
+                prev_tier_kernel = true;
                 mark(t.top ? "input top" : "input");
                 const float* in = X[i];
                 const bf* in16 = X16[i];
@@ -626,8 +635,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                         gh_pending[i] = false;
                     }
                     for (int l = 0; l < NL; ++l) {
-                        SRNN_TRY(gru_cell_gen(B, H, in16, t.w_ih16[l], t.b_ih[l], GHL[i][l], hid[i] + (size_t)l * B * H,
-                                              hid16[i] + (size_t)l * B * H, st));
+                        g_pdl = pdl;
+                        const int rc_c = gru_cell_gen(B, H, in16, t.w_ih16[l], t.b_ih[l], GHL[i][l], hid[i] + (size_t)l * B * H,
+                                                      hid16[i] + (size_t)l * B * H, st);
+                        g_pdl = 0;
+                        SRNN_TRY(rc_c);
                         mark("cell");
                         in16 = hid16[i] + (size_t)l * B * H;
                     }
@@ -652,7 +664,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 }
                 if (bf16 && gemm_umma_pair_wide_ok(t.fs * H, B)) {      // big upsampling (tier 2 at C2): one wave of CTA pairs
                     GemmOperands o{t.w_up16, in16, t.b_up, nullptr, OUT[i], nullptr, t.fs * H, H, H, 0, t.fs * H, 0, nullptr};
-                    SRNN_TRY(gemm_umma_pair_wide(o, B, H, st));
+                    g_pdl = pdl;
+                    const int rc_u = gemm_umma_pair_wide(o, B, H, st);
+                    g_pdl = 0;
+                    SRNN_TRY(rc_u);
                     if (time_tiers && getenv("SRNN_UP_TWICE")) {     // timing experiment: the same launch with its weights in L2
                         mark("upsample (first)");
                         SRNN_TRY(gemm_umma_pair_wide(o, B, H, st));
@@ -660,9 +675,13 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 } else if (bf16 && gemm_umma_swap_pair_ok(t.fs * H, B)) {
                     GemmOperands o{t.w_up16, in16, t.b_up, nullptr, OUT[i], nullptr, t.fs * H, H, H, 0, t.fs * H, 0, nullptr};
                     SRNN_TRY(gemm_umma_swap_pair(o, B, H, st));
-                } else if (bf16)
-                    SRNN_TRY(gemm_umma(t.w_up16, t.fs * H, in16, B, H, H, H, t.b_up, nullptr, 0, OUT[i], nullptr,
-                                       t.fs * H, 0, 128, bn_for(t.fs * H, 1), st));
+                } else if (bf16) {
+                    g_pdl = pdl;
+                    const int rc_u = gemm_umma(t.w_up16, t.fs * H, in16, B, H, H, H, t.b_up, nullptr, 0, OUT[i], nullptr,
+                                               t.fs * H, 0, 128, bn_for(t.fs * H, 1), st);
+                    g_pdl = 0;
+                    SRNN_TRY(rc_u);
+                }
                 else
                     SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
                 mark(t.top ? "upsample top" : "upsample");
@@ -671,6 +690,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             const float* up0 = OUT[0] + (size_t)(pos % FS0) * H;                     // model.py:504-513
             if (persist) {
                 if (pos % FS0) continue;             // one persistent launch covers the FS0 samples of a tier-0 frame
+                prev_tier_kernel = false;
                 if (shadow_gh) {                     // next step's recurrent projections: on the spare SMs, beside this launch
                     bool any = false;
                     for (int i = 0; i < NT; ++i) any = any || gh_todo[i];

@@ -41,6 +41,38 @@ int fail(int code, const char* fmt, ...);
                                 #kernel, cudaGetErrorString(_e));                                \
     } while (0)
 
+// Programmatic dependent launch: while g_pdl is set (generation schedule, consecutive tier kernels), the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the grid may start -- barrier init, TMEM allocation, tensor-map
+// prefetch -- while its predecessor drains; every kernel launched through this macro executes griddepcontrol.wait before it
+// touches global memory and griddepcontrol.launch_dependents at its start (both are no-ops in a plain launch).
+extern thread_local int g_pdl;
+#define SRNN_LAUNCH_PDL(kernel, grid_, block_, smem_, stream_, ...)                                  \
+    do {                                                                                         \
+        if (::srnn::g_pdl) {                                                                     \
+            cudaLaunchConfig_t _cfg = {};                                                        \
+            _cfg.gridDim = (grid_);                                                              \
+            _cfg.blockDim = (block_);                                                            \
+            _cfg.dynamicSmemBytes = (smem_);                                                     \
+            _cfg.stream = (stream_);                                                             \
+            cudaLaunchAttribute _at[1];                                                          \
+            _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                      \
+            _at[0].val.programmaticStreamSerializationAllowed = 1;                               \
+            _cfg.attrs = _at;                                                                    \
+            _cfg.numAttrs = 1;                                                                   \
+            cudaError_t _e = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                     \
+            ::srnn::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+            if (_e != cudaSuccess)                                                               \
+                return ::srnn::fail(SRNN_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__,  \
+                                    #kernel, cudaGetErrorString(_e));                            \
+        } else {                                                                                 \
+            SRNN_LAUNCH(kernel, grid_, block_, smem_, stream_, __VA_ARGS__);                        \
+        }                                                                                        \
+    } while (0)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+#endif
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- packed weights of one FrameLevelRNN tier (model.py:67-178) --------------------------------

@@ -393,11 +393,13 @@ k_gemm_umma(const __grid_constant__ GemmArgs args) {
         }
         fence_barrier_init();
     }
+    pdl_trigger();
     if (warp == 1) tmem_alloc_rt(tmem_slot, nbuf == 2 ? 2 * TCOLS : TCOLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps UMMA operands in uniform regs)
+    pdl_wait();                                    // programmatic dependent launch: operands come from the preceding kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -504,6 +506,7 @@ static int g_gemm_sms = -1;
 // > 0: the next single-CTA launches use at most this many CTAs (persistent tile loop, deep ring) -- a GEMM that is to run on the
 // SMs another, co-resident kernel leaves free (the recurrent projections beside the persistent sample kernel)
 static thread_local int g_gemm_cta_cap = 0;
+thread_local int g_pdl = 0;
 void gemm_umma_set_cta_cap(int cap) { g_gemm_cta_cap = cap; }
 static constexpr int TCOLS_OF(int bn) { return bn < 32 ? 32 : bn; }
 template <int BM, int BN, bool ROWS, bool MNMAJ = false>
@@ -539,7 +542,7 @@ static int launch_gemm_umma(const GemmArgs& args, int nprob, int max_feat, cudaS
     long long launch_ctas = ctas;
     if (deep && g_gemm_sms > 0 && ctas > g_gemm_sms) launch_ctas = g_gemm_sms;
     if (cap > 0 && launch_ctas > cap) launch_ctas = cap;
-    SRNN_LAUNCH((k_gemm_umma<BM, BN, ROWS, MNMAJ>), dim3((unsigned)launch_ctas), GEMM_THREADS, smem, st, a);
+    SRNN_LAUNCH_PDL((k_gemm_umma<BM, BN, ROWS, MNMAJ>), dim3((unsigned)launch_ctas), dim3(GEMM_THREADS), smem, st, a);
     return SRNN_OK;
 }
 
@@ -801,11 +804,13 @@ k_gemm_umma_pair_wide(const __grid_constant__ GemmArgs args) {
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
+    pdl_trigger();
     if (warp == 1) tmem_alloc2_rt(tmem_slot, 512);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {                           // TMA producer (both CTAs): own activation rows + own halves of the weights
@@ -936,7 +941,7 @@ int gemm_umma_pair_wide(const GemmOperands& o, int n_rows, int K, cudaStream_t s
         SRNN_CUDA(cudaFuncSetAttribute(k_gemm_umma_pair_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM));
         attr_set = true;
     }
-    SRNN_LAUNCH(k_gemm_umma_pair_wide, dim3(2 * args.gx * args.gy), GEMM_THREADS, WIDE_SMEM, st, args);
+    SRNN_LAUNCH_PDL(k_gemm_umma_pair_wide, dim3(2 * args.gx * args.gy), dim3(GEMM_THREADS), (size_t)WIDE_SMEM, st, args);
     return SRNN_OK;
 }
 

@@ -594,11 +594,13 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         mbar_init(bar_d, GP_ISSUERS);
         fence_barrier_init();
     }
+    pdl_trigger();
     if (threadIdx.x < GC_NB) sBias[threadIdx.x] = p.b_ih[(threadIdx.x / GC_US) * H + u0 + (threadIdx.x % GC_US)];
     if (warp == 5) tmem_alloc<GP_TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                    // x, gh and the state come from the preceding kernels
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 4) {
@@ -702,7 +704,7 @@ int gru_cell_gen(int B, int H, const bf* x16, const bf* w_ih16, const float* b_i
         attr_set = true;
     }
     GruCellParams p{B, H, b_ih, GH, h, h16};
-    SRNN_LAUNCH(k_gru_cell_gen, dim3(H / GC_US, (B + GP_ROWS - 1) / GP_ROWS), GP_THREADS, smem, st, tmX, tmW, p);
+    SRNN_LAUNCH_PDL(k_gru_cell_gen, dim3(H / GC_US, (B + GP_ROWS - 1) / GP_ROWS), dim3(GP_THREADS), smem, st, tmX, tmW, p);
     return SRNN_OK;
 }
 

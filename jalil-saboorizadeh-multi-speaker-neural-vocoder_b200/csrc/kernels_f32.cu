@@ -377,6 +377,8 @@ k_tier_input_gen(const uint8_t* __restrict__ seq, int seq_ld, int start_static,
                                  const float* __restrict__ b_in, const float* __restrict__ upper, int up_ld,
                                  float* __restrict__ X, __nv_bfloat16* __restrict__ X16, int B, int H, int kin, int top) {
     extern __shared__ float a_s[];                                   // [kin][TIG_RB]: the assembled frames of TIG_RB utterances
+    pdl_trigger();
+    pdl_wait();
     const int b0 = blockIdx.x * TIG_RB;
     const int start = start_static + (step_base ? *step_base : 0);
     for (int e = threadIdx.x; e < kin * TIG_RB; e += blockDim.x) {
@@ -431,7 +433,7 @@ int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base
                    const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
                    __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st) {
     const int threads = H >= 256 ? 256 : 64;
-    SRNN_LAUNCH(k_tier_input_gen, dim3(cdiv(B, TIG_RB), cdiv(H, threads)), threads, (size_t)kin * TIG_RB * sizeof(float), st, seq,
+    SRNN_LAUNCH_PDL(k_tier_input_gen, dim3(cdiv(B, TIG_RB), cdiv(H, threads)), threads, (size_t)kin * TIG_RB * sizeof(float), st, seq,
                 seq_ld, off, step_base, n, cond, cond_rows, cond_frames, spk, cond_dim, spk_dim, lut, w_in_t, b_in, upper,
                 up_ld, X, X16, B, H, kin, top ? 1 : 0);
     return SRNN_OK;
