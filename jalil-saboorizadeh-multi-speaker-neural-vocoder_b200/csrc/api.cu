@@ -541,7 +541,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // behind.  With the persistent sample kernel on RG x NS CTAs (128 at C2) the remaining SMs (20) are idle for the ~180 us
     // of a launch, so these GEMMs (96 tiles at C2) run there, capped to that many CTAs, beside the sample kernel instead of in
     // front of the next tier step ("shadow" schedule; SRNN_NO_SHADOW_GH=1 restores the fork beside the input expansion).
-    const int spare_sms = persist ? ctx->n_sms - ((B + 31) / 32) * (H / 64) : 0;
+    int spare_sms = persist ? ctx->n_sms - ((B + 31) / 32) * (H / 64) : 0;
+    if (getenv("SRNN_SHADOW_CTAS") && atoi(getenv("SRNN_SHADOW_CTAS")) > 0 && atoi(getenv("SRNN_SHADOW_CTAS")) < spare_sms)
+        spare_sms = atoi(getenv("SRNN_SHADOW_CTAS"));          // experiment: fewer CTAs for the shadow GEMMs
     const bool shadow_gh = bf16 && fused_cell && persist && spare_sms >= 8 && !skip_tiers && !getenv("SRNN_NO_SHADOW_GH");
     // consecutive kernels of a tier step (input expansion -> cells -> upsampling) are launched as programmatic dependents
     const bool pdl = bf16 && fused_cell && !time_tiers_early && !getenv("SRNN_NO_PDL");
@@ -571,6 +573,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     }
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
+    if (persist) SRNN_CUDA(cudaMemsetAsync(gctr, 0, sizeof(unsigned) * 2 * RG, st));     // group barrier counters: once per call
     long long* trace = nullptr;
     if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 64));
     const bool time_kernels = persist && getenv("SRNN_TIME_KERNELS");
@@ -828,6 +831,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 fprintf(stderr, " [%lld,%lld]", trace[k * 64 + 16 + 2 * kb] - trace[k * 64 + 3], trace[k * 64 + 17 + 2 * kb] - trace[k * 64 + 3]);
             fprintf(stderr, "\n");
         }
+        fprintf(stderr, "[srnn trace] last launch: entry -> step 0 = %lld, step 0 = %lld, step 1 = %lld, step 2 = %lld cycles\n",
+                trace[0] - trace[63], trace[64] - trace[0], trace[128] - trace[64], trace[192] - trace[128]);
         fprintf(stderr, "[srnn trace] k_mlp_persist CTA0 cycles/step:");
         for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%.0f", names[j], acc[j] / (FS0 - 2));
         fprintf(stderr, " | step=%.0f\n", tot / (FS0 - 3));

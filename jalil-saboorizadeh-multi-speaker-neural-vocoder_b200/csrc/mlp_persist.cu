@@ -116,6 +116,11 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
 
     const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
     const int row0 = rg * 32 + sl * RPC;                  // first owned row (global utterance index)
+    // The group counters are never reset between launches (a memset node in front of every launch sat on the serial path):
+    // launch m of a generation call -- first sample i0 = lookback + m * nsteps -- starts from the 2 * nsteps * NS arrivals per
+    // launch that its predecessors left behind.  The caller zeroes the counters once per generation call.
+    const unsigned cbase = (unsigned)((i0 - p.lookback) / p.nsteps) * 2u * (unsigned)p.nsteps * (unsigned)NS;
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[63] = clock64();
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmWh);
@@ -170,7 +175,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 // its hidden GEMM is done with the X1 stages)
                 if (k) mbar_wait(bar_d2, (k - 1) & 1);
                 {   // group barrier A, waiting side: arrivals so far = (2k+1) * NS once every slice has published X1
-                    const unsigned target = (unsigned)(2 * k + 1) * (unsigned)NS;
+                    const unsigned target = cbase + (unsigned)(2 * k + 1) * (unsigned)NS;
                     const unsigned* ctr = p.ctr + rg;
                     while (ld_acquire_gpu(ctr) < target) {
                     }
@@ -354,7 +359,7 @@ k_mlp_persist(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             tc_fence_before();
             // ---- group barrier B: all slices' partial logits are in global memory ----
             MP_TRACE(7);
-            group_barrier(ctr, (++bar_no) * NS, tidE);
+            group_barrier(ctr, cbase + (++bar_no) * NS, tidE);
             MP_TRACE(8);
             // ---- reduce the NS split-K partials of the owned rows (all 128 E threads, every load in flight) ----
             {
@@ -486,7 +491,8 @@ bool mlp_persist_supported(int H, int FS, int B, int n_sms) {
     return RG * NS <= n_sms;
 }
 
-// x1 must hold RG*32 rows; part RG*NS*32*256 floats; ctr RG counters (zeroed here).
+// x1 must hold RG*32 rows; part RG*NS*32*256 floats; ctr RG counters, zeroed by the caller once per generation call
+// (launches must start at sample lookback + m * nsteps: the kernel derives its counter base from that).
 int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
                        cudaStream_t st) {
     const int H = p.H, NS = H / 64, RG = (p.B + 31) / 32;
@@ -501,7 +507,6 @@ int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out1
         SRNN_CUDA(cudaFuncSetAttribute(k_mlp_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    SRNN_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(unsigned) * RG, st));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(RG * NS);
     cfg.blockDim = dim3(MP_THREADS);
