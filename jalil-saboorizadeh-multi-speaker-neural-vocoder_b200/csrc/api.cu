@@ -833,6 +833,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         }
         fprintf(stderr, "[srnn trace] last launch: entry -> step 0 = %lld, step 0 = %lld, step 1 = %lld, step 2 = %lld cycles\n",
                 trace[0] - trace[63], trace[64] - trace[0], trace[128] - trace[64], trace[192] - trace[128]);
+        for (int k = 0; k < 2 && k < FS0; ++k) {
+            fprintf(stderr, "[srnn trace] step %d phases:", k);
+            for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%lld", names[j], trace[k * 64 + j + 1] - trace[k * 64 + j]);
+            fprintf(stderr, "\n");
+        }
         fprintf(stderr, "[srnn trace] k_mlp_persist CTA0 cycles/step:");
         for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%.0f", names[j], acc[j] / (FS0 - 2));
         fprintf(stderr, " | step=%.0f\n", tot / (FS0 - 3));

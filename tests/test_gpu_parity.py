@@ -250,6 +250,30 @@ def test_generate_large_batch_runs_in_independent_chunks():
     assert torch.equal(shared[:160], one)
 
 
+def test_generate_schedule_variants_are_bit_identical(monkeypatch):
+    """The generation schedule devices -- recurrent projections in the shadow of the sample kernel, programmatic dependent
+    launches -- only reorder / overlap launches: with each of them switched off the samples and log-probabilities must be
+    bit-identical (dim 1024 x 256 utterances is the configuration that enables both; 5 periods)."""
+    torch.manual_seed(5)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c).cuda()
+    gen = S.Generator(m, cuda=True, mode=S.MODE_BF16)
+    B, n_cond = 256, 5
+    g = torch.Generator().manual_seed(11)
+    cond, spk = torch.rand(B, n_cond, 86, generator=g), torch.randint(0, 6, (B,), generator=g)
+    uni = torch.rand(80 * n_cond, B, generator=g)
+    for k in ("SRNN_NO_SHADOW_GH", "SRNN_NO_PDL"):
+        monkeypatch.delenv(k, raising=False)
+    _, ref, lp = gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)
+    for k, v in (("SRNN_NO_SHADOW_GH", "1"), ("SRNN_NO_PDL", "1")):
+        monkeypatch.setenv(k, v)
+        _, out, lp2 = gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)
+        monkeypatch.delenv(k)
+        assert torch.equal(ref, out), k
+        assert torch.equal(lp, lp2), k
+
+
 @pytest.mark.parametrize("dim,B,T", [(64, 3, 160), (128, 5, 240), (256, 130, 80)])
 def test_predict_bf16_mode_against_oracle(dim, B, T):
     torch.manual_seed(dim + 1)
