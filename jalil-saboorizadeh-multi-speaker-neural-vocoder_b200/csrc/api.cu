@@ -533,6 +533,23 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         SRNN_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         SRNN_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     }
+    // tile of the per-sample MLP GEMMs in the one-launch-per-contraction schedule: the instantiated shape with the most tiles
+    // that still fit one wave of SMs (64 x 32 up to 288 utterances at dim 1024; 128 x 64 at 1024, 128 x 256 at 4096 -- with
+    // 64 x 32 throughout, 4096 utterances meant 2048 tiny tiles per launch)
+    auto mlp_tile = [&](int n_feat, int& bm, int& bn) {
+        static const int cand[6][2] = {{64, 32}, {64, 64}, {128, 32}, {128, 64}, {128, 128}, {128, 256}};
+        int best = -1, best_tiles = 0;
+        for (int k = 0; k < 6; ++k) {
+            const int tiles = cdiv(n_feat, cand[k][0]) * cdiv(B, cand[k][1]);
+            if (tiles <= ctx->n_sms && tiles > best_tiles) { best = k; best_tiles = tiles; }
+        }
+        if (best < 0) best = 5;
+        bm = cand[best][0];
+        bn = cand[best][1];
+    };
+    int bm_hid = 64, bn_hid = 32, bm_out = 64, bn_out = 32;
+    mlp_tile(H, bm_hid, bn_hid);
+    mlp_tile(Q, bm_out, bn_out);
     auto bn_for = [&](int n_feat, int nprob) {
         if (bn_tier < 256) return bn_tier;
         return cdiv(n_feat, 128) * cdiv(B, 128) * nprob <= ctx->n_sms ? 128 : 256;
@@ -731,8 +748,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             if (bf16) {
                 SRNN_TRY(mlp_gather_bf16(seq, Lseq, pos - FS0, step_base, ctx->tbl16, up0, (long long)FS0 * H, 0, X1h, B,
                                          1, H, FS0, st));
-                SRNN_TRY(gemm_umma(ctx->w_hid16, H, X1h, B, H, H, H, ctx->b_hid, nullptr, 0, nullptr, X2h, H, 1, 64, 32, st));
-                SRNN_TRY(gemm_umma(ctx->w_out16, Q, X2h, B, H, H, H, ctx->b_out, nullptr, 0, LG, nullptr, Q, 0, 64, 32, st));
+                SRNN_TRY(gemm_umma(ctx->w_hid16, H, X1h, B, H, H, H, ctx->b_hid, nullptr, 0, nullptr, X2h, H, 1, bm_hid, bn_hid, st));
+                SRNN_TRY(gemm_umma(ctx->w_out16, Q, X2h, B, H, H, H, ctx->b_out, nullptr, 0, LG, nullptr, Q, 0, bm_out, bn_out, st));
             } else {
                 SRNN_TRY(mlp_gather(seq, Lseq, pos - FS0, step_base, ctx->tbl, up0, (long long)FS0 * H, 0, X1, B, 1, H,
                                     FS0, st));
@@ -877,13 +894,14 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
         SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
         const bool persist = mode == SRNN_MODE_BF16 && mlp_persist_supported(ctx->H, ctx->FS0, B, n_sms);
         // Batches beyond what the persistent sample-level kernel can keep co-resident (RG * NS CTAs <= SMs: 288 utterances at
-        // dim 1024): two balanced utterance chunks run back to back through the persistent path (utterances are independent),
-        // which beats the one-GEMM-launch-per-contraction schedule up to 576 utterances (measured at 320/512/576/864:
-        // 791/1241/1282/1285x real-time chunked vs 697/1041/1188/1325x; profiles/README.md, C4 sweep).
+        // dim 1024): balanced utterance chunks run back to back through the persistent path (utterances are independent), which
+        // beats the one-GEMM-launch-per-contraction schedule up to ~800 utterances (measured chunked / unchunked, x real-time:
+        // 512 utterances 1430 / 1009, 768: ~1430 / 1399, 1024: 1427 / 1684; profiles/README.md, C4 sweep) -- at most 3 chunks.
         if (mode == SRNN_MODE_BF16 && !persist && mlp_persist_supported(ctx->H, ctx->FS0, 32, n_sms)) {
             const int NS = ctx->H / 64, max_chunk = (n_sms / NS) * 32;
             const int chunks = (B + max_chunk - 1) / max_chunk;
-            if (chunks <= 2) {
+            static const int max_chunks = getenv("SRNN_MAX_CHUNKS") ? atoi(getenv("SRNN_MAX_CHUNKS")) : 3;
+            if (chunks <= max_chunks) {
                 const int per = ((B + chunks - 1) / chunks + 31) / 32 * 32;
                 const size_t T = (size_t)n_cond * ctx->lookback;
                 for (int b0 = 0; b0 < B; b0 += per) {

@@ -250,6 +250,24 @@ def test_generate_large_batch_runs_in_independent_chunks():
     assert torch.equal(shared[:160], one)
 
 
+def test_generate_one_launch_per_contraction_tiles_at_large_batch():
+    """MODE_BF16_GRAPH (one GEMM launch per contraction) picks its MLP tile from the batch size (128 x 64 at 1100 utterances,
+    64 x 32 at 256): each output element is the same K-ordered tcgen05 accumulation whatever the tile, so the first 256
+    utterances of a 1100-utterance call must equal a 256-utterance call bit for bit."""
+    torch.manual_seed(6)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c).cuda()
+    gen = S.Generator(m, cuda=True, mode=S.MODE_BF16_GRAPH)
+    B, n_cond = 1100, 1
+    g = torch.Generator().manual_seed(12)
+    cond, spk, uni = torch.rand(B, n_cond, 86, generator=g), torch.randint(0, 6, (B,), generator=g), torch.rand(80, B, generator=g)
+    _, whole, lp = gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)
+    _, part, lpp = gen(256, 0, cond[:256], spk[:256], uniforms=uni[:, :256].contiguous(), return_samples=True, return_logp=True)
+    assert torch.equal(whole[:256], part)
+    assert torch.equal(lp[:256], lpp)
+
+
 def test_generate_schedule_variants_are_bit_identical(monkeypatch):
     """The generation schedule devices -- recurrent projections in the shadow of the sample kernel, programmatic dependent
     launches -- only reorder / overlap launches: with each of them switched off the samples and log-probabilities must be
