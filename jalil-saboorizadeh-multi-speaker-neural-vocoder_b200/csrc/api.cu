@@ -588,6 +588,23 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             SRNN_TRY(launch_gh(i, st, 0));                                           // first step: from h0, outside the graph
         }
     }
+    // Same idea for the top tier's input expansion (k_tier_input_split): everything but the last tier-0 frame of the previous
+    // period (and the conditioner / speaker columns) is accumulated beside the last sample launch of that period; the serial
+    // path keeps K = FS0 columns.  XP (the partial sums) lives in the top tier's GI buffer, unused by the fused-cell schedule.
+    const bool shadow_in = shadow_gh && !getenv("SRNN_NO_SHADOW_IN");
+    const TierPacked& ttop = ctx->tiers[NT - 1];
+    float* XP = GI[NT - 1];
+    const int xp_lo = ttop.n - FS0 > 0 ? ttop.n - FS0 : 0, xp_hi = ttop.n;
+    cudaEvent_t ev_xp = nullptr;
+    bool xp_pending = false;
+    auto launch_xp = [&](int off, cudaStream_t s) -> int {
+        return tier_input_split(false, seq, Lseq, off, step_base, ttop.n, B, cond, cond_rows, n_cond, spk, c.cond_dim, ctx->lut,
+                                ttop.w_in_t, ttop.b_in, XP, nullptr, nullptr, H, ttop.kin, xp_lo, xp_hi, s);
+    };
+    if (shadow_in) {
+        SRNN_CUDA(cudaEventCreateWithFlags(&ev_xp, cudaEventDisableTiming));
+        SRNN_TRY(launch_xp(-ttop.n, st));                                            // first period: the q_zero prefix
+    }
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
     if (persist) SRNN_CUDA(cudaMemsetAsync(gctr, 0, sizeof(unsigned) * 2 * RG, st));     // group barrier counters: once per call
@@ -636,7 +653,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     SRNN_CUDA(cudaEventRecord(ev_join, st2));
                 }
                 g_pdl = pdl && prev_tier_kernel;
-                int rc_in = tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
+                int rc_in = (t.top && shadow_in)
+                    ? tier_input_split(true, seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
+                                       ctx->lut, t.w_in_t, t.b_in, XP, X[i], X16[i], H, t.kin, xp_lo, xp_hi, st)
+                    : tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
                                            c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
                                            H, t.kin, t.top, st);
                 g_pdl = 0;
@@ -712,7 +732,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 if (pos % FS0) continue;             // one persistent launch covers the FS0 samples of a tier-0 frame
                 prev_tier_kernel = false;
                 if (shadow_gh) {                     // next step's recurrent projections: on the spare SMs, beside this launch
-                    bool any = false;
+                    const bool xp_now = shadow_in && pos == lookback - FS0;      // last sample launch of the period
+                    bool any = xp_now;
                     for (int i = 0; i < NT; ++i) any = any || gh_todo[i];
                     if (any) {
                         SRNN_CUDA(cudaEventRecord(ev_fork, st));
@@ -723,6 +744,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                             SRNN_CUDA(cudaEventRecord(ev_gh[i], st2));
                             gh_todo[i] = false;
                             gh_pending[i] = true;
+                        }
+                        if (xp_now) {                    // next period's top-tier input, all but its last FS0 sample columns
+                            SRNN_TRY(launch_xp(lookback - ttop.n, st2));
+                            SRNN_CUDA(cudaEventRecord(ev_xp, st2));
+                            xp_pending = true;
                         }
                     }
                 }
@@ -763,6 +789,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             if (!gh_pending[i]) continue;
             SRNN_CUDA(cudaStreamWaitEvent(st, ev_gh[i], 0));
             gh_pending[i] = false;
+        }
+        if (xp_pending) {
+            SRNN_CUDA(cudaStreamWaitEvent(st, ev_xp, 0));
+            xp_pending = false;
         }
         SRNN_TRY(add_int(step_base, lookback, st));
         return SRNN_OK;
@@ -870,6 +900,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     SRNN_CUDA(cudaStreamDestroy(st));
     for (int i = 0; i < SRNN_MAX_TIERS; ++i)
         if (ev_gh[i]) SRNN_CUDA(cudaEventDestroy(ev_gh[i]));
+    if (ev_xp) SRNN_CUDA(cudaEventDestroy(ev_xp));
     if (st2) {
         SRNN_CUDA(cudaStreamDestroy(st2));
         SRNN_CUDA(cudaEventDestroy(ev_fork));

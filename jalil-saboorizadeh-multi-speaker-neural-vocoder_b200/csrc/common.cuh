@@ -201,6 +201,10 @@ int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base
                    int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, int spk_dim, const float* lut,
                    const float* w_in_t, const float* b_in, const float* upper, int up_ld, float* X,
                    __nv_bfloat16* X16, int H, int kin, bool top, cudaStream_t st);
+int tier_input_split(bool tail, const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
+                     int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, const float* lut, const float* w_in_t,
+                     const float* b_in, float* partial, float* X, __nv_bfloat16* X16, int H, int kin, int k_lo, int k_hi,
+                     cudaStream_t st);
 int transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t st);
 // GRU cell tail (model.py:244): h' from gi (+bias already in), gh (+bias already in), h
 int gru_gates(const float* gi, int gi_ld, const float* gh, int gh_ld, const float* h_prev, int hp_ld,

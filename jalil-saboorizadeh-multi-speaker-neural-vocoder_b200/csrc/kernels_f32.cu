@@ -439,6 +439,100 @@ int tier_input_gen(const uint8_t* seq, int seq_ld, int off, const int* step_base
     return SRNN_OK;
 }
 
+// Top-tier input expansion in two parts (bf16 generation schedule): the top tier consumes the lookback samples of the previous
+// period, and all of them but the last tier-0 frame -- plus the conditioner and speaker columns -- are known while the last
+// sample launch of that period still runs.  TAIL = false ("shadow", beside that launch):
+//   partial[b,:] = b_in + sum over k outside [k_lo, k_hi) of a[b,k] . W_in^T[k,:]
+// TAIL = true (on the serial path at the start of the next period):
+//   X[b,:] = partial[b,:] + sum over k in [k_lo, k_hi) of a[b,k] . W_in^T[k,:]      (fp32 and bf16 copies)
+// with a[b,:] = [lut[prev n samples] | cond | onehot(spk)] as in k_tier_input_gen.  The conditioner frame is clamped to the
+// last one: the shadow part of the final period prepares a period that never runs.
+template <bool TAIL>
+__global__ void __launch_bounds__(256)
+k_tier_input_split(const uint8_t* __restrict__ seq, int seq_ld, int start_static, const int* __restrict__ step_base, int n,
+                   const float* __restrict__ cond, int cond_rows, int cond_frames, const int64_t* __restrict__ spk,
+                   int cond_dim, const float* __restrict__ lut, const float* __restrict__ w_in_t,
+                   const float* __restrict__ b_in, float* __restrict__ partial, float* __restrict__ X,
+                   __nv_bfloat16* __restrict__ X16, int B, int H, int kin, int k_lo, int k_hi) {
+    extern __shared__ float a_s[];                                   // [kin][TIG_RB]
+    pdl_trigger();
+    pdl_wait();
+    const int b0 = blockIdx.x * TIG_RB;
+    const int start = start_static + *step_base;
+    int frame = start / n;
+    if (frame > cond_frames - 1) frame = cond_frames - 1;
+    for (int e = threadIdx.x; e < kin * TIG_RB; e += blockDim.x) {
+        const int r = e % TIG_RB, i = e / TIG_RB;
+        const bool in_tail = i >= k_lo && i < k_hi;
+        if (in_tail != TAIL) continue;
+        const int b = b0 + r < B ? b0 + r : B - 1;
+        float v;
+        if (i < n) {
+            v = lut[seq[(size_t)b * seq_ld + start + i]];
+        } else {
+            const int crow = cond_rows == 1 ? 0 : b;
+            if (i < n + cond_dim) v = cond[((size_t)crow * cond_frames + frame) * cond_dim + (i - n)];
+            else v = ((i - n - cond_dim) == (int)spk[crow]) ? 1.f : 0.f;
+        }
+        a_s[e] = v;
+    }
+    __syncthreads();
+    const int h = blockIdx.y * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    float acc[TIG_RB];
+#pragma unroll
+    for (int r = 0; r < TIG_RB; ++r) {
+        if (TAIL) acc[r] = b0 + r < B ? partial[(size_t)(b0 + r) * H + h] : 0.f;
+        else acc[r] = b_in[h];
+    }
+    const float* w = w_in_t + h;
+    for (int seg = 0; seg < 2; ++seg) {                            // TAIL: [k_lo, k_hi); shadow: [0, k_lo) then [k_hi, kin)
+        const int ka = TAIL ? (seg ? 0 : k_lo) : (seg ? k_hi : 0);
+        const int kb = TAIL ? (seg ? 0 : k_hi) : (seg ? kin : k_lo);
+        for (int k0 = ka; k0 < kb; k0 += 16) {
+            float wv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) wv[u] = k0 + u < kb ? __ldg(w + (size_t)(k0 + u) * H) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                if (k0 + u < kb) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB);
+                    const float4 a1 = *reinterpret_cast<const float4*>(a_s + (k0 + u) * TIG_RB + 4);
+                    acc[0] = fmaf(a0.x, wv[u], acc[0]); acc[1] = fmaf(a0.y, wv[u], acc[1]);
+                    acc[2] = fmaf(a0.z, wv[u], acc[2]); acc[3] = fmaf(a0.w, wv[u], acc[3]);
+                    acc[4] = fmaf(a1.x, wv[u], acc[4]); acc[5] = fmaf(a1.y, wv[u], acc[5]);
+                    acc[6] = fmaf(a1.z, wv[u], acc[6]); acc[7] = fmaf(a1.w, wv[u], acc[7]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TIG_RB; ++r) {
+        if (b0 + r >= B) break;
+        if (TAIL) {
+            X[(size_t)(b0 + r) * H + h] = acc[r];
+            X16[(size_t)(b0 + r) * H + h] = __float2bfloat16(acc[r]);
+        } else {
+            partial[(size_t)(b0 + r) * H + h] = acc[r];
+        }
+    }
+}
+int tier_input_split(bool tail, const uint8_t* seq, int seq_ld, int off, const int* step_base, int n, int B, const float* cond,
+                     int cond_rows, int cond_frames, const int64_t* spk, int cond_dim, const float* lut, const float* w_in_t,
+                     const float* b_in, float* partial, float* X, __nv_bfloat16* X16, int H, int kin, int k_lo, int k_hi,
+                     cudaStream_t st) {
+    const int threads = H >= 256 ? 256 : 64;
+    const dim3 grid(cdiv(B, TIG_RB), cdiv(H, threads));
+    const size_t smem = (size_t)kin * TIG_RB * sizeof(float);
+    if (tail)
+        SRNN_LAUNCH(k_tier_input_split<true>, grid, threads, smem, st, seq, seq_ld, off, step_base, n, cond, cond_rows,
+                    cond_frames, spk, cond_dim, lut, w_in_t, b_in, partial, X, X16, B, H, kin, k_lo, k_hi);
+    else
+        SRNN_LAUNCH(k_tier_input_split<false>, grid, threads, smem, st, seq, seq_ld, off, step_base, n, cond, cond_rows,
+                    cond_frames, spk, cond_dim, lut, w_in_t, b_in, partial, X, X16, B, H, kin, k_lo, k_hi);
+    return SRNN_OK;
+}
+
 // (rows, cols) -> (cols, rows)
 __global__ void k_transpose_f32(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
     const size_t total = (size_t)rows * cols;
