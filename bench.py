@@ -26,9 +26,9 @@ C2 = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, u
           cond_dim=86, spk_dim=6)
 F_ALG = 6.423e6      # FLOP per generated sample per utterance, embedding-o-conv folded; what the kernels execute
 F_DENSE = 16.889e6   # the reference graph's dense work, for context
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_mlp_persist launch at B = 256 from the `ncu --set full` capture
-# summarised in profiles/r1_k_mlp_persist_ncu_full.txt (cold L2: ncu flushes caches between replays)
-NCU_TRAFFIC_MLP_PERSIST_B256 = 34.14e6 + 0.03e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the sample-level kernel at B = 256 from the `ncu --set full`
+# captures summarised in profiles/ (cold L2: ncu flushes caches between replays)
+NCU_TRAFFIC = {"k_mlp_persist": 34.14e6 + 0.03e6}
 F_MLP = 2.0 * (1024 * 1024 + 1024 * 256) + 20 * 1024   # k_mlp_persist's share of F_ALG per sample per utterance: hidden +
                                                        # output contraction + the folded-table adds (SURVEY 8d components)
 SAMPLE_RATE = 16000
@@ -81,61 +81,90 @@ def synth_inputs(B, n_cond, seed):
     return cond, spk, uni
 
 
-def cpu_port_rate(n_cond, B, threads=None):
-    """The oracle (CPU port of the reference algorithm) on a bounded sample of the same workload."""
+C1 = dict(frame_sizes=[16], n_rnn=1, dim=1024, learn_h0=True, q_levels=256, ulaw=True, weight_norm=False,
+          cond_dim=43, spk_dim=6)      # BASELINE.json configs[0] / BASELINE.md 3: the reference's own CPU-runnable case
+
+
+def host_threads():
+    """All host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_port_rate(n_cond, B, cfg=None, shared_cond=False):
+    """The oracle (CPU port of the reference algorithm, oracle/srnn_oracle.py) on a bounded sample of the workload."""
     import torch
     from oracle import srnn_oracle as O
     import srnn_b200 as S
-    if threads:
-        torch.set_num_threads(threads)
+    cfg = cfg or C2
+    threads = host_threads()
     torch.manual_seed(77977)
-    m = S.SampleRNN(**C2)
+    m = S.SampleRNN(**cfg)
     sd = {"model." + k: v.detach() for k, v in m.state_dict().items()}
-    w = O.unpack_state_dict(sd, O.Config(**C2))
-    cond, spk, uni = synth_inputs(B, n_cond, 0)
+    w = O.unpack_state_dict(sd, O.Config(**cfg))
+    g = torch.Generator().manual_seed(0)
+    lookback = m.lookback
+    cond = torch.rand(B, n_cond, cfg["cond_dim"], generator=g)
+    spk = torch.randint(0, cfg["spk_dim"], (B,), generator=g)
+    uni = torch.rand(n_cond * lookback, B, generator=g)
     gen = O.Generator(w)
     t0 = time.perf_counter()
     gen(B, cond.numpy(), spk.numpy(), uni.numpy())
     dt = time.perf_counter() - t0
-    return B * n_cond * 80 / dt, dt, torch.get_num_threads()
+    return B * n_cond * lookback / dt, dt, threads
+
+
+def workload_config(args, world):
+    """The `config` object both arms print: BASELINE.json configs[1] (C2) at the batch / length of this run."""
+    return {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond %d, weight-norm" % C2["cond_dim"],
+            "batch_per_gpu": args.batch, "total_batch": args.batch * world, "samples_per_utterance": args.n_cond * 80}
 
 
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU implementation of the path = the oracle port (the reference itself is a
-    Python program under /root/reference, which does not exist on the GPU box), all host threads, bounded sample."""
+    Python program under /root/reference, which does not exist on the GPU box), all host threads, each step a bounded
+    sample of the arm's workload (same model, same batch, fewer conditioner frames) sized so that the whole
+    --steps/--warmup run stays within --ref-budget-s seconds."""
     if rank != 0:
         return
-    n_cond = args.ref_n_cond
+    B = args.batch
+    # calibrate on one conditioner frame, then size the per-step sample for the time budget
+    r1, dt1, th = cpu_port_rate(1, B)
+    per_step = args.ref_budget_s / max(1, args.steps + args.warmup)
+    n_cond = max(1, min(args.ref_n_cond, int(per_step / max(dt1, 1e-3))))
     rates, times = [], []
     for i in range(args.warmup + args.steps):
-        r, dt, th = cpu_port_rate(n_cond, args.batch)
+        r, dt, th = cpu_port_rate(n_cond, B)
         if i >= args.warmup:
             rates.append(r)
             times.append(dt)
     v = sum(rates) / len(rates)
-    sample = "C2 model, B=%d utterances x %d cond frames (%d samples each) per step" % (args.batch, n_cond, n_cond * 80)
+    sample = ("bounded sample per step: %d of the workload's %d conditioner frames (%d samples) for all %d utterances; "
+              "oracle port, %d host threads" % (n_cond, args.n_cond, n_cond * 80, B, th))
     print(json.dumps({
         "impl": "reference", "metric": "generated samples/sec", "value": v, "unit": "samples/s",
         "x_realtime_16k": v / SAMPLE_RATE, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond %d, weight-norm" % C2["cond_dim"],
-                   "batch_per_gpu": args.batch, "total_batch": args.batch, "samples_per_utterance": n_cond * 80, "sample": sample},
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": th, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def run_train(args, rank, world, local):
-    """Secondary line (BASELINE.json configs[2], "C3"): teacher-forced training step = forward + NLL(bits) + backward +
-    gradient all-reduce (N>1) + fused clamp/Adam, batch 128 x T 1040 per GPU, synthetic tokens/conditioners."""
+def train_block(args, rank, world, dev, steps, warmup):
+    """BASELINE.json configs[2] ("C3"): teacher-forced training step = forward + NLL(bits) + backward + staged gradient
+    all-reduce over NVLink (N>1) + fused mean/clamp/Adam, batch 128 x T 1040 per GPU, bf16, synthetic tokens/conditioners.
+    Returns the `train` record of the bench line (process group already initialised by the caller when world > 1)."""
     import torch
     import torch.distributed as dist
     import srnn_b200 as S
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     mode = S.MODE_FP32 if args.mode == "fp32" else S.MODE_BF16
     lib = S._lib.load()
     torch.manual_seed(77977)
@@ -143,9 +172,10 @@ def run_train(args, rank, world, local):
     pred = S.Predictor(model, mode=mode)
     opt = S.ClampAdam(pred.parameters(), lr=1e-4, model=model)
     B, T = args.train_batch, args.train_T
-    g = torch.Generator().manual_seed(100 + rank)
-    data = torch.randint(0, 256, (B, 80 + T * (args.steps + args.warmup) + T), generator=g).to(dev)
-    cond = torch.rand(B, (T // 80) * (args.steps + args.warmup + 1) + 1, C2["cond_dim"], generator=g).to(dev)
+    n_it = steps + warmup
+    g = torch.Generator().manual_seed(100 + rank)                      # every rank trains on its own rows
+    data = torch.randint(0, 256, (B, 80 + T * n_it + T), generator=g).to(dev)
+    cond = torch.rand(B, (T // 80) * (n_it + 1) + 1, C2["cond_dim"], generator=g).to(dev)
     spk = torch.randint(0, 6, (B, 1), generator=g).to(dev)
     losses = []
 
@@ -157,14 +187,14 @@ def run_train(args, rank, world, local):
 
         def closure():
             out = pred(x, i == 0, c, spk, None, None)
-            loss = S.sequence_nll_loss_bits(out, y)
+            loss = S.sequence_nll_loss_bits(out, y)                    # fused: srnn_nll_loss_bits / srnn_predict_bwd_nll
             loss.backward()
             return loss.detach()
 
         opt.zero_grad()
         losses.append(opt.step(closure))
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     if world > 1:
         dist.barrier()
@@ -172,33 +202,110 @@ def run_train(args, rank, world, local):
     l0 = lib.srnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.warmup, args.warmup + args.steps):
+    for i in range(warmup, n_it):
         step(i)
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    # data-parallel equivalence inside the bench run: the parameters must stay bit-identical on every rank
+    chk = torch.stack([p.detach().double().sum() for p in pred.parameters()]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool((lo == hi).item())
+    assert same, "parameters diverged across ranks: %r vs %r" % (float(lo), float(hi))
     secs = float(t.item()) / 1e3
-    tokens = world * B * T * args.steps
+    tokens = world * B * T * steps
     peak_tf, _, peak_src = measured_peaks()
     f_step = 3 * F_ALG                                          # fwd + bwd ~ 3x forward, folded form (what the kernels execute)
     ach = tokens / secs * f_step / 1e12 / world
-    if rank == 0:
-        print(json.dumps({
-            "metric": "training tokens/sec (teacher-forced step)", "value": tokens / secs, "unit": "tokens/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
-            "config": {"workload": "C3 training step: 3-tier [20,4] SampleRNN dim 1024, batch %d x T %d per GPU, Adam lr 1e-4 "
-                                   "with element-wise gradient clamp" % (B, T), "allreduce": "mean over ranks before the clamp"},
-            "loss_bits_first_last": [float(losses[0]), float(losses[-1])],
-            "gpu_launches": int(lib.srnn_launch_count() - l0),
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
-                         "flops_per_token": f_step, "kernel": "whole training step"},
-        }))
+    launches = int(lib.srnn_launch_count() - l0)
+    del opt, pred, model, data, cond
+    torch.cuda.empty_cache()
+    return {
+        "metric": "training tokens/sec (teacher-forced step)", "value": tokens / secs, "unit": "tokens/s", "n_gpus": world,
+        "tokens_per_s_per_gpu": tokens / secs / world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / steps,
+        "higher_is_better": True, "scaling": "weak", "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
+        "config": {"workload": "C3 training step: 3-tier [20,4] SampleRNN dim 1024, batch %d x T %d per GPU, Adam lr 1e-4 "
+                               "with element-wise gradient clamp" % (B, T),
+                   "allreduce": "fp32 sum over ranks in backward-stage buckets on a side stream (NCCL); mean folded into the "
+                                "clamp+Adam kernel" if world > 1 else "none (1 GPU)",
+                   "loss": "fused (srnn_nll_loss_bits + srnn_predict_bwd_nll), no torch kernel in the step"},
+        "loss_bits_first_last": [float(losses[0]), float(losses[-1])],
+        "params_identical_across_ranks": same,
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                     "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                     "flops_per_token": f_step, "kernel": "whole training step"},
+    }
+
+
+def fp32_mode_block(S, model, B, dev, n_cond=2):
+    """Throughput of the fp32 parity mode (the mode the 1e-3 / bit-exact-index gates are proven on), same model and batch."""
+    import torch
+    gen = S.Generator(model, cuda=True, mode=S.MODE_FP32)
+    cond, spk, uni = [t.to(dev) for t in synth_inputs(B, n_cond, 7)]
+    gen(B, 0, cond, spk, uniforms=uni, device_output=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gen(B, 0, cond, spk, uniforms=uni, device_output=True)
+    e1.record()
+    torch.cuda.synchronize()
+    v = B * n_cond * 80 / (e0.elapsed_time(e1) / 1e3)
+    return {"value": v, "unit": "samples/s", "x_realtime_16k": v / SAMPLE_RATE, "samples_per_utterance": n_cond * 80,
+            "note": "SRNN_MODE_FP32: every contraction as an fp32 FFMA GEMM; the mode of the 1e-3 logit / bit-exact index gates"}
+
+
+def run_sweep(args, rank, world, local):
+    """BASELINE.json configs[3] ("C4"): total batch 1 ... 4096 utterances x 10 s (160 000 samples), utterances sharded over
+    the ranks (strong scaling over the batch, no collective); one JSON line per batch size: latency of the first period
+    (80 samples), latency of the whole utterance, throughput."""
+    import torch
+    import torch.distributed as dist
+    import srnn_b200 as S
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mode = S.MODE_FP32 if args.mode == "fp32" else S.MODE_BF16
+    torch.manual_seed(77977)
+    model = S.SampleRNN(**C2).to(dev)
+    gen = S.Generator(model, cuda=True, mode=mode)
+    n_cond = args.sweep_seconds * SAMPLE_RATE // 80
+    for total in [int(b) for b in args.sweep_batches.split(",")]:
+        lo, hi = S.shard_range(total, rank, world)
+        B = hi - lo
+        t_first = t_all = 0.0
+        if B > 0:
+            cond, spk, uni = [t.to(dev) for t in synth_inputs(B, n_cond, 2000 + rank)]
+            gen(B, 0, cond[:, :1].contiguous(), spk, uniforms=uni[:80].contiguous(), device_output=True)   # warm-up
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            gen(B, 0, cond[:, :1].contiguous(), spk, uniforms=uni[:80].contiguous(), device_output=True)
+            ev[1].record()
+            ev[2].record()
+            gen(B, 0, cond, spk, uniforms=uni, device_output=True)
+            ev[3].record()
+            torch.cuda.synchronize()
+            t_first, t_all = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+            del cond, spk, uni
+        t = torch.tensor([t_first, t_all], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            secs = float(t[1]) / 1e3
+            v = total * n_cond * 80 / secs
+            print(json.dumps({"workload": "C4 batch sweep", "total_batch": total, "n_gpus": world, "batch_per_gpu": -(-total // world),
+                              "samples_per_utterance": n_cond * 80, "latency_first_period_ms": float(t[0]),
+                              "latency_last_sample_ms": float(t[1]), "value": v, "unit": "samples/s",
+                              "x_realtime_16k": v / SAMPLE_RATE, "us_per_sample_step": 1e6 * secs / (n_cond * 80),
+                              "dtype": "bf16" if mode == S.MODE_BF16 else "f32"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -212,15 +319,21 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("SRNN_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16", "bf16_graph"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU")
     ap.add_argument("--n-cond", type=int, default=100, help="conditioner frames (x80 samples) per step")
-    ap.add_argument("--ref-n-cond", type=int, default=8, help="reference arm: cond frames per step (~4 s of CPU work each)")
+    ap.add_argument("--ref-n-cond", type=int, default=8, help="reference arm: at most this many cond frames per step")
+    ap.add_argument("--ref-budget-s", type=float, default=120.0, help="reference arm: CPU seconds for the whole run")
     ap.add_argument("--cpu-n-cond", type=int, default=24, help="cpu_baseline sample: cond frames (~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="generate", choices=["generate", "train"],
-                    help="generate = the headline metric (default); train = C3 teacher-forced training step")
+    ap.add_argument("--workload", default="generate", choices=["generate", "train", "sweep"],
+                    help="generate = the headline metric + a `train` sub-record (default); train = only the C3 training "
+                         "step; sweep = C4 batch sweep (one line per batch size)")
     ap.add_argument("--cond-dim", type=int, default=86,
                     help="conditioner width: 86 = look-ahead (C2, default); 43 = the core of the bottle-neck variant (C5)")
     ap.add_argument("--train-batch", type=int, default=128)
     ap.add_argument("--train-T", type=int, default=1040)
+    ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` sub-record of the default run")
+    ap.add_argument("--sweep-batches", default="1,4,16,64,256,1024,4096")
+    ap.add_argument("--sweep-seconds", type=int, default=10)
     args = ap.parse_args()
     C2["cond_dim"] = args.cond_dim
 
@@ -229,8 +342,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
-    if args.workload == "train":
-        return run_train(args, rank, world, local)
+    if args.workload == "sweep":
+        return run_sweep(args, rank, world, local)
 
     import torch
     import torch.distributed as dist
@@ -239,6 +352,14 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "train":
+        rec = train_block(args, rank, world, dev, args.steps, args.warmup)
+        if rank == 0:
+            rec["vs_baseline"] = None
+            print(json.dumps(rec))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     mode = {"fp32": S.MODE_FP32, "bf16": S.MODE_BF16, "bf16_graph": S.MODE_BF16_GRAPH}.get(args.mode)
     if mode is None:
         mode = S.MODE_BF16 if getattr(S.package, "HAS_BF16", False) else S.MODE_FP32
@@ -296,8 +417,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     secs_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 3))
 
-    # Dominant kernel (k_mlp_persist, one launch per tier-0 frame = FS0 samples x B utterances): CUDA events around every
-    # launch on the library's generation stream, over one more (untimed-for-`value`) pass with direct launches.
+    # Dominant kernel (the persistent sample-level kernel, one launch per tier-0 frame = FS0 samples x B utterances): CUDA
+    # events around every launch on the library's generation stream, over one more (untimed-for-`value`) pass with direct launches.
     kern = None
     if mode == S.MODE_BF16:
         import ctypes
@@ -319,11 +440,12 @@ def main():
     peak_tf, peak_gbs, peak_src = measured_peaks()
     ach_step = value * F_ALG / 1e12 / world                                     # per-GPU TFLOP/s, algorithmic, whole step
     fs0 = C2["frame_sizes"][0]
+    kname = lib.srnn_sample_kernel_name().decode()
     if kern:
         flops_launch = F_MLP * B * fs0
-        ach, kname = flops_launch / kern[0] / 1e12, "srnn::k_mlp_persist"
-        traffic = NCU_TRAFFIC_MLP_PERSIST_B256 if B == 256 else None
-        kinfo = {"kernel": kname, "launches_timed": kern[1], "avg_launch_us": kern[0] * 1e6, "flops_per_launch": flops_launch,
+        ach = flops_launch / kern[0] / 1e12
+        traffic = NCU_TRAFFIC.get(kname) if B == 256 else None
+        kinfo = {"kernel": "srnn::" + kname, "launches_timed": kern[1], "avg_launch_us": kern[0] * 1e6, "flops_per_launch": flops_launch,
                  "share_of_step": kern[2] / (secs / args.steps),
                  "how": "CUDA events around each launch on the generation stream (direct launches, SRNN_TIME_KERNELS)"}
     else:
@@ -331,14 +453,16 @@ def main():
         ach, kinfo = ach_step, {"kernel": "whole generation step (all launches of srnn_generate)"}
     h2d = cond_h.numel() * 4 + spk_h.numel() * 8 + uni_h.numel() * 4
     d2h = audio_h.numel() * 4
+    cfg = workload_config(args, world)
+    cfg.update({"l2": "192 MiB flush write between timed iterations", "us_per_sample_step": 1e6 * secs / args.steps / T,
+                "schedule": "default (shadow recurrent GEMMs, programmatic dependent launches, split top-tier input expansion: "
+                            "re-associates one fp32 sum, inside the bf16 gate)"})
     line = {
         "metric": "generated samples/sec", "value": value, "unit": "samples/s", "x_realtime_16k": value / SAMPLE_RATE,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if mode == S.MODE_FP32 else "bf16", "data": "synthetic",
-        "config": {"workload": "C2 generation: 3-tier [20,4] SampleRNN, n_rnn 2, dim 1024, q 256, cond %d, weight-norm" % C2["cond_dim"],
-                   "batch_per_gpu": B, "total_batch": B * world, "samples_per_utterance": T,
-                   "l2": "192 MiB flush write between timed iterations", "us_per_sample_step": 1e6 * secs / args.steps / T},
+        "config": cfg,
         "e2e": {"value": e2e, "unit": "samples/s", "x_realtime_16k": e2e / SAMPLE_RATE, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
@@ -349,10 +473,21 @@ def main():
                      "flops_per_sample": F_ALG, "whole_step_achieved": ach_step, "whole_step_frac": ach_step / peak_tf,
                      "achieved_dense_equiv": value * F_DENSE / 1e12 / world, **kinfo},
     }
+    if mode != S.MODE_FP32:
+        line["fp32_parity_mode"] = fp32_mode_block(S, model, B, dev)
+    del gen, flush, cond_d, uni_d
+    torch.cuda.empty_cache()
+    if not args.no_train:
+        line["train"] = train_block(args, rank, world, dev, args.train_steps, 3)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, dt, th = cpu_port_rate(args.cpu_n_cond, B)
         line["cpu_baseline"] = {"value": r, "unit": "samples/s", "cores": th, "kind": "port",
                                 "sample": "C2 model, B=%d x %d cond frames (%.1f s of CPU work)" % (B, args.cpu_n_cond, dt)}
+        # the reference's own CPU case -- C1, one utterance, shared conditioner; bounded to 250 of its 1000 frames
+        r1, dt1, _ = cpu_port_rate(250, 1, cfg=C1)
+        line["cpu_baseline"]["c1"] = {"value": r1, "unit": "samples/s", "x_realtime_16k": r1 / SAMPLE_RATE, "cores": th, "kind": "port",
+                                      "sample": "C1: 2-tier [16] SampleRNN dim 1024 cond 43, B=1, 250 of 1000 cond frames "
+                                                "(4000 samples, %.1f s of CPU work)" % dt1}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

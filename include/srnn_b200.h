@@ -119,20 +119,38 @@ SRNN_API int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t
  * srnn_pack_weights, grads = the same struct pointing at WRITABLE gradient buffers of identical shapes (null entries
  * are skipped; non-null ones are overwritten).  Hidden-state carries are detached (model.py:348): h0 receives a
  * gradient only for tiers that started from it in that forward pass, zeros otherwise (torch-0.4 zero_grad semantics,
- * SURVEY App. C #12).  Available for SRNN_MODE_FP32 forward passes. */
+ * SURVEY App. C #12).  Runs in the arithmetic mode of that forward pass (SRNN_MODE_FP32 or SRNN_MODE_BF16). */
 SRNN_API int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* params,
                               const srnn_params* grads, void* stream);
+
+/* srnn_predict_bwd with the loss folded in: backward of sequence_nll_loss_bits(logp, target) (nn.py:66-70,
+ * trainer/__init__.py:102-103).  target (B, T) int64 in [0,Q); gscale = device pointer to the upstream scalar gradient of
+ * the loss (NULL = 1).  dL/dlogits = (exp(logp) - onehot(target)) * g * log2(e) / (B*T) is produced by one kernel straight
+ * into the buffers the output-layer GEMMs read: no dense (B,T,Q) dL/dlogp is materialised. */
+SRNN_API int srnn_predict_bwd_nll(srnn_ctx* ctx, const float* logp, const int64_t* target, const float* gscale,
+                                  const srnn_params* params, const srnn_params* grads, void* stream);
 
 /* Data-parallel training (no counterpart in the single-GPU reference): `stream` waits until the last srnn_predict_bwd on
  * this context has finalised every gradient below the top tier (MLP, embedding, lower tiers), so that their NCCL all-reduce
  * can overlap the top tier's backward pass. */
 SRNN_API int srnn_bwd_wait_early(srnn_ctx* ctx, void* stream);
+/* Finer-grained form.  A backward pass finalises gradients in this order: stage 0 = sample-level MLP + embedding,
+ * stage 1 + 2i = tier i's upsampling (conv_t weight_g / weight_v and bias), stage 2 + 2i = the rest of tier i, lowest tier
+ * first; `stream` waits for that stage, so a bucketed NCCL all-reduce can follow the backward pass stage by stage. */
+SRNN_API int srnn_bwd_wait_stage(srnn_ctx* ctx, int32_t stage, void* stream);
 
 /* optim.py:10-13 element-wise clamp of every gradient to [-clamp, clamp] fused with torch.optim.Adam's update
  * (train.py:238: betas (0.9, 0.999), eps 1e-8, no weight decay) over `count` tensors in one launch; step = 1, 2, ... */
 SRNN_API int srnn_clamp_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
                                   float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2,
                                   float eps, int32_t step, float clamp, void* stream);
+
+/* The same with every gradient multiplied by grad_scale before the clamp (1 / world_size after a sum all-reduce: the mean
+ * over ranks, the clamp and Adam in one pass; SURVEY 8e "average -> clamp -> Adam"). */
+SRNN_API int srnn_clamp_adam_step_scaled(int32_t count, float* const* params, const float* const* grads,
+                                         float* const* exp_avg, float* const* exp_avg_sq, const int64_t* sizes, float lr,
+                                         float beta1, float beta2, float eps, int32_t step, float clamp, float grad_scale,
+                                         void* stream);
 
 /* sequence_nll_loss_bits (nn.py:66-70): loss_out (1 device float) = -mean_r logp[r, target[r]] * log2(e), rows = B*T;
  * deterministic two-stage reduction. */
@@ -182,6 +200,8 @@ SRNN_API int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const fl
 /* Measurement hook: CUDA-event time (ms) and launch count of the persistent sample-level kernel over the last
  * srnn_generate call made with the environment variable SRNN_TIME_KERNELS set (direct launches instead of the graph). */
 SRNN_API int srnn_timed_kernel(const srnn_ctx* ctx, double* ms, int64_t* launches);
+/* Name of the persistent sample-level kernel the last SRNN_MODE_BF16 srnn_generate call ran ("k_mlp_persist", ...). */
+SRNN_API const char* srnn_sample_kernel_name(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 SRNN_API int64_t srnn_launch_count(void);
 

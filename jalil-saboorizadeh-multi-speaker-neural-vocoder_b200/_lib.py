@@ -37,6 +37,7 @@ class Params(C.Structure):
 _SIGNATURES = {
     "srnn_last_error": (C.c_char_p, []),
     "srnn_version": (C.c_int, []),
+    "srnn_sample_kernel_name": (C.c_char_p, []),
     "srnn_launch_count": (C.c_int64, []),
     "srnn_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "srnn_destroy": (C.c_int, [C.c_void_p]),
@@ -48,11 +49,17 @@ _SIGNATURES = {
     "srnn_clamp_adam_step": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_int32, C.c_float, C.c_void_p]),
+    "srnn_predict_bwd_nll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.POINTER(Params),
+                                       C.c_void_p]),
+    "srnn_clamp_adam_step_scaled": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_float, C.c_float, C.c_float,
+                                              C.c_float, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "srnn_mlp_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "srnn_gru_seq_fwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
     "srnn_gru_seq_bwd": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9 + [C.c_int32, C.c_void_p]),
     "srnn_quantize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "srnn_bwd_wait_early": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srnn_bwd_wait_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "srnn_timed_kernel": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "srnn_nll_loss_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "srnn_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

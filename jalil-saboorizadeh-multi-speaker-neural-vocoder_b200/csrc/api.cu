@@ -99,7 +99,7 @@ int srnn_create(const srnn_config* cfg, srnn_ctx** out) {
     c->lookback = n;
     cudaGetDevice(&c->device);
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
-    cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming);
+    for (auto& e : c->ev_stage) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = c;
     return SRNN_OK;
 }
@@ -108,7 +108,7 @@ int srnn_destroy(srnn_ctx* ctx) {
     if (!ctx) return SRNN_OK;
     cudaDeviceSynchronize();
     ctx->weights.release();
-    if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
+    for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
     if (ctx->ws) cudaFree(ctx->ws);
     delete ctx;
     return SRNN_OK;
@@ -418,12 +418,36 @@ int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     return rc;
 }
 
+// Backward of sequence_nll_loss_bits(srnn_predict_fwd(...), target) in one pass (nn.py:66-70 + trainer/__init__.py:102-103):
+// the loss gradient is folded into the log-softmax backward, dL/dlogits = (exp(logp) - onehot(target)) * g * log2(e) / (B*T),
+// so no dense dL/dlogp exists.  target (B, T) int64; gscale = device pointer to the upstream scalar gradient (null = 1).
+int srnn_predict_bwd_nll(srnn_ctx* ctx, const float* logp, const int64_t* target, const float* gscale,
+                         const srnn_params* params, const srnn_params* grads, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    if (!logp || !target || !params || !grads) return fail(SRNN_ERR_ARG, "null argument");
+    if (!ctx->fwd.valid) return fail(SRNN_ERR_STATE, "srnn_predict_bwd_nll needs a preceding srnn_predict_fwd on this context");
+    const int rc = ctx->fwd.mode == SRNN_MODE_FP32
+                       ? predict_bwd_f32(ctx, logp, nullptr, params, grads, (cudaStream_t)stream, target, gscale)
+                       : predict_bwd_bf16(ctx, logp, nullptr, params, grads, (cudaStream_t)stream, target, gscale);
+    ctx->fwd.valid = false;
+    return rc;
+}
+
 // Data-parallel overlap: make `stream` wait until the last srnn_predict_bwd on this context has finished every gradient that
 // does not belong to the top tier (sample-level MLP, embedding, lower tiers); the caller can then all-reduce those on
 // `stream` while the top tier's backward pass is still running on the compute stream.
 int srnn_bwd_wait_early(srnn_ctx* ctx, void* stream) {
-    if (!ctx || !ctx->ev_early) return fail(SRNN_ERR_ARG, "null context");
-    SRNN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_early, 0));
+    if (!ctx) return fail(SRNN_ERR_ARG, "null context");
+    return srnn_bwd_wait_stage(ctx, 2 * (ctx->cfg.n_tiers - 1), stream);
+}
+
+// Finer-grained form: the backward pass finalises gradients in the order  stage 0 = sample-level MLP + embedding,
+// stage 1 + 2i = tier i's upsampling (conv_t weight_g / weight_v, bias), stage 2 + 2i = the rest of tier i (lowest tier first).
+// `stream` waits for stage `stage` of the last srnn_predict_bwd[_nll] on this context.
+int srnn_bwd_wait_stage(srnn_ctx* ctx, int32_t stage, void* stream) {
+    if (!ctx) return fail(SRNN_ERR_ARG, "null context");
+    if (stage < 0 || stage > 2 * ctx->cfg.n_tiers || !ctx->ev_stage[stage]) return fail(SRNN_ERR_ARG, "bad stage %d", stage);
+    SRNN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_stage[stage], 0));
     return SRNN_OK;
 }
 
@@ -438,6 +462,17 @@ int srnn_clamp_adam_step(int32_t count, float* const* params, const float* const
                       (cudaStream_t)stream);
 }
 
+// The same with every gradient multiplied by grad_scale before the clamp: data-parallel training passes 1 / world_size after
+// the sum all-reduce, so "mean over ranks -> clamp -> Adam" (optim.py:10-13 on the full-batch gradient) is one pass.
+int srnn_clamp_adam_step_scaled(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                                float* const* exp_avg_sq, const int64_t* sizes, float lr, float beta1, float beta2, float eps,
+                                int32_t step, float clamp, float grad_scale, void* stream) {
+    if (count < 0 || (count && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes))) return fail(SRNN_ERR_ARG, "bad argument");
+    if (step < 1) return fail(SRNN_ERR_ARG, "step must be >= 1");
+    return clamp_adam(count, params, grads, exp_avg, exp_avg_sq, (const long long*)sizes, lr, beta1, beta2, eps, step, clamp,
+                      (cudaStream_t)stream, grad_scale);
+}
+
 // Measurement hook: accumulated CUDA-event time (ms) and launch count of the persistent sample-level kernel over the last
 // srnn_generate call that ran with the environment variable SRNN_TIME_KERNELS set (which issues the launches directly
 // instead of through the CUDA graph so that events can bracket them on their stream).
@@ -447,6 +482,10 @@ int srnn_timed_kernel(const srnn_ctx* ctx, double* ms, int64_t* launches) {
     *launches = ctx->timed_launches;
     return SRNN_OK;
 }
+
+// Name of the persistent sample-level kernel the last bf16 srnn_generate call of this process ran (bench.py's roofline line).
+namespace srnn { const char* g_sample_kernel = "k_mlp_persist"; }
+const char* srnn_sample_kernel_name(void) { return srnn::g_sample_kernel; }
 
 // mean NLL in bits of log-probabilities against targets (nn.py:66-70); loss_out = one device float
 int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, int32_t rows, float* loss_out, void* stream) {

@@ -132,6 +132,34 @@ __global__ void k_logsoftmax_bwd(const float* __restrict__ dlogp, const float* _
     for (int i = 0; i < 8; ++i) dlogits[o + i] = g[i] - expf(logp[o + i]) * s;
 }
 
+// Fused backward of sequence_nll_loss_bits (nn.py:66-70) through log_softmax: with L = -mean_r logp[r, target[r]] * log2(e)
+// and an upstream scalar gradient *gscale (1 if null), dL/dlogits[r, :] = (exp(logp[r, :]) - onehot(target[r])) * g * log2(e) / rows.
+// One warp per row; writes the fp32 gradient (bias column sums) and, when d16 is given, the bf16 copy the tensor-core
+// GEMMs read -- no dense dL/dlogp is ever materialised.
+__global__ void k_nll_logsoftmax_bwd(const float* __restrict__ logp, const int64_t* __restrict__ target,
+                                     const float* __restrict__ gscale, float* __restrict__ dlogits,
+                                     __nv_bfloat16* __restrict__ d16, int rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float s = (gscale ? __ldg(gscale) : 1.f) * 1.4426950408889634f / (float)rows;
+    long long tq = target[row];
+    const int tgt = tq < 0 ? 0 : (tq > SRNN_Q - 1 ? SRNN_Q - 1 : (int)tq);
+    const size_t o = (size_t)row * SRNN_Q + lane * 8;
+    const float4 a = *reinterpret_cast<const float4*>(logp + o), b = *reinterpret_cast<const float4*>(logp + o + 4);
+    float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = (expf(g[i]) - (lane * 8 + i == tgt ? 1.f : 0.f)) * s;
+    *reinterpret_cast<float4*>(dlogits + o) = make_float4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<float4*>(dlogits + o + 4) = make_float4(g[4], g[5], g[6], g[7]);
+    if (d16) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+        *reinterpret_cast<uint4*>(d16 + o) = *reinterpret_cast<const uint4*>(h);
+    }
+}
+
 __global__ void k_relu_mask(const float* __restrict__ dx, const float* __restrict__ x, float* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = x[i] > 0.f ? dx[i] : 0.f;
@@ -608,7 +636,7 @@ size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T) {
 }
 
 int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int64_t* nll_target, const float* nll_gscale) {
     const FwdPlan& F = ctx->fwd;
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
@@ -657,7 +685,8 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     (void)wmf;
 
     // ---- log_softmax backward ----
-    SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
+    if (nll_target) SRNN_LAUNCH(k_nll_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, logp, nll_target, nll_gscale, dlogits, (__nv_bfloat16*)nullptr, R);
+    else SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
     // ---- output layer: logits = x2 W_o^T + b_o ----
     SRNN_TRY(gemm_dw(Q, H, R, dlogits, Q, F.X2, H, dWo, H, st));
     SRNN_TRY(wn_bwd(dWo, P->mlp_output, G->mlp_output, Q, H, st));
@@ -673,7 +702,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
     // ---- folded table: dTbl, then back onto W_in (H,Q,FS) and E (Q,Q) ----
     SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, dB, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
     SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
-    if (NT == 1 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));   // single tier: the MLP gradients are the early set
+    SRNN_CUDA(cudaEventRecord(ctx->ev_stage[0], st));                           // MLP + embedding gradients are final
     // ---- frame tiers, lowest first: each receives dUP (M, fs*H) from below ----
     const float* dUP = dB;                            // tier 0's upsampled output is the MLP conditioning c0
     int xb = 0;
@@ -688,6 +717,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
         SRNN_TRY(colsum(dUP, M, t.fs * H, t.fs * H, csp, dbup, st));
         SRNN_TRY(unpack_up_grad(dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs, st));
         SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
+        SRNN_CUDA(cudaEventRecord(ctx->ev_stage[1 + 2 * i], st));                 // tier i's upsampling gradients are final
         float* dY = dYa;
         float* dYn = dYb;
         SRNN_TRY(gemm_dx(M, H, t.fs * H, dUP, t.fs * H, t.w_up, H, nullptr, 0, dY, H, st));
@@ -758,7 +788,7 @@ int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const 
         }
         // every gradient below the top tier is complete: a data-parallel caller may start reducing those while the top
         // tier's backward pass runs (srnn_bwd_wait_early)
-        if (i == NT - 2 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));
+        SRNN_CUDA(cudaEventRecord(ctx->ev_stage[2 + 2 * i], st));
         (void)xb;
     }
     return SRNN_OK;
@@ -836,7 +866,7 @@ size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T) {
 }
 
 int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int64_t* nll_target, const float* nll_gscale) {
     const FwdPlan& F = ctx->fwd;
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
@@ -891,8 +921,12 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     bf* DX16 = b.take<bf>(maxM * H);
 
     // ---- log_softmax backward; bf16 copies of dlogits in both orientations ----
-    SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
-    SRNN_TRY(f32_to_bf16_pad(dlogits, R, Q, Q, D16, R, Q, st));
+    if (nll_target) {                                // fused loss: dlogits (fp32 + bf16) straight from logp and the targets
+        SRNN_LAUNCH(k_nll_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, logp, nll_target, nll_gscale, dlogits, D16, R);
+    } else {
+        SRNN_LAUNCH(k_logsoftmax_bwd, cdiv(R, 8), 256, 0, st, dlogp, logp, dlogits, R);
+        SRNN_TRY(f32_to_bf16_pad(dlogits, R, Q, Q, D16, R, Q, st));
+    }
     // ---- output layer ----
     SRNN_TRY(tc_dw_tn(Q, H, R, D16, Q, F.X2h, H, dWo, dTblP, dtblp_floats, st));
     SRNN_TRY(wn_bwd(dWo, P->mlp_output, G->mlp_output, Q, H, st));
@@ -906,7 +940,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     // ---- folded table ----
     SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, DP1, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
     SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
-    if (NT == 1 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));
+    SRNN_CUDA(cudaEventRecord(ctx->ev_stage[0], st));                           // MLP + embedding gradients are final
     // ---- frame tiers, lowest first ----
     const bf* dUP = DP1;
     for (int i = 0; i < NT; ++i) {
@@ -919,6 +953,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
         SRNN_TRY(colsum(dUP, M, NU, NU, csp, dbup, st));
         SRNN_TRY(unpack_up_grad(dWup, dbup, dwf, (float*)tg.upsampling.bias, H, t.fs, st));
         SRNN_TRY(wn_bwd(dwf, tp.upsampling, tg.upsampling, H, H * t.fs, st));
+        SRNN_CUDA(cudaEventRecord(ctx->ev_stage[1 + 2 * i], st));                 // tier i's upsampling gradients are final
         float* dY = dYa;
         float* dYn = dYb;
         SRNN_TRY(tc_dx(M, H, NU, dUP, NU, t.w_up16_t, nullptr, 0, dY, nullptr, nullptr, H, st));
@@ -989,7 +1024,7 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
             SRNN_TRY(f32_to_bf16_pad(dXf, M, H, H, DX16, M, H, st));     // d upper for the tier above, (M_{i+1}, fs_{i+1}*H)
             dUP = DX16;
         }
-        if (i == NT - 2 && ctx->ev_early) SRNN_CUDA(cudaEventRecord(ctx->ev_early, st));
+        SRNN_CUDA(cudaEventRecord(ctx->ev_stage[2 + 2 * i], st));
     }
     return SRNN_OK;
 }
@@ -1006,7 +1041,7 @@ struct AdamArgs {
     int first_chunk[ADAM_MAX + 1];
     long long n[ADAM_MAX];
     int count;
-    float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, clamp;
+    float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, clamp, grad_scale;
 };
 __global__ void k_clamp_adam(const __grid_constant__ AdamArgs a) {
     int t = 0;
@@ -1019,7 +1054,7 @@ __global__ void k_clamp_adam(const __grid_constant__ AdamArgs a) {
     for (int i = threadIdx.x; i < ADAM_CHUNK; i += blockDim.x) {
         const long long idx = base + i;
         if (idx >= a.n[t]) break;
-        float gg = fminf(fmaxf(g[idx], -a.clamp), a.clamp);                 // optim.py:10-13 hardtanh
+        float gg = fminf(fmaxf(g[idx] * a.grad_scale, -a.clamp), a.clamp);  // (mean over ranks, then) optim.py:10-13 hardtanh
         const float mm = a.beta1 * m[idx] + (1.f - a.beta1) * gg;
         const float vv = a.beta2 * v[idx] + (1.f - a.beta2) * gg * gg;
         m[idx] = mm;
@@ -1029,7 +1064,8 @@ __global__ void k_clamp_adam(const __grid_constant__ AdamArgs a) {
 }
 
 int clamp_adam(int count, float* const* params, const float* const* grads, float* const* m, float* const* v,
-               const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st) {
+               const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st,
+               float grad_scale) {
     for (int s0 = 0; s0 < count; s0 += ADAM_MAX) {
         AdamArgs a;
         memset(&a, 0, sizeof(a));
@@ -1053,6 +1089,7 @@ int clamp_adam(int count, float* const* params, const float* const* grads, float
         a.beta2 = beta2;
         a.eps = eps;
         a.clamp = clamp;
+        a.grad_scale = grad_scale;
         if (chunks) SRNN_LAUNCH(k_clamp_adam, chunks, 256, 0, st, a);
     }
     return SRNN_OK;

@@ -161,7 +161,9 @@ struct srnn_ctx {
     __nv_bfloat16* w_hid16_t = nullptr;   // (H, H) transposed
     __nv_bfloat16* w_out16_t = nullptr;   // (H, Q) transposed
     unsigned* gru_ctr = nullptr;  // frame-barrier counter of the persistent GRU kernels
-    cudaEvent_t ev_early = nullptr;   // recorded by srnn_predict_bwd once every gradient below the top tier is final
+    // recorded by srnn_predict_bwd as the gradients become final: [0] sample-level MLP + embedding, [1 + 2i] tier i's
+    // upsampling, [2 + 2i] the rest of tier i (srnn_bwd_wait_stage: data-parallel all-reduce overlapping the backward pass)
+    cudaEvent_t ev_stage[2 * SRNN_MAX_TIERS + 1] = {};
     int n_sms = 0;
     srnn::Arena weights;      // freed on destroy
     // grow-only scratch for predict / generate
@@ -232,15 +234,17 @@ int add_int(int* p, int v, cudaStream_t st);
 
 // ---- backward pass + optimizer (backward.cu) --------------------------------------------------------
 size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T);
+// nll_target != null: the upstream gradient is sequence_nll_loss_bits' (fused, dlogp ignored); nll_gscale = device scalar or null
 int predict_bwd_f32(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
-                    cudaStream_t st);
+                    cudaStream_t st, const int64_t* nll_target = nullptr, const float* nll_gscale = nullptr);
 size_t backward_scratch_bytes_bf16(const srnn_ctx* ctx, int B, int T);
 int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const srnn_params* P, const srnn_params* G,
-                     cudaStream_t st);
+                     cudaStream_t st, const int64_t* nll_target = nullptr, const float* nll_gscale = nullptr);
 int gru_seq_bwd_f32(int B, int Fr, int H, const float* GI, const float* GH, const float* Y, const float* h0, const float* dY,
                     const float* w_hh, float* dGI, float* dGH, float* dh0, float* scratch, cudaStream_t st);
 int clamp_adam(int count, float* const* params, const float* const* grads, float* const* m, float* const* v,
-               const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st);
+               const long long* sizes, float lr, float beta1, float beta2, float eps, int step, float clamp, cudaStream_t st,
+               float grad_scale = 1.f);
 
 // ---- tcgen05 / TMA kernels (gemm_umma.cu) ------------------------------------------------------------
 int gemm_umma(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act, int n_rows, int K, int ld_w, int ld_act,

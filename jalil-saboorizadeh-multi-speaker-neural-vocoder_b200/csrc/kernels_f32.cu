@@ -142,7 +142,7 @@ int fill_u8(uint8_t* dst, uint8_t v, size_t n, cudaStream_t st) {
 
 __global__ void k_i64_to_u8(const int64_t* __restrict__ s, uint8_t* __restrict__ d, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        d[i] = (uint8_t)(s[i] & 0xff);
+        d[i] = (uint8_t)(s[i] < 0 ? 0 : (s[i] > SRNN_Q - 1 ? SRNN_Q - 1 : s[i]));   // clamp, like data.quantize (uquantize(1.0) = 256)
 }
 int i64_to_u8(const int64_t* src, uint8_t* dst, size_t n, cudaStream_t st) {
     if (!n) return SRNN_OK;
@@ -797,7 +797,7 @@ __global__ void k_nll_partial(const float* __restrict__ logp, const int64_t* __r
     __shared__ float red[256];
     float s = 0.f;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
-        s -= logp[(size_t)r * SRNN_Q + (int)(target[r] & 0xff)];
+        s -= logp[(size_t)r * SRNN_Q + (int)(target[r] < 0 ? 0 : (target[r] > SRNN_Q - 1 ? SRNN_Q - 1 : target[r]))];
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o; o >>= 1) {

@@ -45,7 +45,10 @@ class TBPTTBatcher:
         self.seq_len, self.batch_size, self.cond_len = int(seq_len), int(batch_size), int(cond_len)
         self.length = int(np.prod(data.shape)) // self.seq_len                        # dataset.py:225 (items)
         self.device = torch.device(device)
-        self.data = torch.as_tensor(data, dtype=torch.float32).to(self.device)
+        # ulaw: float audio in [-1, 1], quantised here.  Linear: the reference quantises every FILE once when the dataset is
+        # created (dataset.py:129-130) and __getitem__ only casts the stored levels with .long() (dataset.py:249-251).
+        self.data = (torch.as_tensor(data, dtype=torch.float32) if self.ulaw else
+                     torch.as_tensor(np.asarray(data).astype(np.int64))).to(self.device)
         self.cond = torch.as_tensor(np.asarray(cond)).to(self.device)                 # float64 as stored (dataset.py:274)
         self.cond_in_seq = self.seq_len // self.cond_len                              # dataset.py:256
         # majority-vote speaker of every (chunk, row): dataset.py:277-281; tiny, done once on the host like the reference
@@ -57,9 +60,9 @@ class TBPTTBatcher:
             for r in range(self.batch_size):
                 votes[k, r] = np.argmax(np.bincount(spk[r][lo:lo + self.cond_in_seq]))
         self.spk = torch.from_numpy(votes).to(self.device)
-        # mu-law quantisation is element-wise: the whole stream is quantised once (one kernel launch); the linear quantiser
-        # normalises every slice by its own min/max (utils.py:11-12), so it runs per batch
-        self.qdata = quantize(self.data, self.q_levels, True) if self.ulaw else None
+        # mu-law quantisation is element-wise: the whole stream is quantised once (one kernel launch); linear-quantised
+        # data is stored as levels already (use ``quantize(file, q_levels, False)`` per file when building such a dataset)
+        self.qdata = quantize(self.data, self.q_levels, True) if self.ulaw else self.data
 
     def __len__(self):
         """number of TBPTT chunks (batches); the reference's len() counts items = chunks * batch_size."""
@@ -71,12 +74,8 @@ class TBPTTBatcher:
         start_data = n_batch * self.seq_len                                           # dataset.py:245-247
         start_target = start_data + self.overlap_len
         end_target = start_target + self.seq_len
-        if self.ulaw:
-            data = self.qdata[:, start_data:end_target - 1].contiguous()
-            target = self.qdata[:, start_target:end_target].contiguous()
-        else:
-            data = quantize(self.data[:, start_data:end_target - 1], self.q_levels, False)
-            target = quantize(self.data[:, start_target:end_target], self.q_levels, False)
+        data = self.qdata[:, start_data:end_target - 1].contiguous()              # dataset.py:249-253
+        target = self.qdata[:, start_target:end_target].contiguous()
         reset = n_batch == 0                                                          # dataset.py:258-263
         from_cond = n_batch * self.cond_in_seq + 1
         cond = self.cond[:, from_cond:from_cond + self.cond_in_seq].contiguous()

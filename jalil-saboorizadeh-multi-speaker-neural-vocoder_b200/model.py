@@ -284,6 +284,18 @@ class _PredictFn(torch.autograd.Function):
         dev = model._ctx_device
         B, Lseq = input_sequences.shape
         T = Lseq - model.lookback + 1
+        # the library reads raw pointers: every shape is checked here (the reference fails in its .view calls, model.py:406-408)
+        if T < model.lookback or T % model.lookback:
+            raise ValueError("input_sequences must be (B, lookback + T - 1) with T a positive multiple of lookback = %d"
+                             % model.lookback)
+        if tuple(cond.shape) != (B, T // model.lookback, model.cond_dim):
+            raise ValueError("cond must be (B, T / lookback, cond_dim) = (%d, %d, %d), got %s"
+                             % (B, T // model.lookback, model.cond_dim, tuple(cond.shape)))
+        if spk.numel() != B:
+            raise ValueError("spk must hold one speaker id per sequence")
+        for name, t, hi in (("input_sequences", input_sequences, model.q_levels), ("spk", spk, model.spk_dim)):
+            if not t.is_cuda and t.numel() and (int(t.min()) < 0 or int(t.max()) >= hi):   # host tensors: free to check
+                raise ValueError("%s holds values outside [0, %d)" % (name, hi))
         seq = input_sequences.to(device=dev, dtype=torch.int64).contiguous()
         if cond.dtype not in (torch.float32, torch.float64):
             cond = cond.float()
@@ -292,7 +304,10 @@ class _PredictFn(torch.autograd.Function):
         mask, ptrs = 0, (C.c_void_p * len(model.frame_level_rnns))()
         for i, rnn in enumerate(model.frame_level_rnns):
             hs = runner.hidden_states[rnn]
-            if hs is None or hs.shape[1] != B:                           # model.py:222-228 start from h0
+            if hs is not None and hs.shape[1] != B:                      # the reference's nn.GRU raises on a carried state
+                raise ValueError("batch size changed from %d to %d with a carried hidden state: call "
+                                 "reset_hidden_states() or pass reset=True" % (hs.shape[1], B))
+            if hs is None:                                               # model.py:222-228 start from h0
                 hs = torch.empty(model.n_rnn, B, model.dim, device=dev, dtype=torch.float32)
                 mask |= 1 << i
             else:
@@ -315,21 +330,54 @@ class _PredictFn(torch.autograd.Function):
         model, params = ctx.model, ctx.params
         (logp,) = ctx.saved_tensors
         dev = model._ctx_device
-        # Gradient destinations: a fresh tensor per parameter (autograd then accumulates it into p.grad), unless the optimizer
-        # has published zeroed gradient views for this step (ClampAdam.zero_grad -> model._grad_sink): the library then
-        # writes straight into them and autograd gets None -- no 46 extra accumulate launches over 229 MB.
-        sink = getattr(model, "_grad_sink", None)
-        model._grad_sink = None
-        direct = sink is not None and all(id(p) in sink for p in params)
-        model._grad_sink_used = direct
-        grads = {id(p): (sink[id(p)] if direct else torch.empty_like(p)) for p in params}
-        G = model._c_params(ptr=lambda t: grads[id(t)].data_ptr() if id(t) in grads else None)
-        P = model._c_params()
         dlogp = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+        grads = _backward_into(model, params, lambda P, G: L.load().srnn_predict_bwd(
+            model._ctx, logp.data_ptr(), dlogp.data_ptr(), C.byref(P), C.byref(G), _stream()))
+        return (None, None, None, None, None) + grads
+
+
+def _backward_into(model, params, call):
+    """Run one library backward pass (``call(P, G)`` -> status) and return the per-parameter gradients for autograd.
+    Gradient destinations: a fresh tensor per parameter (autograd then accumulates it into p.grad), unless the optimizer has
+    published zeroed gradient views for this step (ClampAdam.zero_grad -> model._grad_sink): the library then writes
+    straight into them and autograd gets None -- no 46 extra accumulate launches over 229 MB."""
+    sink = getattr(model, "_grad_sink", None)
+    model._grad_sink = None
+    direct = sink is not None and all(id(p) in sink for p in params)
+    model._grad_sink_used = direct
+    grads = {id(p): (sink[id(p)] if direct else torch.empty_like(p)) for p in params}
+    G = model._c_params(ptr=lambda t: grads[id(t)].data_ptr() if id(t) in grads else None)
+    P = model._c_params()
+    with torch.cuda.device(model._ctx_device):
+        L.check(call(P, G))
+    return tuple(None if direct else grads[id(p)] for p in params)
+
+
+class _PredictNllFn(torch.autograd.Function):
+    """``sequence_nll_loss_bits(Predictor.forward(...), target)`` as ONE autograd node over the parameters (nn.py:66-70 +
+    trainer/__init__.py:102-103): forward = srnn_nll_loss_bits, backward = srnn_predict_bwd_nll, which folds the loss
+    gradient into the log-softmax backward.  No dense (B, T, Q) dL/dlogp and no torch kernel in the step."""
+
+    @staticmethod
+    def forward(ctx, model, logp, target, *params):
+        dev = model._ctx_device
+        target = target.to(device=dev, dtype=torch.int64).contiguous()
+        if target.numel() * logp.shape[-1] != logp.numel():
+            raise ValueError("target must hold one class index per log-prob row")
+        loss = torch.empty((), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            L.check(L.load().srnn_predict_bwd(model._ctx, logp.data_ptr(), dlogp.data_ptr(), C.byref(P), C.byref(G),
-                                              _stream()))
-        return (None, None, None, None, None) + tuple(None if direct else grads[id(p)] for p in params)
+            L.check(L.load().srnn_nll_loss_bits(model._ctx, logp.data_ptr(), target.data_ptr(), int(target.numel()),
+                                                loss.data_ptr(), _stream()))
+        ctx.model, ctx.params, ctx.logp, ctx.target = model, params, logp, target
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        model, params, logp, target = ctx.model, ctx.params, ctx.logp, ctx.target
+        g = g.to(device=model._ctx_device, dtype=torch.float32).contiguous()
+        grads = _backward_into(model, params, lambda P, G: L.load().srnn_predict_bwd_nll(
+            model._ctx, logp.data_ptr(), target.data_ptr(), g.data_ptr(), C.byref(P), C.byref(G), _stream()))
+        return (None, None, None) + grads
 
 
 class Predictor(Runner, tnn.Module):
@@ -343,7 +391,9 @@ class Predictor(Runner, tnn.Module):
         if reset:
             self.reset_hidden_states()                                   # model.py:358-359
         params = [p for p in self.model.parameters() if p.requires_grad] if torch.is_grad_enabled() else []
-        return _PredictFn.apply(self, input_sequences, cond, spk, self.mode, *params)
+        out = _PredictFn.apply(self, input_sequences, cond, spk, self.mode, *params)
+        out._srnn_rec = (self.model, tuple(params))    # lets sequence_nll_loss_bits fuse the loss into the backward pass
+        return out
 
 
 class Generator(Runner):
@@ -382,12 +432,17 @@ class Generator(Runner):
                 cond, cond_rows = cond.expand(n_seqs, -1, -1).contiguous(), n_seqs
             else:
                 raise ValueError("spk must hold one id per conditioner row")
+        if not spk.is_cuda and spk.numel() and (int(spk.min()) < 0 or int(spk.max()) >= model.spk_dim):
+            raise ValueError("spk holds ids outside [0, %d)" % model.spk_dim)
         spk = spk.to(device=dev, dtype=torch.int64).contiguous()
         T = n_cond * model.lookback                                      # model.py:455
         if uniforms is None:
-            g = torch.Generator(device=dev)
-            g.manual_seed(int(seed) if seed is not None else torch.seed() % (2 ** 31))
-            uniforms = torch.rand(T, n_seqs, device=dev, dtype=torch.float32, generator=g)
+            if seed is not None:
+                g = torch.Generator(device=dev)
+                g.manual_seed(int(seed))
+                uniforms = torch.rand(T, n_seqs, device=dev, dtype=torch.float32, generator=g)
+            else:       # consume the global CUDA stream like the reference's multinomial (model.py:517): no re-seeding
+                uniforms = torch.rand(T, n_seqs, device=dev, dtype=torch.float32)
         else:
             uniforms = torch.as_tensor(uniforms).to(device=dev, dtype=torch.float32).contiguous()
             if tuple(uniforms.shape) != (T, n_seqs):

@@ -22,27 +22,45 @@ class ClampAdam:
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, clamp=1.0, process_group=None, model=None):
         self.params = [p for p in params if p.requires_grad]
-        # bucket order: everything below the top tier first (its gradients are final before the top tier's backward pass
-        # runs, srnn_bwd_wait_early), the top tier's parameters last
-        self._n_early = 0
+        # Bucket order = the order in which srnn_predict_bwd finalises gradients (srnn_bwd_wait_stage): sample-level MLP +
+        # embedding, then per tier (lowest first) its upsampling and the rest.  Each stage is all-reduced on a side stream as
+        # soon as its event fires, i.e. while the backward pass of the following stages still runs.
+        self._stages = []                   # [(stage id, first element, one-past-last element)]
         if model is not None:
-            late = {id(p) for p in model.frame_level_rnns[-1].parameters()}
-            early = [p for p in self.params if id(p) not in late]
-            self.params = early + [p for p in self.params if id(p) in late]
-            self._n_early = sum(p.numel() for p in early)
+            groups = [(0, list(model.sample_level_mlp.parameters()))]
+            for i, rnn in enumerate(model.frame_level_rnns):
+                up = list(rnn.upsampling.parameters())
+                ids = {id(p) for p in up}
+                groups.append((1 + 2 * i, up))
+                groups.append((2 + 2 * i, [p for p in rnn.parameters() if id(p) not in ids]))
+            mine = {id(p) for p in self.params}
+            ordered, seen, off = [], set(), 0
+            for sid, ps in groups:
+                ps = [p for p in ps if id(p) in mine and id(p) not in seen]
+                seen.update(id(p) for p in ps)
+                n = sum(p.numel() for p in ps)
+                if n:
+                    self._stages.append((sid, off, off + n))
+                ordered += ps
+                off += n
+            rest = [p for p in self.params if id(p) not in seen]       # parameters the backward pass does not know about
+            if rest:
+                self._stages = []
+            self.params = ordered + rest
         self._comm_stream = None
         self.lr, self.betas, self.eps, self.clamp = lr, betas, eps, clamp
         self.step_count = 0
-        self.exp_avg = [torch.zeros_like(p) for p in self.params]
-        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg = self.exp_avg_sq = None          # allocated on the parameters' device at the first step
         self.process_group = process_group
         self.model = model                  # the SampleRNN whose packed weights must be refreshed after an update
         self.param_groups = [{"params": self.params, "lr": lr}]       # enough for torch LR schedulers' read access
         self._flat = None
         self._views = None
+        self._grad_scale = 1.0
 
     def _bucket(self):
-        """(Re)build the flat gradient bucket when the parameters moved (e.g. ``.cuda()`` after construction)."""
+        """(Re)build the flat gradient bucket and the Adam moments when the parameters moved (e.g. ``.cuda()`` after
+        construction); the moments follow the parameters' device."""
         p0 = self.params[0]
         if self._flat is None or self._flat.device != p0.device:
             self._flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=p0.device)
@@ -51,6 +69,12 @@ class ClampAdam:
                 n = p.numel()
                 self._views.append(self._flat[off:off + n].view_as(p))
                 off += n
+        if self.exp_avg is None:
+            self.exp_avg = [torch.zeros_like(p) for p in self.params]
+            self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        elif self.exp_avg[0].device != p0.device:
+            self.exp_avg = [t.to(p0.device) for t in self.exp_avg]
+            self.exp_avg_sq = [t.to(p0.device) for t in self.exp_avg_sq]
         return self._flat
 
     def _adopt(self):
@@ -72,23 +96,26 @@ class ClampAdam:
 
     def _allreduce(self, overlap=False):
         import torch.distributed as dist
+        self._grad_scale = 1.0
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) == 1:
             return
-        flat, n0 = self._flat, self._n_early
-        if overlap and flat.is_cuda and 0 < n0 < flat.numel():
-            # two buckets over NVLink: the early one is reduced on a side stream as soon as the library signals that those
-            # gradients are final, i.e. while the top tier's backward pass still runs on the compute stream
+        flat = self._flat
+        if overlap and flat.is_cuda and len(self._stages) > 1:
+            # one NCCL all-reduce per backward stage over NVLink, enqueued on a side stream behind that stage's event: the
+            # MLP bucket is reduced while the tiers' backward passes run, tier i's while tier i+1's runs, ...
             if self._comm_stream is None:
                 self._comm_stream = torch.cuda.Stream(device=flat.device)
-            comm = self._comm_stream
-            L.check(L.load().srnn_bwd_wait_early(self.model._ctx, C.c_void_p(comm.cuda_stream)))
-            with torch.cuda.stream(comm):
-                work = dist.all_reduce(flat[:n0], group=self.process_group, async_op=True)
-            dist.all_reduce(flat[n0:], group=self.process_group)
-            work.wait()                                                # the compute stream waits for the early bucket
+            comm, lib, works = self._comm_stream, L.load(), []
+            for sid, a, b in self._stages:
+                L.check(lib.srnn_bwd_wait_stage(self.model._ctx, sid, C.c_void_p(comm.cuda_stream)))
+                with torch.cuda.stream(comm):
+                    works.append(dist.all_reduce(flat[a:b], group=self.process_group, async_op=True))
+            for w in works:
+                w.wait()                                               # the compute stream waits for the collectives
         else:
             dist.all_reduce(flat, group=self.process_group)           # sum over ranks, in place, one collective
-        flat.mul_(1.0 / dist.get_world_size(self.process_group))      # mean BEFORE the clamp (optim.py:10-13 clamps the full-batch gradient)
+        # the mean BEFORE the clamp (optim.py:10-13 clamps the full-batch gradient) is folded into k_clamp_adam
+        self._grad_scale = 1.0 / dist.get_world_size(self.process_group)
 
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -105,11 +132,14 @@ class ClampAdam:
         sizes = (C.c_int64 * n)(*[p.numel() for p in self.params])
         lr = self.param_groups[0]["lr"]
         dev = self.params[0].device
+        for t in list(self.params) + [p.grad for p in self.params] + self.exp_avg + self.exp_avg_sq:
+            if t.device != dev or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise L.SrnnError("ClampAdam: every parameter, gradient and moment must be contiguous fp32 on one CUDA device")
         with torch.cuda.device(dev):
-            L.check(L.load().srnn_clamp_adam_step(n, arr([p.data for p in self.params]), arr([p.grad for p in self.params]),
-                                                  arr(self.exp_avg), arr(self.exp_avg_sq), sizes, lr, self.betas[0],
-                                                  self.betas[1], self.eps, self.step_count, self.clamp,
-                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            L.check(L.load().srnn_clamp_adam_step_scaled(
+                n, arr([p.data for p in self.params]), arr([p.grad for p in self.params]), arr(self.exp_avg),
+                arr(self.exp_avg_sq), sizes, lr, self.betas[0], self.betas[1], self.eps, self.step_count, self.clamp,
+                self._grad_scale, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         # the library updated the parameters behind torch's back: make SampleRNN re-pack them on the next forward
         if self.model is not None:
             self.model._packed_key = None
@@ -121,9 +151,41 @@ class ClampAdam:
 
 
 def sequence_nll_loss_bits(logp, target, model=None):
-    """nn.py:66-70 through the fused CUDA reduction when no gradient is needed; autograd-friendly torch expression
-    otherwise (the gradient of the loss w.r.t. the log-probs is a constant scatter, there is nothing to fuse)."""
-    import math
-    Q = logp.shape[-1]
-    picked = logp.reshape(-1, Q).gather(1, target.reshape(-1, 1).long().to(logp.device))
-    return -picked.mean() * math.log(math.e, 2)
+    """nn.py:66-70: ``nll_loss(logp.view(-1, Q), target.view(-1)) * log2(e)``, mean over B*T, in bits.
+
+    ``logp`` straight from ``Predictor.forward`` (the training closure, trainer/__init__.py:100-103): the loss is the CUDA
+    reduction ``srnn_nll_loss_bits`` and its backward is ``srnn_predict_bwd_nll`` -- the constant loss gradient is folded
+    into the log-softmax backward kernel, which writes ``dlogits`` (fp32 + bf16) where the output-layer GEMMs read them, so
+    neither a dense dL/dlogp nor any torch kernel runs in the step.  Any other CUDA fp32 ``logp`` needs ``model=`` (the
+    SampleRNN whose context owns the reduction scratch); its backward is the plain scatter.  No CPU path."""
+    from . import model as M
+    rec = getattr(logp, "_srnn_rec", None)
+    if rec is not None and logp.grad_fn is not None:
+        mdl, params = rec
+        return M._PredictNllFn.apply(mdl, logp.detach(), target, *params)
+    mdl = rec[0] if rec is not None else model
+    if mdl is None or not logp.is_cuda:
+        raise L.SrnnError("sequence_nll_loss_bits runs on the CUDA library only: pass Predictor output or model=")
+    return _NllBitsFn.apply(mdl, logp, target)
+
+
+class _NllBitsFn(torch.autograd.Function):
+    """Generic form for log-probs that did not come from Predictor.forward: fused forward reduction, scatter backward."""
+
+    @staticmethod
+    def forward(ctx, mdl, logp, target):
+        lp = logp.detach().to(torch.float32).contiguous()
+        tgt = target.to(device=lp.device, dtype=torch.int64).contiguous()
+        loss = torch.empty((), device=lp.device, dtype=torch.float32)
+        with torch.cuda.device(lp.device):
+            L.check(L.load().srnn_nll_loss_bits(mdl._context(), lp.data_ptr(), tgt.data_ptr(), int(tgt.numel()),
+                                                loss.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ctx.shape, ctx.tgt = logp.shape, tgt
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        Q = ctx.shape[-1]
+        d = torch.zeros(ctx.tgt.numel(), Q, device=ctx.tgt.device, dtype=torch.float32)
+        d.scatter_(1, ctx.tgt.reshape(-1, 1), (-g * (1.4426950408889634 / ctx.tgt.numel())).expand(ctx.tgt.numel(), 1))
+        return None, d.reshape(ctx.shape), None

@@ -48,6 +48,27 @@ def test_gpu_quantisers_against_reference():
 
 
 @pytest.mark.gpu
+def test_gpu_tbptt_linear_batches_against_reference():
+    """ulaw=False: the stored data is already quantised per file (dataset.py:129-130); items are exact slices cast to int64
+    (dataset.py:249-251), input and target of one sample always agree."""
+    import srnn_b200 as S
+    stored = np.stack([D.linear_quantize(r, Q) for r in Z["data"]])
+    bt = S.TBPTTBatcher(stored, Z["cond"], Z["global_spk"], OVERLAP, Q, False, SEQ, BS, COND_LEN)
+    n_items = int(Z["lin/n_items"])
+    for k in range(n_items // BS):
+        data, reset, target, cond, spk = bt.batch(k)
+        assert data.dtype == torch.int64 and target.dtype == torch.int64
+        for r in range(BS):
+            idx = k * BS + r
+            assert np.array_equal(data[r].cpu().numpy(), Z[f"lin/{idx}/data"])
+            assert np.array_equal(target[r].cpu().numpy(), Z[f"lin/{idx}/target"])
+            assert np.array_equal(cond[r].cpu().numpy(), Z[f"lin/{idx}/cond"])
+            assert int(spk[r, 0]) == int(Z[f"lin/{idx}/spk"][0]) and bool(reset) == bool(Z[f"lin/{idx}/reset"])
+        # the same sample seen as an input and as a target is the same level
+        assert torch.equal(data[:, OVERLAP:], target[:, :-1])
+
+
+@pytest.mark.gpu
 def test_gpu_tbptt_batches_against_reference():
     import srnn_b200 as S
     bt = S.TBPTTBatcher(Z["data"], Z["cond"], Z["global_spk"], OVERLAP, Q, True, SEQ, BS, COND_LEN)

@@ -77,7 +77,9 @@ def test_clamp_adam_against_oracle_formula():
 
 
 # B = 100: both 64-row halves of the persistent GRU kernels; B = 130: beyond them, the frame-by-frame fallback schedule
-@pytest.mark.parametrize("dim,B,T", [(64, 3, 160), (128, 5, 80), (64, 100, 80), (64, 130, 80)])
+# (1024, 8, 1040) and (1024, 72, 1040) are BASELINE.json configs[2] (C3) at its own width and sequence length: 13 / 52-frame
+# persistent GRU launches, the CTA-pair GEMMs and the 20-tap table gradient at H = 1024; B = 72 runs both 64-row halves
+@pytest.mark.parametrize("dim,B,T", [(64, 3, 160), (128, 5, 80), (64, 100, 80), (64, 130, 80), (1024, 8, 1040), (1024, 72, 1040)])
 def test_bf16_backward_against_oracle(dim, B, T):
     """tcgen05 training path: gradients within bf16 accuracy of the fp32 oracle (relative L2 per tensor)."""
     torch.manual_seed(dim + 7)

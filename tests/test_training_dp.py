@@ -35,7 +35,7 @@ def _gloo_worker(rank, world, port, out):
     opt._adopt()
     opt._allreduce()
     if rank == 0:
-        out.put([float(p.grad.mean()) for p in ps] + [float(opt._flat.numel())])
+        out.put([float(p.grad.mean()) * opt._grad_scale for p in ps] + [float(opt._flat.numel())])   # the mean is folded into the Adam kernel
     dist.barrier()
     dist.destroy_process_group()
 
