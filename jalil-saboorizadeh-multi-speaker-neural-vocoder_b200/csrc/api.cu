@@ -499,9 +499,10 @@ int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, 
 // Generator.__call__  (model.py:445-520): one CUDA graph per top-tier period (lookback samples), replayed n_cond
 // times.  fp32 mode: FFMA GEMMs.  bf16 mode: the same schedule with every H-wide contraction on tcgen05 (gemm_umma).
 // ------------------------------------------------------------------------------------------------
+// cluster_rows: 0 = k_mlp_persist (16-CTA row groups over L2), 16 / 24 = k_mlp_cluster (8-CTA clusters, rows per cluster)
 static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_cond, const float* cond, int cond_rows,
                           const int64_t* spk, const float* uniforms, int u_ld, uint8_t* samples_out, float* audio_out,
-                          float* logp_out, cudaStream_t user) {
+                          float* logp_out, cudaStream_t user, int cluster_rows = 0) {
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
     const int T = n_cond * lookback, Lseq = lookback + T;
@@ -515,6 +516,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     float* part = nullptr;
     unsigned* gctr = nullptr;
     const int RG = (B + 31) / 32, NS = H / 64;
+    const int n_clusters = cluster_rows ? (B + cluster_rows - 1) / cluster_rows : 0;
+    const size_t x1_rows = (size_t)RG * 32 > (size_t)n_clusters * cluster_rows ? (size_t)RG * 32 : (size_t)n_clusters * cluster_rows;
+    const int sample_ctas = cluster_rows ? n_clusters * 8 : RG * NS;
     for (int pass = 0; pass < 2; ++pass) {
         Bump b(pass ? ctx->ws : nullptr);
         seq = b.take<uint8_t>((size_t)B * Lseq);
@@ -534,9 +538,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         X1 = b.take<float>((size_t)B * H);
         X2 = b.take<float>((size_t)B * H);
         LG = b.take<float>((size_t)B * Q);
-        X1h = b.take<bf>((size_t)RG * 32 * H);
+        X1h = b.take<bf>(x1_rows * H);
         X2h = b.take<bf>((size_t)B * H);
-        part = b.take<float>(persist ? (size_t)RG * NS * 32 * Q : 1);
+        part = b.take<float>(persist && !cluster_rows ? (size_t)RG * NS * 32 * Q : 1);
         gctr = b.take<unsigned>(2 * RG);
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
     }
@@ -597,7 +601,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // behind.  With the persistent sample kernel on RG x NS CTAs (128 at C2) the remaining SMs (20) are idle for the ~180 us
     // of a launch, so these GEMMs (96 tiles at C2) run there, capped to that many CTAs, beside the sample kernel instead of in
     // front of the next tier step ("shadow" schedule; SRNN_NO_SHADOW_GH=1 restores the fork beside the input expansion).
-    int spare_sms = persist ? ctx->n_sms - ((B + 31) / 32) * (H / 64) : 0;
+    int spare_sms = persist ? ctx->n_sms - sample_ctas : 0;
+    if (cluster_rows && spare_sms > 24) spare_sms = 24;      // leave whole GPCs free: a cluster needs 8 free SMs of ONE GPC
     if (getenv("SRNN_SHADOW_CTAS") && atoi(getenv("SRNN_SHADOW_CTAS")) > 0 && atoi(getenv("SRNN_SHADOW_CTAS")) < spare_sms)
         spare_sms = atoi(getenv("SRNN_SHADOW_CTAS"));          // experiment: fewer CTAs for the shadow GEMMs
     const bool shadow_gh = bf16 && fused_cell && persist && spare_sms >= 8 && !skip_tiers && !getenv("SRNN_NO_SHADOW_GH");
@@ -645,10 +650,14 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         SRNN_TRY(launch_xp(-ttop.n, st));                                            // first period: the q_zero prefix
     }
 
-    if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * (size_t)RG * 32 * H, st));
+    if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * x1_rows * H, st));
     if (persist) SRNN_CUDA(cudaMemsetAsync(gctr, 0, sizeof(unsigned) * 2 * RG, st));     // group barrier counters: once per call
     long long* trace = nullptr;
-    if (persist && getenv("SRNN_TRACE")) SRNN_CUDA(cudaMallocManaged((void**)&trace, sizeof(long long) * FS0 * 64));
+    const size_t trace_n = (size_t)(cluster_rows ? 8 : 1) * FS0 * 64;
+    if (persist && getenv("SRNN_TRACE")) {
+        SRNN_CUDA(cudaMalloc((void**)&trace, sizeof(long long) * trace_n));
+        SRNN_CUDA(cudaMemset(trace, 0, sizeof(long long) * trace_n));
+    }
     const bool time_kernels = persist && getenv("SRNN_TIME_KERNELS");
     const bool time_tiers = getenv("SRNN_TIME_TIERS") != nullptr;   // development aid: per-kernel durations of the tier steps
     bool use_graph = !getenv("SRNN_NO_GRAPH") && !time_kernels && !time_tiers;
@@ -795,18 +804,23 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 mp.B = B; mp.H = H; mp.FS = FS0; mp.nsteps = FS0; mp.pos0 = pos; mp.lookback = lookback;
                 mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
                 mp.tbl = ctx->tbl16; mp.b_hid = ctx->b_hid; mp.b_out = ctx->b_out; mp.x1 = X1h; mp.part = part;
+                mp.dbg = getenv("SRNN_MC_DBG") ? atoi(getenv("SRNN_MC_DBG")) : 0;
                 mp.ctr = gctr; mp.uniforms = uniforms; mp.u_ld = u_ld; mp.logp_out = logp_out; mp.trace = trace;
+                auto launch_sample = [&]() -> int {
+                    return cluster_rows ? mlp_cluster_launch(ctx->w_hid16, ctx->w_out16, mp, cluster_rows, st)
+                                        : mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st);
+                };
                 if (time_kernels) {
                     cudaEvent_t e0, e1;
                     SRNN_CUDA(cudaEventCreate(&e0));
                     SRNN_CUDA(cudaEventCreate(&e1));
                     SRNN_CUDA(cudaEventRecord(e0, st));
-                    SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
+                    SRNN_TRY(launch_sample());
                     SRNN_CUDA(cudaEventRecord(e1, st));
                     tev.push_back(e0);
                     tev.push_back(e1);
                 } else {
-                    SRNN_TRY(mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st));
+                    SRNN_TRY(launch_sample());
                 }
                 continue;
             }
@@ -897,10 +911,57 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         ctx->timed_ms = tot;
         ctx->timed_launches = (long long)(tev.size() / 2);
     }
+    if (trace && cluster_rows) {   // debugging aid: phase durations (SM cycles) of the 8 CTAs of cluster 0, last launch
+        SRNN_CUDA(cudaStreamSynchronize(st));
+        std::vector<long long> ht(trace_n);
+        SRNN_CUDA(cudaMemcpy(ht.data(), trace, sizeof(long long) * trace_n, cudaMemcpyDeviceToHost));
+        static const char* nm[9] = {"tbl+waitP", "x1 rows", "signal", "flags+TMA+MMA1", "epi1", "MMA2", "epi2+push", "land wait",
+                                    "reduce+sample"};
+        for (int cta = 0; cta < 8; ++cta) {
+            const long long* tr = ht.data() + (size_t)cta * FS0 * 64;
+            double acc[9] = {0}, tot = 0, woke = 0, lastmma = 0;
+            for (int k = 2; k < FS0; ++k) {
+                for (int j = 0; j < 9; ++j) acc[j] += (double)(tr[k * 64 + j + 1] - tr[k * 64 + j]);
+                woke += (double)(tr[k * 64 + 10] - tr[k * 64 + 3]);
+                lastmma += (double)(tr[k * 64 + 14] - tr[k * 64 + 3]);
+            }
+            for (int k = 3; k < FS0; ++k) tot += (double)(tr[k * 64] - tr[(k - 1) * 64]);
+            fprintf(stderr, "[srnn trace] k_mlp_cluster CTA%d:", cta);
+            for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%.0f", nm[j], acc[j] / (FS0 - 2));
+            double red = 0, smx = 0;
+            for (int k = 2; k < FS0; ++k) {
+                red += (double)(tr[k * 64 + 11] - tr[k * 64 + 8]);
+                smx += (double)(tr[k * 64 + 12] - tr[k * 64 + 11]);
+            }
+            {
+                double ga[4] = {0}, d1 = 0, m2 = 0;
+                for (int k = 2; k < FS0; ++k) {
+                    for (int g2 = 0; g2 < 4; ++g2) ga[g2] += (double)(tr[k * 64 + 16 + g2] - tr[k * 64 + 10]);
+                    d1 += (double)(tr[k * 64 + 4] - tr[k * 64 + 10]);
+                    m2 += (double)(tr[k * 64 + 15] - tr[k * 64 + 5]);
+                }
+                fprintf(stderr, " [since TMA issue: group landed %.0f %.0f %.0f %.0f, D1 done %.0f; MMA2 issued %.0f after x2]",
+                        ga[0] / (FS0 - 2), ga[1] / (FS0 - 2), ga[2] / (FS0 - 2), ga[3] / (FS0 - 2), d1 / (FS0 - 2), m2 / (FS0 - 2));
+            }
+            fprintf(stderr, " (reduce %.0f softmax+sample %.0f) | flags@%.0f lastMMA@%.0f (since signal) | step=%.0f | entry->step0=%lld step0=%lld\n",
+                    red / (FS0 - 2), smx / (FS0 - 2), woke / (FS0 - 2), lastmma / (FS0 - 2), tot / (FS0 - 3), tr[0] - tr[63], tr[64] - tr[0]);
+        }
+        cudaFree(trace);
+        trace = nullptr;
+    }
     if (trace) {   // debugging aid: average phase durations (SM cycles) of CTA 0 over the last persistent launch
         SRNN_CUDA(cudaStreamSynchronize(st));
-        static const char* names[9] = {"wait P", "x1 slice", "barrier A", "TMA+MMA1", "epilogue1", "MMA2", "epilogue2",
-                                       "barrier B", "reduce+sample"};
+        {
+            long long* ht = (long long*)malloc(sizeof(long long) * trace_n);
+            cudaMemcpy(ht, trace, sizeof(long long) * trace_n, cudaMemcpyDeviceToHost);
+            cudaFree(trace);
+            trace = ht;
+        }
+        static const char* names_v1[9] = {"wait P", "x1 slice", "barrier A", "TMA+MMA1", "epilogue1", "MMA2", "epilogue2",
+                                          "barrier B", "reduce+sample"};
+        static const char* names_v2[9] = {"tbl loads+wait P", "x1 rows", "signal", "flags+TMA+MMA1", "epilogue1", "MMA2",
+                                          "epilogue2+push", "land wait", "reduce+sample"};
+        const char* const* names = cluster_rows ? names_v2 : names_v1;
         double acc[9] = {0}, tot = 0;
         double w[5] = {0};
         for (int k = 2; k < FS0; ++k) {
@@ -924,10 +985,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%lld", names[j], trace[k * 64 + j + 1] - trace[k * 64 + j]);
             fprintf(stderr, "\n");
         }
-        fprintf(stderr, "[srnn trace] k_mlp_persist CTA0 cycles/step:");
+        fprintf(stderr, "[srnn trace] %s CTA0 cycles/step:", cluster_rows ? "k_mlp_cluster" : "k_mlp_persist");
         for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%.0f", names[j], acc[j] / (FS0 - 2));
         fprintf(stderr, " | step=%.0f\n", tot / (FS0 - 3));
-        cudaFree(trace);
+        free(trace);
     }
     SRNN_CUDA(cudaEventRecord(ev_out, st));
     SRNN_CUDA(cudaStreamWaitEvent(user, ev_out, 0));
@@ -962,7 +1023,17 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
         const bool bf16 = mode != SRNN_MODE_FP32;
         int n_sms = 0;
         SRNN_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        const bool persist = mode == SRNN_MODE_BF16 && mlp_persist_supported(ctx->H, ctx->FS0, B, n_sms);
+        // sample-level kernel: the 8-CTA cluster form (H = 1024) when the batch fits the co-resident clusters, else the 16-CTA
+        // row-group form over L2 (any H % 64 == 0); SRNN_MLP_V1=1 forces the latter
+        const int maxc = (mode == SRNN_MODE_BF16 && ctx->H == 1024 && !getenv("SRNN_MLP_V1")) ? mlp_cluster_max_clusters() : 0;
+        auto cluster_rows_for = [&](int b) {
+            if (!mlp_cluster_supported(ctx->H, ctx->FS0, b, maxc)) return 0;
+            if (getenv("SRNN_CLUSTER_ROWS")) return atoi(getenv("SRNN_CLUSTER_ROWS")) == 16 && (b + 15) / 16 <= maxc ? 16 : 24;
+            return mlp_cluster_rows(b, maxc);
+        };
+        const int crows = cluster_rows_for(B);
+        const bool persist = mode == SRNN_MODE_BF16 && (crows || mlp_persist_supported(ctx->H, ctx->FS0, B, n_sms));
+        if (mode == SRNN_MODE_BF16) srnn::g_sample_kernel = crows ? "k_mlp_cluster" : "k_mlp_persist";
         // Batches beyond what the persistent sample-level kernel can keep co-resident (RG * NS CTAs <= SMs: 288 utterances at
         // dim 1024): balanced utterance chunks run back to back through the persistent path (utterances are independent), which
         // beats the one-GEMM-launch-per-contraction schedule up to ~800 utterances (measured chunked / unchunked, x real-time:
@@ -981,13 +1052,14 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
                                             own ? Bc : 1, spk + (own ? b0 : 0), uniforms + b0, B,
                                             samples_out ? samples_out + (size_t)b0 * T : nullptr,
                                             audio_out ? audio_out + (size_t)b0 * T : nullptr,
-                                            logp_out ? logp_out + (size_t)b0 * T * SRNN_Q : nullptr, (cudaStream_t)stream));
+                                            logp_out ? logp_out + (size_t)b0 * T * SRNN_Q : nullptr, (cudaStream_t)stream,
+                                            cluster_rows_for(Bc)));
                 }
                 return SRNN_OK;
             }
         }
         return generate_graph(ctx, bf16, persist, B, n_cond, cond, cond_rows, spk, uniforms, B, samples_out, audio_out,
-                              logp_out, (cudaStream_t)stream);
+                              logp_out, (cudaStream_t)stream, crows);
     }
     return fail(SRNN_ERR_UNSUPPORTED, "generate: mode %d not available", mode);
 }

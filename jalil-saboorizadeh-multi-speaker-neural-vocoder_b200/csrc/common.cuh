@@ -266,9 +266,17 @@ struct MlpPersistParams {
     int u_ld;
     float* logp_out;              // (B, T, 256) or null
     long long* trace;             // optional (nsteps, 10) clock64 stamps of CTA 0 (SRNN_TRACE=1), else null
+    int dbg = 0;                  // development switches of k_mlp_cluster (SRNN_MC_DBG), 0 in production
 };
 int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
                        cudaStream_t st);
+// cluster form (mlp_cluster.cu, H = 1024): rows_per_cluster = 16 or 24; p.x1 holds ceil(B / rows) * rows rows; part / ctr unused
+bool mlp_cluster_supported(int H, int FS, int B, int max_clusters);
+int mlp_cluster_rows(int B, int max_clusters);
+int mlp_cluster_max_clusters();
+int mlp_cluster_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p, int rows_per_cluster,
+                       cudaStream_t st);
+extern const char* g_sample_kernel;
 size_t mlp_persist_smem(int H);
 bool mlp_persist_supported(int H, int FS, int B, int n_sms);
 struct GemmOperands {

@@ -28,7 +28,7 @@ namespace srnn {
 
 using namespace ptx;
 
-constexpr int MC_THREADS = 416;
+constexpr int MC_THREADS = 384;            // 12 warps = 3 per SM sub-partition: 168 registers per thread (13 warps: 128)
 constexpr int MC_CS = 8;                 // CTAs per cluster = feature slices of 128
 constexpr int MC_H = 1024;
 constexpr int MC_KB = 16;                // k-blocks of 64
@@ -82,6 +82,15 @@ __device__ __forceinline__ void mc_bf16x8_to_f32(const uint4& u, float* f) {
     }
 }
 
+// exact warp-wide float maximum through the order-preserving float -> int map and one redux.sync
+__device__ __forceinline__ float mc_warp_max(float m) {
+    int k = __float_as_int(m);
+    k ^= (k >> 31) & 0x7fffffff;
+    k = __reduce_max_sync(0xffffffffu, k);
+    k ^= (k >> 31) & 0x7fffffff;
+    return __int_as_float(k);
+}
+
 template <int RPC>
 struct McLayout {
     static constexpr int R = 8 * RPC;                          // rows per cluster
@@ -103,7 +112,7 @@ struct McLayout {
 
 #define MC_TRACE(slot)                                                                      \
     do {                                                                                    \
-        if (p.trace && blockIdx.x == 0 && tidE == 0) p.trace[k * 64 + (slot)] = clock64();  \
+        if (p.trace && cl == 0 && tidE == 0) p.trace[(c * p.nsteps + k) * 64 + (slot)] = clock64();  \
     } while (0)
 
 template <int RPC>
@@ -115,7 +124,10 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     const int FS = p.FS;
     const int cl = blockIdx.x / MC_CS;
     const int c = (int)cluster_ctarank();                 // feature slice = rank in the cluster
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index as a warp-uniform value (shfl from lane 0): the MMA issuers' descriptors derive from it, and operands the
+    // compiler cannot prove uniform make it wrap EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST loop (measured: +50 % on the
+    // hidden GEMM)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -139,11 +151,13 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     uint64_t* p_ready = bars + 10;
     uint64_t* p_free = bars + 11;
     uint64_t* q_ready = bars + 12;                        // [3]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 16);
+    uint64_t* wl_full = bars + 16;                        // [RPC] prologue: a W_hid k-block tile landed in the staging slot
+    uint64_t* wl_free = bars + 20;                        // [RPC] ... and has been moved to tensor memory
+    uint32_t* tmem_slot = (uint32_t*)(bars + 31);
 
     const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
     const int row0 = cl * R + c * RPC;                    // first owned row (global utterance index)
-    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[63] = clock64();
+    if (p.trace && cl == 0 && threadIdx.x == 0) p.trace[(c * p.nsteps) * 64 + 63] = clock64();
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmWh);
@@ -161,9 +175,13 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         mbar_init(&q_ready[0], 1);
         mbar_init(&q_ready[1], 1);
         mbar_init(&q_ready[2], 1);
+        for (int j = 0; j < RPC; ++j) {
+            mbar_init(&wl_full[j], 1);
+            mbar_init(&wl_free[j], 128);
+        }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc<MC_TMEM_COLS>(tmem_slot);
+    if (warp == 8) tmem_alloc<MC_TMEM_COLS>(tmem_slot);
     // owned rows' sample ring: the FS most recent samples before i0 (written by earlier launches / the q_zero prefix)
     for (int e = threadIdx.x; e < RPC * 32; e += MC_THREADS) {
         const int rl = e >> 5, w = e & 31;
@@ -179,58 +197,120 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps the MMA operands in uniform registers)
     const uint32_t tm_d = tmem + MC_COL_D;
 
-    // ---- W_hid slice, k-blocks 0..11 -> tensor memory (warps 0..7: TMEM lane quadrant = warp & 3, six k-blocks per half) ----
-    if (warp < 8) {
-        const int q4 = warp & 3, half = warp >> 2;
-        const __nv_bfloat16* src = w_hid16 + (size_t)(c * 128 + q4 * 32 + lane) * H;
+    // G warps: P_g = c0 + taps 0..FS-3 for step g (two steps of slack); thread t owns features 8t..8t+7 of every owned row
+    auto g_step = [&](int g) {
+        const int f0 = threadIdx.x * 8;
+        const int i = i0 + g;
+        if (g >= 3)   // sample i-3 (tap FS-3, the newest one this prefetch uses) has been drawn.  Three barriers by
+                      // step % 3: E can be up to two steps past the awaited one, which would alias a phase parity.
+            mbar_wait(&q_ready[g % 3], (g / 3 - 1) & 1);
+        // L2 -> SM ingest is the shared resource of a step (x1 tile 48 KB by TMA, this gather 110 KB): the gather of step g runs
+        // in step g-1 AFTER that step's x1 tile has landed, i.e. under the epilogues / output GEMM / reduce, never beside the TMA
+        // loads the hidden GEMM is waiting for (measured: +1300 cycles per step when they overlap).
+        if (g >= 1 && !(p.dbg & 2)) mbar_wait(&full[3], (g - 1) & 1);
+        float acc[RPC][8];
+#pragma unroll
+        for (int r = 0; r < RPC; ++r) {
+            const int b = row0 + r;
+            const int bc = b < p.B ? b : p.B - 1;         // clamp: padded rows compute garbage that is never used
+            const float4* cp = reinterpret_cast<const float4*>(p.c0 + (size_t)bc * FS * H + (size_t)(i % FS) * H + f0);
+            // c0 is rewritten between launches by the upsampling kernel: read at L2 (like seq), not through the non-coherent path
+            const float4 ca = __ldcg(cp), cb = __ldcg(cp + 1);
+            acc[r][0] = ca.x; acc[r][1] = ca.y; acc[r][2] = ca.z; acc[r][3] = ca.w;
+            acc[r][4] = cb.x; acc[r][5] = cb.y; acc[r][6] = cb.z; acc[r][7] = cb.w;
+        }
+        // latency-bound L2 gather: six taps x RPC rows (18 loads of 16 bytes per thread) in flight at a time
+        for (int j0 = 0; j0 < FS - 2; j0 += 6) {
+            uint4 tv[6][RPC];
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) {
+                const int j = j0 + jj < FS - 2 ? j0 + jj : FS - 3;      // tail: re-load the last tap, not accumulated
+#pragma unroll
+                for (int r = 0; r < RPC; ++r) {
+                    const int qj = sQ[r * 32 + ((i - FS + j) & 31)];
+                    tv[jj][r] = __ldg(reinterpret_cast<const uint4*>(p.tbl + ((size_t)j * SRNN_Q + qj) * H + f0));
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) {
+                if (j0 + jj < FS - 2) {
+#pragma unroll
+                    for (int r = 0; r < RPC; ++r) {
+                        float f[8];
+                        mc_bf16x8_to_f32(tv[jj][r], f);
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) acc[r][v] += f[v];
+                    }
+                }
+            }
+        }
+        if (g >= 1) mbar_wait(p_free, (g - 1) & 1);       // E has consumed P of the previous step (single buffer)
+#pragma unroll
+        for (int r = 0; r < RPC; ++r) {
+            float4* pp = reinterpret_cast<float4*>(sP + r * H + f0);
+            pp[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            pp[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+        }
+        mbar_arrive(p_ready);
+    };
+
+    // ---- prologue, overlapped: (E warps + TMA) W_hid slice k-blocks 0..11 -> tensor memory; (G warps) P of the first sample ----
+    // Each thread owns one TMEM lane = one feature row, so reading the weights straight from global memory touches 32 different
+    // 128-byte lines per warp instruction (measured: 20 k cycles per launch).  Instead TMA streams 128-row x 128-byte swizzled
+    // tiles through RPC staging slots in the (still idle) x1 tile and every thread picks its row out of shared memory.
+    if (warp == 8) {
+        if (elect_one()) {
+            for (int kb = 0; kb < MC_KB_TMEM; ++kb) {     // first what the E warps are waiting for
+                const int slot = kb % RPC, round = kb / RPC;
+                if (round) mbar_wait(&wl_free[slot], (round - 1) & 1);
+                mbar_expect_tx(&wl_full[slot], 16384);
+                tma_load_2d(sX1 + (size_t)slot * 16384, &tmWh, &wl_full[slot], kb * 64, c * 128);
+            }
+            // the shared-memory part (W_hid k-blocks 12..15, then the W_out slice) is first needed by the hidden GEMM of step 0:
+            // it streams in under that step's gather / exchange
+            mbar_expect_tx(w_ready, 131072);
+            for (int j = 0; j < MC_KB - MC_KB_TMEM; ++j)
+                tma_load_2d(sWhT + (size_t)j * 16384, &tmWh, w_ready, (MC_KB_TMEM + j) * 64, c * 128);
+            for (int t2 = 0; t2 < 2; ++t2)
+                for (int kb2 = 0; kb2 < 2; ++kb2)
+                    tma_load_2d(sWo + (size_t)(t2 * 2 + kb2) * 16384, &tmWo, w_ready, c * 128 + kb2 * 64, t2 * 128);
+        }
+    } else if (warp >= 4 && warp < 8) {
+        const int q4 = warp & 3, row = q4 * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll 1
-        for (int kb = half * (MC_KB_TMEM / 2); kb < (half + 1) * (MC_KB_TMEM / 2); ++kb) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(src + kb * 64);
-            uint4 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(s4 + j);
+        for (int kb = 0; kb < MC_KB_TMEM; ++kb) {
+            const int slot = kb % RPC, round = kb / RPC;
+            mbar_wait(&wl_full[slot], round & 1);
+            const uint8_t* tile = sX1 + (size_t)slot * 16384 + row * 128;
             uint32_t r0[16], r1[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                r0[4 * j] = v[j].x; r0[4 * j + 1] = v[j].y; r0[4 * j + 2] = v[j].z; r0[4 * j + 3] = v[j].w;
-                r1[4 * j] = v[4 + j].x; r1[4 * j + 1] = v[4 + j].y; r1[4 * j + 2] = v[4 + j].z; r1[4 * j + 3] = v[4 + j].w;
+            for (int j = 0; j < 4; ++j) {                 // 16-byte chunk j of the row sits at chunk position j ^ (row & 7)
+                const uint4 a = *reinterpret_cast<const uint4*>(tile + ((j ^ (row & 7)) << 4));
+                const uint4 b2 = *reinterpret_cast<const uint4*>(tile + (((4 + j) ^ (row & 7)) << 4));
+                r0[4 * j] = a.x; r0[4 * j + 1] = a.y; r0[4 * j + 2] = a.z; r0[4 * j + 3] = a.w;
+                r1[4 * j] = b2.x; r1[4 * j + 1] = b2.y; r1[4 * j + 2] = b2.z; r1[4 * j + 3] = b2.w;
             }
             mc_tmem_st16(tbase + kb * 32, r0);
             mc_tmem_st16(tbase + kb * 32 + 16, r1);
+            // Release the slot only AFTER the tensor-memory stores have consumed the loaded registers: an mbarrier arrive issued
+            // right behind the LDS instructions can overtake them while they queue behind the G warps' global loads in the LSU,
+            // and the next TMA tile then lands in the slot before it has been read (measured: corrupted columns in launches >= 2).
+            mbar_arrive(&wl_free[slot]);
         }
         mc_tmem_st_wait();
-    } else if (warp == 8 && lane == 0) {
-        // ---- the shared-memory part of the weights: W_hid k-blocks 12..15 and the W_out slice, once per launch ----
-        mbar_expect_tx(w_ready, 131072);
-        for (int j = 0; j < MC_KB - MC_KB_TMEM; ++j)
-            tma_load_2d(sWhT + (size_t)j * 16384, &tmWh, w_ready, (MC_KB_TMEM + j) * 64, c * 128);
-        for (int t2 = 0; t2 < 2; ++t2)
-            for (int kb2 = 0; kb2 < 2; ++kb2)
-                tma_load_2d(sWo + (size_t)(t2 * 2 + kb2) * 16384, &tmWo, w_ready, c * 128 + kb2 * 64, t2 * 128);
+    } else if (warp < 4) {
+        g_step(0);                                        // P of the first sample while the weights stream in
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                   // every CTA's barriers are initialised before any remote arrive / copy
     tc_fence_after();
 
-    if (warp == 8) {
-        // ===================== TMA producer: x1 tile of every step =====================
-        if (lane == 0) {
-            for (int k = 0; k < p.nsteps; ++k) {
-                mc_wait_acq_cluster(x1_flag, k & 1);      // all 8 CTAs have published their x1 rows of this step
-                mc_fence_proxy_async_all();               // generic-proxy global writes (acquired above) -> visible to TMA reads
-                if (p.trace && blockIdx.x == 0) p.trace[k * 64 + 10] = clock64();
-                for (int g = 0; g < 4; ++g) {
-                    mbar_expect_tx(&full[g], 4 * Lay::KB_BYTES);
-                    tma_load_3d(sX1 + (size_t)g * 4 * Lay::KB_BYTES, &tmX1, &full[g], 0, cl * R, g * 4);
-                }
-            }
-        }
-    } else if (warp >= 9) {
+    if (warp >= 8) {
         // ===================== MMA issuers (one thread each; k-block kb belongs to issuer kb % 4) =====================
-        const int w = warp - 9;
-        if (lane == 0) {
+        const int w = warp - 8;
+        if (elect_one()) {                                // elect.sync: the compiler then issues each tcgen05.mma once, no ELECT loop
             constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
             mbar_wait(w_ready, 0);
             const uint64_t dWhT = umma_desc_sw128(smem_u32(sWhT));    // + (kb - 12) * (16384 >> 4)
@@ -239,6 +319,16 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             const uint64_t dX2 = umma_desc_sw128(smem_u32(sX2)) + (uint64_t)((w & 1) * (Lay::KB_BYTES >> 4));
             const uint32_t d = tm_d + (uint32_t)w * NT;               // this issuer's private accumulator (both GEMMs)
             for (int k = 0; k < p.nsteps; ++k) {
+                if (w == 0) {                             // issuer 0 is also the TMA producer of the x1 tile
+                    mc_wait_acq_cluster(x1_flag, k & 1);  // all 8 CTAs have published their x1 rows of this step
+                    mc_fence_proxy_async_all();           // generic-proxy global writes (acquired above) -> visible to TMA reads
+                    if (p.trace && cl == 0) p.trace[(c * p.nsteps + k) * 64 + 10] = clock64();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        mbar_expect_tx(&full[g], 4 * Lay::KB_BYTES);
+                        tma_load_3d(sX1 + (size_t)g * 4 * Lay::KB_BYTES, &tmX1, &full[g], 0, cl * R, g * 4);
+                    }
+                }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const int kb = w + 4 * g;
@@ -256,12 +346,13 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     }
                 }
                 umma_commit(bar_d1);
-                if (p.trace && blockIdx.x == 0 && w == 0) p.trace[k * 64 + 14] = clock64();
+                if (p.trace && cl == 0 && w == 0) p.trace[(c * p.nsteps + k) * 64 + 14] = clock64();
                 mbar_wait(x2_ready, k & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) umma_bf16(d, dWo + 2 * j, dX2 + 2 * j, idesc, j != 0);
                 umma_commit(bar_d2);
+                if (p.trace && cl == 0 && w == 0) p.trace[(c * p.nsteps + k) * 64 + 15] = clock64();
             }
         }
     } else if (warp >= 4) {
@@ -273,7 +364,28 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         const int ub = row0 + tidE;
         const bool u_mine = tidE < RPC && ub < p.B;
         float u_next = u_mine ? __ldg(p.uniforms + (size_t)(i0 - p.lookback) * p.u_ld + ub) : 0.f;
+        float bo[8];                                      // output bias of the logits this lane reduces (lane * 8 ..)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bo[j] = __ldg(p.b_out + lane * 8 + j);
         const uint32_t l_flag = smem_u32(x1_flag), l_land = smem_u32(sLand), l_landbar = smem_u32(land_full), l_stg = smem_u32(sX1);
+        if (p.dbg & 1) {                                  // self-check (SRNN_MC_DBG=1): read the TMEM-resident weights back, compare with global memory
+            const int row = q4 * 32 + lane;
+            int bad = 0, first = -1;
+            for (int kb = 0; kb < MC_KB_TMEM; ++kb) {
+                float v0[16], v1[16];
+                tmem_ld16(tmem + lane_base + kb * 32, v0);
+                tmem_ld16(tmem + lane_base + kb * 32 + 16, v1);
+                const uint32_t* g = reinterpret_cast<const uint32_t*>(w_hid16 + (size_t)(c * 128 + row) * H + kb * 64);
+                for (int j = 0; j < 16; ++j) {
+                    if (__float_as_uint(v0[j]) != g[j]) { ++bad; if (first < 0) first = kb * 32 + j; }
+                    if (__float_as_uint(v1[j]) != g[16 + j]) { ++bad; if (first < 0) first = kb * 32 + 16 + j; }
+                }
+            }
+            if (bad) printf("TMEMBAD cl %d c %d row %d: %d words differ, first column %d (i0 %d)\n", cl, c, row, bad, first, i0);
+            tc_fence_before();
+            mc_bar_sync(1, 128);
+            tc_fence_after();
+        }
         for (int k = 0; k < p.nsteps; ++k) {
             const int i = i0 + k;
             // ---- E1: x1 = relu(P + Tbl[FS-1][newest] + Tbl[FS-2][second newest]) for the owned rows -> global exchange buffer ----
@@ -326,10 +438,11 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 const int chunk = (f & 63) >> 3;
 #pragma unroll
                 for (int h2 = 0; h2 < NT / 16; ++h2) {
+                    if (16 * h2 >= R) break;              // columns beyond the real rows (the overrun atom) are never read
                     float v[16];
                     tmem_ld16(tm_d + lane_base + 16 * h2, v);
 #pragma unroll
-                    for (int w = 1; w < 4; ++w) {
+                    for (int w = 1; w < 4; ++w) {         // fixed order: issuer 0, 1, 2, 3
                         float x[16];
                         tmem_ld16(tm_d + lane_base + w * NT + 16 * h2, x);
 #pragma unroll
@@ -360,13 +473,15 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     const int o = t2 * 128 + 32 * q4 + lane;
 #pragma unroll
                     for (int h2 = 0; h2 < NT / 16; ++h2) {
-                        float v[16], x[16];
-                        tmem_ld16(tm_d + lane_base + (2 * t2) * NT + 16 * h2, v);
-                        tmem_ld16(tm_d + lane_base + (2 * t2 + 1) * NT + 16 * h2, x);
+                        if (16 * h2 >= R) break;
+                        uint32_t v[16], x[16];
+                        tmem_ld16_nowait(tm_d + lane_base + (2 * t2) * NT + 16 * h2, v);
+                        tmem_ld16_nowait(tm_d + lane_base + (2 * t2 + 1) * NT + 16 * h2, x);
+                        tmem_ld_wait();
 #pragma unroll
                         for (int n = 0; n < 16; ++n) {
                             const int row = 16 * h2 + n;
-                            if (row < R) stg[row * SRNN_Q + o] = v[n] + x[n];
+                            if (row < R) stg[row * SRNN_Q + o] = __uint_as_float(v[n]) + __uint_as_float(x[n]);
                         }
                     }
                 }
@@ -374,38 +489,33 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             tc_fence_before();
             fence_proxy_async_smem();                     // staging writes -> visible to the bulk-copy engine
             mc_bar_sync(1, 128);
-            if (tidE < MC_CS)                             // rows d*RPC .. +RPC of the staging -> slot c of CTA d's landing zone
-                mc_bulk_s2c(mc_mapa(l_land + (uint32_t)(c * RPC * 1024), (uint32_t)tidE), l_stg + (uint32_t)(tidE * RPC * 1024),
-                            RPC * 1024, mc_mapa(l_landbar, (uint32_t)tidE));
+            if (tidE < MC_CS) {                           // rows d*RPC .. +RPC of the staging -> slot c of CTA d's landing zone;
+                const uint32_t d = (uint32_t)((c + tidE) & (MC_CS - 1));   // rotated: no owner is last in every sender's queue
+                mc_bulk_s2c(mc_mapa(l_land + (uint32_t)(c * RPC * 1024), d), l_stg + d * (RPC * 1024), RPC * 1024,
+                            mc_mapa(l_landbar, d));
+            }
             MC_TRACE(7);
             // ---- the 8 split-K partials of the owned rows have landed: reduce in fixed order, + bias ----
             mbar_wait(land_full, k & 1);
             MC_TRACE(8);
-            for (int e = tidE; e < RPC * (SRNN_Q / 4); e += 128) {
-                const int r2 = e / (SRNN_Q / 4), o4 = (e % (SRNN_Q / 4)) * 4;
-                float4 acc = __ldg(reinterpret_cast<const float4*>(p.b_out + o4));
-#pragma unroll
-                for (int s = 0; s < MC_CS; ++s) {         // fixed summation order: slice 0, 1, 2, ...
-                    const float4 a = *reinterpret_cast<const float4*>(sLand + (s * RPC + r2) * SRNN_Q + o4);
-                    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-                }
-                *reinterpret_cast<float4*>(sLogit + r2 * SRNN_Q + o4) = acc;
-            }
-            mc_bar_sync(1, 128);
-            // ---- log-softmax + defined sampler, one warp per owned row ----
+            // ---- reduce (fixed order: bias, slice 0, 1, ...) + log-softmax + defined sampler, one warp per owned row ----
             if (warp - 4 < RPC) {
                 const int r2 = warp - 4;
                 const int bb = row0 + r2;
                 float v[8];
-                {
-                    const float4* lp = reinterpret_cast<const float4*>(sLogit + r2 * SRNN_Q + lane * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = bo[j];
+#pragma unroll
+                for (int s = 0; s < MC_CS; ++s) {
+                    const float4* lp = reinterpret_cast<const float4*>(sLand + (s * RPC + r2) * SRNN_Q + lane * 8);
                     const float4 a0 = lp[0], a1 = lp[1];
-                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
                 }
+                MC_TRACE(11);
                 float m = v[0];
 #pragma unroll
                 for (int j = 1; j < 8; ++j) m = fmaxf(m, v[j]);
-                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                m = mc_warp_max(m);
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s += expf(v[j] - m);
@@ -432,59 +542,19 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     sQ[r2 * 32 + (i & 31)] = 128;
                 }
             }
+            MC_TRACE(12);
             mc_bar_sync(1, 128);                          // sample i of every owned row is in sQ
             if (tidE == 0) mbar_arrive(&q_ready[k % 3]);
             MC_TRACE(9);
         }
     } else {
-        // ===================== G warps: prefetch P_g = c0 + taps 0..FS-3 for step g (two steps of slack) ==========
-        const int tidG = threadIdx.x;
-        const int f0 = tidG * 8;
-        for (int g = 0; g < p.nsteps; ++g) {
-            const int i = i0 + g;
-            if (g >= 3)   // sample i-3 (tap FS-3, the newest one this prefetch uses) has been drawn.  Three barriers by
-                          // step % 3: E can be up to two steps past the awaited one, which would alias a phase parity.
-                mbar_wait(&q_ready[g % 3], (g / 3 - 1) & 1);
-            float acc[RPC][8];
-#pragma unroll
-            for (int r = 0; r < RPC; ++r) {
-                const int b = row0 + r;
-                const int bc = b < p.B ? b : p.B - 1;     // clamp: padded rows compute garbage that is never used
-                const float4* cp = reinterpret_cast<const float4*>(p.c0 + (size_t)bc * FS * H + (size_t)(i % FS) * H + f0);
-                const float4 ca = __ldg(cp), cb = __ldg(cp + 1);
-                acc[r][0] = ca.x; acc[r][1] = ca.y; acc[r][2] = ca.z; acc[r][3] = ca.w;
-                acc[r][4] = cb.x; acc[r][5] = cb.y; acc[r][6] = cb.z; acc[r][7] = cb.w;
-            }
-#pragma unroll 3
-            for (int j = 0; j < FS - 2; ++j) {
-                uint4 tv[RPC];
-#pragma unroll
-                for (int r = 0; r < RPC; ++r) {
-                    const int qj = sQ[r * 32 + ((i - FS + j) & 31)];
-                    tv[r] = __ldg(reinterpret_cast<const uint4*>(p.tbl + ((size_t)j * SRNN_Q + qj) * H + f0));
-                }
-#pragma unroll
-                for (int r = 0; r < RPC; ++r) {
-                    float f[8];
-                    mc_bf16x8_to_f32(tv[r], f);
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) acc[r][v] += f[v];
-                }
-            }
-            if (g >= 1) mbar_wait(p_free, (g - 1) & 1);   // E has consumed P of the previous step (single buffer)
-#pragma unroll
-            for (int r = 0; r < RPC; ++r) {
-                float4* pp = reinterpret_cast<float4*>(sP + r * H + f0);
-                pp[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-                pp[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-            }
-            mbar_arrive(p_ready);
-        }
+        // ===================== G warps: P of the following samples (the first one was prefetched during the prologue) ==========
+        for (int g = 1; g < p.nsteps; ++g) g_step(g);
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                   // no CTA leaves while a peer may still signal or copy into it
-    if (warp == 9) tmem_dealloc<MC_TMEM_COLS>(tmem);
+    if (warp == 8) tmem_dealloc<MC_TMEM_COLS>(tmem);
 }
 
 bool mlp_cluster_supported(int H, int FS, int B, int max_clusters) {

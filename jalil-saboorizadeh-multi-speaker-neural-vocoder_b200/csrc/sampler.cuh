@@ -30,8 +30,7 @@ __device__ __forceinline__ int sampler_warp(const float (&p)[8], float u, int la
     int cnt = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) cnt += (__fadd_rn(excl, loc[i]) <= thr) ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);        // integer warp reduction in one instruction (redux.sync): exact
     return cnt > 255 ? 255 : cnt;
 }
 

@@ -237,6 +237,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+// all bulk stores of this thread COMPLETE (their global writes performed), not merely their shared-memory source read
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory");
 }

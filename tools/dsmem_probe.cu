@@ -100,6 +100,22 @@ __global__ void __launch_bounds__(256, 1) k_probe(int variant, int iters, uint8_
 #pragma unroll
                 for (int d = 0; d < CS; ++d) arrive_remote_release(mapa(lbar, d));
                 wait_cluster(x1_full, it & 1);
+            } else if (variant == 4) {
+                // smem staging [kb][2 rows][128 B] (destination swizzle) -> 128 bulk copies smem -> peer smem (one per thread:
+                // dest = tid >> 4, k-block = tid & 15), each completing 256 B on the destination's barrier
+                if (tid == 0) mbar_expect_tx(x1_full, 32768);
+                uint8_t* stg = smem + 32768 + 16384 + 1024;
+                *reinterpret_cast<uint4*>(stg + kb * 256 + rl * 128 + ((ch ^ (n & 7)) << 4)) = v0;
+                *reinterpret_cast<uint4*>(stg + kb * 256 + rl * 128 + (((ch + 1) ^ (n & 7)) << 4)) = v1;
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                {
+                    const int d = tid >> 4, kq = tid & 15, n0 = 2 * (int)c;
+                    const uint32_t dst = mapa(lx1 + kq * 2048 + (n0 >> 3) * 1024 + (n0 & 7) * 128, d);
+                    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                                 "r"(smem_u32(stg) + kq * 256), "r"(256), "r"(mapa(lbar, d)) : "memory");
+                }
+                wait_cluster(x1_full, it & 1);
             } else {   // variants 2, 3
                 if (tid == 0) mbar_expect_tx(x1_full, 32768);
                 // staging layout [kb][rl][128 B] with the destination row's swizzle
@@ -128,7 +144,7 @@ __global__ void __launch_bounds__(256, 1) k_probe(int variant, int iters, uint8_
             }
             // ---------------- B ----------------
             if (tid == 0) mbar_expect_tx(part_full, 16384);
-            if (variant != 3) {
+            if (variant < 3) {
 #pragma unroll
                 for (int d = 0; d < CS; ++d) {
                     const uint32_t rb = mapa(lpbar, d);
@@ -189,7 +205,7 @@ int main() {
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     uint8_t* stage; long long* dres; int* derr;
     cudaMalloc(&stage, 148 * 4096); cudaMalloc(&dres, 64); cudaMalloc(&derr, 4);
-    for (int grid : {128, 144}) {
+    for (int grid : {120}) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute a[1];
@@ -199,7 +215,7 @@ int main() {
         int n = -1;
         cudaError_t e = cudaOccupancyMaxActiveClusters(&n, k_probe, &cfg);
         printf("grid %d: max active 8-CTA clusters at %d KB smem: %d (%s)\n", grid, smem / 1024, n, cudaGetErrorString(e));
-        for (int variant = 0; variant < 4; ++variant) {
+        for (int variant = 0; variant < 5; ++variant) {
             cudaMemset(dres, 0, 64); cudaMemset(derr, 0, 4);
             const int iters = 208;
             e = cudaLaunchKernelEx(&cfg, k_probe, variant, iters, stage, dres, derr);
