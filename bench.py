@@ -326,6 +326,9 @@ def main():
     ap.add_argument("--workload", default="generate", choices=["generate", "train", "sweep"],
                     help="generate = the headline metric + a `train` sub-record (default); train = only the C3 training "
                          "step; sweep = C4 batch sweep (one line per batch size)")
+    ap.add_argument("--ind-cond-dim", type=int, default=0,
+                    help="> 0: BASELINE.json configs[4], the bottle-neck variant (run_sampleneck.sh: 30): k=1 conditioner chain "
+                         "43 -> 40 -> 30 -> 20 -> ind_cond_dim in front of the top tier (thesis-derived, parity unpinned); implies --cond-dim 43")
     ap.add_argument("--cond-dim", type=int, default=86,
                     help="conditioner width: 86 = look-ahead (C2, default); 43 = the core of the bottle-neck variant (C5)")
     ap.add_argument("--train-batch", type=int, default=128)
@@ -335,6 +338,8 @@ def main():
     ap.add_argument("--sweep-batches", default="1,4,16,64,256,1024,4096")
     ap.add_argument("--sweep-seconds", type=int, default=10)
     args = ap.parse_args()
+    if args.ind_cond_dim > 0:
+        args.cond_dim = 43
     C2["cond_dim"] = args.cond_dim
 
     rank = int(os.environ.get("RANK", 0))
@@ -366,8 +371,12 @@ def main():
     lib = S._lib.load()
 
     torch.manual_seed(77977)                                   # train.py:62; same weights on every rank
-    model = S.SampleRNN(**C2).to(dev)
-    gen = S.Generator(model, cuda=True, mode=mode)
+    if args.ind_cond_dim > 0:
+        full = S.BottleneckSampleRNN(ind_cond_dim=args.ind_cond_dim, **C2).to(dev)
+        model, gen = full.core, S.BottleneckGenerator(full, cuda=True, mode=mode)
+    else:
+        model = S.SampleRNN(**C2).to(dev)
+        gen = S.Generator(model, cuda=True, mode=mode)
     B, n_cond = args.batch, args.n_cond
     T = n_cond * 80
     cond_h, spk_h, uni_h = [t.pin_memory() for t in synth_inputs(B, n_cond, 1000 + rank)]   # each rank: its own utterances
@@ -473,11 +482,14 @@ def main():
                      "flops_per_sample": F_ALG, "whole_step_achieved": ach_step, "whole_step_frac": ach_step / peak_tf,
                      "achieved_dense_equiv": value * F_DENSE / 1e12 / world, **kinfo},
     }
-    if mode != S.MODE_FP32:
+    if args.ind_cond_dim > 0:
+        line["config"]["workload"] = ("C5 generation: bottle-neck variant, conditioner chain 43 -> 40 -> 30 -> 20 -> %d -> 1024 in front of "
+                                      "the 3-tier [20,4] SampleRNN dim 1024 (thesis-derived chain, parity unpinned)" % args.ind_cond_dim)
+    elif mode != S.MODE_FP32:
         line["fp32_parity_mode"] = fp32_mode_block(S, model, B, dev)
     del gen, flush, cond_d, uni_d
     torch.cuda.empty_cache()
-    if not args.no_train:
+    if not args.no_train and args.ind_cond_dim == 0:
         line["train"] = train_block(args, rank, world, dev, args.train_steps, 3)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r, dt, th = cpu_port_rate(args.cpu_n_cond, B)

@@ -32,6 +32,7 @@ extern "C" {
 #define SRNN_MAX_TIERS 4
 #define SRNN_MAX_RNN   4
 #define SRNN_Q         256   /* q_levels supported by the kernels (train.py:36 default) */
+#define SRNN_MAX_CHAIN 8     /* layers of the bottle-neck conditioner chain */
 
 #define SRNN_OK            0
 #define SRNN_ERR_ARG      -1
@@ -167,6 +168,22 @@ SRNN_API int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t*
 SRNN_API int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, int32_t cond_rows,
                   const int64_t* spk, const float* uniforms, uint8_t* samples_out, float* audio_out,
                   float* logp_out, int32_t mode, void* stream);
+
+/* ---- bottle-neck conditioner chain (BASELINE.json configs[4], run_sampleneck.sh:18-19 `--ind_cond_dim 30`) ------------- */
+/* The voice-conversion variant replaces the single cond_expand Conv1d(cond_dim -> H) by a chain of k = 1 Conv1d layers
+ * cond_dim -> 40 -> 30 -> 20 -> ind_cond_dim -> H.  Its source lives on a branch that is NOT in the reference tree
+ * (run_sampleneck.sh:2), so shapes and the ReLU after every chain layer follow the thesis (doc/Barbany_report.pdf 3.2.1):
+ * PARITY UNPINNED.  This entry point runs the chain up to ind_cond_dim; its output is the `cond` of a SampleRNN built with
+ * cond_dim = ind_cond_dim, whose cond_expand is the last layer.  layers[l]: weight (dims[l+1], dims[l], 1) or the weight_norm
+ * pair, bias (dims[l+1]) or NULL; cond (rows, dims[0]) fp32 -> out (rows, dims[n_layers]) fp32;
+ * scratch: sum_l dims[l+1]*dims[l] floats (the folded weights). */
+typedef struct {
+    int32_t n_layers;
+    int32_t dims[SRNN_MAX_CHAIN + 1];
+    srnn_conv_params layers[SRNN_MAX_CHAIN];
+} srnn_cond_chain;
+SRNN_API int srnn_cond_chain_fwd(const srnn_cond_chain* chain, const float* cond, int32_t rows, float* out, float* scratch,
+                                 void* stream);
 
 /* ---- per-kernel test hooks -------------------------------------------------------------------- */
 /* The defined sampler replacing Tensor.multinomial (model.py:517): p (rows, 256) fp32 unnormalised,

@@ -5,7 +5,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsrnn_b200.so")
 
-MAX_TIERS, MAX_RNN, Q = 4, 4, 256
+MAX_TIERS, MAX_RNN, Q, MAX_CHAIN = 4, 4, 256, 8
 MODE_FP32, MODE_BF16, MODE_BF16_GRAPH = 0, 1, 2
 
 f32p = C.POINTER(C.c_float)
@@ -34,7 +34,12 @@ class Params(C.Structure):
                 ("mlp_hidden", ConvParams), ("mlp_output", ConvParams)]
 
 
+class CondChain(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_CHAIN + 1)), ("layers", ConvParams * MAX_CHAIN)]
+
+
 _SIGNATURES = {
+    "srnn_cond_chain_fwd": (C.c_int, [C.POINTER(CondChain), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srnn_last_error": (C.c_char_p, []),
     "srnn_version": (C.c_int, []),
     "srnn_sample_kernel_name": (C.c_char_p, []),

@@ -483,6 +483,24 @@ int srnn_timed_kernel(const srnn_ctx* ctx, double* ms, int64_t* launches) {
     return SRNN_OK;
 }
 
+// Bottle-neck conditioner chain (thesis-derived, parity unpinned; see include/srnn_b200.h): fold weight-norm, run the k = 1 chain.
+int srnn_cond_chain_fwd(const srnn_cond_chain* chain, const float* cond, int32_t rows, float* out, float* scratch, void* stream) {
+    if (!chain || !cond || !out || !scratch || rows < 0) return fail(SRNN_ERR_ARG, "null argument");
+    if (chain->n_layers < 1 || chain->n_layers > SRNN_MAX_CHAIN) return fail(SRNN_ERR_ARG, "bad chain length");
+    const float* w[SRNN_MAX_CHAIN];
+    const float* b[SRNN_MAX_CHAIN];
+    size_t off = 0;
+    for (int l = 0; l < chain->n_layers; ++l) {
+        const int din = chain->dims[l], dout = chain->dims[l + 1];
+        if (din < 1 || dout < 1) return fail(SRNN_ERR_ARG, "bad chain width");
+        SRNN_TRY(wn_fold(chain->layers[l], scratch + off, dout, din, (cudaStream_t)stream));
+        w[l] = scratch + off;
+        b[l] = chain->layers[l].bias;
+        off += (size_t)din * dout;
+    }
+    return cond_chain_fwd(chain->n_layers, chain->dims, w, b, cond, rows, out, (cudaStream_t)stream);
+}
+
 // Name of the persistent sample-level kernel the last bf16 srnn_generate call of this process ran (bench.py's roofline line).
 namespace srnn { const char* g_sample_kernel = "k_mlp_persist"; }
 const char* srnn_sample_kernel_name(void) { return srnn::g_sample_kernel; }

@@ -231,6 +231,8 @@ int sample_rows(const float* p, const float* u, int rows, int* idx, cudaStream_t
 int dequant_audio(const uint8_t* seq, int seq_ld, int off, const float* lut, uint8_t* samples, float* audio,
                   int B, int T, cudaStream_t st);
 int add_int(int* p, int v, cudaStream_t st);
+int cond_chain_fwd(int n_layers, const int* dims, const float* const* w, const float* const* b, const float* cond, int rows,
+                   float* out, cudaStream_t st);
 
 // ---- backward pass + optimizer (backward.cu) --------------------------------------------------------
 size_t backward_scratch_bytes(const srnn_ctx* ctx, int B, int T);

@@ -826,5 +826,54 @@ int add_int(int* p, int v, cudaStream_t st) {
     return SRNN_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Bottle-neck conditioner chain of the voice-conversion variant (BASELINE.json configs[4]; run_sampleneck.sh:18-19
+// `--ind_cond_dim`).  The branch that holds its source is not in the reference tree, so the layer shapes follow the thesis
+// (doc/Barbany_report.pdf 3.2.1, Fig. 3.4): k = 1 Conv1d layers cond_dim -> 40 -> 30 -> 20 -> ind_cond_dim with a ReLU after
+// each, in front of the top tier's cond_expand (ind_cond_dim -> H).  PARITY UNPINNED: no reference code to compare against.
+// One block per conditioner frame; activations ping-pong in shared memory; weights (dims[l+1], dims[l]) row-major fp32.
+// ------------------------------------------------------------------------------------------------
+struct ChainArgs {
+    int n_layers;
+    int dims[SRNN_MAX_CHAIN + 1];
+    const float* w[SRNN_MAX_CHAIN];
+    const float* b[SRNN_MAX_CHAIN];
+};
+__global__ void k_cond_chain(const __grid_constant__ ChainArgs a, const float* __restrict__ cond, int rows, float* __restrict__ out) {
+    __shared__ float act[2][128];
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    for (int i = threadIdx.x; i < a.dims[0]; i += blockDim.x) act[0][i] = cond[(size_t)row * a.dims[0] + i];
+    __syncthreads();
+    int cur = 0;
+    for (int l = 0; l < a.n_layers; ++l) {
+        const int din = a.dims[l], dout = a.dims[l + 1];
+        for (int o = threadIdx.x; o < dout; o += blockDim.x) {
+            const float* wr = a.w[l] + (size_t)o * din;
+            float s = a.b[l] ? a.b[l][o] : 0.f;
+            for (int i = 0; i < din; ++i) s = fmaf(wr[i], act[cur][i], s);      // sequential over the inputs: the oracle's order
+            act[cur ^ 1][o] = fmaxf(s, 0.f);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const int dl = a.dims[a.n_layers];
+    for (int o = threadIdx.x; o < dl; o += blockDim.x) out[(size_t)row * dl + o] = act[cur][o];
+}
+int cond_chain_fwd(int n_layers, const int* dims, const float* const* w, const float* const* b, const float* cond, int rows,
+                   float* out, cudaStream_t st) {
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_layers = n_layers;
+    for (int l = 0; l <= n_layers; ++l) {
+        if (dims[l] < 1 || dims[l] > 128) return fail(SRNN_ERR_ARG, "conditioner chain widths must be in [1, 128]");
+        a.dims[l] = dims[l];
+    }
+    for (int l = 0; l < n_layers; ++l) { a.w[l] = w[l]; a.b[l] = b[l]; }
+    if (rows) SRNN_LAUNCH(k_cond_chain, rows, 64, 0, st, a, cond, rows, out);
+    return SRNN_OK;
+}
+
 }  // namespace srnn
 
