@@ -963,6 +963,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             }
             fprintf(stderr, " (reduce %.0f softmax+sample %.0f) | flags@%.0f lastMMA@%.0f (since signal) | step=%.0f | entry->step0=%lld step0=%lld\n",
                     red / (FS0 - 2), smx / (FS0 - 2), woke / (FS0 - 2), lastmma / (FS0 - 2), tot / (FS0 - 3), tr[0] - tr[63], tr[64] - tr[0]);
+            fprintf(stderr, "[srnn trace]    prologue CTA%d (cycles since entry): init+alloc+sync %lld, weights in TMEM %lld, P(0) gathered %lld, cluster sync done %lld, step 0 starts %lld\n",
+                    cta, tr[20] - tr[63], tr[21] - tr[63], tr[22] - tr[63], tr[23] - tr[63], tr[0] - tr[63]);
         }
         cudaFree(trace);
         trace = nullptr;

@@ -108,6 +108,9 @@ struct McLayout {
     static constexpr uint32_t OFF_U = OFF_Q + 128;
     static constexpr uint32_t OFF_BAR = OFF_U + 64;
     static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;                 // + alignment slack
+    // prologue staging slots of 16 KB for the W_hid tiles on their way to tensor memory: the x1 tile, the x2 tile and the
+    // landing zone are contiguous and idle until the first step
+    static constexpr int NSLOT = (OFF_P - OFF_X1) / 16384;
 };
 
 #define MC_TRACE(slot)                                                                      \
@@ -151,8 +154,8 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     uint64_t* p_ready = bars + 10;
     uint64_t* p_free = bars + 11;
     uint64_t* q_ready = bars + 12;                        // [3]
-    uint64_t* wl_full = bars + 16;                        // [RPC] prologue: a W_hid k-block tile landed in the staging slot
-    uint64_t* wl_free = bars + 20;                        // [RPC] ... and has been moved to tensor memory
+    uint64_t* wl_full = bars + 16;                        // [NSLOT <= 5] prologue: a W_hid k-block tile landed in the staging slot
+    uint64_t* wl_free = bars + 21;                        // [NSLOT <= 5] ... and has been moved to tensor memory
     uint32_t* tmem_slot = (uint32_t*)(bars + 31);
 
     const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
@@ -175,7 +178,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         mbar_init(&q_ready[0], 1);
         mbar_init(&q_ready[1], 1);
         mbar_init(&q_ready[2], 1);
-        for (int j = 0; j < RPC; ++j) {
+        for (int j = 0; j < Lay::NSLOT; ++j) {
             mbar_init(&wl_full[j], 1);
             mbar_init(&wl_free[j], 128);
         }
@@ -194,6 +197,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.trace && cl == 0 && threadIdx.x == 0) p.trace[(c * p.nsteps) * 64 + 20] = clock64();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps the MMA operands in uniform registers)
     const uint32_t tm_d = tmem + MC_COL_D;
 
@@ -219,11 +223,13 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             acc[r][0] = ca.x; acc[r][1] = ca.y; acc[r][2] = ca.z; acc[r][3] = ca.w;
             acc[r][4] = cb.x; acc[r][5] = cb.y; acc[r][6] = cb.z; acc[r][7] = cb.w;
         }
-        // latency-bound L2 gather: six taps x RPC rows (18 loads of 16 bytes per thread) in flight at a time
-        for (int j0 = 0; j0 < FS - 2; j0 += 6) {
-            uint4 tv[6][RPC];
+        // latency-bound L2 gather: six taps x RPC rows (18 loads of 16 bytes per thread) in flight at a time (nine: slower, the
+        // outstanding-load limit of the SM serialises them)
+        constexpr int GB = 6;
+        for (int j0 = 0; j0 < FS - 2; j0 += GB) {
+            uint4 tv[GB][RPC];
 #pragma unroll
-            for (int jj = 0; jj < 6; ++jj) {
+            for (int jj = 0; jj < GB; ++jj) {
                 const int j = j0 + jj < FS - 2 ? j0 + jj : FS - 3;      // tail: re-load the last tap, not accumulated
 #pragma unroll
                 for (int r = 0; r < RPC; ++r) {
@@ -232,7 +238,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 }
             }
 #pragma unroll
-            for (int jj = 0; jj < 6; ++jj) {
+            for (int jj = 0; jj < GB; ++jj) {
                 if (j0 + jj < FS - 2) {
 #pragma unroll
                     for (int r = 0; r < RPC; ++r) {
@@ -254,14 +260,16 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         mbar_arrive(p_ready);
     };
 
+    float bo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // E warps: output bias of the logits this lane reduces (lane * 8 ..)
+    float u_first = 0.f;                                    // E threads < RPC: uniform of the first sample
     // ---- prologue, overlapped: (E warps + TMA) W_hid slice k-blocks 0..11 -> tensor memory; (G warps) P of the first sample ----
     // Each thread owns one TMEM lane = one feature row, so reading the weights straight from global memory touches 32 different
     // 128-byte lines per warp instruction (measured: 20 k cycles per launch).  Instead TMA streams 128-row x 128-byte swizzled
-    // tiles through RPC staging slots in the (still idle) x1 tile and every thread picks its row out of shared memory.
+    // tiles through NSLOT staging slots in the (still idle) x1 / x2 / landing area and every thread picks its row out of shared memory.
     if (warp == 8) {
         if (elect_one()) {
             for (int kb = 0; kb < MC_KB_TMEM; ++kb) {     // first what the E warps are waiting for
-                const int slot = kb % RPC, round = kb / RPC;
+                const int slot = kb % Lay::NSLOT, round = kb / Lay::NSLOT;
                 if (round) mbar_wait(&wl_free[slot], (round - 1) & 1);
                 mbar_expect_tx(&wl_full[slot], 16384);
                 tma_load_2d(sX1 + (size_t)slot * 16384, &tmWh, &wl_full[slot], kb * 64, c * 128);
@@ -276,11 +284,18 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                     tma_load_2d(sWo + (size_t)(t2 * 2 + kb2) * 16384, &tmWo, w_ready, c * 128 + kb2 * 64, t2 * 128);
         }
     } else if (warp >= 4 && warp < 8) {
+        // per-launch constants of the E warps, requested before the staging loop so that their (DRAM) latency is hidden
+        {
+            const int tidE0 = threadIdx.x - 128, ub0 = row0 + tidE0;
+            if (tidE0 < RPC && ub0 < p.B) u_first = __ldg(p.uniforms + (size_t)(i0 - p.lookback) * p.u_ld + ub0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bo[j] = __ldg(p.b_out + lane * 8 + j);
+        }
         const int q4 = warp & 3, row = q4 * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll 1
         for (int kb = 0; kb < MC_KB_TMEM; ++kb) {
-            const int slot = kb % RPC, round = kb / RPC;
+            const int slot = kb % Lay::NSLOT, round = kb / Lay::NSLOT;
             mbar_wait(&wl_full[slot], round & 1);
             const uint8_t* tile = sX1 + (size_t)slot * 16384 + row * 128;
             uint32_t r0[16], r1[16];
@@ -299,13 +314,16 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             mbar_arrive(&wl_free[slot]);
         }
         mc_tmem_st_wait();
+        if (p.trace && cl == 0 && threadIdx.x == 128) p.trace[(c * p.nsteps) * 64 + 21] = clock64();
     } else if (warp < 4) {
         g_step(0);                                        // P of the first sample while the weights stream in
+        if (p.trace && cl == 0 && threadIdx.x == 0) p.trace[(c * p.nsteps) * 64 + 22] = clock64();
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                   // every CTA's barriers are initialised before any remote arrive / copy
     tc_fence_after();
+    if (p.trace && cl == 0 && threadIdx.x == 0) p.trace[(c * p.nsteps) * 64 + 23] = clock64();
 
     if (warp >= 8) {
         // ===================== MMA issuers (one thread each; k-block kb belongs to issuer kb % 4) =====================
@@ -363,10 +381,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         const uint32_t lane_base = (uint32_t)(32 * q4) << 16;
         const int ub = row0 + tidE;
         const bool u_mine = tidE < RPC && ub < p.B;
-        float u_next = u_mine ? __ldg(p.uniforms + (size_t)(i0 - p.lookback) * p.u_ld + ub) : 0.f;
-        float bo[8];                                      // output bias of the logits this lane reduces (lane * 8 ..)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bo[j] = __ldg(p.b_out + lane * 8 + j);
+        float u_next = u_first;
         const uint32_t l_flag = smem_u32(x1_flag), l_land = smem_u32(sLand), l_landbar = smem_u32(land_full), l_stg = smem_u32(sX1);
         if (p.dbg & 1) {                                  // self-check (SRNN_MC_DBG=1): read the TMEM-resident weights back, compare with global memory
             const int row = q4 * 32 + lane;
@@ -516,11 +531,13 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
 #pragma unroll
                 for (int j = 1; j < 8; ++j) m = fmaxf(m, v[j]);
                 m = mc_warp_max(m);
+                // MUFU-based exp / log (ex2.approx, lg2.approx; relative error ~2^-21): the libm forms cost ~20 instructions each
+                // and 17 of them sit on the serial path of every sample; far inside the bf16 mode's stated tolerance
                 float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s += expf(v[j] - m);
+                for (int j = 0; j < 8; ++j) s += __expf(v[j] - m);
                 for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                const float lse = m + logf(s);
+                const float lse = m + __logf(s);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] -= lse;
                 const int t = i - p.lookback;
@@ -531,7 +548,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                         o4[1] = make_float4(v[4], v[5], v[6], v[7]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = expf(v[j]);
+                    for (int j = 0; j < 8; ++j) v[j] = __expf(v[j]);
                     const float u = sU[r2];
                     const int idx = sampler_warp(v, u, lane);
                     if (lane == 0) {
