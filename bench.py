@@ -262,6 +262,39 @@ def fp32_mode_block(S, model, B, dev, n_cond=2):
             "note": "SRNN_MODE_FP32: every contraction as an fp32 FFMA GEMM; the mode of the 1e-3 logit / bit-exact index gates"}
 
 
+def x3_mode_block(S, model, B, dev, n_cond=2):
+    """The tensor-core parity mode (SRNN_MODE_BF16X3: fp32 control flow, dense contractions as split-bf16 tcgen05 products):
+    throughput on the same model and batch, and its agreement with the fp32 mode on the same uniforms -- max relative log-prob
+    difference |dlogp| / max(1, |logp|) over the steps both runs shared a history for (up to the first differing sample of
+    each utterance) and the fraction of identical sampled indices."""
+    import torch
+    cond, spk, uni = [t.to(dev) for t in synth_inputs(B, n_cond, 7)]
+    out = {}
+    for name, mode in (("fp32", S.MODE_FP32), ("x3", S.MODE_BF16X3)):
+        gen = S.Generator(model, cuda=True, mode=mode)
+        gen(B, 0, cond, spk, uniforms=uni, device_output=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gen(B, 0, cond, spk, uniforms=uni, device_output=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_ms"] = e0.elapsed_time(e1)
+        _, smp, lp = gen(B, 0, cond, spk, uniforms=uni, device_output=True, return_samples=True, return_logp=True)
+        out[name] = (smp.long(), lp)
+    (s0, l0), (s1, l1) = out["fp32"], out["x3"]
+    same = (s0 == s1)
+    shared = torch.cumprod(torch.cat([torch.ones_like(same[:, :1]), same[:, :-1]], 1).long(), 1).bool()   # history identical so far
+    rel = ((l0 - l1).abs() / l0.abs().clamp(min=1.0)).amax(-1)
+    v = B * n_cond * 80 / (out["x3_ms"] / 1e3)
+    return {"value": v, "unit": "samples/s", "x_realtime_16k": v / SAMPLE_RATE, "samples_per_utterance": n_cond * 80,
+            "max_rel_dlogp": float(rel[shared].max()), "index_match": float(same.float().mean()),
+            "index_match_shared_history": float(same[shared].float().mean()),
+            "speedup_vs_fp32_mode": out["fp32_ms"] / out["x3_ms"],
+            "note": "SRNN_MODE_BF16X3 against SRNN_MODE_FP32 on the same uniforms: W.x as Wh.xh + Wl.xh + Wh.xl on tcgen05 "
+                    "(one GEMM over K' = 3K, fp32 accumulation); gate 1e-3 relative on log-probs"}
+
+
 def run_sweep(args, rank, world, local):
     """BASELINE.json configs[3] ("C4"): total batch 1 ... 4096 utterances x 10 s (160 000 samples), utterances sharded over
     the ranks (strong scaling over the batch, no collective); one JSON line per batch size: latency of the first period
@@ -488,6 +521,7 @@ def main():
                                       "the 3-tier [20,4] SampleRNN dim 1024 (thesis-derived chain, parity unpinned)" % args.ind_cond_dim)
     elif mode != S.MODE_FP32:
         line["fp32_parity_mode"] = fp32_mode_block(S, model, B, dev)
+        line["parity_mode"] = x3_mode_block(S, model, B, dev)
     del gen, flush, cond_d, uni_d
     torch.cuda.empty_cache()
     if not args.no_train and args.ind_cond_dim == 0:

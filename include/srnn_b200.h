@@ -45,6 +45,11 @@ extern "C" {
 #define SRNN_MODE_BF16   1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: the speed mode */
 #define SRNN_MODE_BF16_GRAPH 2 /* generation only: bf16 arithmetic, one tcgen05 GEMM launch per contraction
                                   (no persistent sample kernel); kept as an A/B reference for the fused kernel */
+#define SRNN_MODE_BF16X3 3   /* tensor-core parity mode: the control flow of SRNN_MODE_FP32 with every dense contraction
+                                (GRU projections, upsampling, MLP hidden / output) on tcgen05 as a split-bf16 product
+                                W.x ~= Wh.xh + Wl.xh + Wh.xl (hi = bf16(v), lo = bf16(v - hi); one GEMM over K' = 3K, fp32
+                                accumulation): holds the 1e-3 logit gate of the fp32 mode at tensor-core speed.  Forward
+                                paths (srnn_predict_fwd, srnn_generate); a backward pass after it runs the fp32 kernels. */
 
 typedef struct srnn_ctx srnn_ctx;
 
@@ -221,6 +226,9 @@ SRNN_API int srnn_timed_kernel(const srnn_ctx* ctx, double* ms, int64_t* launche
 SRNN_API const char* srnn_sample_kernel_name(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 SRNN_API int64_t srnn_launch_count(void);
+/* Number of srnn_generate calls on this context that replayed the instantiated CUDA graph of the previous call instead of
+ * capturing a new one (same batch, length, mode, schedule switches, caller pointers and scratch; SRNN_NO_GRAPH_CACHE=1 disables). */
+SRNN_API int64_t srnn_graph_reuse_count(const srnn_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsrnn_b200.so")
 
 MAX_TIERS, MAX_RNN, Q, MAX_CHAIN = 4, 4, 256, 8
-MODE_FP32, MODE_BF16, MODE_BF16_GRAPH = 0, 1, 2
+MODE_FP32, MODE_BF16, MODE_BF16_GRAPH, MODE_BF16X3 = 0, 1, 2, 3
 
 f32p = C.POINTER(C.c_float)
 
@@ -44,6 +44,7 @@ _SIGNATURES = {
     "srnn_version": (C.c_int, []),
     "srnn_sample_kernel_name": (C.c_char_p, []),
     "srnn_launch_count": (C.c_int64, []),
+    "srnn_graph_reuse_count": (C.c_int64, [C.c_void_p]),
     "srnn_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "srnn_destroy": (C.c_int, [C.c_void_p]),
     "srnn_lookback": (C.c_int, [C.c_void_p]),

@@ -70,6 +70,7 @@ extern "C" {
 const char* srnn_last_error(void) { return g_err; }
 int srnn_version(void) { return 100; }
 int64_t srnn_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t srnn_graph_reuse_count(const srnn_ctx* ctx) { return ctx ? (int64_t)ctx->gen_graph.reuses : 0; }
 
 int srnn_create(const srnn_config* cfg, srnn_ctx** out) {
     if (!cfg || !out) return fail(SRNN_ERR_ARG, "null argument");
@@ -109,6 +110,8 @@ int srnn_destroy(srnn_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->weights.release();
     for (auto& e : ctx->ev_stage) if (e) cudaEventDestroy(e);
+    if (ctx->gen_graph.exec) cudaGraphExecDestroy(ctx->gen_graph.exec);
+    if (ctx->gen_graph.graph) cudaGraphDestroy(ctx->gen_graph.graph);
     if (ctx->ws) cudaFree(ctx->ws);
     delete ctx;
     return SRNN_OK;
@@ -243,6 +246,40 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
         SRNN_TRY(f32_to_bf16_pad(ctx->tbl, FS0 * Q, H, H, ctx->tbl16, FS0 * Q, H, st));
     }
     ctx->packed = true;
+    ctx->x3_valid = false;
+    return SRNN_OK;
+}
+
+// SRNN_MODE_BF16X3: split-bf16 copies [hi | lo | hi] of the dense weights, (re)built on the first use after srnn_pack_weights
+static int ensure_x3(srnn_ctx* ctx, cudaStream_t st) {
+    if (ctx->x3_valid) return SRNN_OK;
+    if (!ctx->has_bf16) return fail(SRNN_ERR_UNSUPPORTED, "split-bf16 tensor-core mode needs dim %% 64 == 0 (dim=%d)", ctx->H);
+    typedef __nv_bfloat16 bf;
+    const srnn_config& c = ctx->cfg;
+    const int H = ctx->H, Q = ctx->Q, L = c.n_rnn;
+    if (!ctx->w_hid3) {
+        for (int i = 0; i < c.n_tiers; ++i) {
+            TierPacked& t = ctx->tiers[i];
+            for (int l = 0; l < L; ++l) {
+                SRNN_TRY(ctx->weights.alloc((void**)&t.w_ih3[l], sizeof(bf) * 9 * H * H));
+                SRNN_TRY(ctx->weights.alloc((void**)&t.w_hh3[l], sizeof(bf) * 9 * H * H));
+            }
+            SRNN_TRY(ctx->weights.alloc((void**)&t.w_up3, sizeof(bf) * 3 * (size_t)t.fs * H * H));
+        }
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_hid3, sizeof(bf) * 3 * H * H));
+        SRNN_TRY(ctx->weights.alloc((void**)&ctx->w_out3, sizeof(bf) * 3 * Q * H));
+    }
+    for (int i = 0; i < c.n_tiers; ++i) {
+        TierPacked& t = ctx->tiers[i];
+        for (int l = 0; l < L; ++l) {
+            SRNN_TRY(split3_bf16(t.w_ih[l], 3 * H, H, H, t.w_ih3[l], 1, st));
+            SRNN_TRY(split3_bf16(t.w_hh[l], 3 * H, H, H, t.w_hh3[l], 1, st));
+        }
+        SRNN_TRY(split3_bf16(t.w_up, (long long)t.fs * H, H, H, t.w_up3, 1, st));
+    }
+    SRNN_TRY(split3_bf16(ctx->w_hid, H, H, H, ctx->w_hid3, 1, st));
+    SRNN_TRY(split3_bf16(ctx->w_out, Q, H, H, ctx->w_out3, 1, st));
+    ctx->x3_valid = true;
     return SRNN_OK;
 }
 
@@ -254,7 +291,7 @@ static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback;
     const int Lseq = lookback + T - 1;
-    const bool bf16 = mode != SRNN_MODE_FP32;
+    const bool bf16 = mode == SRNN_MODE_BF16;
     typedef __nv_bfloat16 bf;
     FwdPlan& P = ctx->fwd;
     for (int pass = 0; pass < 2; ++pass) {
@@ -282,6 +319,7 @@ static int plan_forward(srnn_ctx* ctx, int B, int T, int mode) {
         P.X2 = b.take<float>(bf16 ? 1 : (size_t)B * T * H);
         P.X1h = b.take<bf>(bf16 ? (size_t)B * T * H : 1);
         P.X2h = b.take<bf>(bf16 ? (size_t)B * T * H : 1);
+        P.S3 = b.take<bf>(mode == SRNN_MODE_BF16X3 ? (size_t)B * T * 3 * H : 1);
         P.bytes = b.off;
         // the backward pass works in the scratch right behind the saved activations: reserve it now, because growing the
         // scratch later would free them
@@ -304,21 +342,33 @@ static int tf_gemm(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act,
     return gemm_umma_multi(&o, 1, rows, K, 128, pick_bn(rows), st);
 }
 
+// SRNN_MODE_BF16X3 contraction C (rows, n_feat) = A (rows, K) . W^T + bias [relu] with fp32 in / out: the activations are split
+// into s3 (rows, 3K) and meet the pre-split weights W3 (n_feat, 3K) in one tcgen05 GEMM (see split3_bf16).  bm / bn = 0: pick.
+static int gemm_x3(int rows, int n_feat, int K, const float* A, long long lda, const __nv_bfloat16* W3, const float* bias, int relu,
+                   float* C, int ldc, __nv_bfloat16* s3, int bm, int bn, cudaStream_t st) {
+    SRNN_TRY(split3_bf16(A, rows, K, lda, s3, 0, st));
+    GemmOperands o{W3, s3, bias, nullptr, C, nullptr, n_feat, 3 * K, 3 * K, 0, ldc, relu, nullptr};
+    if (!bm && rows >= 256 && ldc % 8 == 0 && n_feat % 16 == 0) return gemm_umma_rows(o, rows, 3 * K, 1, nullptr, st);
+    return gemm_umma_multi(&o, 1, rows, 3 * K, bm ? bm : 128, bn ? bn : pick_bn(rows), st);
+}
+
 int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_seq, const void* cond,
                      int32_t cond_is_f64, const int64_t* spk, float* const* hidden_io, int32_t reset_mask,
                      float* logp_out, int32_t mode, void* stream) {
     SRNN_TRY(check_ready(ctx));
     if (!input_seq || !cond || !spk || !hidden_io || !logp_out) return fail(SRNN_ERR_ARG, "null argument");
     if (B < 1 || T < 1 || T % ctx->lookback) return fail(SRNN_ERR_ARG, "T=%d must be a positive multiple of lookback=%d", T, ctx->lookback);
-    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16) return fail(SRNN_ERR_UNSUPPORTED, "predict_fwd: mode %d not available", mode);
-    if (mode == SRNN_MODE_BF16 && !ctx->has_bf16)
+    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16 && mode != SRNN_MODE_BF16X3)
+        return fail(SRNN_ERR_UNSUPPORTED, "predict_fwd: mode %d not available", mode);
+    if (mode != SRNN_MODE_FP32 && !ctx->has_bf16)
         return fail(SRNN_ERR_UNSUPPORTED, "bf16 tensor-core mode needs dim %% 64 == 0 (dim=%d)", ctx->H);
     cudaStream_t st = (cudaStream_t)stream;
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback;
     const int Lseq = lookback + T - 1;
-    const bool bf16 = mode == SRNN_MODE_BF16;
+    const bool bf16 = mode == SRNN_MODE_BF16, x3 = mode == SRNN_MODE_BF16X3;
     ctx->fwd.valid = false;
+    if (x3) SRNN_TRY(ensure_x3(ctx, st));
     SRNN_TRY(plan_forward(ctx, B, T, mode));
     FwdPlan& P = ctx->fwd;
 
@@ -347,6 +397,8 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
             if (bf16) {
                 SRNN_TRY(f32_to_bf16_pad(h0, B, H, H, h016, B, H, st));
                 SRNN_TRY(tf_gemm(t.w_ih16[l], 3 * H, in16, M, H, t.b_ih[l], GI, nullptr, 3 * H, 0, st));
+            } else if (x3) {
+                SRNN_TRY(gemm_x3(M, 3 * H, H, in, H, t.w_ih3[l], t.b_ih[l], 0, GI, 3 * H, P.S3, 0, 0, st));
             } else {
                 SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI, 3 * H, st));
             }
@@ -365,6 +417,8 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
                     const __nv_bfloat16* hp16 = f ? Y16 + (size_t)(f - 1) * H : h016;
                     SRNN_TRY(gemm_umma(t.w_hh16[l], 3 * H, hp16, B, H, H, hp_ld, t.b_hh[l], nullptr, 0, gh, nullptr,
                                        F * 3 * H, 0, 128, pick_bn(B), st));
+                } else if (x3) {
+                    SRNN_TRY(gemm_x3(B, 3 * H, H, hp, hp_ld, t.w_hh3[l], t.b_hh[l], 0, gh, F * 3 * H, P.S3, 0, 0, st));
                 } else {
                     SRNN_TRY(gemm_f32(B, 3 * H, H, hp, hp_ld, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, gh, F * 3 * H, st));
                 }
@@ -378,6 +432,8 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
         if (bf16)
             SRNN_TRY(tf_gemm(t.w_up16, t.fs * H, in16, M, H, t.b_up, (i == 0 && P.UP16) ? nullptr : P.UP[i],
                              (i == 0 && P.UP16) ? P.UP16 : nullptr, t.fs * H, 0, st));
+        else if (x3)
+            SRNN_TRY(gemm_x3(M, t.fs * H, H, in, H, t.w_up3, t.b_up, 0, P.UP[i], t.fs * H, P.S3, 0, 0, st));
         else
             SRNN_TRY(gemm_f32(M, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, P.UP[i], t.fs * H, st));
         upper = P.UP[i];
@@ -391,8 +447,13 @@ int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_s
         SRNN_TRY(tf_gemm(ctx->w_out16, Q, P.X2h, R, H, ctx->b_out, logp_out, nullptr, Q, 0, st));
     } else {
         SRNN_TRY(mlp_gather(P.seq, Lseq, lookback - FS0, nullptr, ctx->tbl, upper, (long long)T * H, H, P.X1, B, T, H, FS0, st));
-        SRNN_TRY(gemm_f32(R, H, H, P.X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, P.X2, H, st));
-        SRNN_TRY(gemm_f32(R, Q, H, P.X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st));
+        if (x3) {
+            SRNN_TRY(gemm_x3(R, H, H, P.X1, H, ctx->w_hid3, ctx->b_hid, 1, P.X2, H, P.S3, 0, 0, st));
+            SRNN_TRY(gemm_x3(R, Q, H, P.X2, H, ctx->w_out3, ctx->b_out, 0, logp_out, Q, P.S3, 0, 0, st));
+        } else {
+            SRNN_TRY(gemm_f32(R, H, H, P.X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, P.X2, H, st));
+            SRNN_TRY(gemm_f32(R, Q, H, P.X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st));
+        }
     }
     SRNN_TRY(logsoftmax_rows(logp_out, R, st));
     P.reset_mask = reset_mask;
@@ -412,7 +473,7 @@ int srnn_predict_bwd(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     SRNN_TRY(check_ready(ctx));
     if (!logp || !dlogp || !params || !grads) return fail(SRNN_ERR_ARG, "null argument");
     if (!ctx->fwd.valid) return fail(SRNN_ERR_STATE, "srnn_predict_bwd needs a preceding srnn_predict_fwd on this context");
-    const int rc = ctx->fwd.mode == SRNN_MODE_FP32 ? predict_bwd_f32(ctx, logp, dlogp, params, grads, (cudaStream_t)stream)
+    const int rc = ctx->fwd.mode != SRNN_MODE_BF16 ? predict_bwd_f32(ctx, logp, dlogp, params, grads, (cudaStream_t)stream)
                                                    : predict_bwd_bf16(ctx, logp, dlogp, params, grads, (cudaStream_t)stream);
     ctx->fwd.valid = false;
     return rc;
@@ -426,7 +487,7 @@ int srnn_predict_bwd_nll(srnn_ctx* ctx, const float* logp, const int64_t* target
     SRNN_TRY(check_ready(ctx));
     if (!logp || !target || !params || !grads) return fail(SRNN_ERR_ARG, "null argument");
     if (!ctx->fwd.valid) return fail(SRNN_ERR_STATE, "srnn_predict_bwd_nll needs a preceding srnn_predict_fwd on this context");
-    const int rc = ctx->fwd.mode == SRNN_MODE_FP32
+    const int rc = ctx->fwd.mode != SRNN_MODE_BF16
                        ? predict_bwd_f32(ctx, logp, nullptr, params, grads, (cudaStream_t)stream, target, gscale)
                        : predict_bwd_bf16(ctx, logp, nullptr, params, grads, (cudaStream_t)stream, target, gscale);
     ctx->fwd.valid = false;
@@ -520,7 +581,7 @@ int srnn_nll_loss_bits(srnn_ctx* ctx, const float* logp, const int64_t* target, 
 // cluster_rows: 0 = k_mlp_persist (16-CTA row groups over L2), 16 / 24 = k_mlp_cluster (8-CTA clusters, rows per cluster)
 static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_cond, const float* cond, int cond_rows,
                           const int64_t* spk, const float* uniforms, int u_ld, uint8_t* samples_out, float* audio_out,
-                          float* logp_out, cudaStream_t user, int cluster_rows = 0) {
+                          float* logp_out, cudaStream_t user, int cluster_rows = 0, bool x3 = false) {
     const srnn_config& c = ctx->cfg;
     const int H = ctx->H, Q = ctx->Q, NT = c.n_tiers, NL = c.n_rnn, lookback = ctx->lookback, FS0 = ctx->FS0;
     const int T = n_cond * lookback, Lseq = lookback + T;
@@ -530,7 +591,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     float *hid[SRNN_MAX_TIERS], *A[SRNN_MAX_TIERS], *X[SRNN_MAX_TIERS], *GI[SRNN_MAX_TIERS], *GH[SRNN_MAX_TIERS],
         *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
     float* GHL[SRNN_MAX_TIERS][SRNN_MAX_RNN];      // per-layer recurrent projections of the fused-cell schedule
-    bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr;
+    bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr, *S3 = nullptr;
     float* part = nullptr;
     unsigned* gctr = nullptr;
     const int RG = (B + 31) / 32, NS = H / 64;
@@ -558,6 +619,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         LG = b.take<float>((size_t)B * Q);
         X1h = b.take<bf>(x1_rows * H);
         X2h = b.take<bf>((size_t)B * H);
+        S3 = b.take<bf>(x3 ? (size_t)B * 3 * H : 1);
         part = b.take<float>(persist && !cluster_rows ? (size_t)RG * NS * 32 * Q : 1);
         gctr = b.take<unsigned>(2 * RG);
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
@@ -689,7 +751,23 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         marks.push_back({name, e});
     };
     const long long before = g_launches.load();
-    if (use_graph) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    // everything the captured kernels bake in: shapes, schedule switches, caller pointers and the scratch base
+    srnn_ctx::GenGraph& gc = ctx->gen_graph;
+    const unsigned long long gkey[] = {(unsigned long long)B, (unsigned long long)n_cond, (unsigned long long)cond_rows,
+                                       (unsigned long long)u_ld, (unsigned long long)cluster_rows,
+                                       (unsigned long long)(bf16 | persist << 1 | x3 << 2 | shadow_gh << 3 | shadow_in << 4 | pdl << 5 |
+                                                            skip_tiers << 6 | fused_cell << 7),
+                                       (unsigned long long)spare_sms, (unsigned long long)(uintptr_t)cond,
+                                       (unsigned long long)(uintptr_t)spk, (unsigned long long)(uintptr_t)uniforms,
+                                       (unsigned long long)(uintptr_t)samples_out, (unsigned long long)(uintptr_t)audio_out,
+                                       (unsigned long long)(uintptr_t)logp_out, (unsigned long long)(uintptr_t)ctx->ws,
+                                       (unsigned long long)(getenv("SRNN_MC_DBG") ? atoi(getenv("SRNN_MC_DBG")) : 0),
+                                       (unsigned long long)((getenv("SRNN_GEMM_DEEP_RING") != nullptr) | (getenv("SRNN_GEMM_SINGLE_BUF") != nullptr) << 1 |
+                                                            (getenv("SRNN_SWAP_PAIR") != nullptr) << 2)};
+    const int ngkey = (int)(sizeof(gkey) / sizeof(gkey[0]));
+    const bool cache_ok = use_graph && !trace && !getenv("SRNN_NO_GRAPH_CACHE");
+    const bool cache_hit = cache_ok && gc.exec && gc.nkey == ngkey && !memcmp(gc.key, gkey, sizeof(gkey));
+    if (use_graph && !cache_hit) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
         prev_tier_kernel = false;
         for (int pos = 0; pos < lookback; ++pos) {                                   // i = *step_base + pos
@@ -758,6 +836,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                             {t.w_ih16[l], in16, t.b_ih[l], nullptr, GI[i], nullptr, 3 * H, H, H, 0, 3 * H, 0},
                             {t.w_hh16[l], h16, t.b_hh[l], nullptr, GH[i], nullptr, 3 * H, H, H, 0, 3 * H, 0}};
                         SRNN_TRY(gemm_umma_multi(ops, 2, B, H, 128, bn_for(3 * H, 2), st));
+                    } else if (x3) {
+                        SRNN_TRY(gemm_x3(B, 3 * H, H, in, H, t.w_ih3[l], t.b_ih[l], 0, GI[i], 3 * H, S3, 128, bn_for(3 * H, 1), st));
+                        SRNN_TRY(gemm_x3(B, 3 * H, H, h, H, t.w_hh3[l], t.b_hh[l], 0, GH[i], 3 * H, S3, 128, bn_for(3 * H, 1), st));
                     } else {
                         SRNN_TRY(gemm_f32(B, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI[i], 3 * H, st));
                         SRNN_TRY(gemm_f32(B, 3 * H, H, h, H, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, GH[i], 3 * H, st));
@@ -788,6 +869,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     g_pdl = 0;
                     SRNN_TRY(rc_u);
                 }
+                else if (x3)
+                    SRNN_TRY(gemm_x3(B, t.fs * H, H, in, H, t.w_up3, t.b_up, 0, OUT[i], t.fs * H, S3, 128, bn_for(t.fs * H, 1), st));
                 else
                     SRNN_TRY(gemm_f32(B, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, OUT[i], t.fs * H, st));
                 mark(t.top ? "upsample top" : "upsample");
@@ -850,8 +933,13 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             } else {
                 SRNN_TRY(mlp_gather(seq, Lseq, pos - FS0, step_base, ctx->tbl, up0, (long long)FS0 * H, 0, X1, B, 1, H,
                                     FS0, st));
-                SRNN_TRY(gemm_f32(B, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
-                SRNN_TRY(gemm_f32(B, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, LG, Q, st));
+                if (x3) {
+                    SRNN_TRY(gemm_x3(B, H, H, X1, H, ctx->w_hid3, ctx->b_hid, 1, X2, H, S3, bm_hid, bn_hid, st));
+                    SRNN_TRY(gemm_x3(B, Q, H, X2, H, ctx->w_out3, ctx->b_out, 0, LG, Q, S3, bm_out, bn_out, st));
+                } else {
+                    SRNN_TRY(gemm_f32(B, H, H, X1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, X2, H, st));
+                    SRNN_TRY(gemm_f32(B, Q, H, X2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, LG, Q, st));
+                }
             }
             SRNN_TRY(softmax_sample(LG, uniforms, u_ld, seq, Lseq, pos, lookback, step_base, logp_out,
                                     (long long)T * Q, B, st));                       // model.py:514-517
@@ -870,7 +958,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (use_graph) {
+    if (cache_hit) {
+        for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(gc.exec, st));
+        g_launches.fetch_add(gc.nodes * (long long)n_cond);
+        ++gc.reuses;
+    } else if (use_graph) {
         const int rc = body();
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         const long long nodes = g_launches.load() - before;
@@ -884,6 +976,17 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         if (ce == cudaSuccess) {
             for (int p = 0; p < n_cond; ++p) SRNN_CUDA(cudaGraphLaunch(exec, st));
             g_launches.fetch_add(nodes * (long long)(n_cond - 1));
+            if (cache_ok) {           // keep it for the next call of the same shape (the previous one is released once idle)
+                if (gc.exec) cudaGraphExecDestroy(gc.exec);
+                if (gc.graph) cudaGraphDestroy(gc.graph);
+                gc.exec = exec;
+                gc.graph = graph;
+                gc.nodes = nodes;
+                gc.nkey = ngkey;
+                memcpy(gc.key, gkey, sizeof(gkey));
+                exec = nullptr;
+                graph = nullptr;
+            }
         } else {
             // e.g. a driver that cannot put the cooperative persistent kernel into a graph: issue the launches directly
             cudaGetLastError();
@@ -1039,6 +1142,11 @@ int srnn_generate(srnn_ctx* ctx, int32_t B, int32_t n_cond, const float* cond, i
     if (cond_rows != 1 && cond_rows != B) return fail(SRNN_ERR_ARG, "cond_rows must be 1 or B");
     if (mode != SRNN_MODE_FP32 && !ctx->has_bf16)
         return fail(SRNN_ERR_UNSUPPORTED, "bf16 tensor-core mode needs dim %% 64 == 0 (dim=%d)", ctx->H);
+    if (mode == SRNN_MODE_BF16X3) {     // fp32 control flow, dense contractions as split-bf16 tcgen05 GEMMs
+        SRNN_TRY(ensure_x3(ctx, (cudaStream_t)stream));
+        return generate_graph(ctx, false, false, B, n_cond, cond, cond_rows, spk, uniforms, B, samples_out, audio_out, logp_out,
+                              (cudaStream_t)stream, 0, true);
+    }
     if (mode == SRNN_MODE_FP32 || mode == SRNN_MODE_BF16 || mode == SRNN_MODE_BF16_GRAPH) {
         const bool bf16 = mode != SRNN_MODE_FP32;
         int n_sms = 0;
@@ -1219,6 +1327,19 @@ int srnn_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* B, c
     if (!A || !B || !C) return fail(SRNN_ERR_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == SRNN_MODE_FP32) return gemm_f32(M, N, K, A, K, B, K, bias, addend, N, relu, C, N, st);
+    if (mode == SRNN_MODE_BF16X3) {   // split-bf16 product on tcgen05 (the contraction of the tensor-core parity mode)
+        if (K % 64 || addend) return fail(SRNN_ERR_ARG, "gemm hook (split bf16): K %% 64 == 0, no addend");
+        const int Np = (N + 127) / 128 * 128;
+        __nv_bfloat16 *a3 = nullptr, *w3 = nullptr;
+        SRNN_CUDA(cudaMallocAsync((void**)&a3, sizeof(__nv_bfloat16) * (size_t)M * 3 * K, st));
+        SRNN_CUDA(cudaMallocAsync((void**)&w3, sizeof(__nv_bfloat16) * (size_t)Np * 3 * K, st));
+        SRNN_CUDA(cudaMemsetAsync(w3, 0, sizeof(__nv_bfloat16) * (size_t)Np * 3 * K, st));
+        int rc = split3_bf16(B, N, K, K, w3, 1, st);
+        if (rc == SRNN_OK) rc = gemm_x3(M, N, K, A, K, w3, bias, relu, C, N, a3, 0, 0, st);
+        cudaFreeAsync(a3, st);
+        cudaFreeAsync(w3, st);
+        return rc;
+    }
     if ((mode & 0xff) == SRNN_MODE_BF16) {
         // tile selector for tests: bits 8..15 = UMMA M (0 -> 128), bits 16..27 = batch-row tile (0 -> 64),
         // bit 28 = ROWS orientation (activation rows on the TMEM lanes; bits 16..27 then give the feature tile),

@@ -99,6 +99,10 @@ struct TierPacked {
     __nv_bfloat16* w_ih16_t[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_hh16_t[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_up16_t = nullptr;
+    // split-bf16 copies (n_feat, 3K) of SRNN_MODE_BF16X3, packed lazily on the first use of that mode (ensure_x3)
+    __nv_bfloat16* w_ih3[SRNN_MAX_RNN] = {};
+    __nv_bfloat16* w_hh3[SRNN_MAX_RNN] = {};
+    __nv_bfloat16* w_up3 = nullptr;
 };
 
 struct Arena {
@@ -134,6 +138,7 @@ struct FwdPlan {
     float* X2 = nullptr;                                      // (B*T, H) relu(hidden)             [fp32 mode]
     __nv_bfloat16* X1h = nullptr;                             // bf16 mode
     __nv_bfloat16* X2h = nullptr;
+    __nv_bfloat16* S3 = nullptr;                              // SRNN_MODE_BF16X3: split copy (rows, 3H) of the current GEMM input
     size_t bytes = 0;
 };
 }  // namespace srnn
@@ -160,6 +165,19 @@ struct srnn_ctx {
     __nv_bfloat16* w_out16 = nullptr;
     __nv_bfloat16* w_hid16_t = nullptr;   // (H, H) transposed
     __nv_bfloat16* w_out16_t = nullptr;   // (H, Q) transposed
+    __nv_bfloat16* w_hid3 = nullptr;      // (H, 3H) / (Q, 3H) split-bf16 copies of SRNN_MODE_BF16X3
+    __nv_bfloat16* w_out3 = nullptr;
+    bool x3_valid = false;                // the *3 copies match the packed fp32 weights
+    // instantiated generation graph of the last srnn_generate shape: reused while every baked-in value (batch, mode, schedule
+    // switches, caller and scratch pointers) is unchanged -- capture + instantiation cost ~1 ms, which short utterances and
+    // small batches feel (the graph itself is position independent: the sample index lives in a device counter)
+    struct GenGraph {
+        unsigned long long key[20] = {};
+        int nkey = 0;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        long long nodes = 0, reuses = 0;
+    } gen_graph;
     unsigned* gru_ctr = nullptr;  // frame-barrier counter of the persistent GRU kernels
     // recorded by srnn_predict_bwd as the gradients become final: [0] sample-level MLP + embedding, [1 + 2i] tier i's
     // upsampling, [2 + 2i] the rest of tier i (srnn_bwd_wait_stage: data-parallel all-reduce overlapping the backward pass)
@@ -321,5 +339,9 @@ int gemm_umma_pair_wide(const GemmOperands& o, int n_rows, int K, cudaStream_t s
 int sum_splits(const float* part, int splits, size_t n, size_t stride, float* out, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);
+// SRNN_MODE_BF16X3 operand form: fp32 (rows, K) -> bf16 (rows, 3K), every value split into hi = bf16(x), lo = bf16(x - hi) and
+// laid out along K as [hi | hi | lo] (activations, weight_order = 0) or [hi | lo | hi] (weights, weight_order = 1), so that ONE
+// tcgen05 GEMM over K' = 3K accumulates Wh.xh + Wl.xh + Wh.xl in fp32 (the dropped Wl.xl term is ~2^-16 relative)
+int split3_bf16(const float* src, long long rows, int K, long long ld_src, __nv_bfloat16* dst, int weight_order, cudaStream_t st);
 
 }  // namespace srnn

@@ -1146,6 +1146,38 @@ int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloa
     return SRNN_OK;
 }
 
+// ---- fp32 -> split bf16 [hi | hi | lo] / [hi | lo | hi] along K (SRNN_MODE_BF16X3 operands; common.cuh) ------------------
+__global__ void k_split3_bf16(const float* __restrict__ src, long long rows, int K, long long ld_src,
+                              __nv_bfloat16* __restrict__ dst, int weight_order) {
+    const int K4 = K >> 2;
+    const long long total = rows * K4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K4;
+        const int c = (int)(i - r * K4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16(x[j]);
+            lo[j] = __float2bfloat16(x[j] - __bfloat162float(hi[j]));
+        }
+        const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+        __nv_bfloat16* d = dst + r * 3 * K + c;
+        *reinterpret_cast<uint2*>(d) = h2;
+        *reinterpret_cast<uint2*>(d + K) = weight_order ? l2 : h2;
+        *reinterpret_cast<uint2*>(d + 2 * K) = weight_order ? h2 : l2;
+    }
+}
+int split3_bf16(const float* src, long long rows, int K, long long ld_src, __nv_bfloat16* dst, int weight_order, cudaStream_t st) {
+    if (K % 4 || ld_src % 4) return fail(SRNN_ERR_ARG, "split3_bf16: K and the leading dimension must be multiples of 4");
+    const long long total = rows * (K >> 2);
+    int grid = (int)((total + 255) / 256 > 16384 ? 16384 : (total + 255) / 256);
+    if (grid < 1) grid = 1;
+    SRNN_LAUNCH(k_split3_bf16, grid, 256, 0, st, src, rows, K, ld_src, dst, weight_order);
+    return SRNN_OK;
+}
+
 // src (rows, cols; fp32 or bf16; leading dimension ld_src) -> dst (cols, ld_dst) bf16 with dst[c][r] = src[r][c];
 // columns rows..ld_dst-1 of dst are zero-filled (K padding of the transposed operand)
 template <typename T>

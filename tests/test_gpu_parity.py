@@ -387,3 +387,132 @@ def test_mlp_fwd_hook(mode):
     else:
         d = (got - ref).abs()
         assert float(d.max()) <= BF16_MAX_ABS and float(d.mean()) <= BF16_MEAN_ABS, (float(d.max()), float(d.mean()))
+
+
+# ---- tensor-core parity mode (SRNN_MODE_BF16X3): the fp32 gates on tcgen05 ------------------------------------------
+def test_gemm_hook_split_bf16():
+    """W.x as Wh.xh + Wl.xh + Wh.xl in one tcgen05 GEMM over K' = 3K: error ~2^-16 per product (plain bf16: 2^-8)."""
+    g = torch.Generator().manual_seed(1)
+    for (M, N, K) in [(5, 128, 64), (130, 256, 1024), (256, 1024, 1024), (300, 3072, 1024), (2000, 256, 1024)]:
+        A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+        bias = torch.randn(N, generator=g)
+        ref = torch.relu(A.double() @ B.double().t() + bias.double())
+        dA, dB, db = A.cuda(), B.cuda(), bias.cuda()
+        out = torch.empty(M, N, device="cuda")
+        L.check(L.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), db.data_ptr(), None, 1, out.data_ptr(),
+                                   S.MODE_BF16X3, stream()))
+        err = (out.cpu().double() - ref).abs().max().item()
+        assert err <= 6e-5 * K ** 0.5, (M, N, K, err)
+        # the plain bf16 product of the same operands is two orders of magnitude further away
+        out16 = torch.empty(M, N, device="cuda")
+        L.check(L.load().srnn_gemm(M, N, K, dA.data_ptr(), dB.data_ptr(), db.data_ptr(), None, 1, out16.data_ptr(),
+                                   S.MODE_BF16, stream()))
+        assert (out16.cpu().double() - ref).abs().max().item() > 20 * err
+
+
+def _seeded(c, seed):
+    torch.manual_seed(seed)
+    m = S.SampleRNN(**c)
+    p = S.Predictor(m, mode=S.MODE_BF16X3)
+    with torch.no_grad():
+        for k, v in p.state_dict().items():
+            if "bias" in k or k.endswith("h0"):
+                v.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in p.state_dict().items()}
+    p.cuda()
+    return m, p, O.unpack_state_dict(sd, O.Config(**c))
+
+
+@pytest.mark.parametrize("cfg,B,T", [
+    (dict(frame_sizes=[20, 4], n_rnn=2, dim=128, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6), 5, 240),
+    (dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6), 8, 160),
+    (dict(frame_sizes=[16], n_rnn=1, dim=64, learn_h0=True, q_levels=256, ulaw=True, weight_norm=False, cond_dim=43, spk_dim=6), 3, 64),
+    (dict(frame_sizes=[4, 2, 2], n_rnn=1, dim=64, learn_h0=False, q_levels=256, ulaw=False, weight_norm=True, cond_dim=5, spk_dim=6), 7, 64),
+])
+def test_predict_split_bf16_mode_holds_the_fp32_gate(cfg, B, T):
+    """Teacher-forced log-probs of SRNN_MODE_BF16X3 against the oracle: the 1e-3 relative gate of the fp32 mode; hidden-state
+    carry over two chunks; and a backward pass after it (fp32 kernels on the saved activations) matches the fp32 mode's."""
+    m, p, w = _seeded(cfg, 5)
+    lb = m.lookback
+    x = torch.randint(0, 256, (B, lb + 2 * T - 1))
+    cond = torch.rand(B, 2 * T // lb, cfg["cond_dim"], dtype=torch.float64)
+    spk = torch.randint(0, 6, (B, 1))
+    ref_p = O.Predictor(w)
+    with torch.no_grad():
+        for i in range(2):
+            xi, ci = x[:, i * T: i * T + lb + T - 1], cond[:, i * T // lb: (i + 1) * T // lb]
+            ref = ref_p.forward(xi, i == 0, ci, spk)
+            got = p(xi, i == 0, ci, spk, None, None)
+            logp_gate(got.cpu().numpy(), ref.numpy())
+    p32 = S.Predictor(m, mode=S.MODE_FP32)
+    grads = []
+    for pred in (p, p32):
+        for q in m.parameters():
+            q.grad = None
+        out = pred(x[:, :lb + T - 1], True, cond[:, :T // lb], spk, None, None)
+        S.sequence_nll_loss_bits(out, x[:, lb:lb + T].cuda()).backward()
+        grads.append([q.grad.detach().clone() for q in m.parameters() if q.grad is not None])
+    assert len(grads[0]) == len(grads[1]) > 0
+    for a, b in zip(*grads):
+        # a unit within ~1e-5 of zero may land on the other side of its ReLU: isolated elements move, the tensor does not
+        assert float((a - b).norm()) <= 1e-7 + 3e-3 * float(b.norm())
+        assert float((a - b).abs().max()) <= 1e-5 + 0.1 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("dim,B", [(128, 37), (1024, 40), (1024, 256)])
+def test_generate_split_bf16_mode_against_oracle(dim, B):
+    """SRNN_MODE_BF16X3 generation: log-probs within the fp32 gate (1e-3 relative) of the oracle teacher-forced on the generated
+    sequence, and the sampled indices equal to the fp32 mode's on the same uniforms up to isolated CDF-boundary ties."""
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=dim, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
+             cond_dim=86, spk_dim=6)
+    m, p, w = _seeded(c, dim)
+    n_cond = 2
+    g = torch.Generator().manual_seed(4)
+    cond, spk, uni = torch.rand(B, n_cond, 86, generator=g), torch.randint(0, 6, (B,), generator=g), torch.rand(n_cond * 80, B, generator=g)
+    _, samples, logp = S.Generator(m, cuda=True, mode=S.MODE_BF16X3)(B, 0, cond, spk, uniforms=uni, return_samples=True,
+                                                                      return_logp=True)
+    seq = torch.cat([torch.full((B, 80), 128, dtype=torch.long), samples.long()], 1)
+    with torch.no_grad():
+        ref = O.Predictor(w).forward(seq[:, :-1], True, cond, spk.reshape(B, 1))
+    logp_gate(logp.numpy(), ref.numpy())
+    _, s32 = S.Generator(m, cuda=True, mode=S.MODE_FP32)(B, 0, cond, spk, uniforms=uni, return_samples=True)
+    same = (s32 == samples)
+    shared = torch.cumprod(torch.cat([torch.ones_like(same[:, :1]), same[:, :-1]], 1).long(), 1).bool()
+    # while the two runs share a history they may differ only where u falls within rounding of a CDF boundary
+    assert float(same[shared].float().mean()) >= 0.999, float(same[shared].float().mean())
+
+
+@pytest.mark.parametrize("mode,dim,B", [(S.MODE_BF16, 1024, 24), (S.MODE_FP32, 64, 5)])
+def test_generate_reuses_the_instantiated_graph(mode, dim, B, monkeypatch):
+    """A second srnn_generate call of the same shape on the same buffers replays the cached graph (no capture, no
+    instantiation); new input VALUES in those buffers are picked up, and the result equals an uncached call bit for bit."""
+    torch.manual_seed(2)
+    c = dict(frame_sizes=[20, 4], n_rnn=2, dim=dim, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c).cuda()
+    gen = S.Generator(m, cuda=True, mode=mode)
+    n_cond = 3
+    g = torch.Generator().manual_seed(8)
+    cond = torch.rand(B, n_cond, 86, generator=g).cuda()
+    spk = torch.randint(0, 6, (B,), generator=g).cuda()
+    uni = torch.rand(80 * n_cond, B, generator=g).cuda()
+    monkeypatch.delenv("SRNN_NO_GRAPH_CACHE", raising=False)
+    reuse = lambda: L.load().srnn_graph_reuse_count(m._ctx)
+    outs = []
+    r0 = None
+    for i in range(4):
+        if i == 2:
+            uni.copy_(torch.rand(80 * n_cond, B, generator=g))          # same buffer, new values
+        res = gen(B, 0, cond, spk, uniforms=uni, device_output=True, return_samples=True, return_logp=True)
+        outs.append([t.clone() for t in res])
+        del res                                                          # output blocks go back to the caching allocator
+        if i == 0:
+            r0 = reuse()
+    assert reuse() - r0 >= 2, "the generation graph was re-captured on every call"
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+    assert all(torch.equal(a, b) for a, b in zip(outs[2], outs[3]))
+    assert not torch.equal(outs[0][1], outs[2][1])
+    monkeypatch.setenv("SRNN_NO_GRAPH_CACHE", "1")
+    before = reuse()
+    res = gen(B, 0, cond, spk, uniforms=uni, device_output=True, return_samples=True, return_logp=True)
+    assert reuse() == before
+    assert all(torch.equal(a, b) for a, b in zip(outs[3], res))
