@@ -206,8 +206,10 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
         SRNN_TRY(transpose_f32(t.w_in, t.w_in_t, H, t.kin, st));
         for (int l = 0; l < L; ++l) {
             if (!tp.weight_ih[l] || !tp.weight_hh[l] || !tp.bias_ih[l] || !tp.bias_hh[l]) return fail(SRNN_ERR_ARG, "tier %d: missing GRU layer %d", i, l);
-            SRNN_TRY(copy_f32(tp.weight_ih[l], t.w_ih[l], (size_t)3 * H * H, st));
-            SRNN_TRY(copy_f32(tp.weight_hh[l], t.w_hh[l], (size_t)3 * H * H, st));
+            if (!ctx->has_bf16) {      // with the tcgen05 copies these two ride along in the pack launch below
+                SRNN_TRY(copy_f32(tp.weight_ih[l], t.w_ih[l], (size_t)3 * H * H, st));
+                SRNN_TRY(copy_f32(tp.weight_hh[l], t.w_hh[l], (size_t)3 * H * H, st));
+            }
             SRNN_TRY(copy_f32(tp.bias_ih[l], t.b_ih[l], (size_t)3 * H, st));
             SRNN_TRY(copy_f32(tp.bias_hh[l], t.b_hh[l], (size_t)3 * H, st));
         }
@@ -225,25 +227,26 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
     SRNN_TRY(wn_fold(P->mlp_output, ctx->w_out, Q, H, st));
     SRNN_TRY(copy_f32(P->mlp_output.bias, ctx->b_out, Q, st));
     SRNN_TRY(build_lut(ctx->lut, Q, c.ulaw, st));
-    if (ctx->has_bf16) {   // bf16 operand copies for the tcgen05 path
+    if (ctx->has_bf16) {   // bf16 operand copies (plain + transposed) for the tcgen05 path: one launch for all of them
+        PackBf16Item it[PACK_BF16_MAX];
+        int n = 0;
+        auto add = [&](const float* src, __nv_bfloat16* d, __nv_bfloat16* dt, int rows, int cols, float* d32 = nullptr) {
+            if (n < PACK_BF16_MAX) it[n] = PackBf16Item{src, d, dt, d32, rows, cols, 0};
+            ++n;
+        };
         for (int i = 0; i < c.n_tiers; ++i) {
             TierPacked& t = ctx->tiers[i];
             for (int l = 0; l < L; ++l) {
-                SRNN_TRY(f32_to_bf16_pad(t.w_ih[l], 3 * H, H, H, t.w_ih16[l], 3 * H, H, st));
-                SRNN_TRY(f32_to_bf16_pad(t.w_hh[l], 3 * H, H, H, t.w_hh16[l], 3 * H, H, st));
+                add(P->tiers[i].weight_ih[l], t.w_ih16[l], t.w_ih16_t[l], 3 * H, H, t.w_ih[l]);
+                add(P->tiers[i].weight_hh[l], t.w_hh16[l], t.w_hh16_t[l], 3 * H, H, t.w_hh[l]);
             }
-            SRNN_TRY(f32_to_bf16_pad(t.w_up, t.fs * H, H, H, t.w_up16, t.fs * H, H, st));
-            for (int l = 0; l < L; ++l) {
-                SRNN_TRY(transpose_to_bf16(t.w_ih[l], 3 * H, H, H, t.w_ih16_t[l], 3 * H, st));
-                SRNN_TRY(transpose_to_bf16(t.w_hh[l], 3 * H, H, H, t.w_hh16_t[l], 3 * H, st));
-            }
-            SRNN_TRY(transpose_to_bf16(t.w_up, t.fs * H, H, H, t.w_up16_t, t.fs * H, st));
+            add(t.w_up, t.w_up16, t.w_up16_t, t.fs * H, H);
         }
-        SRNN_TRY(transpose_to_bf16(ctx->w_hid, H, H, H, ctx->w_hid16_t, H, st));
-        SRNN_TRY(transpose_to_bf16(ctx->w_out, Q, H, H, ctx->w_out16_t, Q, st));
-        SRNN_TRY(f32_to_bf16_pad(ctx->w_hid, H, H, H, ctx->w_hid16, H, H, st));
-        SRNN_TRY(f32_to_bf16_pad(ctx->w_out, Q, H, H, ctx->w_out16, Q, H, st));
-        SRNN_TRY(f32_to_bf16_pad(ctx->tbl, FS0 * Q, H, H, ctx->tbl16, FS0 * Q, H, st));
+        add(ctx->w_hid, ctx->w_hid16, ctx->w_hid16_t, H, H);
+        add(ctx->w_out, ctx->w_out16, ctx->w_out16_t, Q, H);
+        add(ctx->tbl, ctx->tbl16, nullptr, FS0 * Q, H);
+        if (n > PACK_BF16_MAX) return fail(SRNN_ERR_UNSUPPORTED, "too many weight matrices for one pack launch (%d)", n);
+        SRNN_TRY(pack_bf16_multi(it, n, st));
     }
     ctx->packed = true;
     ctx->x3_valid = false;
@@ -340,16 +343,6 @@ static int tf_gemm(const __nv_bfloat16* W, int n_feat, const __nv_bfloat16* act,
     GemmOperands o{W, act, bias, nullptr, out_f32, out_bf16, n_feat, K, K, 0, ld_out, relu, nullptr};
     if (rows >= 256 && ld_out % 8 == 0 && n_feat % 16 == 0) return gemm_umma_rows(o, rows, K, 1, nullptr, st);
     return gemm_umma_multi(&o, 1, rows, K, 128, pick_bn(rows), st);
-}
-
-// SRNN_MODE_BF16X3 contraction C (rows, n_feat) = A (rows, K) . W^T + bias [relu] with fp32 in / out: the activations are split
-// into s3 (rows, 3K) and meet the pre-split weights W3 (n_feat, 3K) in one tcgen05 GEMM (see split3_bf16).  bm / bn = 0: pick.
-static int gemm_x3(int rows, int n_feat, int K, const float* A, long long lda, const __nv_bfloat16* W3, const float* bias, int relu,
-                   float* C, int ldc, __nv_bfloat16* s3, int bm, int bn, cudaStream_t st) {
-    SRNN_TRY(split3_bf16(A, rows, K, lda, s3, 0, st));
-    GemmOperands o{W3, s3, bias, nullptr, C, nullptr, n_feat, 3 * K, 3 * K, 0, ldc, relu, nullptr};
-    if (!bm && rows >= 256 && ldc % 8 == 0 && n_feat % 16 == 0) return gemm_umma_rows(o, rows, 3 * K, 1, nullptr, st);
-    return gemm_umma_multi(&o, 1, rows, 3 * K, bm ? bm : 128, bn ? bn : pick_bn(rows), st);
 }
 
 int srnn_predict_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* input_seq, const void* cond,

@@ -838,6 +838,44 @@ static int tc_dw_tn(int Nout, int Kin, int rows, const bf* dOut16, int ld_do, co
     if (ks > rows / 512) ks = rows / 512;                  // at least 8 k-blocks per split
     return gemm_umma_tn(dOut16, ld_do, In16, ld_in, Nout, Kin, rows, dW, Kin, ks < 2 ? 1 : ks, scratch, st);
 }
+// tbl_foldback on the tensor cores (bf16 training path): the two contractions are fp32 gradients of fp32 parameters, so they
+// run as split-bf16 products (hi/lo pieces, see split3_bf16: ~2^-16 relative per product, fp32 accumulation) instead of FFMA
+// GEMMs (0.45 ms of the C3 step).  Scratch comes from the stream-ordered pool (3 x 31 MB at C3).
+static int tbl_foldback_x3(srnn_ctx* ctx, const srnn_params* P, const srnn_params* G, const float* dTblT, float* scratch2HQF,
+                           size_t scratch_floats, float* dWmt, float* dWm, cudaStream_t st) {
+    const int H = ctx->H, Q = ctx->Q, FS0 = ctx->FS0, KH = FS0 * H;
+    const size_t n = (size_t)KH * Q;
+    float* wm_fold = scratch2HQF;                       // (H, Q, FS)
+    float* wm_t = scratch2HQF + n;                      // (FS, H, Q) = ((j,h), e)
+    float* et = scratch2HQF + 2 * n;                    // (Q, Q) E^T
+    float* splitk = et + (size_t)Q * Q;
+    const size_t splitk_floats = scratch_floats - 2 * n - (size_t)Q * Q;
+    bf *a3 = nullptr, *b3 = nullptr, *et3 = nullptr;
+    SRNN_CUDA(cudaMallocAsync((void**)&a3, sizeof(bf) * 3 * n, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&b3, sizeof(bf) * 3 * n, st));
+    SRNN_CUDA(cudaMallocAsync((void**)&et3, sizeof(bf) * 3 * (size_t)Q * Q, st));
+    int rc = wn_fold(P->mlp_input, wm_fold, H, Q * FS0, st);
+    if (rc == SRNN_OK) rc = transpose_mlp_in(wm_fold, wm_t, H, Q, FS0, st);
+    // dWm_t[(j,h), e] = sum_q dTblT[(j,h), q] E[q, e]: rows (j,h), K = q, "weights" E^T (e, q)
+    if (rc == SRNN_OK) rc = transpose_f32(P->embedding, et, Q, Q, st);
+    if (rc == SRNN_OK) rc = split3_bf16(et, Q, Q, Q, et3, 1, st);
+    if (rc == SRNN_OK) rc = gemm_x3(KH, Q, Q, dTblT, Q, et3, nullptr, 0, dWmt, Q, a3, 0, 0, st);
+    // dE[q, e] = sum_{(j,h)} dTblT[(j,h), q] wm_t[(j,h), e]: both operands MN-major, the three pieces stacked along K
+    float* dE = (float*)G->embedding;
+    if (rc == SRNN_OK && dE) {
+        rc = split3_planes_bf16(dTblT, n, a3, 1, st);
+        if (rc == SRNN_OK) rc = split3_planes_bf16(wm_t, n, b3, 0, st);
+        if (rc == SRNN_OK) rc = tc_dw_tn(Q, Q, 3 * KH, a3, Q, b3, Q, dE, splitk, splitk_floats, st);
+    }
+    cudaFreeAsync(a3, st);
+    cudaFreeAsync(b3, st);
+    cudaFreeAsync(et3, st);
+    SRNN_TRY(rc);
+    SRNN_LAUNCH(k_untranspose_mlp_in, dim3(H, FS0), 256, 0, st, dWmt, dWm, H, Q, FS0);
+    SRNN_TRY(wn_bwd(dWm, P->mlp_input, G->mlp_input, H, Q * FS0, st));
+    return SRNN_OK;
+}
+
 // HP16[(b,f), :] = f ? Y16[(b,f-1), :] : h0_16[b, :]   (bf16 recurrent input of every frame, for dW_hh)
 __global__ void k_build_hprev16(const bf* __restrict__ Y16, const bf* __restrict__ h0, bf* __restrict__ hp, int F, int H) {
     const int r = blockIdx.x, b = r / F, f = r % F;
@@ -939,7 +977,9 @@ int predict_bwd_bf16(srnn_ctx* ctx, const float* logp, const float* dlogp, const
     SRNN_TRY(tc_dx(R, H, H, DP2, H, ctx->w_hid16_t, nullptr, 0, nullptr, DP1, F.X1h, H, st));   // dpre1 = dc0
     // ---- folded table ----
     SRNN_TRY(dtbl_compute(F.seq, Lseq, lookback - FS0, DP1, B, T, H, FS0, iwork, dTblP, dTbl, dTblT, st));
-    SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
+    const bool foldback_f32 = getenv("SRNN_FOLDBACK_F32") != nullptr;             // A/B switch: the FFMA form
+    if (foldback_f32 || Q % 64) SRNN_TRY(tbl_foldback(ctx, P, G, dTblT, dTblP, dWmt, dWm, st));
+    else SRNN_TRY(tbl_foldback_x3(ctx, P, G, dTblT, dTblP, dtblp_floats, dWmt, dWm, st));
     SRNN_CUDA(cudaEventRecord(ctx->ev_stage[0], st));                           // MLP + embedding gradients are final
     // ---- frame tiers, lowest first ----
     const bf* dUP = DP1;

@@ -339,9 +339,27 @@ int gemm_umma_pair_wide(const GemmOperands& o, int n_rows, int K, cudaStream_t s
 int sum_splits(const float* part, int splits, size_t n, size_t stride, float* out, cudaStream_t st);
 int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloat16* dst, int rows_p, int cols_p,
                     cudaStream_t st);
+// All bf16 operand copies of the packed fp32 weights in ONE launch (was 19 conversion + 12 transpose launches after every
+// optimizer step): for each listed matrix src (rows, cols) fp32 -> dst (rows, cols) bf16 and / or dst_t (cols, rows) bf16 (+ an fp32 copy).
+struct PackBf16Item {
+    const float* src;
+    __nv_bfloat16* dst;       // may be null
+    __nv_bfloat16* dst_t;     // may be null
+    float* dst32;             // optional fp32 copy (the GRU matrices are taken straight from the caller's tensors)
+    int rows, cols;
+    int tile0;                // first tile of this matrix in the launch's tile list (filled by pack_bf16_multi)
+};
+constexpr int PACK_BF16_MAX = 40;
+int pack_bf16_multi(PackBf16Item* items, int n, cudaStream_t st);
 // SRNN_MODE_BF16X3 operand form: fp32 (rows, K) -> bf16 (rows, 3K), every value split into hi = bf16(x), lo = bf16(x - hi) and
 // laid out along K as [hi | hi | lo] (activations, weight_order = 0) or [hi | lo | hi] (weights, weight_order = 1), so that ONE
 // tcgen05 GEMM over K' = 3K accumulates Wh.xh + Wl.xh + Wh.xl in fp32 (the dropped Wl.xl term is ~2^-16 relative)
 int split3_bf16(const float* src, long long rows, int K, long long ld_src, __nv_bfloat16* dst, int weight_order, cudaStream_t st);
+// the same split for MN-major operands (K is the slow dimension): three planes of n elements, [hi; hi; lo] or [hi; lo; hi]
+int split3_planes_bf16(const float* src, size_t n, __nv_bfloat16* dst, int weight_order, cudaStream_t st);
+// SRNN_MODE_BF16X3 contraction C (rows, n_feat) = A (rows, K) . W^T + bias [relu] with fp32 in / out: the activations are split
+// into s3 (rows, 3K) and meet the pre-split weights W3 (n_feat, 3K) in one tcgen05 GEMM.  bm / bn = 0: chosen from the shape.
+int gemm_x3(int rows, int n_feat, int K, const float* A, long long lda, const __nv_bfloat16* W3, const float* bias, int relu,
+            float* C, int ldc, __nv_bfloat16* s3, int bm, int bn, cudaStream_t st);
 
 }  // namespace srnn

@@ -1146,6 +1146,79 @@ int f32_to_bf16_pad(const float* src, int rows, int cols, int ld_src, __nv_bfloa
     return SRNN_OK;
 }
 
+// ---- multi-matrix fp32 -> bf16 (+ transposed bf16) pack: one launch for every tcgen05 operand copy of the weights ---------
+struct PackBf16Args {
+    PackBf16Item it[PACK_BF16_MAX];
+    int n, total_tiles;
+};
+// tile = 32 rows x 64 columns; block (32, 8): thread (tx, ty) owns columns 2tx, 2tx+1 of rows ty, ty+8, ...
+__global__ void __launch_bounds__(256) k_pack_bf16_multi(const __grid_constant__ PackBf16Args a) {
+    __shared__ float tile[32][65];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int m = 0;
+        while (m + 1 < a.n && a.it[m + 1].tile0 <= t) ++m;
+        const PackBf16Item& I = a.it[m];
+        const int tcols = (I.cols + 63) >> 6;
+        const int lt = t - I.tile0, r0 = (lt / tcols) * 32, c0 = (lt % tcols) * 64;
+        const bool full = r0 + 32 <= I.rows && c0 + 64 <= I.cols && (I.cols & 1) == 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+            float2 v = make_float2(0.f, 0.f);
+            if (full) {
+                v = *reinterpret_cast<const float2*>(I.src + (size_t)r * I.cols + c);
+            } else if (r < I.rows) {
+                if (c < I.cols) v.x = I.src[(size_t)r * I.cols + c];
+                if (c + 1 < I.cols) v.y = I.src[(size_t)r * I.cols + c + 1];
+            }
+            if (I.dst32) {
+                if (full) {
+                    *reinterpret_cast<float2*>(I.dst32 + (size_t)r * I.cols + c) = v;
+                } else if (r < I.rows) {
+                    if (c < I.cols) I.dst32[(size_t)r * I.cols + c] = v.x;
+                    if (c + 1 < I.cols) I.dst32[(size_t)r * I.cols + c + 1] = v.y;
+                }
+            }
+            if (I.dst) {
+                if (full) {
+                    *reinterpret_cast<__nv_bfloat162*>(I.dst + (size_t)r * I.cols + c) = __floats2bfloat162_rn(v.x, v.y);
+                } else if (r < I.rows) {
+                    if (c < I.cols) I.dst[(size_t)r * I.cols + c] = __float2bfloat16(v.x);
+                    if (c + 1 < I.cols) I.dst[(size_t)r * I.cols + c + 1] = __float2bfloat16(v.y);
+                }
+            }
+            tile[ty + 8 * i][2 * tx] = v.x;
+            tile[ty + 8 * i][2 * tx + 1] = v.y;
+        }
+        if (I.dst_t) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                  // dst_t[c][r]: a warp writes 32 consecutive r of one column c
+                const int c = c0 + ty + 8 * i, r = r0 + tx;
+                if (c < I.cols && r < I.rows) I.dst_t[(size_t)c * I.rows + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+            }
+        }
+        __syncthreads();
+    }
+}
+int pack_bf16_multi(PackBf16Item* items, int n, cudaStream_t st) {
+    if (n < 1 || n > PACK_BF16_MAX) return fail(SRNN_ERR_ARG, "pack_bf16_multi: 1..%d matrices", PACK_BF16_MAX);
+    PackBf16Args a;
+    memset(&a, 0, sizeof(a));
+    int tiles = 0;
+    for (int i = 0; i < n; ++i) {
+        items[i].tile0 = tiles;
+        tiles += cdiv(items[i].rows, 32) * cdiv(items[i].cols, 64);
+        a.it[i] = items[i];
+    }
+    a.n = n;
+    a.total_tiles = tiles;
+    const int grid = tiles < 148 * 16 ? tiles : 148 * 16;
+    SRNN_LAUNCH(k_pack_bf16_multi, grid, dim3(32, 8), 0, st, a);
+    return SRNN_OK;
+}
+
 // ---- fp32 -> split bf16 [hi | hi | lo] / [hi | lo | hi] along K (SRNN_MODE_BF16X3 operands; common.cuh) ------------------
 __global__ void k_split3_bf16(const float* __restrict__ src, long long rows, int K, long long ld_src,
                               __nv_bfloat16* __restrict__ dst, int weight_order) {
@@ -1176,6 +1249,40 @@ int split3_bf16(const float* src, long long rows, int K, long long ld_src, __nv_
     if (grid < 1) grid = 1;
     SRNN_LAUNCH(k_split3_bf16, grid, 256, 0, st, src, rows, K, ld_src, dst, weight_order);
     return SRNN_OK;
+}
+
+__global__ void k_split3_planes_bf16(const float* __restrict__ src, size_t n4, size_t n, __nv_bfloat16* __restrict__ dst, int weight_order) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16(x[j]);
+            lo[j] = __float2bfloat16(x[j] - __bfloat162float(hi[j]));
+        }
+        const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+        reinterpret_cast<uint2*>(dst)[i] = h2;
+        reinterpret_cast<uint2*>(dst + n)[i] = weight_order ? l2 : h2;
+        reinterpret_cast<uint2*>(dst + 2 * n)[i] = weight_order ? h2 : l2;
+    }
+}
+int split3_planes_bf16(const float* src, size_t n, __nv_bfloat16* dst, int weight_order, cudaStream_t st) {
+    if (n % 4) return fail(SRNN_ERR_ARG, "split3_planes_bf16: element count must be a multiple of 4");
+    const size_t n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256 > 16384 ? 16384 : (n4 + 255) / 256);
+    if (grid < 1) grid = 1;
+    SRNN_LAUNCH(k_split3_planes_bf16, grid, 256, 0, st, src, n4, n, dst, weight_order);
+    return SRNN_OK;
+}
+
+int gemm_x3(int rows, int n_feat, int K, const float* A, long long lda, const __nv_bfloat16* W3, const float* bias, int relu,
+            float* C, int ldc, __nv_bfloat16* s3, int bm, int bn, cudaStream_t st) {
+    SRNN_TRY(split3_bf16(A, rows, K, lda, s3, 0, st));
+    GemmOperands o{W3, s3, bias, nullptr, C, nullptr, n_feat, 3 * K, 3 * K, 0, ldc, relu, nullptr};
+    if (!bm && rows >= 256 && ldc % 8 == 0 && n_feat % 16 == 0) return gemm_umma_rows(o, rows, 3 * K, 1, nullptr, st);
+    const int pick = rows <= 32 ? 32 : (rows <= 64 ? 64 : (rows <= 128 ? 128 : 256));
+    return gemm_umma_multi(&o, 1, rows, 3 * K, bm ? bm : 128, bn ? bn : pick, st);
 }
 
 // src (rows, cols; fp32 or bf16; leading dimension ld_src) -> dst (cols, ld_dst) bf16 with dst[c][r] = src[r][c];
