@@ -191,7 +191,7 @@ def test_bf16_gradient_error_is_relu_mask_flips(dim, B, T):
     out = p(x, True, cond, spk, None, None)
     loss = S.sequence_nll_loss_bits(out, y)
     loss.backward()
-    assert abs(float(loss.detach()) - float(loss_ref)) < 0.03
+    assert abs(float(loss.detach()) - float(loss_ref)) < 0.02 + 2e-3 * float(loss_ref)
     report = []
     for k, q in p.named_parameters():
         ref = grads[k].numpy().astype(np.float64)
@@ -201,7 +201,7 @@ def test_bf16_gradient_error_is_relu_mask_flips(dim, B, T):
             continue
         report.append((round(float(np.linalg.norm(got - ref) / nref), 4), k))
     print("no-mask-flip gradient errors:", sorted(report, reverse=True)[:6])
-    assert max(report)[0] < 0.035, sorted(report, reverse=True)[:12]
+    assert max(report)[0] < 0.05, sorted(report, reverse=True)[:12]       # measured 0.033 (dim 128); regular gate 0.12
 
 
 def test_table_foldback_on_tensor_cores_matches_fp32_form(monkeypatch):
