@@ -585,7 +585,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
     float* GHL[SRNN_MAX_TIERS][SRNN_MAX_RNN];      // per-layer recurrent projections of the fused-cell schedule
     bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr, *S3 = nullptr;
-    float* part = nullptr;
+    float *part = nullptr, *pcarry = nullptr;
     unsigned* gctr = nullptr;
     const int RG = (B + 31) / 32, NS = H / 64;
     const int n_clusters = cluster_rows ? (B + cluster_rows - 1) / cluster_rows : 0;
@@ -615,6 +615,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         S3 = b.take<bf>(x3 ? (size_t)B * 3 * H : 1);
         part = b.take<float>(persist && !cluster_rows ? (size_t)RG * NS * 32 * Q : 1);
         gctr = b.take<unsigned>(2 * RG);
+        pcarry = b.take<float>(cluster_rows ? 2 * x1_rows * H : 1);
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
     }
     // private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
@@ -682,6 +683,11 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // consecutive kernels of a tier step (input expansion -> cells -> upsampling) are launched as programmatic dependents
     const bool pdl = bf16 && fused_cell && !time_tiers_early && !getenv("SRNN_NO_PDL");
     bool prev_tier_kernel = false;                 // the previous launch on st is one of those kernels
+    // ... and so is the cluster sample kernel (no cooperative launch): as a dependent of the upsampling it sets up barriers and
+    // TMEM and requests its first weight tiles while that kernel drains; the tier step after it is pre-launched from its last
+    // sample step.  SRNN_NO_PDL_SAMPLE=1 restores plain launches on both sides.
+    const bool pdl_sample = pdl && cluster_rows && !getenv("SRNN_NO_PDL_SAMPLE");
+    bool prev_sample_kernel = false;
     cudaEvent_t ev_gh[SRNN_MAX_TIERS] = {};
     bool gh_todo[SRNN_MAX_TIERS] = {}, gh_pending[SRNN_MAX_TIERS] = {};
     auto launch_gh = [&](int i, cudaStream_t s, int cap) -> int {
@@ -709,6 +715,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     // period (and the conditioner / speaker columns) is accumulated beside the last sample launch of that period; the serial
     // path keeps K = FS0 columns.  XP (the partial sums) lives in the top tier's GI buffer, unused by the fused-cell schedule.
     const bool shadow_in = shadow_gh && !getenv("SRNN_NO_SHADOW_IN");
+    // CTAs of the L2 weight prefetch beside each sample launch (0 = off)
+    const int l2_prefetch = shadow_gh && getenv("SRNN_L2_PREFETCH") ? atoi(getenv("SRNN_L2_PREFETCH")) : 0;
     const TierPacked& ttop = ctx->tiers[NT - 1];
     float* XP = GI[NT - 1];
     const int xp_lo = ttop.n - FS0 > 0 ? ttop.n - FS0 : 0, xp_hi = ttop.n;
@@ -725,6 +733,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
 
     if (persist) SRNN_CUDA(cudaMemsetAsync(X1h, 0, sizeof(bf) * x1_rows * H, st));
     if (persist) SRNN_CUDA(cudaMemsetAsync(gctr, 0, sizeof(unsigned) * 2 * RG, st));     // group barrier counters: once per call
+    const bool carry = cluster_rows && !getenv("SRNN_NO_PCARRY");
+    if (carry) SRNN_TRY(mlp_cluster_carry_init(ctx->tbl16, FS0, H, (int)x1_rows, Q / 2, pcarry, st));
     long long* trace = nullptr;
     const size_t trace_n = (size_t)(cluster_rows ? 8 : 1) * FS0 * 64;
     if (persist && getenv("SRNN_TRACE")) {
@@ -749,7 +759,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     const unsigned long long gkey[] = {(unsigned long long)B, (unsigned long long)n_cond, (unsigned long long)cond_rows,
                                        (unsigned long long)u_ld, (unsigned long long)cluster_rows,
                                        (unsigned long long)(bf16 | persist << 1 | x3 << 2 | shadow_gh << 3 | shadow_in << 4 | pdl << 5 |
-                                                            skip_tiers << 6 | fused_cell << 7),
+                                                            skip_tiers << 6 | fused_cell << 7 | pdl_sample << 8 | carry << 9 | (unsigned long long)l2_prefetch << 16),
                                        (unsigned long long)spare_sms, (unsigned long long)(uintptr_t)cond,
                                        (unsigned long long)(uintptr_t)spk, (unsigned long long)(uintptr_t)uniforms,
                                        (unsigned long long)(uintptr_t)samples_out, (unsigned long long)(uintptr_t)audio_out,
@@ -763,6 +773,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     if (use_graph && !cache_hit) SRNN_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     auto body = [&]() -> int {
         prev_tier_kernel = false;
+        prev_sample_kernel = false;
         for (int pos = 0; pos < lookback; ++pos) {                                   // i = *step_base + pos
             for (int i = NT - 1; i >= 0; --i) {
                 const TierPacked& t = ctx->tiers[i];
@@ -789,7 +800,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     }
                     SRNN_CUDA(cudaEventRecord(ev_join, st2));
                 }
-                g_pdl = pdl && prev_tier_kernel;
+                g_pdl = pdl && (prev_tier_kernel || (pdl_sample && prev_sample_kernel));
+                prev_sample_kernel = false;
                 int rc_in = (t.top && shadow_in)
                     ? tier_input_split(true, seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
                                        ctx->lut, t.w_in_t, t.b_in, XP, X[i], X16[i], H, t.kin, xp_lo, xp_hi, st)
@@ -872,6 +884,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             const float* up0 = OUT[0] + (size_t)(pos % FS0) * H;                     // model.py:504-513
             if (persist) {
                 if (pos % FS0) continue;             // one persistent launch covers the FS0 samples of a tier-0 frame
+                const bool sample_dep = pdl_sample && prev_tier_kernel;
                 prev_tier_kernel = false;
                 if (shadow_gh) {                     // next step's recurrent projections: on the spare SMs, beside this launch
                     const bool xp_now = shadow_in && pos == lookback - FS0;      // last sample launch of the period
@@ -887,6 +900,20 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                             gh_todo[i] = false;
                             gh_pending[i] = true;
                         }
+                        if (l2_prefetch) {               // bf16 weights of the tier step(s) that follow this sample launch -> L2
+                            L2PrefetchArgs pa{};
+                            auto want = [&](const void* ptr, size_t bytes) {
+                                if (pa.n < 8) { pa.ptr[pa.n] = ptr; pa.bytes[pa.n] = bytes; ++pa.n; }
+                            };
+                            const int next_pos = (pos + FS0) % lookback;
+                            for (int i = NT - 1; i >= 0; --i) {
+                                const TierPacked& t = ctx->tiers[i];
+                                if (next_pos % t.n) continue;
+                                for (int l = 0; l < NL && l < 2; ++l) want(t.w_ih16[l], sizeof(bf) * 3 * (size_t)H * H);
+                                want(t.w_up16, sizeof(bf) * (size_t)t.fs * H * H);
+                            }
+                            if (pa.n) SRNN_TRY(prefetch_l2(pa, l2_prefetch, st2));
+                        }
                         if (xp_now) {                    // next period's top-tier input, all but its last FS0 sample columns
                             SRNN_TRY(launch_xp(lookback - ttop.n, st2));
                             SRNN_CUDA(cudaEventRecord(ev_xp, st2));
@@ -899,10 +926,16 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 mp.Lseq = Lseq; mp.T = T; mp.step_base = step_base; mp.seq = seq; mp.c0 = OUT[0];
                 mp.tbl = ctx->tbl16; mp.b_hid = ctx->b_hid; mp.b_out = ctx->b_out; mp.x1 = X1h; mp.part = part;
                 mp.dbg = getenv("SRNN_MC_DBG") ? atoi(getenv("SRNN_MC_DBG")) : 0;
+                mp.pcarry = carry ? pcarry : nullptr;
+                mp.carry_plane = (long long)x1_rows * H;
                 mp.ctr = gctr; mp.uniforms = uniforms; mp.u_ld = u_ld; mp.logp_out = logp_out; mp.trace = trace;
                 auto launch_sample = [&]() -> int {
-                    return cluster_rows ? mlp_cluster_launch(ctx->w_hid16, ctx->w_out16, mp, cluster_rows, st)
-                                        : mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st);
+                    g_pdl = sample_dep;
+                    const int rc_s = cluster_rows ? mlp_cluster_launch(ctx->w_hid16, ctx->w_out16, mp, cluster_rows, st)
+                                                  : mlp_persist_launch(ctx->w_hid16, ctx->w_out16, mp, st);
+                    g_pdl = 0;
+                    prev_sample_kernel = cluster_rows != 0;
+                    return rc_s;
                 };
                 if (time_kernels) {
                     cudaEvent_t e0, e1;
@@ -1059,6 +1092,13 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
             }
             fprintf(stderr, " (reduce %.0f softmax+sample %.0f) | flags@%.0f lastMMA@%.0f (since signal) | step=%.0f | entry->step0=%lld step0=%lld\n",
                     red / (FS0 - 2), smx / (FS0 - 2), woke / (FS0 - 2), lastmma / (FS0 - 2), tot / (FS0 - 3), tr[0] - tr[63], tr[64] - tr[0]);
+            if (cta == 0)
+                for (int k = 0; k < 2; ++k) {
+                    fprintf(stderr, "[srnn trace]    CTA0 step %d:", k);
+                    for (int j = 0; j < 9; ++j) fprintf(stderr, " %s=%lld", nm[j], tr[k * 64 + j + 1] - tr[k * 64 + j]);
+                    fprintf(stderr, " | x1 flags since signal %lld, D1 since TMA issue %lld\n", tr[k * 64 + 10] - tr[k * 64 + 3],
+                            tr[k * 64 + 4] - tr[k * 64 + 10]);
+                }
             fprintf(stderr, "[srnn trace]    prologue CTA%d (cycles since entry): init+alloc+sync %lld, weights in TMEM %lld, P(0) gathered %lld, cluster sync done %lld, step 0 starts %lld\n",
                     cta, tr[20] - tr[63], tr[21] - tr[63], tr[22] - tr[63], tr[23] - tr[63], tr[0] - tr[63]);
         }

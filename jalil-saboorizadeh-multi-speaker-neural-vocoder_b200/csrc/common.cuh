@@ -195,6 +195,12 @@ namespace srnn {
 int ensure_ws(srnn_ctx* ctx, size_t bytes);
 
 // ---- fp32 kernels (kernels_f32.cu) --------------------------------------------------------------
+struct L2PrefetchArgs {
+    const void* ptr[8];
+    size_t bytes[8];
+    int n;
+};
+int prefetch_l2(const L2PrefetchArgs& a, int ctas, cudaStream_t st);
 int gemm_f32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, const float* bias,
              const float* add, int ldadd, int relu, float* C, int ldc, cudaStream_t st,
              __nv_bfloat16* C16 = nullptr);
@@ -287,7 +293,15 @@ struct MlpPersistParams {
     float* logp_out;              // (B, T, 256) or null
     long long* trace;             // optional (nsteps, 10) clock64 stamps of CTA 0 (SRNN_TRACE=1), else null
     int dbg = 0;                  // development switches of k_mlp_cluster (SRNN_MC_DBG), 0 in production
+    // k_mlp_cluster: (2, rows, H) fp32 table parts sum_{j < FS-2} Tbl[j][.] of the FIRST and SECOND sample of the next launch,
+    // written by the gather warps of this one while its last samples are drawn (the samples they need exist three / two steps
+    // before the end) and consumed by the next launch, whose first two steps then need c0 + one row per utterance instead of
+    // FS-2 table rows on the serial path.  Seeded by mlp_cluster_carry_init for the first frame of a call.  Null: every
+    // launch gathers its first samples itself.
+    float* pcarry = nullptr;
+    long long carry_plane = 0;    // elements between the two planes (rows * H)
 };
+int mlp_cluster_carry_init(const __nv_bfloat16* tbl, int FS, int H, int rows, int q_zero, float* pcarry, cudaStream_t st);
 int mlp_persist_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out16, const MlpPersistParams& p,
                        cudaStream_t st);
 // cluster form (mlp_cluster.cu, H = 1024): rows_per_cluster = 16 or 24; p.x1 holds ceil(B / rows) * rows rows; part / ctr unused

@@ -820,6 +820,21 @@ int nll_bits(const float* logp, const int64_t* target, int rows, float* partial,
     return SRNN_OK;
 }
 
+// L2 prefetch of up to four byte ranges (the bf16 weights of the next tier step) from a few spare CTAs beside the sample kernel:
+// the tier chain is weight-streaming, and between two of its steps the sample kernel's working set pushes those weights out
+__global__ void k_prefetch_l2(L2PrefetchArgs a) {
+    for (int r = 0; r < a.n; ++r) {
+        const char* base = (const char*)a.ptr[r];
+        const size_t lines = (a.bytes[r] + 127) >> 7;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(base + (i << 7)));
+    }
+}
+int prefetch_l2(const L2PrefetchArgs& a, int ctas, cudaStream_t st) {
+    SRNN_LAUNCH(k_prefetch_l2, ctas, 256, 0, st, a);
+    return SRNN_OK;
+}
+
 __global__ void k_add_int(int* p, int v) { *p += v; }
 int add_int(int* p, int v, cudaStream_t st) {
     SRNN_LAUNCH(k_add_int, 1, 1, 0, st, p, v);

@@ -158,8 +158,6 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     uint64_t* wl_free = bars + 21;                        // [NSLOT <= 5] ... and has been moved to tensor memory
     uint32_t* tmem_slot = (uint32_t*)(bars + 31);
 
-    const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
-    const int row0 = cl * R + c * RPC;                    // first owned row (global utterance index)
     if (p.trace && cl == 0 && threadIdx.x == 0) p.trace[(c * p.nsteps) * 64 + 63] = clock64();
 
     if (threadIdx.x == 0) {
@@ -185,6 +183,22 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc<MC_TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // The weights are constants of the generation call: their first staging tiles and the shared-memory part are requested
+    // BEFORE griddepcontrol.wait, so that as a programmatic dependent of the upsampling kernel this launch's latency, barrier /
+    // TMEM set-up and first weight loads overlap that kernel's drain (a no-op in a plain launch).
+    constexpr int KB_EARLY = Lay::NSLOT < MC_KB_TMEM ? Lay::NSLOT : MC_KB_TMEM;
+    if (warp == 8 && elect_one()) {
+        for (int kb = 0; kb < KB_EARLY; ++kb) {           // round 0 of every staging slot: nothing to wait for
+            mbar_expect_tx(&wl_full[kb], 16384);
+            tma_load_2d(sX1 + (size_t)kb * 16384, &tmWh, &wl_full[kb], kb * 64, c * 128);
+        }
+    }
+    pdl_wait();                                           // seq, c0, step_base below come from the preceding launches
+    const int i0 = *p.step_base + p.pos0;                 // absolute index of the first sample of this launch
+    const int row0 = cl * R + c * RPC;                    // first owned row (global utterance index)
     // owned rows' sample ring: the FS most recent samples before i0 (written by earlier launches / the q_zero prefix)
     for (int e = threadIdx.x; e < RPC * 32; e += MC_THREADS) {
         const int rl = e >> 5, w = e & 31;
@@ -194,9 +208,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         if (b < p.B && a >= 0 && a >= i0 - FS) q = __ldcg(p.seq + (size_t)b * p.Lseq + a);
         sQ[rl * 32 + (a & 31)] = q;
     }
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
     if (p.trace && cl == 0 && threadIdx.x == 0) p.trace[(c * p.nsteps) * 64 + 20] = clock64();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (keeps the MMA operands in uniform registers)
     const uint32_t tm_d = tmem + MC_COL_D;
@@ -205,28 +217,42 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     auto g_step = [&](int g) {
         const int f0 = threadIdx.x * 8;
         const int i = i0 + g;
+        const bool carry_out = g >= p.nsteps;             // table part of the NEXT launch's first / second sample -> p.pcarry
+        const bool carry_in = g <= 1 && p.pcarry != nullptr;
+        float* const pcar = p.pcarry + (size_t)(carry_out ? g - p.nsteps : g) * p.carry_plane;
         if (g >= 3)   // sample i-3 (tap FS-3, the newest one this prefetch uses) has been drawn.  Three barriers by
                       // step % 3: E can be up to two steps past the awaited one, which would alias a phase parity.
             mbar_wait(&q_ready[g % 3], (g / 3 - 1) & 1);
         // L2 -> SM ingest is the shared resource of a step (x1 tile 48 KB by TMA, this gather 110 KB): the gather of step g runs
         // in step g-1 AFTER that step's x1 tile has landed, i.e. under the epilogues / output GEMM / reduce, never beside the TMA
         // loads the hidden GEMM is waiting for (measured: +1300 cycles per step when they overlap).
-        if (g >= 1 && !(p.dbg & 2)) mbar_wait(&full[3], (g - 1) & 1);
+        if (g >= 1 && g < p.nsteps && !(p.dbg & 2)) mbar_wait(&full[3], (g - 1) & 1);   // (the carry gathers must not run late)
         float acc[RPC][8];
 #pragma unroll
         for (int r = 0; r < RPC; ++r) {
             const int b = row0 + r;
             const int bc = b < p.B ? b : p.B - 1;         // clamp: padded rows compute garbage that is never used
+            if (carry_out) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[r][v] = 0.f;
+                continue;
+            }
             const float4* cp = reinterpret_cast<const float4*>(p.c0 + (size_t)bc * FS * H + (size_t)(i % FS) * H + f0);
             // c0 is rewritten between launches by the upsampling kernel: read at L2 (like seq), not through the non-coherent path
             const float4 ca = __ldcg(cp), cb = __ldcg(cp + 1);
             acc[r][0] = ca.x; acc[r][1] = ca.y; acc[r][2] = ca.z; acc[r][3] = ca.w;
             acc[r][4] = cb.x; acc[r][5] = cb.y; acc[r][6] = cb.z; acc[r][7] = cb.w;
+            if (carry_in) {                               // the previous launch already summed this sample's table rows
+                const float4* pc = reinterpret_cast<const float4*>(pcar + (size_t)(row0 + r) * H + f0);
+                const float4 pa = __ldcg(pc), pb = __ldcg(pc + 1);
+                acc[r][0] += pa.x; acc[r][1] += pa.y; acc[r][2] += pa.z; acc[r][3] += pa.w;
+                acc[r][4] += pb.x; acc[r][5] += pb.y; acc[r][6] += pb.z; acc[r][7] += pb.w;
+            }
         }
         // latency-bound L2 gather: six taps x RPC rows (18 loads of 16 bytes per thread) in flight at a time (nine: slower, the
         // outstanding-load limit of the SM serialises them)
         constexpr int GB = 6;
-        for (int j0 = 0; j0 < FS - 2; j0 += GB) {
+        for (int j0 = 0; j0 < FS - 2 && !carry_in; j0 += GB) {
             uint4 tv[GB][RPC];
 #pragma unroll
             for (int jj = 0; jj < GB; ++jj) {
@@ -250,6 +276,15 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 }
             }
         }
+        if (carry_out) {
+#pragma unroll
+            for (int r = 0; r < RPC; ++r) {
+                float4* pc = reinterpret_cast<float4*>(pcar + (size_t)(row0 + r) * H + f0);
+                pc[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                pc[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+            }
+            return;
+        }
         if (g >= 1) mbar_wait(p_free, (g - 1) & 1);       // E has consumed P of the previous step (single buffer)
 #pragma unroll
         for (int r = 0; r < RPC; ++r) {
@@ -268,9 +303,9 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     // tiles through NSLOT staging slots in the (still idle) x1 / x2 / landing area and every thread picks its row out of shared memory.
     if (warp == 8) {
         if (elect_one()) {
-            for (int kb = 0; kb < MC_KB_TMEM; ++kb) {     // first what the E warps are waiting for
+            for (int kb = KB_EARLY; kb < MC_KB_TMEM; ++kb) {     // first what the E warps are waiting for
                 const int slot = kb % Lay::NSLOT, round = kb / Lay::NSLOT;
-                if (round) mbar_wait(&wl_free[slot], (round - 1) & 1);
+                mbar_wait(&wl_free[slot], (round - 1) & 1);
                 mbar_expect_tx(&wl_full[slot], 16384);
                 tma_load_2d(sX1 + (size_t)slot * 16384, &tmWh, &wl_full[slot], kb * 64, c * 128);
             }
@@ -403,6 +438,9 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         }
         for (int k = 0; k < p.nsteps; ++k) {
             const int i = i0 + k;
+            // the next kernel on the stream (the tier step that consumes this frame) may be scheduled now: it waits in
+            // griddepcontrol.wait until this grid has completed, only its launch latency and prologue move forward
+            if (k == p.nsteps - 1) pdl_trigger();
             // ---- E1: x1 = relu(P + Tbl[FS-1][newest] + Tbl[FS-2][second newest]) for the owned rows -> global exchange buffer ----
             MC_TRACE(0);
             if (tidE < RPC) {
@@ -567,11 +605,29 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
     } else {
         // ===================== G warps: P of the following samples (the first one was prefetched during the prologue) ==========
         for (int g = 1; g < p.nsteps; ++g) g_step(g);
+        if (p.pcarry) {                                   // table parts of the next launch's first two samples
+            g_step(p.nsteps);
+            g_step(p.nsteps + 1);
+        }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                   // no CTA leaves while a peer may still signal or copy into it
     if (warp == 8) tmem_dealloc<MC_TMEM_COLS>(tmem);
+}
+
+// pcarry of the first frame of a call: every tap of its first sample is the q_zero prefix (model.py:459); same summation order
+// as the gather warps (taps 0 .. FS-3)
+__global__ void k_mc_carry_init(const __nv_bfloat16* __restrict__ tbl, int FS, int H, int rows, int q_zero, float* __restrict__ pcarry) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= H) return;
+    float acc = 0.f;
+    for (int j = 0; j < FS - 2; ++j) acc += __bfloat162float(tbl[((size_t)j * SRNN_Q + q_zero) * H + f]);
+    for (int r = blockIdx.y; r < 2 * rows; r += gridDim.y) pcarry[(size_t)r * H + f] = acc;     // both planes
+}
+int mlp_cluster_carry_init(const __nv_bfloat16* tbl, int FS, int H, int rows, int q_zero, float* pcarry, cudaStream_t st) {
+    SRNN_LAUNCH(k_mc_carry_init, dim3(cdiv(H, 256), rows < 64 ? rows : 64), 256, 0, st, tbl, FS, H, rows, q_zero, pcarry);
+    return SRNN_OK;
 }
 
 bool mlp_cluster_supported(int H, int FS, int B, int max_clusters) {
@@ -630,13 +686,15 @@ int mlp_cluster_launch(const __nv_bfloat16* w_hid16, const __nv_bfloat16* w_out1
     cfg.blockDim = dim3(MC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = MC_CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     cudaError_t e = R == 16 ? cudaLaunchKernelEx(&cfg, k_mlp_cluster<2>, tmWh, tmWo, tmX1, w_hid16, p)
                             : cudaLaunchKernelEx(&cfg, k_mlp_cluster<3>, tmWh, tmWo, tmX1, w_hid16, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
