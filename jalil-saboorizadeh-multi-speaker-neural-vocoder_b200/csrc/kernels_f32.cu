@@ -676,9 +676,99 @@ k_mlp_gather_bf16v(const uint8_t* __restrict__ seq, int seq_ld, int start_static
     }
     *reinterpret_cast<uint4*>(x1 + (size_t)r * H + f0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
+// Teacher-forced form for many tokens: the L2-bound version above re-reads FS table rows (2 KB each) per token -- 5.4 GB of L2
+// traffic at C3, 0.68 ms.  Here a CTA keeps a 16-FEATURE SLICE of the whole table (FS x 256 rows of 32 bytes = 160 KB at FS = 20)
+// in shared memory and walks a range of tokens; every table read is a 16-byte shared-memory load, global traffic is the
+// conditioning in and x1 out.  A thread owns 4 consecutive tokens x 8 features (the FS + 3 sample bytes it needs are loaded
+// once).  Same summation order as above (conditioning, then taps 0 .. FS-1): bit-identical results.
+template <int FS>
+__global__ void __launch_bounds__(512, 1)
+k_mlp_gather_slice(const uint8_t* __restrict__ seq, int seq_ld, int start, const __nv_bfloat16* __restrict__ tbl,
+                   const __nv_bfloat16* __restrict__ upper16, long long up_bstride, long long up_tstride,
+                   __nv_bfloat16* __restrict__ x1, int B, int T, int H, long long groups_per_cta) {
+    extern __shared__ uint4 s_tbl[];                         // [FS * 256 rows][2 halves of 8 features]
+    const int f0s = blockIdx.x * 16;
+    for (int i = threadIdx.x; i < FS * SRNN_Q * 2; i += blockDim.x)
+        s_tbl[i] = __ldg(reinterpret_cast<const uint4*>(tbl + (size_t)(i >> 1) * H + f0s + 8 * (i & 1)));
+    __syncthreads();
+    const int TG = T >> 2;                                   // groups of 4 tokens per utterance
+    const long long n_groups = (long long)B * TG;
+    const long long g0 = (long long)blockIdx.y * groups_per_cta;
+    const long long g1 = g0 + groups_per_cta < n_groups ? g0 + groups_per_cta : n_groups;
+    for (long long it = 2 * g0 + threadIdx.x; it < 2 * g1; it += blockDim.x) {
+        const int h = (int)(it & 1);
+        const long long g = it >> 1;
+        const int b = (int)(g / TG), t0 = (int)(g % TG) * 4;
+        const uint8_t* sp = seq + (size_t)b * seq_ld + start + t0;
+        int q[FS + 3];
+#pragma unroll
+        for (int j = 0; j < FS + 3; ++j) q[j] = sp[j];
+        float acc[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 u = *reinterpret_cast<const uint4*>(upper16 + (size_t)b * up_bstride + (size_t)(t0 + k) * up_tstride + f0s + 8 * h);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                acc[k][2 * i] = f.x;
+                acc[k][2 * i + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < FS; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 v = s_tbl[(j * SRNN_Q + q[j + k]) * 2 + h];
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(h2[i]);
+                    acc[k][2 * i] += f.x;
+                    acc[k][2 * i + 1] += f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(fmaxf(acc[k][2 * i], 0.f), fmaxf(acc[k][2 * i + 1], 0.f));
+                o[i] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            *reinterpret_cast<uint4*>(x1 + ((size_t)b * T + t0 + k) * H + f0s + 8 * h) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+template <int FS>
+static int launch_gather_slice(const uint8_t* seq, int seq_ld, int off, const __nv_bfloat16* tbl, const __nv_bfloat16* upper16,
+                               long long up_bstride, long long up_tstride, __nv_bfloat16* x1, int B, int T, int H, cudaStream_t st) {
+    const size_t smem = (size_t)FS * SRNN_Q * 32;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SRNN_CUDA(cudaFuncSetAttribute(k_mlp_gather_slice<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const long long n_groups = (long long)B * (T / 4);
+    int chunks = (int)(n_groups / 2048);                     // >= 2048 groups (8192 tokens) per CTA to amortise the slice load
+    if (chunks < 1) chunks = 1;
+    if (chunks > 16) chunks = 16;
+    const long long per = (n_groups + chunks - 1) / chunks;
+    SRNN_LAUNCH((k_mlp_gather_slice<FS>), dim3(H / 16, chunks), 512, smem, st, seq, seq_ld, off, tbl, upper16, up_bstride, up_tstride,
+                x1, B, T, H, per);
+    return SRNN_OK;
+}
+
 int mlp_gather_bf16(const uint8_t* seq, int seq_ld, int off, const int* step_base, const __nv_bfloat16* tbl,
                     const float* upper, long long up_bstride, long long up_tstride, __nv_bfloat16* x1, int B, int T,
                     int H, int FS, cudaStream_t st, const __nv_bfloat16* upper16) {
+    // many tokens, bf16 conditioning, static window: table slices resident in shared memory (SRNN_GATHER_V1=1: the L2 form)
+    if (upper16 && !step_base && (long long)B * T >= 32768 && T % 4 == 0 && H % 16 == 0 && up_bstride % 8 == 0 && up_tstride % 8 == 0 &&
+        (FS == 20 || FS == 16) && !getenv("SRNN_GATHER_V1")) {
+        return FS == 20 ? launch_gather_slice<20>(seq, seq_ld, off, tbl, upper16, up_bstride, up_tstride, x1, B, T, H, st)
+                        : launch_gather_slice<16>(seq, seq_ld, off, tbl, upper16, up_bstride, up_tstride, x1, B, T, H, st);
+    }
     const bool vec_ok = H % 8 == 0 && H <= 2048 && 256 % (H / 8) == 0 && up_bstride % 8 == 0 && up_tstride % 8 == 0;
     if (upper16 && !vec_ok) return fail(SRNN_ERR_UNSUPPORTED, "bf16 conditioning needs the vectorised gather (dim %d)", H);
     if (vec_ok) {

@@ -516,3 +516,26 @@ def test_generate_reuses_the_instantiated_graph(mode, dim, B, monkeypatch):
     res = gen(B, 0, cond, spk, uniforms=uni, device_output=True, return_samples=True, return_logp=True)
     assert reuse() == before
     assert all(torch.equal(a, b) for a, b in zip(outs[3], res))
+
+
+def test_teacher_forced_table_gather_from_shared_memory_is_bit_identical(monkeypatch):
+    """Above 32 768 tokens the bf16 teacher-forced pass gathers from 16-feature table slices held in shared memory
+    (k_mlp_gather_slice) instead of re-reading table rows from L2 (k_mlp_gather_bf16v, SRNN_GATHER_V1=1).  Both sum the
+    conditioning and the taps in the same order, so every log-probability must be bit-identical."""
+    torch.manual_seed(31)
+    c = dict(frame_sizes=[20, 4], n_rnn=1, dim=128, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6)
+    m = S.SampleRNN(**c).cuda()
+    p = S.Predictor(m, mode=S.MODE_BF16)
+    B, T = 33, 1040
+    x = torch.randint(0, 256, (B, 80 + T - 1))
+    cond, spk = torch.rand(B, T // 80, 86), torch.randint(0, 6, (B, 1))
+    outs = []
+    for v1 in (False, True):
+        if v1:
+            monkeypatch.setenv("SRNN_GATHER_V1", "1")
+        else:
+            monkeypatch.delenv("SRNN_GATHER_V1", raising=False)
+        with torch.no_grad():
+            outs.append(p(x, True, cond, spk, None, None).clone())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
