@@ -233,8 +233,9 @@ def train_block(args, rank, world, dev, steps, warmup):
         "higher_is_better": True, "scaling": "weak", "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
         "config": {"workload": "C3 training step: 3-tier [20,4] SampleRNN dim 1024, batch %d x T %d per GPU, Adam lr 1e-4 "
                                "with element-wise gradient clamp" % (B, T),
-                   "allreduce": "fp32 sum over ranks in backward-stage buckets on a side stream (NCCL); mean folded into the "
-                                "clamp+Adam kernel" if world > 1 else "none (1 GPU)",
+                   "allreduce": ("fp32 sum over ranks in backward-stage buckets on a side stream (NCCL, NCCL_MAX_CTAS=%s); mean folded "
+                                 "into the clamp+Adam kernel" % os.environ.get("NCCL_MAX_CTAS", "default"))
+                                if world > 1 else "none (1 GPU)",
                    "loss": "fused (srnn_nll_loss_bits + srnn_predict_bwd_nll), no torch kernel in the step"},
         "loss_bits_first_last": [float(losses[0]), float(losses[-1])],
         "params_identical_across_ranks": same,
@@ -379,6 +380,10 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    # The gradient all-reduce runs beside the backward pass, whose persistent GRU kernels need their 128 CTAs co-resident on
+    # the 148 SMs: NCCL is held to 16 CTAs (measured at 8 GPUs, ms per C3 step: 8 -> 8.83, 16 -> 8.66, 32 -> 8.86, default 8.83)
+    if world > 1:
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if args.workload == "sweep":
