@@ -570,28 +570,30 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 for (int j = 1; j < 8; ++j) m = fmaxf(m, v[j]);
                 m = mc_warp_max(m);
                 // MUFU-based exp / log (ex2.approx, lg2.approx; relative error ~2^-21): the libm forms cost ~20 instructions each
-                // and 17 of them sit on the serial path of every sample; far inside the bf16 mode's stated tolerance
-                float s = 0.f;
+                // and sit on the serial path of every sample; far inside the bf16 mode's stated tolerance.
+                // The defined sampler normalises by its own total (idx = #{k: cdf[k] <= u * total}), so it is fed the
+                // UNNORMALISED e = exp(logit - max): the log-sum-exp (warp sum, log, 8 subtractions, 8 more exponentials) leaves
+                // the serial path and is only evaluated -- after the sample has been published -- when log-probs are requested.
+                float e[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s += __expf(v[j] - m);
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                const float lse = m + __logf(s);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] -= lse;
+                for (int j = 0; j < 8; ++j) e[j] = __expf(v[j] - m);
                 const int t = i - p.lookback;
                 if (bb < p.B) {
-                    if (p.logp_out) {
-                        float4* o4 = reinterpret_cast<float4*>(p.logp_out + ((size_t)bb * p.T + t) * SRNN_Q + lane * 8);
-                        o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        o4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __expf(v[j]);
                     const float u = sU[r2];
-                    const int idx = sampler_warp(v, u, lane);
+                    const int idx = sampler_warp(e, u, lane);
                     if (lane == 0) {
                         p.seq[(size_t)bb * p.Lseq + i] = (uint8_t)idx;
                         sQ[r2 * 32 + (i & 31)] = (uint8_t)idx;
+                    }
+                    if (p.logp_out) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s += e[j];
+                        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        const float lse = m + __logf(s);
+                        float4* o4 = reinterpret_cast<float4*>(p.logp_out + ((size_t)bb * p.T + t) * SRNN_Q + lane * 8);
+                        o4[0] = make_float4(v[0] - lse, v[1] - lse, v[2] - lse, v[3] - lse);
+                        o4[1] = make_float4(v[4] - lse, v[5] - lse, v[6] - lse, v[7] - lse);
                     }
                 } else if (lane == 0) {
                     sQ[r2 * 32 + (i & 31)] = 128;
