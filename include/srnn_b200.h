@@ -205,6 +205,15 @@ SRNN_API int srnn_dequant_lut(const srnn_ctx* ctx, float* out, void* stream);
  * upper (B, T, H) fp32 conditioning from tier 0 -> logp_out (B, T, Q) fp32 log-probabilities. */
 SRNN_API int srnn_mlp_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* prev_samples, const float* upper,
                           float* logp_out, int32_t mode, void* stream);
+/* FrameLevelRNN.forward (model.py:180-263) of tier `tier` (0 = lowest) on the context's packed weights, F frames:
+ * prev_samples (B, F, n_frame_samples) fp32 = 2*dequantize(window) as the reference passes it; upper (B, F, H) fp32 conditioning
+ * from the tier above, or null on the top tier, which instead takes cond (B, F, cond_dim) fp32 and spk (B) int64 (one speaker
+ * per utterance, model.py:206-217); hidden_io (n_rnn, B, H) fp32: read unless `reset` (then the tier starts from its h0,
+ * model.py:222-228) and always overwritten with the new state; out (B, F*frame_size, H) fp32 = the upsampled output.
+ * SRNN_MODE_FP32 or SRNN_MODE_BF16X3.  The per-module form of what srnn_predict_fwd runs fused; inference only. */
+SRNN_API int srnn_tier_fwd(srnn_ctx* ctx, int32_t tier, int32_t B, int32_t F, const float* prev_samples, const float* upper,
+                           const float* cond, const int64_t* spk, float* hidden_io, int32_t reset, float* out, int32_t mode,
+                           void* stream);
 /* One GRU layer over F frames = `self.rnn(input, hidden)` (model.py:244; torch nn.GRU, gate row blocks r, z, n) given the
  * input projections: gi (B*F, 3H) = W_ih x + b_ih with row b*F+f, w_hh (3H, H), b_hh (3H), h0 (B, H) ->
  * y (B*F, H) = h_f, gh (B*F, 3H) = W_hh h_{f-1} + b_hh (kept for the backward pass), h_last (B, H) or NULL.

@@ -1252,9 +1252,11 @@ int srnn_mlp_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* prev_sample
                  int32_t mode, void* stream) {
     SRNN_TRY(check_ready(ctx));
     if (!prev_samples || !upper || !logp_out || B < 1 || T < 1) return fail(SRNN_ERR_ARG, "bad argument");
-    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16) return fail(SRNN_ERR_UNSUPPORTED, "mlp_fwd: mode %d not available", mode);
-    if (mode == SRNN_MODE_BF16 && !ctx->has_bf16) return fail(SRNN_ERR_UNSUPPORTED, "bf16 mode needs dim %% 64 == 0");
+    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16 && mode != SRNN_MODE_BF16X3)
+        return fail(SRNN_ERR_UNSUPPORTED, "mlp_fwd: mode %d not available", mode);
+    if (mode != SRNN_MODE_FP32 && !ctx->has_bf16) return fail(SRNN_ERR_UNSUPPORTED, "tensor-core modes need dim %% 64 == 0");
     cudaStream_t st = (cudaStream_t)stream;
+    if (mode == SRNN_MODE_BF16X3) SRNN_TRY(ensure_x3(ctx, st));
     const int H = ctx->H, Q = ctx->Q, FS0 = ctx->FS0, R = B * T, W = T + FS0 - 1;
     uint8_t* seq = nullptr;
     SRNN_CUDA(cudaMallocAsync((void**)&seq, (size_t)B * W, st));
@@ -1274,14 +1276,77 @@ int srnn_mlp_fwd(srnn_ctx* ctx, int32_t B, int32_t T, const int64_t* prev_sample
         SRNN_CUDA(cudaMallocAsync((void**)&x1, sizeof(float) * (size_t)R * H, st));
         SRNN_CUDA(cudaMallocAsync((void**)&x2, sizeof(float) * (size_t)R * H, st));
         rc = mlp_gather(seq, W, 0, nullptr, ctx->tbl, upper, (long long)T * H, H, x1, B, T, H, FS0, st);
-        if (rc == SRNN_OK) rc = gemm_f32(R, H, H, x1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, x2, H, st);
-        if (rc == SRNN_OK) rc = gemm_f32(R, Q, H, x2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st);
+        if (mode == SRNN_MODE_BF16X3) {
+            __nv_bfloat16* s3 = nullptr;
+            SRNN_CUDA(cudaMallocAsync((void**)&s3, sizeof(__nv_bfloat16) * (size_t)R * 3 * H, st));
+            if (rc == SRNN_OK) rc = gemm_x3(R, H, H, x1, H, ctx->w_hid3, ctx->b_hid, 1, x2, H, s3, 0, 0, st);
+            if (rc == SRNN_OK) rc = gemm_x3(R, Q, H, x2, H, ctx->w_out3, ctx->b_out, 0, logp_out, Q, s3, 0, 0, st);
+            cudaFreeAsync(s3, st);
+        } else {
+            if (rc == SRNN_OK) rc = gemm_f32(R, H, H, x1, H, ctx->w_hid, H, ctx->b_hid, nullptr, 0, 1, x2, H, st);
+            if (rc == SRNN_OK) rc = gemm_f32(R, Q, H, x2, H, ctx->w_out, H, ctx->b_out, nullptr, 0, 0, logp_out, Q, st);
+        }
         cudaFreeAsync(x1, st);
         cudaFreeAsync(x2, st);
     }
     if (rc == SRNN_OK) rc = logsoftmax_rows(logp_out, R, st);
     cudaFreeAsync(seq, st);
     return rc;
+}
+
+// FrameLevelRNN.forward (model.py:180-263) for one tier: the per-module form of the tier loop of srnn_predict_fwd (same kernels:
+// input expansion GEMM with the upper conditioning as addend, frame-by-frame GRU, learned upsampling as a GEMM).
+int srnn_tier_fwd(srnn_ctx* ctx, int32_t tier, int32_t B, int32_t F, const float* prev_samples, const float* upper,
+                  const float* cond, const int64_t* spk, float* hidden_io, int32_t reset, float* out, int32_t mode, void* stream) {
+    SRNN_TRY(check_ready(ctx));
+    const srnn_config& c = ctx->cfg;
+    if (tier < 0 || tier >= c.n_tiers || B < 1 || F < 1 || !prev_samples || !hidden_io || !out) return fail(SRNN_ERR_ARG, "tier_fwd: bad argument");
+    if (mode != SRNN_MODE_FP32 && mode != SRNN_MODE_BF16X3) return fail(SRNN_ERR_UNSUPPORTED, "tier_fwd: mode %d not available", mode);
+    const TierPacked& t = ctx->tiers[tier];
+    if (t.top ? (!cond || !spk || upper) : (!upper || cond || spk))
+        return fail(SRNN_ERR_ARG, "tier_fwd: the top tier takes cond + spk, the others the upper tier's conditioning (model.py:199-217)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool x3 = mode == SRNN_MODE_BF16X3;
+    if (x3) SRNN_TRY(ensure_x3(ctx, st));
+    const int H = ctx->H, NL = c.n_rnn, M = B * F;
+    ctx->fwd.valid = false;                      // the scratch below overlays the saved activations of a teacher-forced pass
+    float *A = nullptr, *X = nullptr, *GI = nullptr, *GH = nullptr, *Y[2] = {nullptr, nullptr}, *h0 = nullptr;
+    __nv_bfloat16* S3 = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        Bump b(pass ? ctx->ws : nullptr);
+        A = b.take<float>((size_t)M * t.kin);
+        X = b.take<float>((size_t)M * H);
+        GI = b.take<float>((size_t)M * 3 * H);
+        GH = b.take<float>((size_t)M * 3 * H);
+        Y[0] = b.take<float>((size_t)M * H);
+        Y[1] = b.take<float>((size_t)M * H);
+        h0 = b.take<float>((size_t)B * H);
+        S3 = b.take<__nv_bfloat16>(x3 ? (size_t)M * 3 * H : 1);
+        if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
+    }
+    SRNN_TRY(tier_assemble_f32(prev_samples, t.n, cond, c.cond_dim, spk, c.spk_dim, M, F, A, t.kin, st));
+    SRNN_TRY(gemm_f32(M, H, t.kin, A, t.kin, t.w_in, t.kin, t.b_in, upper, H, 0, X, H, st));
+    const float* in = X;
+    for (int l = 0; l < NL; ++l) {
+        float* y = Y[l & 1];
+        float* hid = hidden_io + (size_t)l * B * H;
+        if (reset) SRNN_TRY(bcast_rows(t.h0 + (size_t)l * H, h0, B, H, st));
+        else SRNN_TRY(copy_f32(hid, h0, (size_t)B * H, st));
+        if (x3) SRNN_TRY(gemm_x3(M, 3 * H, H, in, H, t.w_ih3[l], t.b_ih[l], 0, GI, 3 * H, S3, 0, 0, st));
+        else SRNN_TRY(gemm_f32(M, 3 * H, H, in, H, t.w_ih[l], H, t.b_ih[l], nullptr, 0, 0, GI, 3 * H, st));
+        for (int f = 0; f < F; ++f) {
+            const float* hp = f ? y + (size_t)(f - 1) * H : h0;
+            const int hp_ld = f ? F * H : H;
+            float* gh = GH + (size_t)f * 3 * H;
+            if (x3) SRNN_TRY(gemm_x3(B, 3 * H, H, hp, hp_ld, t.w_hh3[l], t.b_hh[l], 0, gh, F * 3 * H, S3, 0, 0, st));
+            else SRNN_TRY(gemm_f32(B, 3 * H, H, hp, hp_ld, t.w_hh[l], H, t.b_hh[l], nullptr, 0, 0, gh, F * 3 * H, st));
+            SRNN_TRY(gru_gates(GI + (size_t)f * 3 * H, F * 3 * H, gh, F * 3 * H, hp, hp_ld, y + (size_t)f * H, F * H,
+                               f == F - 1 ? hid : nullptr, B, H, st, nullptr, F * H));
+        }
+        in = y;
+    }
+    if (x3) return gemm_x3(M, t.fs * H, H, in, H, t.w_up3, t.b_up, 0, out, t.fs * H, S3, 0, 0, st);
+    return gemm_f32(M, t.fs * H, H, in, H, t.w_up, H, t.b_up, nullptr, 0, 0, out, t.fs * H, st);
 }
 
 // One GRU layer over F frames (torch nn.GRU as used at model.py:133-159,244).  FP32: the frame-by-frame fp32 schedule;

@@ -195,6 +195,8 @@ namespace srnn {
 int ensure_ws(srnn_ctx* ctx, size_t bytes);
 
 // ---- fp32 kernels (kernels_f32.cu) --------------------------------------------------------------
+int tier_assemble_f32(const float* prev, int n, const float* cond, int cond_dim, const int64_t* spk, int spk_dim, int rows, int F,
+                      float* A, int kin, cudaStream_t st);
 struct L2PrefetchArgs {
     const void* ptr[8];
     size_t bytes[8];

@@ -910,6 +910,24 @@ int nll_bits(const float* logp, const int64_t* target, int rows, float* partial,
     return SRNN_OK;
 }
 
+// srnn_tier_fwd: tier input rows [prev_samples | cond | onehot(spk)] from the reference-style float tensors
+__global__ void k_tier_assemble_f32(const float* __restrict__ prev, int n, const float* __restrict__ cond, int cond_dim,
+                                    const int64_t* __restrict__ spk, int spk_dim, int F, float* __restrict__ A, int kin) {
+    const int r = blockIdx.x, b = r / F;
+    for (int c = threadIdx.x; c < kin; c += blockDim.x) {
+        float v;
+        if (c < n) v = prev[(size_t)r * n + c];
+        else if (c < n + cond_dim) v = cond[(size_t)r * cond_dim + (c - n)];
+        else v = (c - n - cond_dim) == (int)spk[b] ? 1.f : 0.f;
+        A[(size_t)r * kin + c] = v;
+    }
+}
+int tier_assemble_f32(const float* prev, int n, const float* cond, int cond_dim, const int64_t* spk, int spk_dim, int rows, int F,
+                      float* A, int kin, cudaStream_t st) {
+    SRNN_LAUNCH(k_tier_assemble_f32, rows, 128, 0, st, prev, n, cond, cond_dim, spk, spk_dim, F, A, kin);
+    return SRNN_OK;
+}
+
 // L2 prefetch of up to four byte ranges (the bf16 weights of the next tier step) from a few spare CTAs beside the sample kernel:
 // the tier chain is weight-streaming, and between two of its steps the sample kernel's working set pushes those weights out
 __global__ void k_prefetch_l2(L2PrefetchArgs a) {

@@ -11,6 +11,7 @@ Reference quirks deliberately NOT reproduced: the ``<spk>
 """
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -102,6 +103,17 @@ class LearnedUpsampling1d(tnn.Module):
         self.conv_t = _Conv((dim, dim, kernel_size), lambda w: tnn.init.uniform_(w, -bound, bound), True)
 
 
+_OWNERS = {}          # id(FrameLevelRNN | SampleLevelMLP) -> (weakref to the owning SampleRNN, tier index or -1)
+
+
+def _owner_of(module):
+    ref, tier = _OWNERS.get(id(module), (None, -1))
+    model = ref() if ref is not None else None
+    if model is not None and not (module is model.sample_level_mlp or any(module is r for r in model.frame_level_rnns)):
+        model = None                                   # a recycled id
+    return model, tier
+
+
 class FrameLevelRNN(tnn.Module):
     """model.py:65-178 (parameters); the forward lives in the CUDA library."""
 
@@ -124,8 +136,46 @@ class FrameLevelRNN(tnn.Module):
         self.rnn = _GRU(dim, n_rnn)
         self.upsampling = LearnedUpsampling1d(dim, frame_size)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("tiers run inside the fused CUDA path: call Predictor / Generator")
+    def forward(self, prev_samples, upper_tier_conditioning, hidden, cond, spk, writer=None, iterations=None):
+        """model.py:180-263 as one C-ABI call (``srnn_tier_fwd``): prev_samples (B, F, n_frame_samples) float =
+        ``2 * dequantize(window)``, upper_tier_conditioning (B, F, dim) or None on the top tier (which takes cond
+        (B, F, cond_dim) and spk (B, 1)); hidden (n_rnn, B, dim) or None (start from h0).  Returns (output (B, F*frame_size,
+        dim), new hidden).  Inference form: Predictor.forward / Generator are the fused (and differentiable) paths; the mode
+        is the owning SampleRNN's ``module_mode`` (fp32, or the split-bf16 tensor-core parity mode)."""
+        model, tier = _owner_of(self)
+        if model is None:
+            raise L.SrnnError("FrameLevelRNN.forward needs the SampleRNN that owns the tier (packed weights live in its context)")
+        h = model._ensure_packed()
+        dev = model._ctx_device
+        B, F, n = prev_samples.shape
+        if n != self.n_frame_samples:
+            raise ValueError("prev_samples must be (B, F, %d)" % self.n_frame_samples)
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        prev = f32(prev_samples)
+        top = self.cond_expand is not None
+        if top == (upper_tier_conditioning is not None):
+            raise ValueError("the top tier takes cond + spk, the lower tiers the upper tier's conditioning (model.py:199-217)")
+        up = cnd = sp = None
+        if top:
+            if tuple(cond.shape) != (B, F, self.cond_dim):
+                raise ValueError("cond must be (B, F, %d), got %s" % (self.cond_dim, tuple(cond.shape)))
+            cnd = f32(cond)
+            sp = spk.detach().reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+            if sp.numel() != B or int(sp.min()) < 0 or int(sp.max()) >= self.spk_dim:
+                raise ValueError("spk must hold one id in [0, %d) per utterance" % self.spk_dim)
+        else:
+            if tuple(upper_tier_conditioning.shape) != (B, F, self.dim):
+                raise ValueError("upper_tier_conditioning must be (B, F, %d)" % self.dim)
+            up = f32(upper_tier_conditioning)
+        n_rnn = self.h0.shape[0]
+        reset = hidden is None
+        hid = torch.empty(n_rnn, B, self.dim, device=dev, dtype=torch.float32) if reset else f32(hidden).clone()
+        out = torch.empty(B, F * self.frame_size, self.dim, device=dev, dtype=torch.float32)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(dev):
+            L.check(L.load().srnn_tier_fwd(h, tier, B, F, ptr(prev), ptr(up), ptr(cnd), ptr(sp), hid.data_ptr(), int(reset),
+                                           out.data_ptr(), model.module_mode, _stream()))
+        return out, hid
 
 
 class SampleLevelMLP(tnn.Module):
@@ -139,8 +189,26 @@ class SampleLevelMLP(tnn.Module):
         self.hidden = _Conv((dim, dim, 1), _kaiming_uniform_, wnorm, dim)
         self.output = _Conv((q_levels, dim, 1), _lecun_uniform_, wnorm, q_levels)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("the MLP runs inside the fused CUDA path: call Predictor / Generator")
+    def forward(self, prev_samples, upper_tier_conditioning):
+        """model.py:308-325 as one C-ABI call (``srnn_mlp_fwd``): prev_samples (B, T + frame_size - 1) int64 sample indices,
+        upper_tier_conditioning (B, T, dim) -> log-probabilities (B, T, q_levels).  Inference form (see FrameLevelRNN.forward)."""
+        model, _ = _owner_of(self)
+        if model is None:
+            raise L.SrnnError("SampleLevelMLP.forward needs the SampleRNN that owns it (packed weights live in its context)")
+        h = model._ensure_packed()
+        dev = model._ctx_device
+        B, T, H = upper_tier_conditioning.shape
+        fs = model.frame_sizes[0]
+        if tuple(prev_samples.shape) != (B, T + fs - 1) or H != model.dim:
+            raise ValueError("prev_samples must be (B, T + %d), upper_tier_conditioning (B, T, %d)" % (fs - 1, model.dim))
+        ps = prev_samples.detach().to(device=dev, dtype=torch.int64).contiguous()
+        if int(ps.min()) < 0 or int(ps.max()) >= self.q_levels:
+            raise ValueError("prev_samples holds indices outside [0, %d)" % self.q_levels)
+        up = upper_tier_conditioning.detach().to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty(B, T, self.q_levels, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            L.check(L.load().srnn_mlp_fwd(h, B, T, ps.data_ptr(), up.data_ptr(), out.data_ptr(), model.module_mode, _stream()))
+        return out
 
 
 class SampleRNN(tnn.Module):
@@ -159,9 +227,20 @@ class SampleRNN(tnn.Module):
             FrameLevelRNN(fs, n, n_rnn, dim, learn_h0, i == top, cond_dim, spk_dim, weight_norm, qrnn)
             for i, (fs, n) in enumerate(zip(self.frame_sizes, ns))])
         self.sample_level_mlp = SampleLevelMLP(self.frame_sizes[0], dim, q_levels, weight_norm)
+        # per-module forward calls (FrameLevelRNN.forward / SampleLevelMLP.forward / Runner.run_rnn) run on this model's
+        # packed weights: weak back-references (plain attributes, not submodules) and the arithmetic mode they use
+        self._bind_modules()
+        self.module_mode = L.MODE_FP32
         self._ctx = None
         self._ctx_device = None
         self._packed_key = None
+
+    def _bind_modules(self):
+        """Register this model as the owner of its tiers / MLP (weak, outside the modules: state_dict, pickling and deepcopy
+        of the modules are unaffected; a copied model re-registers when its context is created)."""
+        for i, rnn in enumerate(self.frame_level_rnns):
+            _OWNERS[id(rnn)] = (weakref.ref(self), i)
+        _OWNERS[id(self.sample_level_mlp)] = (weakref.ref(self), -1)
 
     # -- reference API ---------------------------------------------------------------------------------------------
     @property
@@ -185,6 +264,7 @@ class SampleRNN(tnn.Module):
         return dev
 
     def _context(self):
+        self._bind_modules()
         dev = self._device()
         if self._ctx is None or self._ctx_device != dev:
             self._release()
@@ -272,8 +352,12 @@ class Runner:
     def reset_hidden_states(self):                                       # model.py:335-336
         self.hidden_states = {rnn: None for rnn in self.model.frame_level_rnns}
 
-    def run_rnn(self, *a, **k):
-        raise NotImplementedError("tiers run inside the fused CUDA path: call Predictor.forward / Generator")
+    def run_rnn(self, rnn, prev_samples, upper_tier_conditioning, cond, spk, writer=None, iterations=None):
+        """model.py:338-349: one tier through ``FrameLevelRNN.forward`` with this runner's hidden state, which is replaced
+        by the (detached) carry."""
+        output, new_hidden = rnn(prev_samples, upper_tier_conditioning, self.hidden_states[rnn], cond, spk, writer, iterations)
+        self.hidden_states[rnn] = new_hidden.detach()
+        return output
 
 
 class _PredictFn(torch.autograd.Function):

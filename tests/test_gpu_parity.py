@@ -539,3 +539,43 @@ def test_teacher_forced_table_gather_from_shared_memory_is_bit_identical(monkeyp
             outs.append(p(x, True, cond, spk, None, None).clone())
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("mode", [S.MODE_FP32, S.MODE_BF16X3])
+@pytest.mark.parametrize("cfg", [
+    dict(frame_sizes=[20, 4], n_rnn=2, dim=64, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6),
+    dict(frame_sizes=[4, 2, 2], n_rnn=1, dim=64, learn_h0=False, q_levels=256, ulaw=False, weight_norm=True, cond_dim=5, spk_dim=6),
+])
+def test_per_module_forward_api_composes_to_predictor(cfg, mode):
+    """The reference's per-module calls -- Runner.run_rnn over FrameLevelRNN.forward, then SampleLevelMLP.forward, in the order
+    and with the tensor shapes of Predictor.forward (model.py:357-436) -- reproduce the fused srnn_predict_fwd and the oracle,
+    including the hidden-state carry over two chunks."""
+    m, p, w = _seeded(cfg, 9)
+    p.mode = S.MODE_FP32
+    m.module_mode = mode
+    lb = m.lookback
+    B, T = 3, 2 * lb
+    x = torch.randint(0, 256, (B, lb + 2 * T - 1))
+    cond = torch.rand(B, 2 * T // lb, cfg["cond_dim"])
+    spk = torch.randint(0, 6, (B, 1))
+    runner = S.Runner(m)
+    ref_p = O.Predictor(w)
+    with torch.no_grad():
+        for i in range(2):
+            xi, ci = x[:, i * T: i * T + lb + T - 1], cond[:, i * T // lb: (i + 1) * T // lb]
+            if i == 0:
+                runner.reset_hidden_states()
+            upper = None
+            for rnn in reversed(m.frame_level_rnns):
+                n = rnn.n_frame_samples
+                win = xi[:, lb - n: xi.shape[1] - n + 1]
+                prev = (2 * m.dequantize(win, m.q_levels)).reshape(B, -1, n)
+                upper = runner.run_rnn(rnn, prev, upper, ci if upper is None else None, spk if upper is None else None)
+            fs0 = m.frame_level_rnns[0].frame_size
+            got = m.sample_level_mlp(xi[:, lb - fs0:], upper)
+            fused = p(xi, i == 0, ci.double(), spk, None, None)
+            ref = ref_p.forward(xi, i == 0, ci.double(), spk)
+            logp_gate(got.cpu().numpy(), ref.numpy())
+            np.testing.assert_allclose(got.cpu().numpy(), fused.cpu().numpy(), atol=2e-4)
+            for rnn in m.frame_level_rnns:
+                np.testing.assert_allclose(runner.hidden_states[rnn].cpu().numpy(), p.hidden_states[rnn].cpu().numpy(), atol=1e-4)
