@@ -29,7 +29,7 @@ F_DENSE = 16.889e6   # the reference graph's dense work, for context
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the sample-level kernel at B = 256 from the `ncu --set full`
 # captures summarised in profiles/ (cold L2: ncu flushes caches between replays)
 NCU_TRAFFIC = {"k_mlp_persist": 34.14e6 + 0.03e6,      # profiles/r1_k_mlp_persist_ncu_full.txt
-               "k_mlp_cluster": 34.17e6 + 0.03e6}      # profiles/r2_k_mlp_cluster_ncu_full.txt (second captured launch)
+               "k_mlp_cluster": 36.35e6 + 0.002e6}     # profiles/r2_k_mlp_cluster_ncu_full.txt (second captured launch)
 F_MLP = 2.0 * (1024 * 1024 + 1024 * 256) + 20 * 1024   # k_mlp_persist's share of F_ALG per sample per utterance: hidden +
                                                        # output contraction + the folded-table adds (SURVEY 8d components)
 SAMPLE_RATE = 16000

@@ -150,6 +150,26 @@ class ClampAdam:
         return loss
 
 
+def gradient_clipping(optimizer, min=-1, max=1, model=None):
+    """optim.py:4-21 ``gradient_clipping(torch.optim.Adam(params))`` (train.py:238-241).  The reference wraps the optimizer's
+    ``step`` so that every gradient is clamped element-wise before the update; here clamp and Adam are one kernel, so a
+    ``torch.optim.Adam`` is converted into the equivalent ``ClampAdam`` (same parameters, lr, betas, eps; fresh moments) and a
+    ``ClampAdam`` is returned with its bound set.  Only the symmetric bound the reference uses is supported."""
+    if -min != max:
+        raise ValueError("gradient_clipping: symmetric bounds only (the reference clamps to [-1, 1])")
+    if isinstance(optimizer, ClampAdam):
+        optimizer.clamp = float(max)
+        return optimizer
+    if not isinstance(optimizer, torch.optim.Adam):
+        raise L.SrnnError("gradient_clipping: only Adam has a fused CUDA step (the reference trains with Adam, train.py:238)")
+    if len(optimizer.param_groups) != 1:
+        raise L.SrnnError("gradient_clipping: one parameter group expected")
+    g = optimizer.param_groups[0]
+    if g.get("weight_decay", 0) or g.get("amsgrad", False):
+        raise L.SrnnError("gradient_clipping: weight_decay / amsgrad are not part of the reference step")
+    return ClampAdam(g["params"], lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], clamp=float(max), model=model)
+
+
 def sequence_nll_loss_bits(logp, target, model=None):
     """nn.py:66-70: ``nll_loss(logp.view(-1, Q), target.view(-1)) * log2(e)``, mean over B*T, in bits.
 

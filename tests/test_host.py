@@ -82,3 +82,16 @@ def test_argument_validation():
     assert lib.srnn_create(C.byref(cfg), C.byref(h)) == -1
     with pytest.raises(NotImplementedError):
         S.SampleRNN([4], 1, 16, True, 256, True, False, 5, 6, qrnn=True)
+
+
+def test_gradient_clipping_wrapper_mirrors_the_reference_call():
+    """train.py:238-241: ``optimizer = gradient_clipping(torch.optim.Adam(predictor.parameters()))``."""
+    import torch
+    import srnn_b200 as S
+    ps = [torch.zeros(3, requires_grad=True), torch.zeros(2, 2, requires_grad=True)]
+    opt = S.gradient_clipping(torch.optim.Adam(ps, lr=3e-4, betas=(0.8, 0.9), eps=1e-6))
+    assert isinstance(opt, S.ClampAdam) and opt.lr == 3e-4 and opt.betas == (0.8, 0.9) and opt.eps == 1e-6 and opt.clamp == 1.0
+    assert [id(p) for p in opt.params] == [id(p) for p in ps]
+    assert S.gradient_clipping(opt) is opt
+    with pytest.raises(Exception):
+        S.gradient_clipping(torch.optim.SGD(ps, lr=0.1))
