@@ -250,6 +250,26 @@ int srnn_pack_weights(srnn_ctx* ctx, const srnn_params* P, void* stream) {
     }
     ctx->packed = true;
     ctx->x3_valid = false;
+    ctx->gi_fold_valid = false;
+    return SRNN_OK;
+}
+
+// Generation-time fold of every tier's input expansion into its first GRU layer (TierPacked::g_in_t, b_gi0), (re)built on the
+// first bf16 generation call after srnn_pack_weights (training re-packs every step and never needs it).
+static int ensure_gi_fold(srnn_ctx* ctx, cudaStream_t st) {
+    if (ctx->gi_fold_valid) return SRNN_OK;
+    const int H = ctx->H;
+    for (int i = 0; i < ctx->cfg.n_tiers; ++i) {
+        TierPacked& t = ctx->tiers[i];
+        if (!t.g_in_t) {
+            SRNN_TRY(ctx->weights.alloc((void**)&t.g_in_t, sizeof(float) * (size_t)t.kin * 3 * H));
+            SRNN_TRY(ctx->weights.alloc((void**)&t.b_gi0, sizeof(float) * 3 * H));
+        }
+        // G^T (kin, 3H) = W_in^T (kin, H) . W_ih0^T;   b_gi0 (1, 3H) = b_in (1, H) . W_ih0^T + b_ih0
+        SRNN_TRY(gemm_f32(t.kin, 3 * H, H, t.w_in_t, H, t.w_ih[0], H, nullptr, nullptr, 0, 0, t.g_in_t, 3 * H, st));
+        SRNN_TRY(gemm_f32(1, 3 * H, H, t.b_in, H, t.w_ih[0], H, t.b_ih[0], nullptr, 0, 0, t.b_gi0, 3 * H, st));
+    }
+    ctx->gi_fold_valid = true;
     return SRNN_OK;
 }
 
@@ -585,7 +605,9 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         *OUT[SRNN_MAX_TIERS], *X1 = nullptr, *X2 = nullptr, *LG = nullptr;
     float* GHL[SRNN_MAX_TIERS][SRNN_MAX_RNN];      // per-layer recurrent projections of the fused-cell schedule
     bf *hid16[SRNN_MAX_TIERS], *X16[SRNN_MAX_TIERS], *X1h = nullptr, *X2h = nullptr, *S3 = nullptr;
-    float *part = nullptr, *pcarry = nullptr;
+    float *part = nullptr, *pcarry = nullptr, *GIP = nullptr;
+    bf* UP16 = nullptr;
+    const int fs_top = ctx->tiers[NT - 1].fs;
     unsigned* gctr = nullptr;
     const int RG = (B + 31) / 32, NS = H / 64;
     const int n_clusters = cluster_rows ? (B + cluster_rows - 1) / cluster_rows : 0;
@@ -616,6 +638,8 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         part = b.take<float>(persist && !cluster_rows ? (size_t)RG * NS * 32 * Q : 1);
         gctr = b.take<unsigned>(2 * RG);
         pcarry = b.take<float>(cluster_rows ? 2 * x1_rows * H : 1);
+        GIP = b.take<float>(bf16 && NT == 2 ? (size_t)B * fs_top * 3 * H : 1);    // input-fold schedule: W_ih0 upper + b_gi0 of tier 0
+        UP16 = b.take<bf>(bf16 && NT == 2 ? (size_t)B * fs_top * H : 1);          // ... and the bf16 top-tier output it contracts
         if (!pass) SRNN_TRY(ensure_ws(ctx, b.off));
     }
     // private capture stream (the caller's stream may be the legacy default stream, which cannot be captured)
@@ -717,17 +741,31 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     const bool shadow_in = shadow_gh && !getenv("SRNN_NO_SHADOW_IN");
     // CTAs of the L2 weight prefetch beside each sample launch (0 = off)
     const int l2_prefetch = shadow_gh && getenv("SRNN_L2_PREFETCH") ? atoi(getenv("SRNN_L2_PREFETCH")) : 0;
+    // Input fold (TierPacked::g_in_t): the input expansion of a tier is folded into its first GRU layer, gi_0 = G a + W_ih0 upper +
+    // b_gi0.  Top tier: the whole of gi_0 is a K = kin contraction whose known columns are summed in the shadow (GP, width 3H
+    // instead of XP, width H); k_gru_cell_lite adds the last FS0 sample columns and does the gate math -- the input kernel
+    // and the first cell GEMM leave the serial path.  Tier 0 of a two-tier model: W_ih0 upper + b_gi0 for all fs_top frames of
+    // the period in ONE tcgen05 GEMM behind the top tier's upsampling (which writes its output in bf16), then per frame the
+    // same lite kernel over the frame's n sample columns.  SRNN_NO_GI_FOLD=1: separate input kernels + cell GEMMs.
+    bool fold_ok = NT <= 2 && gru_cell_lite_supported(ctx->tiers[NT - 1].n - (ctx->tiers[NT - 1].n - FS0 > 0 ? ctx->tiers[NT - 1].n - FS0 : 0));
+    if (NT == 2) fold_ok = fold_ok && gru_cell_lite_supported(ctx->tiers[0].n);
+    const bool gi_fold = shadow_in && fold_ok && !getenv("SRNN_NO_GI_FOLD");
+    if (gi_fold) SRNN_TRY(ensure_gi_fold(ctx, st));
     const TierPacked& ttop = ctx->tiers[NT - 1];
-    float* XP = GI[NT - 1];
+    float* XP = GI[NT - 1];                        // gi_fold: GP (B, 3H)
     const int xp_lo = ttop.n - FS0 > 0 ? ttop.n - FS0 : 0, xp_hi = ttop.n;
-    cudaEvent_t ev_xp = nullptr;
-    bool xp_pending = false;
+    cudaEvent_t ev_xp = nullptr, ev_gip = nullptr;
+    bool xp_pending = false, gip_todo = false, gip_pending = false;
     auto launch_xp = [&](int off, cudaStream_t s) -> int {
+        if (gi_fold)
+            return tier_input_split(false, seq, Lseq, off, step_base, ttop.n, B, cond, cond_rows, n_cond, spk, c.cond_dim, ctx->lut,
+                                    ttop.g_in_t, ttop.b_gi0, XP, nullptr, nullptr, 3 * H, ttop.kin, xp_lo, xp_hi, s);
         return tier_input_split(false, seq, Lseq, off, step_base, ttop.n, B, cond, cond_rows, n_cond, spk, c.cond_dim, ctx->lut,
                                 ttop.w_in_t, ttop.b_in, XP, nullptr, nullptr, H, ttop.kin, xp_lo, xp_hi, s);
     };
     if (shadow_in) {
         SRNN_CUDA(cudaEventCreateWithFlags(&ev_xp, cudaEventDisableTiming));
+        SRNN_CUDA(cudaEventCreateWithFlags(&ev_gip, cudaEventDisableTiming));
         SRNN_TRY(launch_xp(-ttop.n, st));                                            // first period: the q_zero prefix
     }
 
@@ -759,7 +797,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     const unsigned long long gkey[] = {(unsigned long long)B, (unsigned long long)n_cond, (unsigned long long)cond_rows,
                                        (unsigned long long)u_ld, (unsigned long long)cluster_rows,
                                        (unsigned long long)(bf16 | persist << 1 | x3 << 2 | shadow_gh << 3 | shadow_in << 4 | pdl << 5 |
-                                                            skip_tiers << 6 | fused_cell << 7 | pdl_sample << 8 | carry << 9 | (unsigned long long)l2_prefetch << 16),
+                                                            skip_tiers << 6 | fused_cell << 7 | pdl_sample << 8 | carry << 9 | gi_fold << 10 | (unsigned long long)l2_prefetch << 16),
                                        (unsigned long long)spare_sms, (unsigned long long)(uintptr_t)cond,
                                        (unsigned long long)(uintptr_t)spk, (unsigned long long)(uintptr_t)uniforms,
                                        (unsigned long long)(uintptr_t)samples_out, (unsigned long long)(uintptr_t)audio_out,
@@ -800,20 +838,54 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     }
                     SRNN_CUDA(cudaEventRecord(ev_join, st2));
                 }
-                g_pdl = pdl && (prev_tier_kernel || (pdl_sample && prev_sample_kernel));
-                prev_sample_kernel = false;
-                int rc_in = (t.top && shadow_in)
-                    ? tier_input_split(true, seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
-                                       ctx->lut, t.w_in_t, t.b_in, XP, X[i], X16[i], H, t.kin, xp_lo, xp_hi, st)
-                    : tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
-                                           c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
-                                           H, t.kin, t.top, st);
-                g_pdl = 0;
-                SRNN_TRY(rc_in);
-                prev_tier_kernel = true;
-                mark(t.top ? "input top" : "input");
+                if (gi_fold) {
+                    // folded first layer: [top: nothing | tier 0, first frame of the period: one GEMM for all its frames] -> lite cell
+                    if (!t.top && (pos / t.n) % fs_top == 0) {
+                        // W_ih0 upper + b_gi0 of the period's FIRST frame on the serial path; the other fs_top - 1 frames follow
+                        // in the shadow of the next sample launch
+                        g_pdl = pdl && prev_tier_kernel;
+                        const int rc_g = gemm_umma(t.w_ih16[0], 3 * H, UP16, B, H, H, fs_top * H, t.b_gi0, nullptr, 0, GIP, nullptr,
+                                                   fs_top * 3 * H, 0, 128, bn_for(3 * H, 1), st);
+                        g_pdl = 0;
+                        SRNN_TRY(rc_g);
+                        gip_todo = fs_top > 1;
+                        mark("gi pre");
+                    } else if (!t.top && gip_pending) {
+                        SRNN_CUDA(cudaStreamWaitEvent(st, ev_gip, 0));
+                        gip_pending = false;
+                    }
+                    if (gh_pending[i]) {                         // gh of this step ran beside the previous sample launch
+                        SRNN_CUDA(cudaStreamWaitEvent(st, ev_gh[i], 0));
+                        gh_pending[i] = false;
+                    }
+                    g_pdl = pdl && (prev_tier_kernel || (pdl_sample && prev_sample_kernel));
+                    prev_sample_kernel = false;
+                    const int rc_l = t.top
+                        ? gru_cell_lite(B, H, XP, 3 * H, t.g_in_t, xp_lo, xp_hi, seq, Lseq, pos - t.n, step_base, ctx->lut, GHL[i][0],
+                                        hid[i], hid16[i], st)
+                        : gru_cell_lite(B, H, GIP + (size_t)((pos / t.n) % fs_top) * 3 * H, (long long)fs_top * 3 * H, t.g_in_t, 0, t.n,
+                                        seq, Lseq, pos - t.n, step_base, ctx->lut, GHL[i][0], hid[i], hid16[i], st);
+                    g_pdl = 0;
+                    SRNN_TRY(rc_l);
+                    prev_tier_kernel = true;
+                    mark("cell lite");
+                }
                 const float* in = X[i];
-                const bf* in16 = X16[i];
+                const bf* in16 = gi_fold ? hid16[i] : X16[i];
+                if (!gi_fold) {
+                    g_pdl = pdl && (prev_tier_kernel || (pdl_sample && prev_sample_kernel));
+                    prev_sample_kernel = false;
+                    int rc_in = (t.top && shadow_in)
+                        ? tier_input_split(true, seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
+                                           ctx->lut, t.w_in_t, t.b_in, XP, X[i], X16[i], H, t.kin, xp_lo, xp_hi, st)
+                        : tier_input_gen(seq, Lseq, pos - t.n, step_base, t.n, B, cond, cond_rows, n_cond, spk, c.cond_dim,
+                                               c.spk_dim, ctx->lut, t.w_in_t, t.b_in, upper, up_ld, X[i], bf16 ? X16[i] : nullptr,
+                                               H, t.kin, t.top, st);
+                    g_pdl = 0;
+                    SRNN_TRY(rc_in);
+                    prev_tier_kernel = true;
+                    mark(t.top ? "input top" : "input");
+                }
                 if (bf16 && fused_cell) {
                     // Fused-cell schedule: the recurrent projections gh_l = W_hh_l h_l + b_hh_l of ALL layers depend only on
                     // the previous step's state, so they go first (two layers per launch); then one launch per layer does
@@ -823,7 +895,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                         SRNN_CUDA(cudaStreamWaitEvent(st, ev_gh[i], 0));
                         gh_pending[i] = false;
                     }
-                    for (int l = 0; l < NL; ++l) {
+                    for (int l = gi_fold ? 1 : 0; l < NL; ++l) {
                         g_pdl = pdl;
                         const int rc_c = gru_cell_gen(B, H, in16, t.w_ih16[l], t.b_ih[l], GHL[i][l], hid[i] + (size_t)l * B * H,
                                                       hid16[i] + (size_t)l * B * H, st);
@@ -854,7 +926,13 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     in = h;
                     in16 = h16;
                 }
-                if (bf16 && gemm_umma_pair_wide_ok(t.fs * H, B)) {      // big upsampling (tier 2 at C2): one wave of CTA pairs
+                if (gi_fold && t.top && NT == 2) {      // consumed only by tier 0's folded first layer: bf16, (B * fs, H) row-major
+                    g_pdl = pdl;
+                    const int rc_u = gemm_umma(t.w_up16, t.fs * H, in16, B, H, H, H, t.b_up, nullptr, 0, nullptr, UP16, t.fs * H, 0, 128,
+                                               bn_for(t.fs * H, 1), st);
+                    g_pdl = 0;
+                    SRNN_TRY(rc_u);
+                } else if (bf16 && gemm_umma_pair_wide_ok(t.fs * H, B)) {      // big upsampling (tier 2 at C2): one wave of CTA pairs
                     GemmOperands o{t.w_up16, in16, t.b_up, nullptr, OUT[i], nullptr, t.fs * H, H, H, 0, t.fs * H, 0, nullptr};
                     g_pdl = pdl;
                     const int rc_u = gemm_umma_pair_wide(o, B, H, st);
@@ -888,17 +966,37 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                 prev_tier_kernel = false;
                 if (shadow_gh) {                     // next step's recurrent projections: on the spare SMs, beside this launch
                     const bool xp_now = shadow_in && pos == lookback - FS0;      // last sample launch of the period
-                    bool any = xp_now;
+                    bool any = xp_now || gip_todo;
                     for (int i = 0; i < NT; ++i) any = any || gh_todo[i];
                     if (any) {
                         SRNN_CUDA(cudaEventRecord(ev_fork, st));
                         SRNN_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
-                        for (int i = NT - 1; i >= 0; --i) {
-                            if (!gh_todo[i]) continue;
-                            SRNN_TRY(launch_gh(i, st2, spare_sms));
-                            SRNN_CUDA(cudaEventRecord(ev_gh[i], st2));
-                            gh_todo[i] = false;
-                            gh_pending[i] = true;
+                        for (int i = 0; i < NT; ++i) {           // lowest tier first: its next step comes first
+                            if (gh_todo[i]) {
+                                SRNN_TRY(launch_gh(i, st2, spare_sms));
+                                SRNN_CUDA(cudaEventRecord(ev_gh[i], st2));
+                                gh_todo[i] = false;
+                                gh_pending[i] = true;
+                            }
+                            if (i == 0 && gip_todo) {            // folded first layer of tier 0: frames 1 .. fs_top-1 of the period
+                                const TierPacked& t0 = ctx->tiers[0];
+                                gemm_umma_set_cta_cap(spare_sms);
+                                int rc_g = SRNN_OK;
+                                for (int f = 1; f < fs_top && rc_g == SRNN_OK; f += 2) {
+                                    const int np = fs_top - f >= 2 ? 2 : 1;
+                                    GemmOperands ops[2];
+                                    for (int q = 0; q < np; ++q)
+                                        ops[q] = GemmOperands{t0.w_ih16[0], UP16 + (size_t)(f + q) * H, t0.b_gi0, nullptr,
+                                                              GIP + (size_t)(f + q) * 3 * H, nullptr, 3 * H, H, fs_top * H, 0,
+                                                              fs_top * 3 * H, 0, nullptr};
+                                    rc_g = gemm_umma_multi(ops, np, B, H, 128, B <= 128 ? bn_tier : 128, st2);
+                                }
+                                gemm_umma_set_cta_cap(0);
+                                SRNN_TRY(rc_g);
+                                SRNN_CUDA(cudaEventRecord(ev_gip, st2));
+                                gip_todo = false;
+                                gip_pending = true;
+                            }
                         }
                         if (l2_prefetch) {               // bf16 weights of the tier step(s) that follow this sample launch -> L2
                             L2PrefetchArgs pa{};
@@ -978,6 +1076,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
         if (xp_pending) {
             SRNN_CUDA(cudaStreamWaitEvent(st, ev_xp, 0));
             xp_pending = false;
+        }
+        if (gip_pending) {
+            SRNN_CUDA(cudaStreamWaitEvent(st, ev_gip, 0));
+            gip_pending = false;
         }
         SRNN_TRY(add_int(step_base, lookback, st));
         return SRNN_OK;
@@ -1157,6 +1259,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     for (int i = 0; i < SRNN_MAX_TIERS; ++i)
         if (ev_gh[i]) SRNN_CUDA(cudaEventDestroy(ev_gh[i]));
     if (ev_xp) SRNN_CUDA(cudaEventDestroy(ev_xp));
+    if (ev_gip) SRNN_CUDA(cudaEventDestroy(ev_gip));
     if (st2) {
         SRNN_CUDA(cudaStreamDestroy(st2));
         SRNN_CUDA(cudaEventDestroy(ev_fork));

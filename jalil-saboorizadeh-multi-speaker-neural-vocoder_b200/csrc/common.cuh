@@ -99,6 +99,10 @@ struct TierPacked {
     __nv_bfloat16* w_ih16_t[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_hh16_t[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_up16_t = nullptr;
+    // generation-time fold of the input expansion into the first GRU layer (ensure_gi_fold):
+    //   gi_0 = W_ih0 (W_in a + b_in + upper) + b_ih0 = G a + W_ih0 upper + b_gi0,   G = W_ih0 W_in,  b_gi0 = b_ih0 + W_ih0 b_in
+    float* g_in_t = nullptr;  // (kin, 3H) = G^T: consecutive threads read consecutive gate rows
+    float* b_gi0 = nullptr;   // (3H)
     // split-bf16 copies (n_feat, 3K) of SRNN_MODE_BF16X3, packed lazily on the first use of that mode (ensure_x3)
     __nv_bfloat16* w_ih3[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_hh3[SRNN_MAX_RNN] = {};
@@ -168,6 +172,7 @@ struct srnn_ctx {
     __nv_bfloat16* w_hid3 = nullptr;      // (H, 3H) / (Q, 3H) split-bf16 copies of SRNN_MODE_BF16X3
     __nv_bfloat16* w_out3 = nullptr;
     bool x3_valid = false;                // the *3 copies match the packed fp32 weights
+    bool gi_fold_valid = false;           // tiers[].g_in_t / b_gi0 match the packed weights
     // instantiated generation graph of the last srnn_generate shape: reused while every baked-in value (batch, mode, schedule
     // switches, caller and scratch pointers) is unchanged -- capture + instantiation cost ~1 ms, which short utterances and
     // small batches feel (the graph itself is position independent: the sample index lives in a device counter)
@@ -335,6 +340,13 @@ bool gru_persist_supported(int B, int H, int n_sms);
 bool gru_cell_gen_supported(int H);
 int gru_cell_gen(int B, int H, const __nv_bfloat16* x16, const __nv_bfloat16* w_ih16, const float* b_ih, const float* GH, float* h,
                  __nv_bfloat16* h16, cudaStream_t st);
+// generation-time first GRU layer with the input expansion folded in (TierPacked::g_in_t): gi = gipre + G[:, k_lo:k_hi) . samples,
+// then the gate math; gipre (B rows, leading dimension gipre_ld) already holds W_ih0 upper + b_gi0 (or the shadow part of the
+// top tier); samples = lut[seq[b][start + k]] for the sample columns k in [k_lo, k_hi)
+bool gru_cell_lite_supported(int n_sample_columns);
+int gru_cell_lite(int B, int H, const float* gipre, long long gipre_ld, const float* g_in_t, int k_lo, int k_hi, const uint8_t* seq,
+                  int seq_ld, int start_static, const int* step_base, const float* lut, const float* GH, float* h,
+                  __nv_bfloat16* h16, cudaStream_t st);
 int gru_persist_fwd(int B, int F, int H, const float* GI, const __nv_bfloat16* w_hh16, const float* b_hh, const float* h0,
                     const __nv_bfloat16* h0_16, float* GH, float* Y, __nv_bfloat16* Y16, float* h_last, unsigned* ctr,
                     cudaStream_t st);

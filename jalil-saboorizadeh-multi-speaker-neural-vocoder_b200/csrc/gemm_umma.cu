@@ -319,6 +319,8 @@ __device__ __forceinline__ void swap_epilogue(const GemmProb& P, float* __restri
             epi_store16<false, true, false, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
         else if (addend && !relu && out_f32 && !out_bf16)      // BPTT carry: dh*z + dGH.W_hh
             epi_store16<true, false, true, false>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
+        else if (!addend && !relu && !out_f32 && out_bf16)     // generation: top-tier upsampling feeding tier 0's folded first layer
+            epi_store16<false, false, false, true>(v, bv, nn, row, m, addend, ld_add, out_f32, out_bf16, ld_out);
         else {                                                 // generic (test hook)
 #pragma unroll
             for (int i = 0; i < 16; ++i) {

@@ -689,6 +689,95 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (warp == 5) tmem_dealloc<GP_TMEM_COLS>(tmem);
 }
 
+// ---- first GRU layer of a tier step with the input expansion folded in (no tensor cores: K = the frame's sample columns) ----
+// Latency-bound by construction (a few hundred bytes per thread from L2), so EVERY global load of a thread is issued before the
+// first use: one L2 round trip for the folded weights (CL_KMAX x 3), the partial sums, the recurrent projections and the state.
+constexpr int CL_RB = 4;        // utterances per CTA: every folded weight loaded from L2 feeds CL_RB FMAs
+constexpr int CL_KMAX = 20;     // sample columns handled with all weights in registers (the frame sizes of every BASELINE config)
+template <int NK>
+__global__ void __launch_bounds__(256)
+k_gru_cell_lite(const float* __restrict__ gipre, long long gipre_ld, const float* __restrict__ g_in_t, int k_lo,
+                const uint8_t* __restrict__ seq, int seq_ld, int start_static, const int* __restrict__ step_base,
+                const float* __restrict__ lut, const float* __restrict__ GH, float* __restrict__ h, bf* __restrict__ h16, int B,
+                int H) {
+    __shared__ float cl_a[NK * CL_RB];                               // dequantised samples [k][row]
+    pdl_trigger();
+    const int b0 = blockIdx.x * CL_RB;
+    const int u = blockIdx.y * blockDim.x + threadIdx.x;
+    const bool live = u < H;
+    // the folded weights are constants of the call: requested before griddepcontrol.wait
+    float wv[NK][3];
+    if (live) {
+        const float* w = g_in_t + (size_t)k_lo * 3 * H + u;
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) wv[k][g] = __ldg(w + (size_t)k * 3 * H + g * H);
+    }
+    pdl_wait();
+    const int start = start_static + (step_base ? *step_base : 0);
+    for (int e = threadIdx.x; e < NK * CL_RB; e += blockDim.x) {
+        const int r = e % CL_RB, k = k_lo + e / CL_RB;
+        const int b = b0 + r < B ? b0 + r : B - 1;
+        cl_a[e] = lut[seq[(size_t)b * seq_ld + start + k]];
+    }
+    float acc[3][CL_RB], gh[3][CL_RB], hp[CL_RB];
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < CL_RB; ++r) {
+            const int b = b0 + r < B ? b0 + r : B - 1;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                acc[g][r] = gipre[(size_t)b * gipre_ld + g * H + u];
+                gh[g][r] = GH[(size_t)b * 3 * H + g * H + u];
+            }
+            hp[r] = h[(size_t)b * H + u];
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+#pragma unroll
+        for (int r = 0; r < CL_RB; ++r) {
+            const float a = cl_a[k * CL_RB + r];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) acc[g][r] = fmaf(a, wv[k][g], acc[g][r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < CL_RB; ++r) {
+        const int b = b0 + r;
+        if (b >= B) break;
+        const float rr = gp_sigmoid(acc[0][r] + gh[0][r]);
+        const float zz = gp_sigmoid(acc[1][r] + gh[1][r]);
+        const float nn = gp_tanh(acc[2][r] + rr * gh[2][r]);
+        const float hn = (1.f - zz) * nn + zz * hp[r];
+        h[(size_t)b * H + u] = hn;
+        h16[(size_t)b * H + u] = __float2bfloat16(hn);
+    }
+}
+bool gru_cell_lite_supported(int nk) { return nk == 20 || nk == 16 || nk == 4 || nk == 2; }
+int gru_cell_lite(int B, int H, const float* gipre, long long gipre_ld, const float* g_in_t, int k_lo, int k_hi, const uint8_t* seq,
+                  int seq_ld, int start_static, const int* step_base, const float* lut, const float* GH, float* h, bf* h16,
+                  cudaStream_t st) {
+    const int threads = H >= 256 ? 256 : 64;
+    const dim3 grid(cdiv(B, CL_RB), cdiv(H, threads));
+#define CL_CASE(NK)                                                                                                            \
+    case NK:                                                                                                                   \
+        SRNN_LAUNCH_PDL(k_gru_cell_lite<NK>, grid, threads, 0, st, gipre, gipre_ld, g_in_t, k_lo, seq, seq_ld, start_static, \
+                        step_base, lut, GH, h, h16, B, H);                                                                     \
+        return SRNN_OK;
+    switch (k_hi - k_lo) {
+        CL_CASE(20)
+        CL_CASE(16)
+        CL_CASE(4)
+        CL_CASE(2)
+    }
+#undef CL_CASE
+    return fail(SRNN_ERR_UNSUPPORTED, "gru_cell_lite: %d sample columns", k_hi - k_lo);
+}
+
 bool gru_cell_gen_supported(int H) { return H % (64 * GC_GKB) == 0 && !getenv("SRNN_NO_GRU_CELL"); }
 
 // x16 (B, H) bf16 input of the layer, w_ih16 (3H, H), b_ih (3H), GH (B, 3H) = W_hh h + b_hh; h / h16 updated in place.

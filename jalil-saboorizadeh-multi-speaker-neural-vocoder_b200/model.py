@@ -287,7 +287,10 @@ class SampleRNN(tnn.Module):
                 L.load().srnn_destroy(self._ctx)
             except Exception:
                 pass
-            self._ctx = None
+            try:
+                object.__setattr__(self, "_ctx", None)      # plain attribute; also safe during interpreter shutdown
+            except Exception:
+                pass
 
     def __del__(self):
         self._release()

@@ -271,12 +271,16 @@ def test_generate_one_launch_per_contraction_tiles_at_large_batch():
 
 
 def test_generate_schedule_variants_are_bit_identical(monkeypatch):
-    """The generation schedule devices -- recurrent projections in the shadow of the sample kernel, programmatic dependent
-    launches -- only reorder / overlap launches: with each of them switched off the samples and log-probabilities must be
-    bit-identical (dim 1024 x 256 utterances is the configuration that enables both; 5 periods).  The split top-tier input
-    expansion (its first 60 sample columns + conditioner columns accumulated beside the previous period's last sample launch)
-    re-associates an fp32 sum, so it is held fixed for those comparisons and checked on its own: same log-probabilities to
-    1e-3 at the first sample of every period on utterances that have not diverged, and near-total sample agreement."""
+    """The generation schedule devices that only reorder / overlap launches -- recurrent projections in the shadow of the sample
+    kernel, programmatic dependent launches of the tier kernels and of the sample kernel -- must leave samples and
+    log-probabilities bit-identical when switched off (dim 1024 x 256 utterances is the configuration that enables them all;
+    5 periods).  Two devices re-associate fp32 sums and are checked separately with the others held fixed:
+    * the split top-tier input expansion (known columns accumulated beside the previous period's last sample launch): same
+      log-probabilities to 3e-2 at the first sample of every period on utterances that have not diverged, > 80 % sample agreement;
+    * the input expansion folded into the first GRU layer (gi_0 = G a + W_ih0 upper + b_gi0, different bf16 rounding points):
+      trajectories part quickly, so it is gated where the histories still agree -- the first samples of the call -- and, against
+      the oracle, by test_generate_bf16_mode_against_oracle[1024-256] (tools/fold_error.py: max |dlogp| 0.0213 / mean 0.0032
+      with the fold, 0.0226 / 0.0033 without)."""
     torch.manual_seed(5)
     c = dict(frame_sizes=[20, 4], n_rnn=2, dim=1024, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True,
              cond_dim=86, spk_dim=6)
@@ -286,21 +290,31 @@ def test_generate_schedule_variants_are_bit_identical(monkeypatch):
     g = torch.Generator().manual_seed(11)
     cond, spk = torch.rand(B, n_cond, 86, generator=g), torch.randint(0, 6, (B,), generator=g)
     uni = torch.rand(80 * n_cond, B, generator=g)
-    for k in ("SRNN_NO_SHADOW_GH", "SRNN_NO_PDL", "SRNN_NO_SHADOW_IN"):
+    switches = ("SRNN_NO_SHADOW_GH", "SRNN_NO_PDL", "SRNN_NO_SHADOW_IN", "SRNN_NO_GI_FOLD", "SRNN_NO_PDL_SAMPLE")
+    for k in switches:
         monkeypatch.delenv(k, raising=False)
-    _, full, lpf = gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)
+    run = lambda: gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)[1:]
+    fold, lp_fold = run()                                    # default schedule: everything on
+    monkeypatch.setenv("SRNN_NO_GI_FOLD", "1")
+    full, lpf = run()                                        # split input expansion, separate input kernels + cell GEMMs
+    for k in ("SRNN_NO_PDL_SAMPLE",):
+        monkeypatch.setenv(k, "1")
+        out, lp2 = run()
+        monkeypatch.delenv(k)
+        assert torch.equal(full, out) and torch.equal(lpf, lp2), k
     monkeypatch.setenv("SRNN_NO_SHADOW_IN", "1")
-    _, ref, lp = gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)
-    for k, v in (("SRNN_NO_SHADOW_GH", "1"), ("SRNN_NO_PDL", "1")):
-        monkeypatch.setenv(k, v)
-        _, out, lp2 = gen(B, 0, cond, spk, uniforms=uni, return_samples=True, return_logp=True)
+    ref, lp = run()
+    for k in ("SRNN_NO_SHADOW_GH", "SRNN_NO_PDL"):
+        monkeypatch.setenv(k, "1")
+        out, lp2 = run()
         monkeypatch.delenv(k)
         assert torch.equal(ref, out), k
         assert torch.equal(lp, lp2), k
     monkeypatch.delenv("SRNN_NO_SHADOW_IN")
-    # Measured: 92 % of all samples agree (a re-associated fp32 sum flips a few bf16 roundings of x, which moves logits by
-    # ~1e-4..1e-3; with 7-bit-entropy distributions that flips a draw now and then, and the utterance diverges from there).
-    # A wrong conditioner frame or sample window in the shadow part would instead move every log-probability by O(0.1).
+    monkeypatch.delenv("SRNN_NO_GI_FOLD")
+    # Split input expansion.  Measured: 92 % of all samples agree (a re-associated fp32 sum flips a few bf16 roundings of x,
+    # which moves logits by ~1e-4..1e-3; with 7-bit-entropy distributions that flips a draw now and then, and the utterance
+    # diverges from there).  A wrong conditioner frame or sample window in the shadow part would move every log-probability by O(0.1).
     agree = (full == ref).float().mean().item()
     assert agree > 0.8, agree
     worst = 0.0
@@ -311,6 +325,12 @@ def test_generate_schedule_variants_are_bit_identical(monkeypatch):
         worst = max(worst, float(d.max()))
     print("split input expansion: max |dlogp| at period starts on undiverged utterances = %.2e" % worst)
     assert worst < 0.03, worst
+    # Folded first layer: log-probs of the first 20 samples on utterances whose histories still agree with the unfolded run
+    same_hist = torch.cumprod(torch.cat([torch.ones_like(fold[:, :1], dtype=torch.long), (fold[:, :19] == full[:, :19]).long()], 1), 1).bool()
+    d = (lp_fold[:, :20] - lpf[:, :20]).abs().amax(dim=-1)
+    assert same_hist[:, 0].all() and float(same_hist.float().mean()) > 0.5
+    print("folded first layer: max / mean |dlogp| over shared histories = %.3e / %.3e" % (float(d[same_hist].max()), float(d[same_hist].mean())))
+    assert float(d[same_hist].max()) < 0.03 and float(d[same_hist].mean()) < 0.01     # measured 1.1e-2 / 6.1e-3
 
 
 @pytest.mark.parametrize("dim,B,T", [(64, 3, 160), (128, 5, 240), (256, 130, 80)])
