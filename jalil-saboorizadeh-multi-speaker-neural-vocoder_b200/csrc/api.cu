@@ -268,6 +268,24 @@ static int ensure_gi_fold(srnn_ctx* ctx, cudaStream_t st) {
         // G^T (kin, 3H) = W_in^T (kin, H) . W_ih0^T;   b_gi0 (1, 3H) = b_in (1, H) . W_ih0^T + b_ih0
         SRNN_TRY(gemm_f32(t.kin, 3 * H, H, t.w_in_t, H, t.w_ih[0], H, nullptr, nullptr, 0, 0, t.g_in_t, 3 * H, st));
         SRNN_TRY(gemm_f32(1, 3 * H, H, t.b_in, H, t.w_ih[0], H, t.b_ih[0], nullptr, 0, 0, t.b_gi0, 3 * H, st));
+        if (!t.top) {          // first frame through the upsampling of the tier above
+            const TierPacked& u = ctx->tiers[i + 1];
+            if (!t.gup0_16) {
+                SRNN_TRY(ctx->weights.alloc((void**)&t.gup0_16, sizeof(__nv_bfloat16) * 3 * (size_t)H * H));
+                SRNN_TRY(ctx->weights.alloc((void**)&t.b_gup0, sizeof(float) * 3 * H));
+            }
+            float *wt = nullptr, *g32 = nullptr;
+            SRNN_CUDA(cudaMallocAsync((void**)&wt, sizeof(float) * (size_t)H * H, st));
+            SRNN_CUDA(cudaMallocAsync((void**)&g32, sizeof(float) * 3 * (size_t)H * H, st));
+            // W_up[0] is rows 0 .. H-1 of w_up, (o, k) row-major; the fp32 GEMM contracts over the second index of both operands
+            int rc = transpose_f32(u.w_up, wt, H, H, st);                                                     // (k, o)
+            if (rc == SRNN_OK) rc = gemm_f32(3 * H, H, H, t.w_ih[0], H, wt, H, nullptr, nullptr, 0, 0, g32, H, st);   // (g, k)
+            if (rc == SRNN_OK) rc = f32_to_bf16_pad(g32, 3 * H, H, H, t.gup0_16, 3 * H, H, st);
+            if (rc == SRNN_OK) rc = gemm_f32(1, 3 * H, H, u.b_up, H, t.w_ih[0], H, t.b_gi0, nullptr, 0, 0, t.b_gup0, 3 * H, st);
+            cudaFreeAsync(wt, st);
+            cudaFreeAsync(g32, st);
+            SRNN_TRY(rc);
+        }
     }
     ctx->gi_fold_valid = true;
     return SRNN_OK;
@@ -755,7 +773,7 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
     float* XP = GI[NT - 1];                        // gi_fold: GP (B, 3H)
     const int xp_lo = ttop.n - FS0 > 0 ? ttop.n - FS0 : 0, xp_hi = ttop.n;
     cudaEvent_t ev_xp = nullptr, ev_gip = nullptr;
-    bool xp_pending = false, gip_todo = false, gip_pending = false;
+    bool xp_pending = false, gip_todo = false, gip_pending = false, up_top_todo = false;
     auto launch_xp = [&](int off, cudaStream_t s) -> int {
         if (gi_fold)
             return tier_input_split(false, seq, Lseq, off, step_base, ttop.n, B, cond, cond_rows, n_cond, spk, c.cond_dim, ctx->lut,
@@ -844,8 +862,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                         // W_ih0 upper + b_gi0 of the period's FIRST frame on the serial path; the other fs_top - 1 frames follow
                         // in the shadow of the next sample launch
                         g_pdl = pdl && prev_tier_kernel;
-                        const int rc_g = gemm_umma(t.w_ih16[0], 3 * H, UP16, B, H, H, fs_top * H, t.b_gi0, nullptr, 0, GIP, nullptr,
-                                                   fs_top * 3 * H, 0, 128, bn_for(3 * H, 1), st);
+                        // (through the folded upsampling of the tier above: straight from its new state; that tier's upsampling
+                        // itself runs in the shadow with the other frames)
+                        const int rc_g = gemm_umma(t.gup0_16, 3 * H, hid16[i + 1] + (size_t)(NL - 1) * B * H, B, H, H, H, t.b_gup0,
+                                                   nullptr, 0, GIP, nullptr, fs_top * 3 * H, 0, 128, bn_for(3 * H, 1), st);
                         g_pdl = 0;
                         SRNN_TRY(rc_g);
                         gip_todo = fs_top > 1;
@@ -926,12 +946,10 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                     in = h;
                     in16 = h16;
                 }
-                if (gi_fold && t.top && NT == 2) {      // consumed only by tier 0's folded first layer: bf16, (B * fs, H) row-major
-                    g_pdl = pdl;
-                    const int rc_u = gemm_umma(t.w_up16, t.fs * H, in16, B, H, H, H, t.b_up, nullptr, 0, nullptr, UP16, t.fs * H, 0, 128,
-                                               bn_for(t.fs * H, 1), st);
-                    g_pdl = 0;
-                    SRNN_TRY(rc_u);
+                if (gi_fold && t.top && NT == 2) {
+                    // consumed only by tier 0's folded first layer, whose first frame goes through gup0_16: off the serial path,
+                    // launched with the shadow work of the next sample launch
+                    up_top_todo = true;
                 } else if (bf16 && gemm_umma_pair_wide_ok(t.fs * H, B)) {      // big upsampling (tier 2 at C2): one wave of CTA pairs
                     GemmOperands o{t.w_up16, in16, t.b_up, nullptr, OUT[i], nullptr, t.fs * H, H, H, 0, t.fs * H, 0, nullptr};
                     g_pdl = pdl;
@@ -982,6 +1000,12 @@ static int generate_graph(srnn_ctx* ctx, bool bf16, bool persist, int B, int n_c
                                 const TierPacked& t0 = ctx->tiers[0];
                                 gemm_umma_set_cta_cap(spare_sms);
                                 int rc_g = SRNN_OK;
+                                if (up_top_todo) {               // the top tier's upsampling (bf16, (B * fs, H) row-major) they contract
+                                    const TierPacked& tt = ctx->tiers[NT - 1];
+                                    rc_g = gemm_umma(tt.w_up16, tt.fs * H, hid16[NT - 1] + (size_t)(NL - 1) * B * H, B, H, H, H, tt.b_up,
+                                                     nullptr, 0, nullptr, UP16, tt.fs * H, 0, 128, B <= 128 ? bn_tier : 128, st2);
+                                    up_top_todo = false;
+                                }
                                 for (int f = 1; f < fs_top && rc_g == SRNN_OK; f += 2) {
                                     const int np = fs_top - f >= 2 ? 2 : 1;
                                     GemmOperands ops[2];

@@ -103,6 +103,11 @@ struct TierPacked {
     //   gi_0 = W_ih0 (W_in a + b_in + upper) + b_ih0 = G a + W_ih0 upper + b_gi0,   G = W_ih0 W_in,  b_gi0 = b_ih0 + W_ih0 b_in
     float* g_in_t = nullptr;  // (kin, 3H) = G^T: consecutive threads read consecutive gate rows
     float* b_gi0 = nullptr;   // (3H)
+    // ... and, for a tier fed by the tier above, through that tier's upsampling for its FIRST frame (j = 0):
+    //   W_ih0 upper_0 + b_gi0 = (W_ih0 W_up[0]) h_above + (W_ih0 b_up[0] + b_gi0): one GEMM straight from the upper tier's state,
+    //   so the upper tier's upsampling itself leaves the serial path
+    __nv_bfloat16* gup0_16 = nullptr;   // (3H, H) bf16
+    float* b_gup0 = nullptr;            // (3H)
     // split-bf16 copies (n_feat, 3K) of SRNN_MODE_BF16X3, packed lazily on the first use of that mode (ensure_x3)
     __nv_bfloat16* w_ih3[SRNN_MAX_RNN] = {};
     __nv_bfloat16* w_hh3[SRNN_MAX_RNN] = {};
