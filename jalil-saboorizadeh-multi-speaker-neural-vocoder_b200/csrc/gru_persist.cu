@@ -600,7 +600,17 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    pdl_wait();                                    // x, gh and the state come from the preceding kernels
+    // the weights are constants of the call: the W part of the first ring stages is requested BEFORE griddepcontrol.wait, so
+    // that as a programmatic dependent (of the lite cell / the previous layer) the launch already streams them while its
+    // predecessor finishes; x, gh and the state come from the preceding kernels and are only touched after the wait
+    const int early = NG < GC_RING ? NG : GC_RING;
+    if (warp == 4 && lane == 0) {
+        for (int g = 0; g < early; ++g) {
+            mbar_expect_tx(&full[g], GC_GROUP_BYTES);
+            tma_load_4d(sRing + (size_t)g * GC_GROUP_BYTES + GC_A_BYTES, &tmW, &full[g], 0, u0, 0, g * GC_GKB);
+        }
+    }
+    pdl_wait();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 4) {
@@ -608,11 +618,13 @@ k_gru_cell_gen(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int g = 0; g < NG; ++g) {
                 const int st = g % GC_RING;
                 const uint32_t ph = (g / GC_RING) & 1;
-                mbar_wait(&empty[st], ph ^ 1);
-                mbar_expect_tx(&full[st], GC_GROUP_BYTES);
                 uint8_t* dst = sRing + (size_t)st * GC_GROUP_BYTES;
+                if (g >= early) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    mbar_expect_tx(&full[st], GC_GROUP_BYTES);
+                    tma_load_4d(dst + GC_A_BYTES, &tmW, &full[st], 0, u0, 0, g * GC_GKB);
+                }
                 tma_load_3d(dst, &tmX, &full[st], 0, rs * GP_ROWS, g * GC_GKB);
-                tma_load_4d(dst + GC_A_BYTES, &tmW, &full[st], 0, u0, 0, g * GC_GKB);
             }
         }
     } else if (warp >= 5) {
