@@ -223,10 +223,12 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
         if (g >= 3)   // sample i-3 (tap FS-3, the newest one this prefetch uses) has been drawn.  Three barriers by
                       // step % 3: E can be up to two steps past the awaited one, which would alias a phase parity.
             mbar_wait(&q_ready[g % 3], (g / 3 - 1) & 1);
-        // L2 -> SM ingest is the shared resource of a step (x1 tile 48 KB by TMA, this gather 110 KB): the gather of step g runs
-        // in step g-1 AFTER that step's x1 tile has landed, i.e. under the epilogues / output GEMM / reduce, never beside the TMA
-        // loads the hidden GEMM is waiting for (measured: +1300 cycles per step when they overlap).
-        if (g >= 1 && g < p.nsteps && !(p.dbg & 2)) mbar_wait(&full[3], (g - 1) & 1);   // (the carry gathers must not run late)
+        // The gather runs as far ahead as its inputs allow (up to two steps: sample i-3 is its newest tap).  Earlier versions held
+        // it back until the current step's x1 tile had landed, so that the latency-bound gather (110 KB per step) never ran beside
+        // the TMA loads the hidden GEMM waits for (+1300 cycles per step then); once the E path had shrunk by ~3 k cycles that rule
+        // made the GATHER the critical path (E waited 1.4 k cycles per step for P): without it 1824 -> 1874x real-time.
+        // SRNN_MC_DBG=2 restores the old rule.
+        if (g >= 1 && g < p.nsteps && (p.dbg & 2)) mbar_wait(&full[3], (g - 1) & 1);
         float acc[RPC][8];
 #pragma unroll
         for (int r = 0; r < RPC; ++r) {
