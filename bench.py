@@ -202,13 +202,17 @@ def train_block(args, rank, world, dev, steps, warmup):
     torch.cuda.synchronize()
     l0 = lib.srnn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]      # per-step stamps: the median exposes a transient
     e0.record()
-    for i in range(warmup, n_it):
+    marks[0].record()
+    for k, i in enumerate(range(warmup, n_it)):
         step(i)
+        marks[k + 1].record()
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    per_step = sorted(marks[k].elapsed_time(marks[k + 1]) for k in range(steps))
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     # data-parallel equivalence inside the bench run: the parameters must stay bit-identical on every rank
     chk = torch.stack([p.detach().double().sum() for p in pred.parameters()]).sum().reshape(1)
@@ -230,6 +234,7 @@ def train_block(args, rank, world, dev, steps, warmup):
     return {
         "metric": "training tokens/sec (teacher-forced step)", "value": tokens / secs, "unit": "tokens/s", "n_gpus": world,
         "tokens_per_s_per_gpu": tokens / secs / world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * secs / steps,
+        "ms_per_step_median_rank0": per_step[len(per_step) // 2], "ms_per_step_max_rank0": per_step[-1],
         "higher_is_better": True, "scaling": "weak", "dtype": "bf16" if mode == S.MODE_BF16 else "f32", "data": "synthetic",
         "config": {"workload": "C3 training step: 3-tier [20,4] SampleRNN dim 1024, batch %d x T %d per GPU, Adam lr 1e-4 "
                                "with element-wise gradient clamp" % (B, T),

@@ -101,6 +101,16 @@ int srnn_create(const srnn_config* cfg, srnn_ctx** out) {
     cudaGetDevice(&c->device);
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
     for (auto& e : c->ev_stage) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    {   // a few paths take stream-ordered scratch (cudaMallocAsync: the table fold-back of every training step, test hooks): keep
+        // the device pool's memory across synchronisation points instead of returning it to the driver (default threshold 0),
+        // or a host sync inside a training loop turns the next step's allocation into a cudaMalloc
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return SRNN_OK;
 }
