@@ -442,7 +442,7 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
             const int i = i0 + k;
             // the next kernel on the stream (the tier step that consumes this frame) may be scheduled now: it waits in
             // griddepcontrol.wait until this grid has completed, only its launch latency and prologue move forward
-            if (k == p.nsteps - 1) pdl_trigger();
+            if (k == p.nsteps - 1) pdl_trigger();     // (one step earlier: no difference)
             // ---- E1: x1 = relu(P + Tbl[FS-1][newest] + Tbl[FS-2][second newest]) for the owned rows -> global exchange buffer ----
             MC_TRACE(0);
             if (tidE < RPC) {
@@ -560,11 +560,17 @@ k_mlp_cluster(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ 
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = bo[j];
+                float4 pa[MC_CS], pb[MC_CS];             // all sixteen shared-memory loads in flight before the first add
 #pragma unroll
                 for (int s = 0; s < MC_CS; ++s) {
                     const float4* lp = reinterpret_cast<const float4*>(sLand + (s * RPC + r2) * SRNN_Q + lane * 8);
-                    const float4 a0 = lp[0], a1 = lp[1];
-                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+                    pa[s] = lp[0];
+                    pb[s] = lp[1];
+                }
+#pragma unroll
+                for (int s = 0; s < MC_CS; ++s) {
+                    v[0] += pa[s].x; v[1] += pa[s].y; v[2] += pa[s].z; v[3] += pa[s].w;
+                    v[4] += pb[s].x; v[5] += pb[s].y; v[6] += pb[s].z; v[7] += pb[s].w;
                 }
                 MC_TRACE(11);
                 float m = v[0];
