@@ -508,8 +508,9 @@ def main():
     d2h = audio_h.numel() * 4
     cfg = workload_config(args, world)
     cfg.update({"l2": "192 MiB flush write between timed iterations", "us_per_sample_step": 1e6 * secs / args.steps / T,
-                "schedule": "default (shadow recurrent GEMMs, programmatic dependent launches, split top-tier input expansion: "
-                            "re-associates one fp32 sum, inside the bf16 gate)"})
+                "schedule": "default (shadow recurrent GEMMs, programmatic dependent launches incl. the sample kernel, input expansion "
+                            "folded into the first GRU layer with its known columns summed in the shadow, table sums carried "
+                            "across sample launches: fp32 sums re-associated / different bf16 rounding points, inside the bf16 gate)"})
     line = {
         "metric": "generated samples/sec", "value": value, "unit": "samples/s", "x_realtime_16k": value / SAMPLE_RATE,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
