@@ -197,6 +197,10 @@ def test_generate_bf16_mode_against_oracle(dim, B, mode):
     dict(frame_sizes=[16], n_rnn=1, dim=128, learn_h0=True, q_levels=256, ulaw=True, weight_norm=False, cond_dim=43, spk_dim=6),   # C1 shape
     dict(frame_sizes=[4, 2, 2], n_rnn=1, dim=64, learn_h0=False, q_levels=256, ulaw=False, weight_norm=True, cond_dim=5, spk_dim=6),
     dict(frame_sizes=[20, 4], n_rnn=3, dim=256, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6),
+    # the folded-input schedule (dim % 256 == 0) on a single-tier model (top tier only: C1 shape) and on one GRU layer per tier
+    # (the folded upsampling then contracts the lite cell's own output)
+    dict(frame_sizes=[16], n_rnn=1, dim=256, learn_h0=True, q_levels=256, ulaw=True, weight_norm=False, cond_dim=43, spk_dim=6),
+    dict(frame_sizes=[20, 4], n_rnn=1, dim=256, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=86, spk_dim=6),
 ])
 def test_generate_bf16_other_architectures(cfg, mode):
     """Single-tier (C1), three-tier / linear-quantised / buffer-h0 and three-GRU-layer models through the tcgen05 generator."""
