@@ -95,3 +95,28 @@ def test_gradient_clipping_wrapper_mirrors_the_reference_call():
     assert S.gradient_clipping(opt) is opt
     with pytest.raises(Exception):
         S.gradient_clipping(torch.optim.SGD(ps, lr=0.1))
+
+
+def test_per_module_forward_has_no_cpu_fallback_and_survives_copies():
+    """FrameLevelRNN.forward / SampleLevelMLP.forward run on the owning SampleRNN's CUDA context: on a CPU model they raise
+    (no fallback); the weak owner registry does not leak into state_dict / pickling / deepcopy of the modules."""
+    import copy
+    import pickle
+    import torch
+    import srnn_b200 as S
+    c = dict(frame_sizes=[4, 2], n_rnn=1, dim=16, learn_h0=True, q_levels=256, ulaw=True, weight_norm=True, cond_dim=5, spk_dim=3)
+    m = S.SampleRNN(**c)
+    top, mlp = m.frame_level_rnns[-1], m.sample_level_mlp
+    with pytest.raises(S.SrnnError):
+        top(torch.zeros(2, 3, 8), None, None, torch.zeros(2, 3, 5), torch.zeros(2, 1, dtype=torch.long))
+    with pytest.raises(S.SrnnError):
+        mlp(torch.zeros(2, 7, dtype=torch.long), torch.zeros(2, 4, 16))
+    keys = set(m.state_dict().keys())
+    m2 = copy.deepcopy(m)
+    assert set(m2.state_dict().keys()) == keys and not any("_owner" in k for k in keys)
+    pickle.loads(pickle.dumps(m.state_dict()))
+    # a copied tier is not registered until its own model binds it (then it resolves to the copy, not the original)
+    m2._bind_modules()
+    from importlib import import_module
+    M = import_module("jalil-saboorizadeh-multi-speaker-neural-vocoder_b200.model")
+    assert M._owner_of(m2.frame_level_rnns[0])[0] is m2 and M._owner_of(m.frame_level_rnns[0])[0] is m
