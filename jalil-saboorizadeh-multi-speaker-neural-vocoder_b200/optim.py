@@ -26,6 +26,7 @@ class ClampAdam:
         # embedding, then per tier (lowest first) its upsampling and the rest.  Each stage is all-reduced on a side stream as
         # soon as its event fires, i.e. while the backward pass of the following stages still runs.
         self._stages = []                   # [(stage id, first element, one-past-last element)]
+        self._stage_params = []             # [(first parameter index, one-past-last)] per stage, same order as _stages
         if model is not None:
             groups = [(0, list(model.sample_level_mlp.parameters()))]
             for i, rnn in enumerate(model.frame_level_rnns):
@@ -41,6 +42,7 @@ class ClampAdam:
                 n = sum(p.numel() for p in ps)
                 if n:
                     self._stages.append((sid, off, off + n))
+                    self._stage_params.append((len(ordered), len(ordered) + len(ps)))
                 ordered += ps
                 off += n
             rest = [p for p in self.params if id(p) not in seen]       # parameters the backward pass does not know about
@@ -94,7 +96,7 @@ class ClampAdam:
         if self.model is not None:      # one backward pass may write its gradients directly into the (zeroed) views
             self.model._grad_sink = {id(p): v for p, v in zip(self.params, self._views)}
 
-    def _allreduce(self, overlap=False):
+    def _allreduce(self, overlap=False, staged_update=False):
         import torch.distributed as dist
         self._grad_scale = 1.0
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.process_group) == 1:
@@ -110,6 +112,11 @@ class ClampAdam:
                 L.check(lib.srnn_bwd_wait_stage(self.model._ctx, sid, C.c_void_p(comm.cuda_stream)))
                 with torch.cuda.stream(comm):
                     works.append(dist.all_reduce(flat[a:b], group=self.process_group, async_op=True))
+            if staged_update:
+                # the caller waits for each stage's collective right before that stage's clamp+Adam launch, so the update of
+                # the early stages runs while the last stage's gradients are still on the wire
+                self._grad_scale = 1.0 / dist.get_world_size(self.process_group)
+                return works
             for w in works:
                 w.wait()                                               # the compute stream waits for the collectives
         else:
@@ -125,21 +132,30 @@ class ClampAdam:
         if self.model is not None:
             self.model._grad_sink_used = False
         self._adopt()
-        self._allreduce(overlap=direct)
+        works = self._allreduce(overlap=direct, staged_update=direct)
         self.step_count += 1
-        n = len(self.params)
-        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
-        sizes = (C.c_int64 * n)(*[p.numel() for p in self.params])
         lr = self.param_groups[0]["lr"]
         dev = self.params[0].device
         for t in list(self.params) + [p.grad for p in self.params] + self.exp_avg + self.exp_avg_sq:
             if t.device != dev or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise L.SrnnError("ClampAdam: every parameter, gradient and moment must be contiguous fp32 on one CUDA device")
-        with torch.cuda.device(dev):
-            L.check(L.load().srnn_clamp_adam_step_scaled(
-                n, arr([p.data for p in self.params]), arr([p.grad for p in self.params]), arr(self.exp_avg),
-                arr(self.exp_avg_sq), sizes, lr, self.betas[0], self.betas[1], self.eps, self.step_count, self.clamp,
-                self._grad_scale, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+        def launch(lo, hi):
+            n = hi - lo
+            arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts[lo:hi]])
+            sizes = (C.c_int64 * n)(*[p.numel() for p in self.params[lo:hi]])
+            with torch.cuda.device(dev):
+                L.check(L.load().srnn_clamp_adam_step_scaled(
+                    n, arr([p.data for p in self.params]), arr([p.grad for p in self.params]), arr(self.exp_avg),
+                    arr(self.exp_avg_sq), sizes, lr, self.betas[0], self.betas[1], self.eps, self.step_count, self.clamp,
+                    self._grad_scale, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+        if works:                                   # data parallel, staged: one clamp+Adam launch per backward stage
+            for w, (lo, hi) in zip(works, self._stage_params):
+                w.wait()                            # the compute stream waits for THIS stage's collective only
+                launch(lo, hi)
+        else:
+            launch(0, len(self.params))
         # the library updated the parameters behind torch's back: make SampleRNN re-pack them on the next forward
         if self.model is not None:
             self.model._packed_key = None
